@@ -1,0 +1,590 @@
+// Model build on the GPU: A = K_offdiag + (1+noise) I [+ Cinv], blocked FP64 Cholesky A = L L^T,
+// W = inv(L) by blocked right-looking substitution, fragment-packing of W for the scoring GEMM,
+// beta = W Y.  All off-diagonal block updates run on the FP64 tensor pipe (DMMA.8x8x4).
+//
+// Replaces (reference file:line): GaussianProcess._computeCorrelations / addData
+// (ego/gaussianprocess/__init__.py:134-149,267-308), linalg.cholesky(R + inv(C)) (:487-498) and
+// the explicit linalg.inv(R) of cdirectGP (ego/acquisition/__init__.py:385-388).
+#include "model.cuh"
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+namespace ibo {
+
+long g_launches = 0;
+static thread_local std::string g_err;
+void set_error(const std::string& s) { g_err = s; }
+const char* get_error() { return g_err.c_str(); }
+
+int grow(double** p, size_t* cap, size_t need) {
+    if (*cap >= need) return IBO_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    size_t want = need + need / 8;
+    cudaError_t e = cudaMalloc((void**)p, want * sizeof(double));
+    if (e != cudaSuccess) {
+        e = cudaMalloc((void**)p, need * sizeof(double));
+        want = need;
+        if (e != cudaSuccess) { set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); cudaGetLastError(); return IBO_E_NOMEM; }
+    }
+    *cap = want;
+    return IBO_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// covariance function on the scaled squared distance r2 = sum_j ((x_j - y_j)/theta_j)^2
+//   (ego/gaussianprocess/kernel.py:87-89,147-149,207-210,246-248; cpp/optimizeGP.cpp:70-112)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double cov_from_r2(int kind, double sf2, double r2) {
+    if (kind <= IBO_KERNEL_SE_ISO) return sf2 * exp(-0.5 * r2);
+    double r = sqrt(r2);
+    if (kind == IBO_KERNEL_MATERN3) {
+        double z = 1.7320508075688772 * r;   // sqrt(3)
+        return sf2 * (1.0 + z) * exp(-z);
+    }
+    double z = 2.23606797749979 * r;         // sqrt(5)
+    return sf2 * (1.0 + z + 5.0 * r2 / 3.0) * exp(-z);
+}
+
+// A[i][j] = k(x_i, x_j) (i != j), 1 + noise on the diagonal, + Cinv; identity in the padding.
+__global__ void build_A_kernel(double* __restrict__ A, const double* __restrict__ Xt, const double* __restrict__ Cinv,
+                               int N, int Np, int d, int kind, double sf2, double noise) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    if (j >= Np) return;
+    double v;
+    if (i >= N || j >= N) v = (i == j) ? 1.0 : 0.0;
+    else if (i == j) v = 1.0 + noise;
+    else {
+        // evaluate with (min,max) ordering so that A is exactly symmetric
+        int a = i < j ? i : j, b = i < j ? j : i;
+        double r2 = 0;
+        for (int t = 0; t < d; t++) { double df = Xt[(size_t)a * d + t] - Xt[(size_t)b * d + t]; r2 += df * df; }
+        v = cov_from_r2(kind, sf2, r2);
+    }
+    if (Cinv && i < N && j < N) v += Cinv[(size_t)i * N + j];
+    A[(size_t)i * Np + j] = v;
+}
+
+// A_rev = J invR J (reversal of the leading N x N part), identity padding -- legacy acqmaxGP path.
+__global__ void build_reversed_kernel(double* __restrict__ A, const double* __restrict__ invR, int N, int Np) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    if (j >= Np) return;
+    double v;
+    if (i >= N || j >= N) v = (i == j) ? 1.0 : 0.0;
+    else v = invR[(size_t)(N - 1 - i) * N + (N - 1 - j)];
+    A[(size_t)i * Np + j] = v;
+}
+
+// W'[i][j] = G[N-1-j][N-1-i] for j <= i < N (G = chol(J invR J)), identity padding, zeros above.
+__global__ void reverse_transpose_kernel(double* __restrict__ W, const double* __restrict__ G, int N, int Np) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    if (j >= Np) return;
+    double v = 0.0;
+    if (i >= N || j >= N) v = (i == j) ? 1.0 : 0.0;
+    else if (j <= i) v = G[(size_t)(N - 1 - j) * Np + (N - 1 - i)];
+    W[(size_t)i * Np + j] = v;
+}
+
+__global__ void set_identity_kernel(double* __restrict__ W, int Np) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    if (j < Np) W[(size_t)i * Np + j] = (i == j) ? 1.0 : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Diagonal block: L_kk = chol(A_kk) in place (lower), D_k = inv(L_kk) (dense 128x128, zeros above).
+// One CTA, 512 threads.  info gets the first failing global pivot (1-based) if A is not SPD.
+// ---------------------------------------------------------------------------------------------
+constexpr int PS = 129;   // smem row stride of the 128x128 block
+__global__ void __launch_bounds__(512) potrf_diag_kernel(double* __restrict__ A, int ld, int kblk,
+                                                         double* __restrict__ Dall, int* __restrict__ info) {
+    extern __shared__ double sm[];
+    double* S = sm;                    // [128][PS]
+    double* XA = sm + 128 * PS;        // [64][64]  XA[t][col]
+    double* XC = XA + 64 * 64;         // [64][64]
+    const int tid = threadIdx.x;
+    double* Ablk = A + (size_t)kblk * 128 * ld + (size_t)kblk * 128;
+    for (int idx = tid; idx < 128 * 128; idx += 512) {
+        int r = idx >> 7, c = idx & 127;
+        S[r * PS + c] = (c <= r) ? Ablk[(size_t)r * ld + c] : 0.0;
+    }
+    __syncthreads();
+    for (int j = 0; j < 128; j++) {
+        double piv = S[j * PS + j];
+        if (!(piv > 0.0)) {   // also catches NaN
+            if (tid == 0) atomicCAS(info, 0, kblk * 128 + j + 1);
+            piv = 1.0;        // keep going with garbage; the host checks info
+        }
+        double inv = 1.0 / sqrt(piv);
+        __syncthreads();
+        if (tid == 0) S[j * PS + j] = sqrt(piv);
+        int i = j + 1 + tid;
+        if (i < 128) S[i * PS + j] *= inv;
+        __syncthreads();
+        int n = 127 - j;
+        for (int idx = tid; idx < n * n; idx += 512) {
+            int a = idx / n, b = idx - a * n;
+            if (b <= a) {
+                int r = j + 1 + a, c = j + 1 + b;
+                S[r * PS + c] -= S[r * PS + j] * S[c * PS + j];
+            }
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < 128 * 128; idx += 512) {
+        int r = idx >> 7, c = idx & 127;
+        if (c <= r) Ablk[(size_t)r * ld + c] = S[r * PS + c];
+    }
+    // ---- inverse of the lower-triangular block, 2x2 split into 64x64 quadrants ----
+    // XA = inv(L11), XC = inv(L22): one thread per column, forward substitution.
+    if (tid < 128) {
+        const int q = tid >> 6, col = tid & 63;
+        const int o = q * 64;
+        double* X = q ? XC : XA;
+        for (int i = 0; i < 64; i++) {
+            double s = (i == col) ? 1.0 : 0.0;
+            for (int t = 0; t < i; t++) s -= S[(o + i) * PS + o + t] * X[t * 64 + col];
+            X[i * 64 + col] = (i < col) ? 0.0 : s / S[(o + i) * PS + o + i];
+        }
+    }
+    __syncthreads();
+    // T = L21 * XA  -> stored in the (unused) upper-right quadrant of S
+    for (int idx = tid; idx < 64 * 64; idx += 512) {
+        int r = idx >> 6, c = idx & 63;
+        double s = 0;
+        for (int t = c; t < 64; t++) s += S[(64 + r) * PS + t] * XA[t * 64 + c];
+        S[r * PS + 64 + c] = s;
+    }
+    __syncthreads();
+    double* D = Dall + (size_t)kblk * 128 * 128;
+    for (int idx = tid; idx < 128 * 128; idx += 512) {
+        int r = idx >> 7, c = idx & 127;
+        double v;
+        if (r < 64) v = (c < 64) ? XA[r * 64 + c] : 0.0;
+        else if (c >= 64) v = XC[(r - 64) * 64 + (c - 64)];
+        else {
+            // -(XC * T)[r-64][c]
+            double s = 0;
+            int rr = r - 64;
+            for (int t = 0; t <= rr; t++) s += XC[rr * 64 + t] * S[t * PS + 64 + c];
+            v = -s;
+        }
+        D[r * 128 + c] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 128x128x(K) tile GEMM on the DMMA pipe from row-major global operands.
+//   8 warps, warp tile 64x32 (8 x 4 DMMA tiles, 64 FP64 accumulators per thread),
+//   cp.async double-buffered 16-deep k-steps into padded (bank-conflict-free) shared memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int AS_STRIDE = 20;    // [128][20]: (row*20 + k) mod 16 distinct over a half-warp
+constexpr int BN_STRIDE = 132;   // [16][132] for the non-transposed B operand
+constexpr int TILE_SMEM_DOUBLES = 2 * (128 * AS_STRIDE) + 2 * (128 * AS_STRIDE);   // A + B(T) buffers (B(N) fits too)
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+// acc[mt][nt][2] += A(128 x K) * op(B); TRANSB: B stored [n][k] (row-major, ldb), else [k][n].
+template <bool TRANSB>
+__device__ __forceinline__ void tile_gemm_core(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
+                                               int K, double (&acc)[8][4][2], double* sm) {
+    double* sA = sm;                         // [2][128*AS_STRIDE]
+    double* sB = sm + 2 * 128 * AS_STRIDE;   // [2][128*AS_STRIDE] or [2][16*BN_STRIDE]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int nk = K / BK;
+    auto load_stage = [&](int kb, int buf) {
+        // A: 128 rows x 16 doubles = 1024 16-byte chunks
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            int idx = tid + c * 256;
+            int r = idx >> 3, ch = idx & 7;
+            cp_async16(sA + buf * 128 * AS_STRIDE + r * AS_STRIDE + ch * 2, A + (size_t)r * lda + kb * BK + ch * 2);
+        }
+        if (TRANSB) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                int idx = tid + c * 256;
+                int r = idx >> 3, ch = idx & 7;
+                cp_async16(sB + buf * 128 * AS_STRIDE + r * AS_STRIDE + ch * 2, B + (size_t)r * ldb + kb * BK + ch * 2);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                int idx = tid + c * 256;
+                int r = idx >> 6, ch = idx & 63;
+                cp_async16(sB + buf * 16 * BN_STRIDE + r * BN_STRIDE + ch * 2, B + (size_t)(kb * BK + r) * ldb + ch * 2);
+            }
+        }
+        cp_async_commit();
+    };
+    load_stage(0, 0);
+    for (int kb = 0; kb < nk; kb++) {
+        const int buf = kb & 1;
+        if (kb + 1 < nk) { load_stage(kb + 1, buf ^ 1); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();
+        const double* a_s = sA + buf * 128 * AS_STRIDE + (wm * 64 + (lane >> 2)) * AS_STRIDE + (lane & 3);
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++) {
+            double af[8], bf[4];
+#pragma unroll
+            for (int mt = 0; mt < 8; mt++) af[mt] = a_s[mt * 8 * AS_STRIDE + ks * 4];
+            if (TRANSB) {
+                const double* b_s = sB + buf * 128 * AS_STRIDE + (wn * 32 + (lane >> 2)) * AS_STRIDE + (lane & 3);
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) bf[nt] = b_s[nt * 8 * AS_STRIDE + ks * 4];
+            } else {
+                const double* b_s = sB + buf * 16 * BN_STRIDE + (ks * 4 + (lane & 3)) * BN_STRIDE + wn * 32 + (lane >> 2);
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) bf[nt] = b_s[nt * 8];
+            }
+#pragma unroll
+            for (int mt = 0; mt < 8; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+        }
+        __syncthreads();
+    }
+}
+
+enum { MODE_CHOL_PANEL = 0, MODE_CHOL_TRAIL = 1, MODE_TRTRI_SCALE = 2, MODE_TRTRI_UPDATE = 3 };
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 1) block_step_kernel(double* __restrict__ A, double* __restrict__ W,
+                                                            const double* __restrict__ D, int Np, int k) {
+    extern __shared__ double sm[];
+    double acc[8][4][2];
+#pragma unroll
+    for (int a = 0; a < 8; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wm = warp >> 2, wn = warp & 3;
+    double* C;
+    bool subtract;
+    if (MODE == MODE_CHOL_PANEL) {
+        // A_ik <- A_ik * D_k^T, i = k+1+blockIdx.x
+        int i = k + 1 + blockIdx.x;
+        C = A + (size_t)i * 128 * Np + (size_t)k * 128;
+        tile_gemm_core<true>(C, Np, D + (size_t)k * 128 * 128, 128, 128, acc, sm);
+        subtract = false;
+    } else if (MODE == MODE_CHOL_TRAIL) {
+        // A_ij -= L_ik L_jk^T for k < j <= i
+        int i = k + 1 + blockIdx.y, j = k + 1 + blockIdx.x;
+        if (j > i) return;
+        C = A + (size_t)i * 128 * Np + (size_t)j * 128;
+        tile_gemm_core<true>(A + (size_t)i * 128 * Np + (size_t)k * 128, Np, A + (size_t)j * 128 * Np + (size_t)k * 128, Np, 128, acc, sm);
+        subtract = true;
+    } else if (MODE == MODE_TRTRI_SCALE) {
+        // W_kj <- D_k * B_kj, j = blockIdx.x <= k   (B lives in W)
+        int j = blockIdx.x;
+        C = W + (size_t)k * 128 * Np + (size_t)j * 128;
+        tile_gemm_core<false>(D + (size_t)k * 128 * 128, 128, C, Np, 128, acc, sm);
+        subtract = false;
+    } else {
+        // B_ij -= L_ik * W_kj for i > k, j <= k
+        int i = k + 1 + blockIdx.y, j = blockIdx.x;
+        C = W + (size_t)i * 128 * Np + (size_t)j * 128;
+        tile_gemm_core<false>(A + (size_t)i * 128 * Np + (size_t)k * 128, Np, W + (size_t)k * 128 * Np + (size_t)j * 128, Np, 128, acc, sm);
+        subtract = true;
+    }
+    // all operand reads are complete (tile_gemm_core ends with __syncthreads) -> in-place write is safe
+#pragma unroll
+    for (int mt = 0; mt < 8; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+            int r = wm * 64 + mt * 8 + (lane >> 2), c = wn * 32 + nt * 8 + 2 * (lane & 3);
+            double2* p = reinterpret_cast<double2*>(C + (size_t)r * Np + c);
+            double2 v;
+            if (subtract) { v = *p; v.x -= acc[mt][nt][0]; v.y -= acc[mt][nt][1]; }
+            else { v.x = acc[mt][nt][0]; v.y = acc[mt][nt][1]; }
+            *p = v;
+        }
+}
+
+// Pack W (row-major, lower) into fragment-major blobs for the scoring GEMM.
+__global__ void pack_w_kernel(const double* __restrict__ W, double* __restrict__ Wpack, int Np, int nb) {
+    // one CTA per (row-block i, k-blob kb <= (i+1)*8-1)
+    int i = blockIdx.y, kb = blockIdx.x;
+    if (kb >= (i + 1) * KB_PER_BLOCK) return;
+    double* blob = Wpack + (wpack_base(i) + kb) * (size_t)BLOB;
+    for (int idx = threadIdx.x; idx < BLOB; idx += blockDim.x) {
+        int r = idx >> 4, kk = idx & 15;
+        blob[blob_offset(r, kk)] = W[(size_t)(i * 128 + r) * Np + kb * BK + kk];
+    }
+}
+
+// out[r] = sum_{c<=r} W[r][c] * v[c]  (one warp per row; fixed summation order)
+__global__ void tri_matvec_kernel(const double* __restrict__ W, const double* __restrict__ v, double* __restrict__ out, int Np) {
+    int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (r >= Np) return;
+    double s = 0;
+    for (int c = lane; c <= r; c += 32) s += W[(size_t)r * Np + c] * v[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[r] = s;
+}
+
+static bool g_attr_done = false;
+static std::mutex g_attr_mu;
+static int set_kernel_attrs() {
+    std::lock_guard<std::mutex> lk(g_attr_mu);
+    if (g_attr_done) return IBO_OK;
+    const int tile_smem = TILE_SMEM_DOUBLES * 8;
+    IBO_CUDA_TRY(cudaFuncSetAttribute(block_step_kernel<MODE_CHOL_PANEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem));
+    IBO_CUDA_TRY(cudaFuncSetAttribute(block_step_kernel<MODE_CHOL_TRAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem));
+    IBO_CUDA_TRY(cudaFuncSetAttribute(block_step_kernel<MODE_TRTRI_SCALE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem));
+    IBO_CUDA_TRY(cudaFuncSetAttribute(block_step_kernel<MODE_TRTRI_UPDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem));
+    IBO_CUDA_TRY(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 * PS + 2 * 64 * 64) * 8));
+    g_attr_done = true;
+    return IBO_OK;
+}
+
+// Factorise m->dA in place, produce dW, dD, dWpack, dBetaY, dBeta1.
+// from_inverse_reversed: dA holds J invR J; W' = reverse-transpose of its Cholesky factor.
+int launch_factorize(ibo_model* m, bool from_inverse_reversed) {
+    int rc = set_kernel_attrs();
+    if (rc) return rc;
+    cudaStream_t st = m->stream;
+    const int Np = m->Np, nb = m->nb;
+    const int tile_smem = TILE_SMEM_DOUBLES * 8;
+    const int potrf_smem = (128 * PS + 2 * 64 * 64) * 8;
+    IBO_CUDA_TRY(cudaMemsetAsync(m->dInfo, 0, sizeof(int), st));
+    for (int k = 0; k < nb; k++) {
+        potrf_diag_kernel<<<1, 512, potrf_smem, st>>>(m->dA, Np, k, m->dD, m->dInfo);
+        g_launches++;
+        int nrem = nb - 1 - k;
+        if (nrem > 0) {
+            block_step_kernel<MODE_CHOL_PANEL><<<nrem, 256, tile_smem, st>>>(m->dA, nullptr, m->dD, Np, k);
+            block_step_kernel<MODE_CHOL_TRAIL><<<dim3(nrem, nrem), 256, tile_smem, st>>>(m->dA, nullptr, m->dD, Np, k);
+            g_launches += 2;
+        }
+    }
+    dim3 g2((Np + 255) / 256, Np);
+    if (from_inverse_reversed) {
+        reverse_transpose_kernel<<<g2, 256, 0, st>>>(m->dW, m->dA, m->N, Np);
+        g_launches++;
+    } else {
+        set_identity_kernel<<<g2, 256, 0, st>>>(m->dW, Np);
+        g_launches++;
+        for (int k = 0; k < nb; k++) {
+            block_step_kernel<MODE_TRTRI_SCALE><<<k + 1, 256, tile_smem, st>>>(m->dA, m->dW, m->dD, Np, k);
+            g_launches++;
+            if (k + 1 < nb) {
+                block_step_kernel<MODE_TRTRI_UPDATE><<<dim3(k + 1, nb - 1 - k), 256, tile_smem, st>>>(m->dA, m->dW, m->dD, Np, k);
+                g_launches++;
+            }
+        }
+    }
+    pack_w_kernel<<<dim3(nb * KB_PER_BLOCK, nb), 256, 0, st>>>(m->dW, m->dWpack, Np, nb);
+    tri_matvec_kernel<<<(Np + 7) / 8, 256, 0, st>>>(m->dW, m->dY, m->dBetaY, Np);
+    g_launches += 2;
+    IBO_CUDA_TRY(cudaGetLastError());
+    return IBO_OK;
+}
+
+}  // namespace ibo
+
+// =============================================================================================
+// C ABI: model lifetime
+// =============================================================================================
+using namespace ibo;
+
+extern "C" const char* ibo_last_error(void) { return ibo::get_error(); }
+extern "C" const char* ibo_version(void) { return "ibo_b200 0.1 (sm_100a)"; }
+extern "C" long ibo_launch_count(void) { return ibo::g_launches; }
+
+extern "C" int ibo_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { set_error(std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e)); cudaGetLastError(); return 0; }
+    return n;
+}
+
+static void free_model(ibo_model* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    double** ptrs[] = {&m->dXt, &m->dInvTheta, &m->dA, &m->dAorig, &m->dW, &m->dD, &m->dWpack, &m->dBetaY, &m->dBeta1, &m->dY,
+                       &m->dPmeans, &m->dPbeta, &m->dPlb, &m->dPwidth, &m->dCand, &m->dSlab, &m->dPart, &m->dOut, &m->dBlkBest, &m->dBest};
+    for (auto p : ptrs) if (*p) { cudaFree(*p); *p = nullptr; }
+    if (m->dInfo) cudaFree(m->dInfo);
+    if (m->dBlkIdx) cudaFree(m->dBlkIdx);
+    if (m->dBestIdx) cudaFree(m->dBestIdx);
+    if (m->hPinned) cudaFreeHost(m->hPinned);
+    for (auto& e : m->ev) if (e) cudaEventDestroy(e);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+static int theta_and_sf2(int kind, const double* hyper, int nhyper, int d, bool clip_ard, std::vector<double>& theta, double* sf2) {
+    theta.assign(d, 1.0);
+    *sf2 = 1.0;
+    bool ard = (kind == IBO_KERNEL_SE_ARD || kind == IBO_KERNEL_MATERN5_ARD);
+    if (ard) {
+        if (nhyper < d) { set_error("ARD kernel needs at least d hyperparameters"); return IBO_E_BADARG; }
+        for (int j = 0; j < d; j++) {
+            double t = hyper[j];
+            if (kind == IBO_KERNEL_SE_ARD && clip_ard) t = fmin(fmax(t, 1e-4), 1e4);   // kernel.py:141
+            theta[j] = t;
+        }
+        if (nhyper > d) *sf2 = exp(2.0 * log(hyper[d]));                                // kernel.py:63
+    } else {
+        if (nhyper < 1) { set_error("isotropic kernel needs theta"); return IBO_E_BADARG; }
+        for (int j = 0; j < d; j++) theta[j] = hyper[0];
+        if (kind != IBO_KERNEL_SE_ISO && nhyper > 1) *sf2 = exp(2.0 * log(hyper[1]));   // kernel.py:203-204,242-243
+    }
+    return IBO_OK;
+}
+
+static int create_common(int device, int kind, const double* hyper, int nhyper, const double* X, const double* Y, int N, int d,
+                         double noise, const double* Cinv, const double* invR, double sf2_override, bool legacy,
+                         int npb, const double* pmeans, const double* pbeta, double ptheta, const double* plb, const double* pwidth,
+                         ibo_model** out, int* info) {
+    if (info) *info = 0;
+    if (!out || !X || !Y || !hyper || N < 1 || d < 1 || kind < 0 || kind > IBO_KERNEL_MATERN5_ARD) { set_error("bad argument"); return IBO_E_BADARG; }
+    if (npb > 0 && (!pmeans || !pbeta || !plb || !pwidth)) { set_error("prior arrays missing"); return IBO_E_BADARG; }
+    *out = nullptr;
+    int ndev = ibo_device_count();
+    if (ndev <= 0) { set_error("no CUDA device available (libibo_b200 has no CPU fallback)"); return IBO_E_CUDA; }
+    if (device < 0 || device >= ndev) { set_error("bad device ordinal"); return IBO_E_BADARG; }
+    std::vector<double> theta; double sf2;
+    int rc = theta_and_sf2(kind, hyper, nhyper, d, !legacy, theta, &sf2);
+    if (rc) return rc;
+    if (legacy) sf2 = sf2_override;
+    IBO_CUDA_TRY(cudaSetDevice(device));
+    ibo_model* m = new ibo_model();
+    m->device = device; m->N = N; m->d = d; m->kind = kind; m->noise = noise; m->sf2 = sf2;
+    m->nb = (N + TM - 1) / TM; m->Np = m->nb * TM;
+    m->npb = npb > 0 ? npb : 0; m->ptheta = ptheta; m->cpp_prior = legacy;
+    const int Np = m->Np, nb = m->nb;
+    auto fail = [&](int code) { free_model(m); return code; };
+#define TRYM(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { set_error(std::string(#expr) + ": " + cudaGetErrorString(e__)); cudaGetLastError(); return fail(e__ == cudaErrorMemoryAllocation ? IBO_E_NOMEM : IBO_E_CUDA); } } while (0)
+    TRYM(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    for (auto& e : m->ev) TRYM(cudaEventCreate(&e));
+    TRYM(cudaMalloc(&m->dXt, sizeof(double) * (size_t)Np * d));
+    TRYM(cudaMalloc(&m->dInvTheta, sizeof(double) * d));
+    TRYM(cudaMalloc(&m->dA, sizeof(double) * (size_t)Np * Np));
+    TRYM(cudaMalloc(&m->dW, sizeof(double) * (size_t)Np * Np));
+    TRYM(cudaMalloc(&m->dD, sizeof(double) * (size_t)nb * 128 * 128));
+    TRYM(cudaMalloc(&m->dWpack, sizeof(double) * wpack_base(nb) * BLOB));
+    TRYM(cudaMalloc(&m->dBetaY, sizeof(double) * Np));
+    TRYM(cudaMalloc(&m->dBeta1, sizeof(double) * Np));
+    TRYM(cudaMalloc(&m->dY, sizeof(double) * Np));
+    TRYM(cudaMalloc(&m->dInfo, sizeof(int)));
+    TRYM(cudaMalloc(&m->dBest, sizeof(double)));
+    TRYM(cudaMalloc(&m->dBestIdx, sizeof(long long)));
+    cudaStream_t st = m->stream;
+    // scaled inputs, zero padded
+    std::vector<double> xt((size_t)Np * d, 0.0), it(d), yp(Np, 0.0), ones(Np, 0.0);
+    for (int j = 0; j < d; j++) it[j] = 1.0 / theta[j];
+    for (int i = 0; i < N; i++) {
+        for (int j = 0; j < d; j++) xt[(size_t)i * d + j] = X[(size_t)i * d + j] / theta[j];
+        yp[i] = Y[i]; ones[i] = 1.0;
+    }
+    TRYM(cudaMemcpyAsync(m->dXt, xt.data(), sizeof(double) * xt.size(), cudaMemcpyHostToDevice, st));
+    TRYM(cudaMemcpyAsync(m->dInvTheta, it.data(), sizeof(double) * d, cudaMemcpyHostToDevice, st));
+    TRYM(cudaMemcpyAsync(m->dY, yp.data(), sizeof(double) * Np, cudaMemcpyHostToDevice, st));
+    if (m->npb > 0) {
+        TRYM(cudaMalloc(&m->dPmeans, sizeof(double) * (size_t)npb * d));
+        TRYM(cudaMalloc(&m->dPbeta, sizeof(double) * npb));
+        TRYM(cudaMalloc(&m->dPlb, sizeof(double) * d));
+        TRYM(cudaMalloc(&m->dPwidth, sizeof(double) * d));
+        TRYM(cudaMemcpyAsync(m->dPmeans, pmeans, sizeof(double) * (size_t)npb * d, cudaMemcpyHostToDevice, st));
+        TRYM(cudaMemcpyAsync(m->dPbeta, pbeta, sizeof(double) * npb, cudaMemcpyHostToDevice, st));
+        TRYM(cudaMemcpyAsync(m->dPlb, plb, sizeof(double) * d, cudaMemcpyHostToDevice, st));
+        TRYM(cudaMemcpyAsync(m->dPwidth, pwidth, sizeof(double) * d, cudaMemcpyHostToDevice, st));
+    }
+    dim3 g2((Np + 255) / 256, Np);
+    double* dTmp = nullptr;
+    if (invR) {
+        TRYM(cudaMalloc(&dTmp, sizeof(double) * (size_t)N * N));
+        TRYM(cudaMemcpyAsync(dTmp, invR, sizeof(double) * (size_t)N * N, cudaMemcpyHostToDevice, st));
+        build_reversed_kernel<<<g2, 256, 0, st>>>(m->dA, dTmp, N, Np);
+    } else {
+        if (Cinv) {
+            TRYM(cudaMalloc(&dTmp, sizeof(double) * (size_t)N * N));
+            TRYM(cudaMemcpyAsync(dTmp, Cinv, sizeof(double) * (size_t)N * N, cudaMemcpyHostToDevice, st));
+        }
+        build_A_kernel<<<g2, 256, 0, st>>>(m->dA, m->dXt, dTmp, N, Np, d, kind, sf2, noise);
+    }
+    g_launches++;
+    if (Np <= 4096 && !invR) {   // keep A for get_matrix(0)
+        TRYM(cudaMalloc(&m->dAorig, sizeof(double) * (size_t)Np * Np));
+        TRYM(cudaMemcpyAsync(m->dAorig, m->dA, sizeof(double) * (size_t)Np * Np, cudaMemcpyDeviceToDevice, st));
+    }
+    rc = launch_factorize(m, invR != nullptr);
+    if (rc) { if (dTmp) cudaFree(dTmp); return fail(rc); }
+    // beta1 = W 1 (prior-mean correction term)
+    TRYM(cudaMemcpyAsync(m->dBeta1, ones.data(), sizeof(double) * Np, cudaMemcpyHostToDevice, st));
+    {
+        double* dOnes = nullptr;
+        TRYM(cudaMalloc(&dOnes, sizeof(double) * Np));
+        TRYM(cudaMemcpyAsync(dOnes, m->dBeta1, sizeof(double) * Np, cudaMemcpyDeviceToDevice, st));
+        tri_matvec_kernel<<<(Np + 7) / 8, 256, 0, st>>>(m->dW, dOnes, m->dBeta1, Np);
+        g_launches++;
+        TRYM(cudaStreamSynchronize(st));
+        cudaFree(dOnes);
+    }
+    int hinfo = 0;
+    TRYM(cudaMemcpy(&hinfo, m->dInfo, sizeof(int), cudaMemcpyDeviceToHost));
+    if (dTmp) cudaFree(dTmp);
+    TRYM(cudaGetLastError());
+    if (hinfo != 0) {
+        if (info) *info = hinfo;
+        set_error("matrix is not positive definite (pivot " + std::to_string(hinfo) + ")");
+        return fail(IBO_E_NOTSPD);
+    }
+#undef TRYM
+    *out = m;
+    return IBO_OK;
+}
+
+extern "C" int ibo_model_create(int device, int kerneltype, const double* hyper, int nhyper, const double* X, const double* Y,
+                                int N, int d, double noise, const double* Cinv, int npbases, const double* pmeans,
+                                const double* pbeta, double ptheta, const double* plowerb, const double* pwidth,
+                                ibo_model** out, int* info) {
+    return create_common(device, kerneltype, hyper, nhyper, X, Y, N, d, noise, Cinv, nullptr, 1.0, false,
+                         npbases, pmeans, pbeta, ptheta, plowerb, pwidth, out, info);
+}
+
+extern "C" int ibo_model_create_from_inverse(int device, int kerneltype, const double* hyper, int nhyper, const double* X,
+                                             const double* Y, int N, int d, double noise, const double* invR, double sf2,
+                                             int npbases, const double* pmeans, const double* pbeta, double ptheta,
+                                             const double* plowerb, const double* pwidth, ibo_model** out, int* info) {
+    if (!invR) { set_error("invR is NULL"); return IBO_E_BADARG; }
+    return create_common(device, kerneltype, hyper, nhyper, X, Y, N, d, noise, nullptr, invR, sf2, true,
+                         npbases, pmeans, pbeta, ptheta, plowerb, pwidth, out, info);
+}
+
+extern "C" int ibo_model_destroy(ibo_model* m) { free_model(m); return IBO_OK; }
+extern "C" int ibo_model_n(const ibo_model* m) { return m ? m->N : IBO_E_BADARG; }
+extern "C" int ibo_model_dim(const ibo_model* m) { return m ? m->d : IBO_E_BADARG; }
+
+extern "C" int ibo_model_set_variance_model(ibo_model* m, ibo_model* aug) {
+    if (!m) { set_error("null model"); return IBO_E_BADARG; }
+    if (aug && (aug->d != m->d || aug->device != m->device)) { set_error("variance model must share dim and device"); return IBO_E_BADARG; }
+    m->var_model = aug;
+    return IBO_OK;
+}
+
+extern "C" int ibo_model_get_matrix(ibo_model* m, int which, double* out) {
+    if (!m || !out || which < 0 || which > 2) { set_error("bad argument"); return IBO_E_BADARG; }
+    IBO_CUDA_TRY(cudaSetDevice(m->device));
+    const double* src = which == 0 ? m->dAorig : (which == 1 ? m->dA : m->dW);
+    if (!src) { set_error("matrix not retained for this model"); return IBO_E_BADARG; }
+    IBO_CUDA_TRY(cudaStreamSynchronize(m->stream));
+    IBO_CUDA_TRY(cudaMemcpy2D(out, sizeof(double) * m->N, src, sizeof(double) * m->Np, sizeof(double) * m->N, m->N, cudaMemcpyDeviceToHost));
+    if (which == 1)
+        for (int i = 0; i < m->N; i++)
+            for (int j = i + 1; j < m->N; j++) out[(size_t)i * m->N + j] = 0.0;
+    return IBO_OK;
+}

@@ -1,0 +1,59 @@
+// Internal model/state structs of libibo_b200.
+#pragma once
+#include "common.cuh"
+#include "../../include/ibo_b200.h"
+#include <vector>
+
+struct ibo_model {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int N = 0, d = 0, kind = 0;
+    int nb = 0;          // 128-row blocks
+    int Np = 0;          // nb * 128 (identity padded)
+    double noise = 0, sf2 = 1;
+    bool cpp_prior = false;
+    // device arrays
+    double* dXt = nullptr;      // scaled training inputs x/theta, [Np][d], rows >= N are zero
+    double* dInvTheta = nullptr;// [d]
+    double* dA = nullptr;       // [Np][Np] row-major: A = R (+Cinv), overwritten by L (lower)
+    double* dAorig = nullptr;   // optional copy of A (kept for get_matrix(0)); N<=4096 only
+    double* dW = nullptr;       // [Np][Np] row-major: W = inv(L), exact zeros above the diagonal
+    double* dD = nullptr;       // [nb][128][128] inverses of the diagonal blocks of L
+    double* dWpack = nullptr;   // packed blobs, wpack_base(nb) * BLOB doubles
+    double* dBetaY = nullptr;   // [Np]  W Y
+    double* dBeta1 = nullptr;   // [Np]  W 1
+    double* dY = nullptr;       // [Np]
+    int* dInfo = nullptr;
+    // prior (RBF network), device copies
+    int npb = 0;
+    double ptheta = 0;
+    double* dPmeans = nullptr;  // [npb][d]
+    double* dPbeta = nullptr;   // [npb]
+    double* dPlb = nullptr;     // [d]
+    double* dPwidth = nullptr;  // [d]
+    // variance model (PrefGP aug): not owned
+    ibo_model* var_model = nullptr;
+    // scoring workspace (grown on demand)
+    double* dCand = nullptr;  size_t candCap = 0;     // candidates of the current call [M][d]
+    double* dSlab = nullptr;  size_t slabCap = 0;     // packed K* of the current chunk
+    double* dPart = nullptr;  size_t partCap = 0;     // [3][nb][chunkM] partial reductions
+    double* dOut = nullptr;   size_t outCap = 0;      // [3][M]: score, mu, s2
+    double* dBlkBest = nullptr; long long* dBlkIdx = nullptr; size_t blkCap = 0;
+    double* dBest = nullptr;  long long* dBestIdx = nullptr;      // final argmax
+    double* hPinned = nullptr; size_t pinnedCap = 0;              // pinned staging for small batches
+    // profile of the last call
+    double prof[6] = {0, 0, 0, 0, 0, 0};
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+struct ibo_cands {
+    ibo_model* owner = nullptr;
+    double* dX = nullptr;   // [M][d] raw coordinates in HBM
+    long M = 0;
+};
+
+namespace ibo {
+int grow(double** p, size_t* cap, size_t need);
+// launches (all on m->stream)
+int launch_factorize(ibo_model* m, bool from_inverse_reversed);
+}  // namespace ibo

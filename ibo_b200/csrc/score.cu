@@ -1,0 +1,582 @@
+// The acquisition hot path on B200:
+//   K1  kstar_kernel    fused cross-covariance K* = k(X, X*) written as fragment-packed blobs
+//   K2  trigemm_kernel  V = W K* (W = inv(L), lower triangular) on the FP64 tensor pipe with
+//                       1-D bulk-TMA (UBLKCP) staged operand blobs and an mbarrier pipeline; V is
+//                       never stored -- each 128x128 block is reduced in registers to
+//                       sum_i V_i^2, sum_i V_i betaY_i, sum_i V_i beta1_i per candidate
+//   K3  epilogue_kernel mu, sigma^2 (clipped), EI / PI / UCB, block argmax
+//   K4  argmax_final    lowest-index-wins reduction of the block winners
+//
+// Replaces (reference file:line): GaussianProcess.posterior (ego/gaussianprocess/__init__.py:169-228),
+// EI/PI/UCB.negf (ego/acquisition/__init__.py:60-75,100-114,138-164), GP_Maximizer::posterior / aMb /
+// negei / negpi / negucb (cpp/optimizeGP.cpp:57-236) and RBFNMeanPrior.mu (ego/gaussianprocess/prior.py:60-66).
+//
+// Determinism: the value computed for a candidate depends only on (model, x): every reduction has a
+// fixed order that is independent of the batch size, of the candidate's position in the batch and of
+// how row-blocks are grouped over CTAs (per-row-block partials are summed in ascending order by K3).
+#include "model.cuh"
+#include <cmath>
+#include <algorithm>
+#include <mutex>
+
+namespace ibo {
+
+__device__ __forceinline__ double cov_r2(int kind, double sf2, double r2) {
+    if (kind <= IBO_KERNEL_SE_ISO) return sf2 * exp(-0.5 * r2);
+    double r = sqrt(r2);
+    if (kind == IBO_KERNEL_MATERN3) {
+        double z = 1.7320508075688772 * r;
+        return sf2 * (1.0 + z) * exp(-z);
+    }
+    double z = 2.23606797749979 * r;
+    return sf2 * (1.0 + z + 5.0 * r2 / 3.0) * exp(-z);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: one CTA = (candidate tile T, training row-block i); warp w produces k-blob i*8+w.
+// Thread (lane) owns candidate n8 = lane/4 of each 8-wide n-tile and training rows k4, k4+4 of each
+// 8-row group -- exactly the two values of its 16-byte slot in the packed B-operand layout.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) kstar_kernel(const double* __restrict__ Xt, const double* __restrict__ cand,
+                                                    const double* __restrict__ inv_theta, double* __restrict__ slab,
+                                                    int N, int d, int nb, long M, long m0, int kind, double sf2) {
+    extern __shared__ double sm[];
+    const int S = d | 1;
+    double* sX = sm;              // [128][S] scaled training rows of block i
+    double* sC = sm + 128 * S;    // [128][S] scaled candidates of tile T
+    const int T = blockIdx.x, i = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    for (int idx = tid; idx < 128 * d; idx += 256) {
+        int r = idx / d, j = idx - r * d;
+        sX[r * S + j] = Xt[(size_t)(i * 128 + r) * d + j];
+        long c = m0 + (long)T * 128 + r;
+        if (c >= M) c = M - 1;
+        sC[r * S + j] = cand[(size_t)c * d + j] * inv_theta[j];
+    }
+    __syncthreads();
+    const int n8 = lane >> 2, k4 = lane & 3;
+    double* blob = slab + ((size_t)T * (nb * KB_PER_BLOCK) + (size_t)i * KB_PER_BLOCK + w) * BLOB;
+    const int rowbase = i * 128 + w * 16;
+#pragma unroll 1
+    for (int ks2 = 0; ks2 < 2; ks2++) {
+        const int ka = w * 16 + ks2 * 8 + k4, kb = ka + 4;
+        const double* xa = sX + ka * S;
+        const double* xb = sX + kb * S;
+        const bool va = (rowbase + ks2 * 8 + k4) < N, vb = (rowbase + ks2 * 8 + k4 + 4) < N;
+#pragma unroll 2
+        for (int nt = 0; nt < 16; nt++) {
+            const double* c = sC + (nt * 8 + n8) * S;
+            double ra = 0, rb = 0;
+            for (int j = 0; j < d; j++) {
+                double cj = c[j];
+                double da = xa[j] - cj, db = xb[j] - cj;
+                ra = fma(da, da, ra);
+                rb = fma(db, db, rb);
+            }
+            double2 v;
+            v.x = va ? cov_r2(kind, sf2, ra) : 0.0;
+            v.y = vb ? cov_r2(kind, sf2, rb) : 0.0;
+            reinterpret_cast<double2*>(blob)[(nt * 2 + ks2) * 32 + lane] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: triangular GEMM + fused reduction.
+// ---------------------------------------------------------------------------------------------
+constexpr int K2_STAGES = 6;
+constexpr int K2_THREADS = 384;   // warpgroups 0,1: 8 DMMA warps (240 regs); warpgroup 2: bulk-copy producer (24 regs)
+constexpr int K2_SMEM = K2_STAGES * 2 * BLOB * 8 + 2 * 3 * 128 * 8 + 2 * K2_STAGES * 8;
+
+__device__ __forceinline__ int group_of(int i, int nb, int G) {
+    int idx = nb - 1 - i, round = idx / G, pos = idx - round * G;
+    return (round & 1) ? (G - 1 - pos) : pos;
+}
+
+__global__ void __launch_bounds__(K2_THREADS, 1)
+trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab, const double* __restrict__ betaY,
+               const double* __restrict__ beta1, double* __restrict__ part, int nb, int G, long Mpad, int want_p1) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    double* sA = reinterpret_cast<double*>(smraw);
+    double* sB = sA + K2_STAGES * BLOB;
+    double* sRed = sB + K2_STAGES * BLOB;                       // [2][3][128]
+    uint64_t* full = reinterpret_cast<uint64_t*>(sRed + 2 * 3 * 128);
+    uint64_t* empty = full + K2_STAGES;
+    const int T = blockIdx.x, g = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < K2_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    __syncthreads();
+    if (warp >= 8) {
+        // ---------------- producer warpgroup: hands its registers to the DMMA warps ----------------
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        // one lane streams the operand blobs with bulk TMA
+        if (warp == 8 && lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            const double* Bbase = slab + (size_t)T * (nb * KB_PER_BLOCK) * BLOB;
+            for (int i = nb - 1; i >= 0; --i) {
+                if (group_of(i, nb, G) != g) continue;
+                const double* Abase = Wpack + wpack_base(i) * BLOB;
+                const int nkb = (i + 1) * KB_PER_BLOCK;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&full[s], 2 * BLOB * 8);
+                    bulk_g2s(sA + s * BLOB, Abase + (size_t)kb * BLOB, BLOB * 8, &full[s]);
+                    bulk_g2s(sB + s * BLOB, Bbase + (size_t)kb * BLOB, BLOB * 8, &full[s]);
+                    if (++s == K2_STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+        return;
+    }
+    // ---------------- consumers: 8 warps, warp tile 64 (rows) x 32 (candidates) ----------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
+    const int wm = warp >> 2, wn = warp & 3;
+    int s = 0; uint32_t ph = 0;
+    int rbcount = 0;
+    for (int i = nb - 1; i >= 0; --i) {
+        if (group_of(i, nb, G) != g) continue;
+        double acc[8][4][2];
+#pragma unroll
+        for (int a = 0; a < 8; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+        const int nkb = (i + 1) * KB_PER_BLOCK;
+        for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&full[s], ph);
+            const double2* a2 = reinterpret_cast<const double2*>(sA + s * BLOB) + (wm * 8 * 2) * 32 + lane;
+            const double2* b2 = reinterpret_cast<const double2*>(sB + s * BLOB) + (wn * 4 * 2) * 32 + lane;
+#pragma unroll
+            for (int ks2 = 0; ks2 < 2; ks2++) {
+                double2 af[8], bf[4];
+#pragma unroll
+                for (int mt = 0; mt < 8; mt++) af[mt] = a2[(mt * 2 + ks2) * 32];
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) bf[nt] = b2[(nt * 2 + ks2) * 32];
+#pragma unroll
+                for (int mt = 0; mt < 8; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt].x, bf[nt].x);
+#pragma unroll
+                for (int mt = 0; mt < 8; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt].y, bf[nt].y);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            if (++s == K2_STAGES) { s = 0; ph ^= 1; }
+        }
+        // ---- fused reduction of this 128 x 128 block of V over its rows ----
+        double by[8], b1[8];
+#pragma unroll
+        for (int mt = 0; mt < 8; mt++) {
+            int r = i * 128 + wm * 64 + mt * 8 + (lane >> 2);
+            by[mt] = betaY[r];
+            b1[mt] = want_p1 ? beta1[r] : 0.0;
+        }
+        double q[4][2], p[4][2], p1[4][2];
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                double sq = 0, sp = 0, s1 = 0;
+#pragma unroll
+                for (int mt = 0; mt < 8; mt++) {
+                    double v = acc[mt][nt][j];
+                    sq = fma(v, v, sq);
+                    sp = fma(v, by[mt], sp);
+                    s1 = fma(v, b1[mt], s1);
+                }
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                    sp += __shfl_xor_sync(0xffffffffu, sp, o);
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                }
+                q[nt][j] = sq; p[nt][j] = sp; p1[nt][j] = s1;
+            }
+        double* red = sRed + (rbcount & 1) * 3 * 128;
+        if (wm == 1 && lane < 4) {
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    int c = wn * 32 + nt * 8 + 2 * lane + j;
+                    red[c] = q[nt][j]; red[128 + c] = p[nt][j]; red[256 + c] = p1[nt][j];
+                }
+        }
+        named_bar_sync(1, 256);
+        if (wm == 0 && lane < 4) {
+            const size_t plane = (size_t)nb * Mpad;
+            double* dst = part + (size_t)i * Mpad + (size_t)T * 128;
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    int c = wn * 32 + nt * 8 + 2 * lane + j;
+                    dst[c] = q[nt][j] + red[c];
+                    dst[plane + c] = p[nt][j] + red[128 + c];
+                    if (want_p1) dst[2 * plane + c] = p1[nt][j] + red[256 + c];
+                }
+        }
+        rbcount++;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: per-candidate epilogue.
+// ---------------------------------------------------------------------------------------------
+struct EpiParams {
+    int nb, d, N, acq, mode_py, npb, want_p1;
+    long M, m0, chunkM, Mpad;
+    double noise, ymax, parm, ptheta;
+    const double *part, *partVar, *cand, *pmeans, *pbeta, *plb, *pwidth;
+    int nbVar; long MpadVar;
+    double *score, *mu, *s2;
+    double* blkBest; long long* blkIdx; long blk0;
+};
+
+__device__ __forceinline__ double erf_nr(double z) {
+    // Numerical-Recipes Chebyshev erf, ego/gaussianprocess/__init__.py:55-71 (same constants, Horner order)
+    double t = 1.0 / (1.0 + 0.5 * fabs(z));
+    double p = 0.17087277;
+    p = -0.82215223 + t * p;
+    p = 1.48851587 + t * p;
+    p = -1.13520398 + t * p;
+    p = 0.27886807 + t * p;
+    p = -0.18628806 + t * p;
+    p = 0.09678418 + t * p;
+    p = 0.37409196 + t * p;
+    p = 1.00002368 + t * p;
+    double ans = 1 - t * exp(-z * z - 1.26551223 + t * p);
+    return z >= 0.0 ? ans : -ans;
+}
+
+__device__ __forceinline__ double acq_value(int acq, int mode_py, double mu, double s2, double ymax, double parm) {
+    double s = sqrt(s2);
+    if (acq == IBO_ACQ_UCB) return mu + parm * s;
+    if (mode_py) {
+        if (acq == IBO_ACQ_EI) {
+            double ydiff = mu - ymax - parm;                                   // acquisition/__init__.py:156
+            double Z = ydiff / s;
+            double cdf = 0.5 * (1 + erf_nr(Z * 0.707106));                     // gaussianprocess/__init__.py:73-74
+            double pdf = exp(-(Z * Z / 2)) * 0.398942;                         // :76-77
+            return ydiff * cdf + s * pdf;                                      // acquisition/__init__.py:160
+        }
+        double Z = (mu - (ymax + parm)) / s;                                   // acquisition/__init__.py:105,110
+        return 0.5 * (1 + erf_nr(Z * 0.707106));
+    }
+    double ydiff = mu - ymax - parm;                                           // cpp/optimizeGP.cpp:200
+    double Z = ydiff / s;
+    double cdf = 0.5 * (1. + erf(Z / 1.4142135623730951));                     // :202
+    if (acq == IBO_ACQ_PI) return cdf;                                         // :225-226
+    double pdf = exp(-(Z * Z / 2.)) / 2.5066282746310002;                      // :203  sqrt(2*pi)
+    return ydiff * cdf + s * pdf;                                              // :204
+}
+
+__global__ void __launch_bounds__(256) epilogue_kernel(EpiParams P) {
+    const long lm = (long)blockIdx.x * 256 + threadIdx.x;    // index within the chunk
+    const long m = P.m0 + lm;
+    double sc = -INFINITY;
+    long long idx = 0x7fffffffffffffffLL;
+    if (lm < P.chunkM && m < P.M) {
+        const size_t plane = (size_t)P.nb * P.Mpad;
+        double q = 0, p = 0, p1 = 0;
+        for (int i = 0; i < P.nb; i++) {
+            p += P.part[plane + (size_t)i * P.Mpad + lm];
+            if (P.want_p1) p1 += P.part[2 * plane + (size_t)i * P.Mpad + lm];
+        }
+        if (P.partVar) { for (int i = 0; i < P.nbVar; i++) q += P.partVar[(size_t)i * P.MpadVar + lm]; }
+        else { for (int i = 0; i < P.nb; i++) q += P.part[(size_t)i * P.Mpad + lm]; }
+        double m0 = 0.0;
+        if (P.npb > 0) {
+            // RBF-network mean prior, ego/gaussianprocess/prior.py:60-66 == cpp/optimizeGP.cpp:116-134
+            const double* x = P.cand + (size_t)m * P.d;
+            for (int b = 0; b < P.npb; b++) {
+                double dd = 0;
+                for (int j = 0; j < P.d; j++) {
+                    double t = (x[j] - P.plb[j]) / P.pwidth[j] - P.pmeans[(size_t)b * P.d + j];
+                    dd += t * t;
+                }
+                m0 += P.pbeta[b] * exp(-P.ptheta * dd);
+            }
+        }
+        double mu = m0 + p - m0 * p1;
+        double s2 = (1.0 + P.noise) - q;
+        const double floor_ = P.mode_py ? 10e-8 : 1e-8;   // gaussianprocess/__init__.py:224 vs cpp/optimizeGP.cpp:150
+        s2 = s2 < floor_ ? floor_ : (s2 > 10.0 ? 10.0 : s2);
+        if (P.mu) P.mu[m] = mu;
+        if (P.s2) P.s2[m] = s2;
+        if (P.acq >= 0) {
+            double v = acq_value(P.acq, P.mode_py, mu, s2, P.ymax, P.parm);
+            if (P.score) P.score[m] = v;
+            if (v == v) { sc = v; idx = m; }   // NaN never wins
+            else idx = m;
+        }
+    }
+    if (P.acq < 0) return;
+    // block argmax, lowest index wins ties
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double os = __shfl_xor_sync(0xffffffffu, sc, o);
+        long long oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (os > sc || (os == sc && oi < idx)) { sc = os; idx = oi; }
+    }
+    __shared__ double ws[8];
+    __shared__ long long wi[8];
+    if ((threadIdx.x & 31) == 0) { ws[threadIdx.x >> 5] = sc; wi[threadIdx.x >> 5] = idx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++)
+            if (ws[w] > sc || (ws[w] == sc && wi[w] < idx)) { sc = ws[w]; idx = wi[w]; }
+        P.blkBest[P.blk0 + blockIdx.x] = sc;
+        P.blkIdx[P.blk0 + blockIdx.x] = idx;
+    }
+}
+
+__global__ void __launch_bounds__(256) argmax_final_kernel(const double* __restrict__ blkBest, const long long* __restrict__ blkIdx,
+                                                           long nblk, double* __restrict__ best, long long* __restrict__ bestIdx) {
+    double sc = -INFINITY;
+    long long idx = 0x7fffffffffffffffLL;
+    for (long b = threadIdx.x; b < nblk; b += 256) {
+        double os = blkBest[b]; long long oi = blkIdx[b];
+        if (os > sc || (os == sc && oi < idx)) { sc = os; idx = oi; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double os = __shfl_xor_sync(0xffffffffu, sc, o);
+        long long oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (os > sc || (os == sc && oi < idx)) { sc = os; idx = oi; }
+    }
+    __shared__ double ws[8];
+    __shared__ long long wi[8];
+    if ((threadIdx.x & 31) == 0) { ws[threadIdx.x >> 5] = sc; wi[threadIdx.x >> 5] = idx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++)
+            if (ws[w] > sc || (ws[w] == sc && wi[w] < idx)) { sc = ws[w]; idx = wi[w]; }
+        *best = sc; *bestIdx = idx;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side orchestration
+// ---------------------------------------------------------------------------------------------
+static std::once_flag g_score_attr_once;
+static cudaError_t g_score_attr_err = cudaSuccess;
+static int g_num_sms = 148;
+static void set_score_attrs() {
+    g_score_attr_err = cudaFuncSetAttribute(trigemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
+    if (g_score_attr_err == cudaSuccess)
+        g_score_attr_err = cudaFuncSetAttribute(kstar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 65 * 8);
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceProp pr;
+    if (cudaGetDeviceProperties(&pr, dev) == cudaSuccess) g_num_sms = pr.multiProcessorCount;
+}
+
+struct ScoreReq {
+    int acq;            // -1: posterior only
+    double ymax, parm;
+    int flags;
+    bool want_score, want_mu, want_s2;
+};
+
+// Runs K1..K4 for M candidates resident at dCand; results land in m->dOut ([score|mu|s2][M]) and
+// m->dBest / m->dBestIdx.  Everything is enqueued on m->stream; no host synchronisation here.
+static int score_device(ibo_model* m, const double* dCand, long M, const ScoreReq& rq) {
+    std::call_once(g_score_attr_once, set_score_attrs);
+    if (g_score_attr_err != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(g_score_attr_err)); return IBO_E_CUDA; }
+    if (m->d > 64) { set_error("d > 64 not supported"); return IBO_E_BADARG; }
+    cudaStream_t st = m->stream;
+    const bool prof = (rq.flags & IBO_FLAG_PROFILE) != 0;
+    ibo_model* vm = m->var_model;
+    const int nb = m->nb;
+    const long tilesTotal = (M + TN - 1) / TN;
+    long chunkTiles = std::min<long>(tilesTotal, 2L * g_num_sms);
+    // keep the slab below ~6 GiB
+    while (chunkTiles > 1 && (double)chunkTiles * nb * KB_PER_BLOCK * BLOB * 8.0 > 6.0e9) chunkTiles = (chunkTiles + 1) / 2;
+    const long Mpad = chunkTiles * TN;
+    int rc;
+    if ((rc = grow(&m->dSlab, &m->slabCap, (size_t)chunkTiles * nb * KB_PER_BLOCK * BLOB))) return rc;
+    if ((rc = grow(&m->dPart, &m->partCap, (size_t)3 * nb * Mpad))) return rc;
+    if ((rc = grow(&m->dOut, &m->outCap, (size_t)3 * M))) return rc;
+    if (vm) {
+        if ((rc = grow(&vm->dSlab, &vm->slabCap, (size_t)chunkTiles * vm->nb * KB_PER_BLOCK * BLOB))) return rc;
+        if ((rc = grow(&vm->dPart, &vm->partCap, (size_t)3 * vm->nb * Mpad))) return rc;
+    }
+    const long nblkTotal = (M + 255) / 256 + tilesTotal;   // generous upper bound (chunk boundaries)
+    if (m->blkCap < (size_t)nblkTotal) {
+        if (m->dBlkBest) cudaFree(m->dBlkBest);
+        if (m->dBlkIdx) cudaFree(m->dBlkIdx);
+        m->dBlkBest = nullptr; m->dBlkIdx = nullptr; m->blkCap = 0;
+        IBO_CUDA_TRY(cudaMalloc(&m->dBlkBest, sizeof(double) * nblkTotal));
+        IBO_CUDA_TRY(cudaMalloc(&m->dBlkIdx, sizeof(long long) * nblkTotal));
+        m->blkCap = nblkTotal;
+    }
+    double tK1 = 0, tK2 = 0, tK3 = 0;
+    long nlaunch = 0, nK2 = 0;
+    if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[0], st));
+    long blk0 = 0;
+    const int kS = m->d | 1;
+    for (long t0 = 0; t0 < tilesTotal; t0 += chunkTiles) {
+        const long tiles = std::min(chunkTiles, tilesTotal - t0);
+        const long m0 = t0 * TN;
+        const long chunkM = std::min<long>(tiles * TN, M - m0);
+        int G = 1;
+        if (tiles < g_num_sms) G = (int)std::min<long>(nb, (g_num_sms + tiles - 1) / tiles);
+        if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[1], st));
+        kstar_kernel<<<dim3((unsigned)tiles, nb), 256, 2 * 128 * kS * 8, st>>>(m->dXt, dCand, m->dInvTheta, m->dSlab, m->N, m->d, nb, M, m0, m->kind, m->sf2);
+        nlaunch++;
+        if (vm) {
+            kstar_kernel<<<dim3((unsigned)tiles, vm->nb), 256, 2 * 128 * kS * 8, st>>>(vm->dXt, dCand, vm->dInvTheta, vm->dSlab, vm->N, vm->d, vm->nb, M, m0, vm->kind, vm->sf2);
+            nlaunch++;
+        }
+        if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[2], st));
+        trigemm_kernel<<<dim3((unsigned)tiles, G), K2_THREADS, K2_SMEM, st>>>(m->dWpack, m->dSlab, m->dBetaY, m->dBeta1, m->dPart, nb, G, Mpad, m->npb > 0);
+        nlaunch++; nK2++;
+        if (vm) {
+            int Gv = 1;
+            if (tiles < g_num_sms) Gv = (int)std::min<long>(vm->nb, (g_num_sms + tiles - 1) / tiles);
+            trigemm_kernel<<<dim3((unsigned)tiles, Gv), K2_THREADS, K2_SMEM, st>>>(vm->dWpack, vm->dSlab, vm->dBetaY, vm->dBeta1, vm->dPart, vm->nb, Gv, Mpad, 0);
+            nlaunch++; nK2++;
+        }
+        if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[3], st));
+        EpiParams P;
+        P.nb = nb; P.d = m->d; P.N = m->N; P.acq = rq.acq; P.mode_py = (rq.flags & IBO_FLAG_MODE_PY) ? 1 : 0;
+        P.npb = m->npb; P.want_p1 = m->npb > 0;
+        P.M = M; P.m0 = m0; P.chunkM = chunkM; P.Mpad = Mpad;
+        P.noise = m->noise; P.ymax = rq.ymax; P.parm = rq.parm; P.ptheta = m->ptheta;
+        P.part = m->dPart; P.partVar = vm ? vm->dPart : nullptr; P.nbVar = vm ? vm->nb : 0; P.MpadVar = Mpad;
+        P.cand = dCand; P.pmeans = m->dPmeans; P.pbeta = m->dPbeta; P.plb = m->dPlb; P.pwidth = m->dPwidth;
+        P.score = rq.want_score ? m->dOut : nullptr;
+        P.mu = rq.want_mu ? m->dOut + M : nullptr;
+        P.s2 = rq.want_s2 ? m->dOut + 2 * M : nullptr;
+        P.blkBest = m->dBlkBest; P.blkIdx = m->dBlkIdx; P.blk0 = blk0;
+        const unsigned nblk = (unsigned)((chunkM + 255) / 256);
+        epilogue_kernel<<<nblk, 256, 0, st>>>(P);
+        nlaunch++;
+        blk0 += nblk;
+        if (prof) {
+            IBO_CUDA_TRY(cudaEventRecord(m->ev[4], st));
+            IBO_CUDA_TRY(cudaEventSynchronize(m->ev[4]));
+            float a, b, c;
+            cudaEventElapsedTime(&a, m->ev[1], m->ev[2]);
+            cudaEventElapsedTime(&b, m->ev[2], m->ev[3]);
+            cudaEventElapsedTime(&c, m->ev[3], m->ev[4]);
+            tK1 += a; tK2 += b; tK3 += c;
+        }
+    }
+    if (rq.acq >= 0) {
+        argmax_final_kernel<<<1, 256, 0, st>>>(m->dBlkBest, m->dBlkIdx, blk0, m->dBest, m->dBestIdx);
+        nlaunch++;
+    }
+    g_launches += nlaunch;
+    if (prof) {
+        IBO_CUDA_TRY(cudaEventRecord(m->ev[5], st));
+        IBO_CUDA_TRY(cudaEventSynchronize(m->ev[5]));
+        float tot; cudaEventElapsedTime(&tot, m->ev[0], m->ev[5]);
+        m->prof[0] = tK1; m->prof[1] = tK2; m->prof[2] = tK3; m->prof[3] = tot; m->prof[4] = (double)nlaunch; m->prof[5] = (double)nK2;
+    }
+    IBO_CUDA_TRY(cudaGetLastError());
+    return IBO_OK;
+}
+
+static int score_host(ibo_model* m, const double* Xs, long M, const ScoreReq& rq, double* scores, double* mu, double* s2,
+                      double* best_score, long* best_idx) {
+    if (!m || !Xs || M < 0) { set_error("bad argument"); return IBO_E_BADARG; }
+    if (M == 0) { if (best_score) *best_score = -INFINITY; if (best_idx) *best_idx = -1; return IBO_OK; }
+    IBO_CUDA_TRY(cudaSetDevice(m->device));
+    int rc;
+    if ((rc = grow(&m->dCand, &m->candCap, (size_t)M * m->d))) return rc;
+    cudaStream_t st = m->stream;
+    IBO_CUDA_TRY(cudaMemcpyAsync(m->dCand, Xs, sizeof(double) * (size_t)M * m->d, cudaMemcpyHostToDevice, st));
+    if ((rc = score_device(m, m->dCand, M, rq))) return rc;
+    if (scores) IBO_CUDA_TRY(cudaMemcpyAsync(scores, m->dOut, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
+    if (mu) IBO_CUDA_TRY(cudaMemcpyAsync(mu, m->dOut + M, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
+    if (s2) IBO_CUDA_TRY(cudaMemcpyAsync(s2, m->dOut + 2 * M, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
+    double hb = 0; long long hi = -1;
+    if (rq.acq >= 0) {
+        IBO_CUDA_TRY(cudaMemcpyAsync(&hb, m->dBest, sizeof(double), cudaMemcpyDeviceToHost, st));
+        IBO_CUDA_TRY(cudaMemcpyAsync(&hi, m->dBestIdx, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    }
+    IBO_CUDA_TRY(cudaStreamSynchronize(st));
+    if (best_score) *best_score = hb;
+    if (best_idx) *best_idx = (long)hi;
+    return IBO_OK;
+}
+
+// used by the DIRECT objective (direct.cpp): negated acquisition for n points
+int eval_neg_acq(ibo_model* m, const double* Xs, long n, int acq, double ymax, double parm, int flags, double* y) {
+    ScoreReq rq{acq, ymax, parm, flags, true, false, false};
+    int rc = score_host(m, Xs, n, rq, y, nullptr, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    for (long i = 0; i < n; i++) y[i] = -y[i];
+    return IBO_OK;
+}
+
+}  // namespace ibo
+
+using namespace ibo;
+
+extern "C" int ibo_posterior_batch(ibo_model* m, const double* Xs, long M, int flags, double* mu, double* s2) {
+    ScoreReq rq{-1, 0.0, 0.0, flags, false, mu != nullptr, s2 != nullptr};
+    return score_host(m, Xs, M, rq, nullptr, mu, s2, nullptr, nullptr);
+}
+
+extern "C" int ibo_score_batch(ibo_model* m, const double* Xs, long M, int acq, double ymax, double parm, int flags,
+                               double* scores, double* mu, double* s2, double* best_score, long* best_idx) {
+    if (acq < 0 || acq > 2) { set_error("unknown acquisition function"); return IBO_E_BADARG; }
+    ScoreReq rq{acq, ymax, parm, flags, scores != nullptr, mu != nullptr, s2 != nullptr};
+    return score_host(m, Xs, M, rq, scores, mu, s2, best_score, best_idx);
+}
+
+extern "C" int ibo_cands_create(ibo_model* m, const double* Xs, long M, ibo_cands** out) {
+    if (!m || !Xs || M < 1 || !out) { set_error("bad argument"); return IBO_E_BADARG; }
+    IBO_CUDA_TRY(cudaSetDevice(m->device));
+    ibo_cands* c = new ibo_cands();
+    c->owner = m; c->M = M;
+    cudaError_t e = cudaMalloc(&c->dX, sizeof(double) * (size_t)M * m->d);
+    if (e != cudaSuccess) { delete c; set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); cudaGetLastError(); return IBO_E_NOMEM; }
+    e = cudaMemcpy(c->dX, Xs, sizeof(double) * (size_t)M * m->d, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(c->dX); delete c; set_error(std::string("cudaMemcpy: ") + cudaGetErrorString(e)); return IBO_E_CUDA; }
+    *out = c;
+    return IBO_OK;
+}
+
+extern "C" int ibo_cands_destroy(ibo_cands* c) {
+    if (!c) return IBO_OK;
+    if (c->owner) cudaSetDevice(c->owner->device);
+    if (c->dX) cudaFree(c->dX);
+    delete c;
+    return IBO_OK;
+}
+
+extern "C" int ibo_score_resident(ibo_model* m, ibo_cands* c, int acq, double ymax, double parm, int flags,
+                                  double* scores_host, double* best_score, long* best_idx, float* ms_device) {
+    if (!m || !c || c->owner != m || acq < 0 || acq > 2) { set_error("bad argument"); return IBO_E_BADARG; }
+    IBO_CUDA_TRY(cudaSetDevice(m->device));
+    cudaStream_t st = m->stream;
+    ScoreReq rq{acq, ymax, parm, flags, true, false, false};
+    IBO_CUDA_TRY(cudaEventRecord(m->ev[6], st));
+    int rc = score_device(m, c->dX, c->M, rq);
+    if (rc) return rc;
+    IBO_CUDA_TRY(cudaEventRecord(m->ev[7], st));
+    double hb = 0; long long hi = -1;
+    if (scores_host) IBO_CUDA_TRY(cudaMemcpyAsync(scores_host, m->dOut, sizeof(double) * c->M, cudaMemcpyDeviceToHost, st));
+    IBO_CUDA_TRY(cudaMemcpyAsync(&hb, m->dBest, sizeof(double), cudaMemcpyDeviceToHost, st));
+    IBO_CUDA_TRY(cudaMemcpyAsync(&hi, m->dBestIdx, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    IBO_CUDA_TRY(cudaStreamSynchronize(st));
+    if (ms_device) { float ms = 0; cudaEventElapsedTime(&ms, m->ev[6], m->ev[7]); *ms_device = ms; }
+    if (best_score) *best_score = hb;
+    if (best_idx) *best_idx = (long)hi;
+    return IBO_OK;
+}
+
+extern "C" int ibo_get_profile(ibo_model* m, double* out6) {
+    if (!m || !out6) { set_error("bad argument"); return IBO_E_BADARG; }
+    for (int i = 0; i < 6; i++) out6[i] = m->prof[i];
+    return IBO_OK;
+}

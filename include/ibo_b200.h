@@ -1,0 +1,165 @@
+/*
+ * ibo_b200.h -- C ABI of libibo_b200.so, the B200 (sm_100a) implementation of IBO's acquisition
+ * hot path: batched GP posterior mean/variance + EI/PI/UCB scoring, and the DIRECT driver
+ * (maximizeEI / fastUCBGallery inner loop).
+ *
+ * This is the drop-in boundary.  Plain pointers and sizes only; all arrays are C-contiguous
+ * FP64 in HOST memory unless a name ends in `_dev`.  Citations are file:line in the reference
+ * (misterwindupbird/IBO):
+ *
+ *   acqmaxGP      replaces  cpp/optimizeGP.cpp:262-349 (bound by ego/acquisition/__init__.py:343-436)
+ *   direct        replaces  cpp/direct.cpp:329-581, cpp/direct.h:57 (bound by ego/utils/optimize.py:310-343)
+ *   ibo_model_*   replaces  GaussianProcess._computeCorrelations/addData
+ *                           (ego/gaussianprocess/__init__.py:134-149,267-308), the Laplace
+ *                           L = chol(R + inv(C)) of PrefGaussianProcess (:487-498), and the explicit
+ *                           inv(R) of cdirectGP (ego/acquisition/__init__.py:385-388)
+ *   ibo_posterior_batch / ibo_score_batch
+ *                 replace   GaussianProcess.posterior/posteriors (ego/gaussianprocess/__init__.py:169-244),
+ *                           EI/PI/UCB.negf (ego/acquisition/__init__.py:60-75,100-114,138-164) and
+ *                           GP_Maximizer::posterior/negei/negpi/negucb (cpp/optimizeGP.cpp:57-236)
+ *   ibo_acqmax    replaces  cdirectGP + acqmaxGP without the explicit inverse
+ *
+ * Return convention of the ibo_* functions: 0 = ok, <0 = error (see IBO_E_*); the legacy symbols
+ * keep the reference's convention (malloc'd double[ndim+1], NULL on failure; caller frees with
+ * libc free(), ego/acquisition/__init__.py:443-447).
+ * There is no CPU fallback: every compute entry point fails with IBO_E_CUDA when no device is usable.
+ */
+#ifndef IBO_B200_H
+#define IBO_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* kernel types: 0..3 as in ego/acquisition/__init__.py:323-333; 4 is the ARD form config #4 names */
+#define IBO_KERNEL_SE_ARD       0   /* hyper = theta[d] (+ optional magnitude)          kernel.py:130-149 */
+#define IBO_KERNEL_SE_ISO       1   /* hyper = theta (+ unused)                         kernel.py:71-89   */
+#define IBO_KERNEL_MATERN3      2   /* hyper = theta, magnitude                         kernel.py:191-210 */
+#define IBO_KERNEL_MATERN5      3   /* hyper = theta, magnitude (intended formula)      kernel.py:230-248 */
+#define IBO_KERNEL_MATERN5_ARD  4   /* hyper = theta[d], magnitude                      (no reference class) */
+
+/* acquisition ids (ego/acquisition/__init__.py:309-321) */
+#define IBO_ACQ_EI   0
+#define IBO_ACQ_PI   1
+#define IBO_ACQ_UCB  2
+
+/* flag word of the scoring entry points */
+#define IBO_FLAG_MODE_CPP      0x0  /* libm erf, exact constants, sigma^2 floor 1e-8  (cpp/optimizeGP.cpp:150-215) */
+#define IBO_FLAG_MODE_PY       0x1  /* Chebyshev erf, 0.707106/0.398942, floor 10e-8  (gaussianprocess/__init__.py:55-77,224) */
+#define IBO_FLAG_KSTAR_EXPAND  0x2  /* cross-covariance through |x|^2+|y|^2-2x.y on the DMMA pipe (default: direct differences) */
+#define IBO_FLAG_DIRECT_SEQ    0x4  /* DIRECT: evaluate rectangle by rectangle in the reference's call order */
+#define IBO_FLAG_PROFILE       0x8  /* record per-kernel CUDA-event times (ibo_get_profile) */
+
+/* error codes */
+#define IBO_OK            0
+#define IBO_E_BADARG     -1
+#define IBO_E_CUDA       -2   /* no device / CUDA runtime error (ibo_last_error() has the text) */
+#define IBO_E_NOTSPD     -3   /* Cholesky failed; *info = 1-based index of the first bad pivot */
+#define IBO_E_NOMEM      -4
+#define IBO_E_COMM       -5
+
+typedef struct ibo_model ibo_model;   /* opaque: owns device memory + one CUDA stream */
+typedef struct ibo_cands ibo_cands;   /* opaque: a candidate set resident in HBM */
+
+const char* ibo_last_error(void);
+const char* ibo_version(void);
+int  ibo_device_count(void);
+
+/* ---- model ---------------------------------------------------------------------------------
+ * A = K_offdiag(X) + (1+noise) I [+ Cinv], L = chol(A), W = inv(L), beta = W Y  on `device`.
+ * X: N x d row-major.  hyper: the kernel's hyperparams array as-is (length nhyper).
+ * Cinv: NULL or N x N row-major (PrefGP Laplace term, inv(C)).
+ * prior: npbases==0 for none; else RBF-network mean prior (ego/gaussianprocess/prior.py:60-66):
+ *        pmeans npbases x d row-major, pbeta[npbases], ptheta, plowerb[d], pwidth[d].
+ * info:  receives 0, or the 1-based failing pivot when IBO_E_NOTSPD is returned (model is not created).
+ */
+int ibo_model_create(int device, int kerneltype, const double* hyper, int nhyper,
+                     const double* X, const double* Y, int N, int d, double noise,
+                     const double* Cinv,
+                     int npbases, const double* pmeans, const double* pbeta, double ptheta,
+                     const double* plowerb, const double* pwidth,
+                     ibo_model** out, int* info);
+
+/* Same model from an explicit inverse (legacy acqmaxGP layout, N x N row-major): factors invR = W'W. */
+int ibo_model_create_from_inverse(int device, int kerneltype, const double* hyper, int nhyper,
+                                  const double* X, const double* Y, int N, int d, double noise,
+                                  const double* invR, double sf2,
+                                  int npbases, const double* pmeans, const double* pbeta, double ptheta,
+                                  const double* plowerb, const double* pwidth,
+                                  ibo_model** out, int* info);
+
+int ibo_model_destroy(ibo_model* m);
+int ibo_model_n(const ibo_model* m);
+int ibo_model_dim(const ibo_model* m);
+/* copy back N x N row-major matrices: which = 0 -> A (=R [+Cinv]), 1 -> L (lower, zeros above), 2 -> W = inv(L) */
+int ibo_model_get_matrix(ibo_model* m, int which, double* out);
+/* secondary ("aug") factor used for the variance only (PrefGaussianProcess.addObservationPoint,
+ * ego/gaussianprocess/__init__.py:214-223,502-519): sigma^2 comes from `aug`, mu from `m`. */
+int ibo_model_set_variance_model(ibo_model* m, ibo_model* aug);
+
+/* ---- batched posterior / scoring -------------------------------------------------------------
+ * Xs: M x d row-major candidates (original coordinates).  Outputs may be NULL when not wanted.
+ * mu[M], s2[M]: posterior mean and *clipped* variance (floor by mode, ceiling 10).
+ * scores[M]: acquisition value being maximised (EI, PI or UCB; i.e. minus the reference's negf).
+ * best_score/best_idx: argmax over the batch, lowest index wins ties; NaN scores never win.
+ * ymax = max(Y) (EI/PI incumbent, ego/acquisition/__init__.py:143), parm = xi (EI/PI) or the UCB multiplier.
+ */
+int ibo_posterior_batch(ibo_model* m, const double* Xs, long M, int flags, double* mu, double* s2);
+int ibo_score_batch(ibo_model* m, const double* Xs, long M, int acq, double ymax, double parm, int flags,
+                    double* scores, double* mu, double* s2, double* best_score, long* best_idx);
+
+/* Candidates kept resident in HBM (the bench's device-resident leg; also used for sharded sets). */
+int ibo_cands_create(ibo_model* m, const double* Xs, long M, ibo_cands** out);
+int ibo_cands_destroy(ibo_cands* c);
+/* Scores a resident set; scores_host may be NULL (then only best_* cross PCIe).  ms_device, if not NULL,
+ * receives the CUDA-event time of the launch sequence on the model's stream. */
+int ibo_score_resident(ibo_model* m, ibo_cands* c, int acq, double ymax, double parm, int flags,
+                       double* scores_host, double* best_score, long* best_idx, float* ms_device);
+
+/* Per-kernel CUDA-event times (ms) and launch counts of the last scoring call made with
+ * IBO_FLAG_PROFILE: out[0]=K1 cross-covariance, out[1]=K2 triangular GEMM + reduce,
+ * out[2]=K3 epilogue/argmax, out[3]=total, out[4]=#launches, out[5]=K2 launches. */
+int ibo_get_profile(ibo_model* m, double* out6);
+/* cumulative count of kernels this library launched in this process */
+long ibo_launch_count(void);
+
+/* ---- DIRECT ----------------------------------------------------------------------------------
+ * Batched DIRECT following the reference's rectangle rules (cpp/direct.cpp:146-235,372-498).
+ * The callback receives n points (n x ndim row-major, original box coordinates) and fills y[n]
+ * with the objective being MINIMISED.
+ */
+typedef void (*ibo_batch_objective_t)(void* user, long n, int ndim, const double* X, double* y);
+int ibo_direct_batched(ibo_batch_objective_t f, void* user, int ndim, const double* lb, const double* ub,
+                       int maxiter, int maxtime, int maxsample, int flags,
+                       double* fmin, double* xmin, long* nsamples, int* iterations);
+
+/* maximise an acquisition over a box with the GPU objective; opt = max value, optx[ndim] */
+int ibo_acqmax(ibo_model* m, const double* lb, const double* ub, int acq, double ymax, double parm, int flags,
+               int maxiter, int maxtime, int maxsample,
+               double* opt, double* optx, long* nsamples, int* iterations);
+
+/* ---- legacy drop-in symbols (same names, same ABI as libego) ---------------------------------- */
+typedef double (*objective_t)(int, double*);                                    /* cpp/direct.h:14 */
+const double* direct(objective_t objective, int ndim, double* lb, double* ub,
+                     int maxiter, int maxtime, int maxsample);                   /* cpp/direct.h:57 */
+const double* acqmaxGP(int ndim, double* lb, double* ub, double* invR, double* X, double* Y, int nx,
+                       int acqfunc, int kerneltype, double* hyperparams,
+                       int npbases, double* pbasismeans, double* pbasisbeta, double pbasistheta,
+                       double* pbasislowerb, double* pbasiswidth,
+                       double parm, double noise, int maxiter, int maxtime, int maxsample);
+                                                                                 /* cpp/optimizeGP.cpp:262-283 */
+
+/* ---- multi-GPU (one process per GPU; NCCL is dlopen'ed on first use) -------------------------- */
+int ibo_comm_unique_id(unsigned char* id128);                 /* rank 0: 128-byte ncclUniqueId */
+int ibo_comm_init(int device, int rank, int nranks, const unsigned char* id128);
+int ibo_comm_destroy(void);
+/* all-reduce of a (score, global index) pair: max score, lowest index wins ties */
+int ibo_comm_argmax(double* score, long* index);
+/* broadcast `count` doubles in HOST memory from root through device buffers over NVLink */
+int ibo_comm_bcast(double* buf, long count, int root);
+int ibo_comm_barrier(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IBO_B200_H */

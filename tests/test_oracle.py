@@ -1,0 +1,173 @@
+"""CPU tests: pin the oracle restatement (oracle/ibo_oracle.py) against
+ (a) golden vectors produced by the reference's own C++ (tests/golden/, made by make_golden.py),
+ (b) the reference library itself when oracle/_ref is present (live, random inputs),
+ (c) the known answers of the reference's unit tests (ego/unittest_IBO.py:107-134)."""
+import ctypes
+import json
+import os
+from ctypes import POINTER, c_double, c_int, c_long
+
+import numpy as np
+import pytest
+
+from oracle import ibo_oracle as orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = np.load(os.path.join(HERE, "golden", "ref_candidates.npz"))
+with open(os.path.join(HERE, "golden", "ref_direct.json")) as fh:
+    GOLD_DIRECT = json.load(fh)
+SCEN = sorted(set(k.split("/")[0] for k in GOLD.files))
+
+
+def gold_model(name):
+    g = lambda k: GOLD["%s/%s" % (name, k)]
+    d = g("X").shape[1]
+    kern = orc.KernelSpec(int(g("kind")), g("hyper"), d)
+    prior = None
+    if "%s/p_means" % name in GOLD.files:
+        prior = orc.PriorSpec(g("p_means"), g("p_beta"), float(g("p_theta")), g("p_lowerb"), g("p_width"))
+    return orc.GPOracle(kern, g("X"), g("Y"), float(g("noise")), prior=prior), g
+
+
+def rel(a, b, floor):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), floor))
+
+
+@pytest.mark.parametrize("name", SCEN)
+def test_cpp_mode_matches_reference_values(name):
+    """explicit-inverse restatement (same invR the reference was given) -> near machine precision"""
+    gp, g = gold_model(name)
+    mu, sig = gp.posterior_cpp(g("Xs"), invR=g("invR"))
+    assert rel(mu, g("mu"), 1e-3) < 1e-12
+    assert rel(sig, g("sigma"), 1e-12) < 1e-12
+    ymax = g("Y").max()
+    assert rel(-orc.ei_cpp(mu, sig, ymax, 0.01), g("negei"), 1e-6) < 1e-10
+    assert rel(-orc.ei_cpp(mu, sig, ymax, 0.1), g("negei_xi1"), 1e-6) < 1e-10
+    assert rel(-orc.pi_cpp(mu, sig, ymax, 0.01), g("negpi"), 1e-6) < 1e-10
+    assert rel(-orc.ucb_cpp(mu, sig, 1.3), g("negucb"), 1e-6) < 1e-12
+
+
+@pytest.mark.parametrize("name", SCEN)
+def test_cholesky_path_matches_reference_values(name):
+    """the NumPy (Cholesky) formulation agrees with the reference's explicit-inverse numbers to 1e-10"""
+    gp, g = gold_model(name)
+    mu, s2 = gp.posterior_batch(g("Xs"), floor=1e-8)
+    assert rel(mu, g("mu"), 1e-3) < 1e-10
+    assert rel(np.sqrt(s2), g("sigma"), 1e-12) < 1e-10
+    ei = orc.score(orc.ACQ_EI, "cpp", mu, s2, g("Y").max(), 0.01)
+    assert rel(-ei, g("negei"), 1e-5) < 1e-10
+    assert int(np.argmax(ei)) == int(np.argmin(g("negei")))
+
+
+@pytest.mark.parametrize("name", ["shekel_iso3", "branin_matern3b", "prior_iso"])
+def test_scalar_faithful_equals_vectorised(name):
+    gp, g = gold_model(name)
+    mu, s2 = gp.posterior_batch(g("Xs")[:12])
+    for i in range(12):
+        m1, v1 = gp.posterior_scalar(g("Xs")[i])
+        assert abs(m1 - mu[i]) <= 1e-12 * max(1.0, abs(mu[i]))
+        assert abs(v1 - s2[i]) <= 1e-12 * max(1.0, abs(s2[i]))
+
+
+def test_python_vs_cpp_ei_gap_is_the_documented_erf_gap():
+    """Chebyshev erf + truncated constants differ from libm by < 5e-7 absolute."""
+    gp, g = gold_model("shekel_iso3")
+    mu, s2 = gp.posterior_batch(g("Xs"))
+    a = orc.score(orc.ACQ_EI, "py", mu, s2, g("Y").max(), 0.01)
+    b = orc.score(orc.ACQ_EI, "cpp", mu, np.maximum(s2, 1e-8), g("Y").max(), 0.01)
+    assert np.max(np.abs(a - b)) < 5e-7
+    assert np.argmax(a) == np.argmax(b)
+
+
+def test_erf_py_accuracy_and_sign():
+    z = np.linspace(-4, 4, 401)
+    import math
+    ref = np.array([math.erf(v) for v in z])
+    assert np.max(np.abs(orc.erf_py(z) - ref)) < 1.3e-7            # gaussianprocess/__init__.py:52
+    nz = z[np.abs(z) > 1e-12]                                      # erf(0) is +1e-9, not 0 (:50-51)
+    assert np.array_equal(orc.erf_py(-nz), -orc.erf_py(nz))
+
+
+def test_training_properties():
+    """ego/unittest_GP.py:77-106 style bounds: sigma^2 small and mu near y at training points."""
+    gp, g = gold_model("branin_ard50")
+    mu, s2 = gp.posterior_batch(g("X"))
+    assert np.all(s2 < 1.0 / (1.0 + gp.noise) + gp.noise)
+    assert np.all(np.abs(mu - g("Y")) < 2 * gp.noise + 0.25)
+
+
+@pytest.mark.parametrize("tag", sorted(GOLD_DIRECT["direct"].keys()))
+def test_direct_restatement_follows_reference_trajectory(tag):
+    rec = GOLD_DIRECT["direct"][tag]
+    b = np.array(rec["bounds"])
+    fns = {"shekel5": orc.shekel5, "branin": lambda x: float(orc.branin(x)),
+           "quad": lambda x: float(np.sum((x - 0.3) ** 2)), "sin6": lambda x: float(np.sum(np.sin(3 * x) + (x - .4) ** 2))}
+    f = fns[tag.split("_")[0]]
+    trace = []
+    fmin, xmin, ns = orc.direct_cpp(f, b[:, 0], b[:, 1], rec["maxiter"], rec["maxsample"], record=trace)
+    assert ns == rec["nsamples"]
+    assert fmin == rec["fmin"]
+    assert np.array_equal(xmin, np.array(rec["xmin"]))
+    tr = np.array(trace)
+    assert np.array_equal(tr[:40], np.array(rec["trace_head"]))
+    assert np.array_equal(tr[-10:], np.array(rec["trace_tail"]))
+
+
+def test_direct_known_answers():
+    """ego/unittest_IBO.py:107-114: Shekel5, 20 iterations -> -10.1532 at (4,4,4,4) to 3 d.p."""
+    rec = GOLD_DIRECT["direct"]["shekel5_it20"]
+    assert round(rec["fmin"], 3) == -10.153
+    assert all(round(v, 2) == 4.0 for v in rec["xmin"])
+    fmin, xmin, ns = orc.direct_cpp(orc.shekel5, [0.] * 4, [10.] * 4, 20, 200000)
+    assert abs(fmin + 10.1532) < 1e-3 and np.all(np.abs(xmin - 4.0) < 5e-3)
+
+
+@pytest.mark.parametrize("key", sorted(GOLD_DIRECT["acqmaxGP"].keys()))
+def test_oracle_acqmax_matches_reference_acqmaxGP(key):
+    """DIRECT restatement over the oracle's C++-mode acquisition reproduces libego's acqmaxGP."""
+    name, acq, parm, it, ms = key.split("|")
+    acq, parm, it, ms = int(acq[3:]), float(parm[4:]), int(it[2:]), int(ms[2:])
+    if name == "hartman_ard200":
+        pytest.skip("pure-Python DIRECT too slow for N=200 x 3000 samples; covered by the GPU parity test")
+    gp, g = gold_model(name)
+    invR = g("invR")
+    ymax = g("Y").max()
+
+    def f(x):
+        mu, sig = gp.posterior_cpp(x[None, :], invR=invR)
+        return -float(orc.score(acq, "cpp", mu, sig ** 2, ymax, parm)[0])
+    b = g("bounds")
+    fmin, xmin, ns = orc.direct_cpp(f, b[:, 0], b[:, 1], it, ms)
+    rec = GOLD_DIRECT["acqmaxGP"][key]
+    assert abs(fmin - rec["fmin"]) <= 1e-9 * max(1e-3, abs(rec["fmin"]))
+    assert np.allclose(xmin, rec["xmin"], rtol=0, atol=1e-12)
+
+
+REF_HARNESS = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libego_harness.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_HARNESS), reason="oracle/_ref not built")
+def test_live_reference_random_model():
+    """The reference's own negei over a fresh random SE-ARD model (N=300, d=5) vs the oracle."""
+    pd = POINTER(c_double)
+    har = ctypes.CDLL(REF_HARNESS)
+    har.ref_set_model.argtypes = [c_int, pd, pd, pd, c_int, c_int, pd, c_int, pd, pd, c_double, pd, pd, c_double, c_double]
+    har.ref_eval.argtypes = [c_int, c_long, pd, pd, pd, pd, c_int]
+    rs = np.random.RandomState(5)
+    N, d, M = 300, 5, 200
+    X = np.ascontiguousarray(rs.rand(N, d)); Y = np.ascontiguousarray(np.sin(3 * X).sum(axis=1))
+    hyper = np.ascontiguousarray(np.array([.4, .5, .6, .7, .8]))
+    gp = orc.GPOracle(orc.KernelSpec(0, hyper, d), X, Y, 0.1)
+    invR = np.ascontiguousarray(gp.invR())
+    Xs = np.ascontiguousarray(rs.rand(M, d))
+    z = np.zeros(1)
+    dp = lambda a: a.ctypes.data_as(pd)
+    har.ref_set_model(d, dp(invR), dp(X), dp(Y), N, 0, dp(hyper), 0, dp(z), dp(z), 0.0, dp(z), dp(z), 0.01, 0.1)
+    v = np.empty(M); mu = np.empty(M); sg = np.empty(M)
+    har.ref_eval(0, M, dp(Xs), dp(v), dp(mu), dp(sg), 2)
+    mu_o, s2_o = gp.posterior_batch(Xs, floor=1e-8)
+    assert rel(mu_o, mu, 1e-3) < 1e-10
+    assert rel(np.sqrt(s2_o), sg, 1e-12) < 1e-10
+    ei = orc.score(orc.ACQ_EI, "cpp", mu_o, s2_o, Y.max(), 0.01)
+    assert rel(-ei, v, 1e-5) < 1e-10
+    assert np.argmax(ei) == np.argmin(v)
