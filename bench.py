@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""
+bench.py -- EI candidate evaluations per second on B200 (BASELINE.json metric).
+
+Workload (config #2 of BASELINE.json): GaussianProcess, SE-ARD kernel, d=6, N=2048
+observations (X ~ U[0,1]^6 seed 0, Y = -Hartman6(X), theta = [.53,.57,2.5,.34,.27,.35], noise 0.1,
+xi 0.01), EI over 2^20 uniform random candidates per GPU (seed 1 + rank).  A "step" is one pass of the
+hot path (K1 cross-covariance -> K2 triangular DMMA GEMM + reduction -> K3 EI epilogue -> argmax) over
+the whole candidate set.  With N>1 every rank scores its own 2^20-candidate shard (weak scaling) and the
+ranks all-reduce the (EI, global index) argmax over NCCL each step.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference      # the reference's own C++ evaluator on the host cores
+
+torch is used only for the multi-process rendezvous (gloo) -- never for device work.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from ctypes import POINTER, c_double, c_float, c_int, c_long
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+THETA = [.53, .57, 2.5, .34, .27, .35]          # ego/utils/testfunctions.py:287
+NOISE, XI = 0.1, 0.01
+METRIC, UNIT = "EI candidate evals/sec (N=2048, d=6)", "evals/s"
+
+_H6_A = np.array([[10, 3, 17, 3.5, 1.7, 8], [.05, 10, 17, .1, 8, 14], [3, 3.5, 1.7, 10, 17, 8], [17, 8, .05, 10, .1, 14]])
+_H6_C = np.array([1, 1.2, 3, 3.2])
+_H6_P = np.array([[.1312, .1696, .5569, .0124, .8283, .5886], [.2329, .4135, .8307, .3736, .1004, .9991],
+                  [.2348, .1451, .3522, .2883, .3047, .6650], [.4047, .8828, .8732, .5743, .1091, .0381]])
+
+
+def hartman6_neg(X):
+    e = np.sum(_H6_A[None, :, :] * (X[:, None, :] - _H6_P[None, :, :]) ** 2, axis=2)
+    return np.sum(_H6_C[None, :] * np.exp(-e), axis=1)
+
+
+def synthetic_model(n_obs, d=6):
+    rs = np.random.RandomState(0)
+    X = rs.rand(n_obs, d)
+    return X, hartman6_neg(X)
+
+
+def synthetic_candidates(M, d, rank):
+    return np.ascontiguousarray(np.random.RandomState(1 + rank).rand(M, d))
+
+
+def flops_per_candidate_k2(N):
+    """algorithmic FP64 flops of the dominant kernel per candidate: TRSM N^2 + the two fused N-long
+    reductions 4N (F(N,d) = N^2 + N(2d+8); the remaining N(2d+4) belong to K1)."""
+    return float(N) * N + 4.0 * N
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's own C++ evaluator (oracle/_ref, built from the untouched sources) or,
+# if that did not travel, the plain-C oracle port
+# ------------------------------------------------------------------------------------------------
+def reference_evaluator():
+    pd = POINTER(c_double)
+    har = os.path.join(ROOT, "oracle", "_ref", "libego_harness.so")
+    if os.path.exists(har):
+        H = ctypes.CDLL(har)
+        H.ref_set_model.argtypes = [c_int, pd, pd, pd, c_int, c_int, pd, c_int, pd, pd, c_double, pd, pd, c_double, c_double]
+        H.ref_eval.argtypes = [c_int, c_long, pd, pd, pd, pd, c_int]
+        cores = os.cpu_count() or 1
+
+        def run(invR, X, Y, hyper, Xs):
+            z = np.zeros(1)
+            dp = lambda a: a.ctypes.data_as(pd)
+            H.ref_set_model(X.shape[1], dp(invR), dp(X), dp(Y), X.shape[0], 0, dp(hyper), 0, dp(z), dp(z), 0.0, dp(z), dp(z), XI, NOISE)
+            out = np.empty(len(Xs))
+            t0 = time.perf_counter()
+            H.ref_eval(0, len(Xs), dp(Xs), dp(out), None, None, cores)
+            return time.perf_counter() - t0, out
+        return "reference", cores, run
+    port = os.path.join(ROOT, "oracle", "_build", "liboracle_port.so")
+    if not os.path.exists(port):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
+    P = ctypes.CDLL(port)
+    P.port_eval.argtypes = [c_int, pd, pd, pd, c_int, c_int, pd, c_int, pd, pd, c_double, pd, pd, c_double, c_double, c_int, c_long, pd, pd, pd, pd]
+
+    def run(invR, X, Y, hyper, Xs):
+        z = np.zeros(1)
+        dp = lambda a: a.ctypes.data_as(pd)
+        out = np.empty(len(Xs))
+        t0 = time.perf_counter()
+        P.port_eval(X.shape[1], dp(invR), dp(X), dp(Y), X.shape[0], 0, dp(hyper), 0, dp(z), dp(z), 0.0, dp(z), dp(z), XI, NOISE, 0,
+                    len(Xs), dp(Xs), dp(out), None, None)
+        return time.perf_counter() - t0, out
+    return "port", 1, run
+
+
+def reference_inputs(n_obs, d):
+    """model arrays in the layout cdirectGP hands to acqmaxGP (ego/acquisition/__init__.py:365-391)"""
+    from oracle import ibo_oracle as orc          # allowed here: cpu_baseline / --impl reference legs only
+    X, Y = synthetic_model(n_obs, d)
+    X = np.ascontiguousarray(X); Y = np.ascontiguousarray(Y)
+    gp = orc.GPOracle(orc.KernelSpec(orc.K_SE_ARD, THETA[:d], d), X, Y, NOISE)
+    return np.ascontiguousarray(gp.invR()), X, Y, np.ascontiguousarray(np.array(THETA[:d]))
+
+
+def cpu_baseline(n_obs, d, seconds=12.0):
+    kind, cores, run = reference_evaluator()
+    invR, X, Y, hyper = reference_inputs(n_obs, d)
+    probe = synthetic_candidates(4 * cores, d, 0)
+    t, _ = run(invR, X, Y, hyper, probe)
+    n = int(min(max(len(probe) * seconds / max(t, 1e-6), 4 * cores), 200000))
+    Xs = synthetic_candidates(n, d, 0)
+    t, _ = run(invR, X, Y, hyper, Xs)
+    return {"value": n / t, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "%d of the workload's candidates, %.1f s on %d host threads (%s)" % (
+                n, t, cores, "reference cpp/optimizeGP.cpp GP_Maximizer::negei via oracle/_ref" if kind == "reference" else "oracle/oracle_port.c")}
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    kind, cores, run = reference_evaluator()
+    invR, X, Y, hyper = reference_inputs(args.n_obs, args.dim)
+    probe = synthetic_candidates(4 * cores, args.dim, 0)
+    t, _ = run(invR, X, Y, hyper, probe)
+    per_step = int(min(max(len(probe) * 4.0 / max(t, 1e-6), 4 * cores), 100000))      # ~4 s of CPU work per step
+    Xs = synthetic_candidates(per_step, args.dim, 0)
+    for _ in range(args.warmup):
+        run(invR, X, Y, hyper, Xs[: max(4 * cores, per_step // 8)])
+    times = [run(invR, X, Y, hyper, Xs)[0] for _ in range(args.steps)]
+    tt = float(np.sum(times))
+    value = per_step * args.steps / tt
+    sample = "each step = %d candidates of the workload on %d host threads" % (per_step, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, args.candidates),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(args, M):
+    return {"workload": "config #2: GaussianProcess SE-ARD d=%d, N=%d observations (Hartman6), EI xi=%.2f over %d uniform random "
+                        "candidates per GPU" % (args.dim, args.n_obs, XI, M),
+            "n_obs": args.n_obs, "dim": args.dim, "candidates_per_gpu": M, "arithmetic": "libm-erf / floor 1e-8 (libego) mode",
+            "l2": "inputs larger than L2: each step streams the packed K* slab (N x M x 8 B = %.1f GB) besides W and the candidates"
+                  % (args.n_obs * M * 8 / 1e9)}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-obs", type=int, default=2048)
+    ap.add_argument("--dim", type=int, default=6)
+    ap.add_argument("--candidates", type=int, default=1 << 20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference_arm(args, rank, world)
+
+    from ibo_b200 import _lib
+    from ibo_b200.gaussianprocess import GaussianProcess
+    from ibo_b200.gaussianprocess.kernel import GaussianKernel_ard
+    L = _lib.lib()
+    ndev = _lib.require_gpu()
+    device = local % ndev
+    dist = None
+    if world > 1:
+        import torch.distributed as dist          # rendezvous + host-side max/barrier only (gloo)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        uid = [None]
+        if rank == 0:
+            buf = ctypes.create_string_buffer(128)
+            _lib.check(L.ibo_comm_unique_id(buf))
+            uid[0] = buf.raw
+        dist.broadcast_object_list(uid, src=0)
+        _lib.check(L.ibo_comm_init(device, rank, world, uid[0]))
+
+    N, d, M = args.n_obs, args.dim, args.candidates
+    X, Y = synthetic_model(N, d)
+    t0 = time.perf_counter()
+    gp = GaussianProcess(GaussianKernel_ard(THETA[:d]), X, Y, noise=NOISE, device=device)
+    model = gp.model                                   # builds R, Cholesky, W = inv(L), packing on the device
+    t_factor = time.perf_counter() - t0
+    ymax = float(np.max(Y))
+    Xs = synthetic_candidates(M, d, rank)
+    cands = _lib.ResidentCandidates(model, Xs)
+    flags = _lib.FLAG_MODE_CPP
+
+    def step_resident():
+        best, bidx, ms = cands.score(_lib.ACQ_EI, ymax, XI, flags)
+        gidx = ctypes.c_long(rank * M + bidx)
+        sc = c_double(best)
+        if world > 1:
+            _lib.check(L.ibo_comm_argmax(ctypes.byref(sc), ctypes.byref(gidx)))
+        return sc.value, gidx.value
+
+    def sync_all():
+        if dist is not None:
+            dist.barrier()
+        _lib.check(L.ibo_device_synchronize(device))
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(device)
+    sync_all()
+    sampler.start()
+    launches0 = L.ibo_launch_count()
+    _lib.check(L.ibo_stream_mark(model.handle, 0))
+    tw0 = time.perf_counter()
+    for _ in range(args.steps):
+        best = step_resident()
+    _lib.check(L.ibo_stream_mark(model.handle, 1))
+    sync_all()
+    tw1 = time.perf_counter()
+    launches = L.ibo_launch_count() - launches0
+    msf = c_float(0)
+    _lib.check(L.ibo_stream_elapsed_ms(model.handle, ctypes.byref(msf)))
+    clocks = sampler.stop()
+    t_dev = msf.value * 1e-3
+    t_wall = tw1 - tw0
+
+    # ---- dominant kernel (K2) timing from CUDA events on the launching stream, same workload ----
+    k2 = []
+    for _ in range(max(2, min(args.steps, 3))):
+        cands.score(_lib.ACQ_EI, ymax, XI, flags | _lib.FLAG_PROFILE)
+        k2.append(model.profile())
+    prof = min(k2, key=lambda p: p["k2_ms"])
+    peak = c_double(0)
+    _lib.check(L.ibo_fp64_peak(device, ctypes.byref(peak)))
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region ----
+    out = np.empty(M)
+    L.ibo_host_register(Xs.ctypes.data_as(ctypes.c_void_p), Xs.nbytes)
+    L.ibo_host_register(out.ctypes.data_as(ctypes.c_void_p), out.nbytes)
+    for _ in range(2):
+        gp.score_batch(Xs, 'ei', xi=XI, mode='cpp', out=out)
+    sync_all()
+    te0 = time.perf_counter()
+    n_e2e = max(2, min(args.steps, 5))
+    for _ in range(n_e2e):
+        sc, b, bi = gp.score_batch(Xs, 'ei', xi=XI, mode='cpp', out=out)
+        gidx = ctypes.c_long(rank * M + bi); scv = c_double(b)
+        if world > 1:
+            _lib.check(L.ibo_comm_argmax(ctypes.byref(scv), ctypes.byref(gidx)))
+    sync_all()
+    te1 = time.perf_counter()
+    t_e2e = (te1 - te0) / n_e2e
+    L.ibo_host_unregister(Xs.ctypes.data_as(ctypes.c_void_p))
+    L.ibo_host_unregister(out.ctypes.data_as(ctypes.c_void_p))
+
+    # max over ranks
+    def rmax(v):
+        if dist is None:
+            return v
+        import torch
+        t = torch.tensor([v], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+    t_dev, t_wall, t_e2e = rmax(t_dev), rmax(t_wall), rmax(t_e2e)
+    t_step = max(t_dev, 0.0) / args.steps
+    value = world * M / t_step
+    k2_s = prof["k2_ms"] * 1e-3 / max(prof["k2_launches"], 1)
+    cand_per_launch = M / max(prof["k2_launches"], 1)
+    achieved = cand_per_launch * flops_per_candidate_k2(N) / k2_s / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(args, M),
+        "clocks": clocks,
+        "e2e": {"value": world * M / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(Xs.nbytes), "d2h_bytes_per_step": int(out.nbytes + 16),
+                "api": "GaussianProcess.score_batch -> ibo_score_batch (host buffers, pinned)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value if peak.value else None,
+                     "traffic": None, "kernel": "trigemm_kernel (K2)", "flops_per_candidate": flops_per_candidate_k2(N),
+                     "candidates_per_launch": cand_per_launch, "avg_launch_ms": 1e3 * k2_s,
+                     "peak_source": "live DMMA.8x8x4 issue-rate microbenchmark on this GPU (ibo_fp64_peak); MEASURED_PEAKS.json "
+                                    "and the profiling guide carry no FP64 figure"},
+        "kernel_ms_per_step": {"k1_kstar": prof["k1_ms"], "k2_trigemm": prof["k2_ms"], "k3_epilogue": prof["k3_ms"], "total": prof["total_ms"]},
+        "wall_ms_per_step": 1e3 * t_wall / args.steps,
+        "model_build_s": t_factor, "best": {"ei": best[0], "index": best[1]},
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(N, d)
+        print(json.dumps(line))
+    if dist is not None:
+        L.ibo_comm_destroy()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -20,6 +20,8 @@ EXPORTED = [
     "ibo_model_get_matrix", "ibo_model_set_variance_model",
     "ibo_posterior_batch", "ibo_score_batch",
     "ibo_cands_create", "ibo_cands_destroy", "ibo_score_resident", "ibo_get_profile", "ibo_launch_count",
+    "ibo_fp64_peak", "ibo_host_register", "ibo_host_unregister", "ibo_stream_mark", "ibo_stream_elapsed_ms",
+    "ibo_device_synchronize",
     "ibo_direct_batched", "ibo_acqmax", "direct", "acqmaxGP",
     "ibo_comm_unique_id", "ibo_comm_init", "ibo_comm_destroy", "ibo_comm_argmax", "ibo_comm_bcast", "ibo_comm_barrier",
 ]
@@ -89,6 +91,12 @@ def lib():
     L.ibo_cands_destroy.argtypes = [c_void_p]
     L.ibo_score_resident.argtypes = [c_void_p, c_void_p, c_int, c_double, c_double, c_int, pd, pd, pl, POINTER(c_float)]
     L.ibo_get_profile.argtypes = [c_void_p, pd]
+    L.ibo_fp64_peak.argtypes = [c_int, pd]
+    L.ibo_host_register.argtypes = [c_void_p, ctypes.c_ulong]
+    L.ibo_host_unregister.argtypes = [c_void_p]
+    L.ibo_stream_mark.argtypes = [c_void_p, c_int]
+    L.ibo_stream_elapsed_ms.argtypes = [c_void_p, POINTER(c_float)]
+    L.ibo_device_synchronize.argtypes = [c_int]
     L.ibo_direct_batched.argtypes = [BATCH_OBJECTIVE, c_void_p, c_int, pd, pd, c_int, c_int, c_int, c_int, pd, pd, pl, pi]
     L.ibo_acqmax.argtypes = [c_void_p, pd, pd, c_int, c_double, c_double, c_int, c_int, c_int, c_int, pd, pd, pl, pi]
     L.direct.restype = POINTER(c_double)
@@ -186,10 +194,12 @@ class Model(object):
         check(lib().ibo_posterior_batch(self._h, dptr(Xs), M, flags, dptr(mu), dptr(s2)))
         return mu, s2
 
-    def score(self, Xs, acq, ymax, parm, flags=FLAG_MODE_PY, want_scores=True, want_posterior=False):
-        Xs = as_f64(Xs, 2)
+    def score(self, Xs, acq, ymax, parm, flags=FLAG_MODE_PY, want_scores=True, want_posterior=False, out=None):
+        """`out` (optional, float64[M]) receives the scores in place (lets callers reuse a pinned buffer)."""
+        if not (isinstance(Xs, np.ndarray) and Xs.dtype == np.float64 and Xs.ndim == 2 and Xs.flags.c_contiguous):
+            Xs = as_f64(Xs, 2)
         M = Xs.shape[0]
-        sc = np.empty(M) if want_scores else None
+        sc = (out if out is not None else np.empty(M)) if want_scores else None
         mu = np.empty(M) if want_posterior else None
         s2 = np.empty(M) if want_posterior else None
         best, bidx = c_double(0), c_long(-1)

@@ -1,0 +1,317 @@
+"""
+GaussianProcess / PrefGaussianProcess with the reference's public surface
+(ego/gaussianprocess/__init__.py:81-527) on top of the CUDA library.
+
+Host code here only owns NumPy buffers and marshals them through ctypes; the correlation matrix,
+its Cholesky factor, and every posterior / acquisition evaluation are computed on the GPU
+(ibo_b200/csrc/model.cu, score.cu).  There is no CPU fallback: without the library or a device
+every numeric method raises.
+
+Differences from the reference that a user can observe (all opt-in or bug fixes):
+  * `posteriors` and the new `score_batch` evaluate whole candidate arrays in one launch sequence;
+    `posterior` keeps the reference's "first point only" contract (:183-184,226).
+  * gradient observations (`G`) are rejected: the reference's gradient branches call functions that
+    do not exist (:199-206,292).
+  * no `pdb.set_trace()` (:382-384) and no library-search spin loop.
+"""
+from time import time
+
+import numpy as np
+
+from .. import _lib
+from .kernel import (GaussianKernel_ard, GaussianKernel_iso, Kernel, MaternKernel3, MaternKernel5,  # noqa: F401
+                     MaternKernel5_ard, SVGaussianKernel_ard, SVGaussianKernel_iso, SVKernel)
+from .prior import GPMeanPrior, RBFNMeanPrior  # noqa: F401
+
+# -----------------------------------------------------------------------------------------------
+# scalar erf / CDF / PDF with the reference's constants (ego/gaussianprocess/__init__.py:55-77).
+# Host-side helpers for scalar callers (PrefGP's Laplace terms); the batched versions live in K3.
+# -----------------------------------------------------------------------------------------------
+_NR = (1.00002368, 0.37409196, 0.09678418, -0.18628806, 0.27886807, -1.13520398, 1.48851587, -0.82215223, 0.17087277)
+
+
+def erf(z):
+    t = 1.0 / (1.0 + 0.5 * abs(z))
+    p = 0.0
+    for c in reversed(_NR):
+        p = c + t * p
+    ans = 1 - t * np.exp(-z * z - 1.26551223 + t * p)
+    return ans if z >= 0.0 else -ans
+
+
+def CDF(x):
+    return 0.5 * (1 + erf(x * 0.707106))
+
+
+def PDF(x):
+    return np.exp(-(x ** 2 / 2)) * 0.398942
+
+
+class GaussianProcess(object):
+
+    def __init__(self, kernel, X=None, Y=None, prior=None, noise=.1, gnoise=1e-4, G=None, device=0):
+        """
+        @param kernel:  kernel object (ibo_b200.gaussianprocess.kernel)
+        @param prior:   GP mean prior (RBFNMeanPrior) or None
+        @param noise:   noise hyperparameter sigma^2_n
+        @param X, Y:    initial training data / observations
+        @param device:  CUDA device ordinal holding the model
+        """
+        self.kernel = kernel
+        self.prior = prior
+        self.noise = noise
+        self.gnoise = np.array(gnoise, ndmin=1)
+        self.device = device
+        if (X is None) != (Y is None):
+            raise ValueError
+        if G is not None:
+            raise NotImplementedError("gradient observations are not supported (dead code in the reference)")
+        self.X = np.zeros((0, 0))
+        self.Y = np.zeros((0))
+        self.G = None
+        self.name = 'GP'
+        self.starttime = time()
+        self._model = None          # _lib.Model for (X, Y, Cinv)
+        self._Cinv = None
+        self._augmodel = None
+        self.augX = None
+        self.selected = None
+        self.endtime = None
+        if X is not None:
+            self.addData(X, Y)
+
+    # ---- device model -------------------------------------------------------------------------
+    def _invalidate(self):
+        for attr in ("_model", "_augmodel"):
+            m = getattr(self, attr, None)
+            if m is not None:
+                m.close()
+            setattr(self, attr, None)
+
+    def _build(self, X, Y, Cinv=None):
+        kind, hyper = self.kernel.spec(X.shape[1])
+        return _lib.Model(kind, hyper, X, Y, self.noise, Cinv=Cinv, prior=self.prior, device=self.device)
+
+    @property
+    def model(self):
+        """the device-resident model (L, W = inv(L), beta), built on first use after a data change"""
+        if self._model is None:
+            if len(self.X) == 0:
+                raise ValueError("GP has no data")
+            self._model = self._build(self.X, self.Y, self._Cinv)
+            if self.augX is not None:
+                self._attach_aug()
+        return self._model
+
+    @property
+    def R(self):
+        """correlation matrix K_offdiag + (1+noise) I (:134-143), computed on the device"""
+        if len(self.X) == 0:
+            return None
+        A = self.model.matrix(0)
+        return A if self._Cinv is None else A - self._Cinv
+
+    @property
+    def L(self):
+        """lower Cholesky factor of R (or of R + inv(C) for a fitted PrefGaussianProcess)"""
+        return None if len(self.X) == 0 else self.model.matrix(1)
+
+    # ---- posterior ----------------------------------------------------------------------------
+    def posterior(self, X, getvar=True):
+        """Posterior mean and variance at a point X (first row if several are given, as the reference)."""
+        if len(self.X) == 0:
+            m = 0.0 if self.prior is None else self.prior.mu(np.array(X, dtype=float, ndmin=2)[0])
+            return (m, 1.0) if getvar else m
+        X = np.array(X, dtype=float, ndmin=2)
+        mu, s2 = self.model.posterior(X[:1], _lib.FLAG_MODE_PY)
+        if getvar:
+            return float(mu[0]), float(s2[0])
+        return float(mu[0])
+
+    def posteriors(self, X):
+        """arrays of posterior means and variances for the points in X, one batched launch (:231-244)"""
+        X = np.asarray(X, dtype=float)
+        if X.ndim == 1:
+            X = X.reshape(-1, 1)
+        if len(self.X) == 0:
+            m = np.array([0.0 if self.prior is None else self.prior.mu(x) for x in X])
+            return m, np.ones(len(X))
+        return self.model.posterior(X, _lib.FLAG_MODE_PY)
+
+    def score_batch(self, Xs, acq='ei', xi=0.01, parm=None, mode='py', want_posterior=False, out=None):
+        """Acquisition values for a candidate array (batched EI.negf / PI.negf / UCB.negf, negated).
+
+        Returns (scores, best_score, best_index[, mu, sigma2]).  `parm` overrides xi (UCB multiplier)."""
+        acq_id = {'ei': _lib.ACQ_EI, 'pi': _lib.ACQ_PI, 'ucb': _lib.ACQ_UCB}[acq]
+        flags = _lib.FLAG_MODE_PY if mode == 'py' else _lib.FLAG_MODE_CPP
+        sc, mu, s2, best, bidx = self.model.score(Xs, acq_id, np.max(self.Y), xi if parm is None else parm, flags,
+                                                  want_posterior=want_posterior, out=out)
+        if want_posterior:
+            return sc, best, bidx, mu, s2
+        return sc, best, bidx
+
+    def mu(self, x):
+        return self.posterior(x, getvar=False)
+
+    def negmu(self, x):
+        return -self.mu(x)
+
+    # ---- data ---------------------------------------------------------------------------------
+    def addData(self, X, Y, G=None):
+        """Add observations and update (:267-308).  X is (N,D) (or one D-vector), Y an N-vector."""
+        if G is not None:
+            raise NotImplementedError("gradient observations are not supported (dead code in the reference)")
+        X = np.array(X, dtype=float, ndmin=2)
+        Y = np.array(Y, dtype=float, ndmin=1).flatten()
+        assert len(Y) == len(X), 'wrong number of Y-observations given'
+        if len(self.X) == 0 and len(self.gnoise) == 1:
+            self.gnoise = np.tile(self.gnoise, X.shape[1])
+        if len(self.X) == 0:
+            self.X, self.Y = X.copy(), Y.copy()
+        else:
+            self.X = np.r_[self.X, X]
+            self.Y = np.r_[self.Y, Y]
+        # the factor of the enlarged matrix has the old factor as its leading block, so rebuilding on the
+        # device is the block append of :300-308 carried out blockwise there
+        self._invalidate()
+
+    def getYfromX(self, qx):
+        for x, y in zip(self.X, self.Y):
+            if np.all(qx == x):
+                return y
+        return None
+
+    def done(self, x):
+        self.selected = x
+        self.endtime = time()
+
+    # aug* attributes exist on every GP in the reference (:118-120)
+    @property
+    def augR(self):
+        return None if self._augmodel is None else self._augmodel.matrix(0) - self._augCinv
+
+    @property
+    def augL(self):
+        return None if self._augmodel is None else self._augmodel.matrix(1)
+
+    def _attach_aug(self):
+        n, na = len(self.X), len(self.augX)
+        Cinv = np.zeros((na, na))
+        if self._Cinv is not None:
+            Cinv[:n, :n] = self._Cinv
+        self._augCinv = Cinv
+        if self._augmodel is not None:
+            self._augmodel.close()
+        self._augmodel = self._build(self.augX, np.zeros(na), Cinv)
+        self._model.set_variance_model(self._augmodel)
+
+    def __del__(self):
+        try:
+            self._invalidate()
+        except Exception:
+            pass
+
+
+class PrefGaussianProcess(GaussianProcess):
+    """
+    GP trained on pairwise preferences with a Laplace approximation (:331-527).  Triples are
+    (xv, xu, d): xv preferred to xu, d = degree (0 standard, 1 greatly preferred).
+
+    The MAP fit and the assembly of C are host-side model fitting ("next" row f-2 of the scope
+    table); everything downstream of (X, Y, C) -- L = chol(R + inv(C)), posteriors, acquisition --
+    runs on the GPU.  `fromLaplace` builds the process directly from a fitted (X, Y, C).
+    """
+
+    def __init__(self, kernel, prefs=None, **kwargs):
+        super(PrefGaussianProcess, self).__init__(kernel, **kwargs)
+        self.preferences = []
+        self.C = None
+        if prefs is not None:
+            self.addPreferences(prefs)
+
+    @classmethod
+    def fromLaplace(cls, kernel, X, Y, C, **kwargs):
+        gp = cls(kernel, **kwargs)
+        gp.X = np.array(X, dtype=float, ndmin=2)
+        gp.Y = np.array(Y, dtype=float).reshape(-1)
+        gp._set_C(np.array(C, dtype=float))
+        return gp
+
+    def _set_C(self, C):
+        """L = chol(R + inv(C)), retrying with C += I up to 10 times when not SPD (:487-498)."""
+        self.C = C
+        for attempt in range(11):
+            self._invalidate()
+            self._Cinv = np.linalg.inv(self.C)
+            try:
+                self.model   # builds and factorises on the device; raises NotPositiveDefinite
+                return
+            except np.linalg.LinAlgError:
+                print('[addPreferences] GP.C matrix is ill-conditioned, adding regularizer delta = %d' % (attempt + 1))
+                self.C = self.C + np.eye(len(self.X))
+        raise np.linalg.LinAlgError("R + inv(C) is not positive definite after 10 regularisation steps")
+
+    def addPreferences(self, prefs, useC=True, showPrefLikelihood=False):
+        from scipy.linalg import solve_triangular
+        from scipy.optimize import fmin_bfgs
+        self.preferences.extend(prefs)
+        # index the distinct points in order of first appearance (:391-408)
+        x2ind, prefinds, winners = {}, [], set()
+        for v, u, d in self.preferences:
+            v, u = tuple(v), tuple(u)
+            winners.add(v)
+            for p in (v, u):
+                if p not in x2ind:
+                    x2ind[p] = len(x2ind)
+            prefinds.append((x2ind[v], x2ind[u], d))
+        newX = np.array([x for x, _ in sorted(x2ind.items(), key=lambda kv: kv[1])], dtype=float)
+        # warm start from the previous latent values (:410-430)
+        lastY = dict((tuple(x), y) for x, y in zip(self.X, self.Y))
+        ymax, ymin = (max(self.Y), min(self.Y)) if len(self.Y) > 0 else (.5, -.5)
+        start = np.array([lastY.get(tuple(x), ymax if tuple(x) in winners else ymin) for x in newX], dtype=float)
+        # R and its factor come from the device (:433-438)
+        self._invalidate()
+        self._Cinv, self.C, self.augX = None, None, None
+        self.X, self.Y = newX, start.copy()
+        Lmat = self.L
+        vi = np.array([p[0] for p in prefinds]); ui = np.array([p[1] for p in prefinds])
+        dg = np.array([p[2] for p in prefinds], dtype=float)
+        verf = np.vectorize(erf, otypes=[float])
+
+        def S(x):
+            # -sum (d+1) log(CDF((x_v - x_u)/sqrt2) + 1e-10) + |L^-1 x|^2 / 2   (:373-386)
+            z = (x[vi] - x[ui]) / np.sqrt(2)
+            cdf = 0.5 * (1 + verf(z * 0.707106))
+            Lx = solve_triangular(Lmat, x, lower=True)
+            return -np.sum((dg + 1) * np.log(cdf + 1e-10)) + np.dot(Lx, Lx) / 2
+
+        self.Y = np.asarray(fmin_bfgs(S, start, disp=0), dtype=float)      # numerical gradients, as :442
+        # ordering fix-up (:445-458)
+        for r, c, _ in self.preferences:
+            r, c = tuple(r), tuple(c)
+            if self.Y[x2ind[r]] <= self.Y[x2ind[c]]:
+                if not any(np.all(np.asarray(c1) == np.asarray(r)) for _, c1, _ in self.preferences):
+                    self.Y[x2ind[r]] = self.Y[x2ind[c]] + .1
+        # Laplace C matrix (:461-486): each preference (a,b) adds w to C[a,a], C[b,b] and -w to C[a,b], C[b,a]
+        self._invalidate()
+        mu_all = self.posteriors(self.X)[0]
+        C = np.eye(len(self.X), dtype=float) * 5
+        for a, b, _ in prefinds:
+            d = (mu_all[a] - mu_all[b]) / (np.sqrt(2) * np.sqrt(self.noise))
+            cdf, pdf = max(CDF(d), 1e-10), max(PDF(d), 1e-10)
+            w = 1.0 / (2 * self.noise) * (pdf ** 2 / cdf ** 2 + d * pdf / cdf)
+            C[a, a] += w; C[b, b] += w
+            C[a, b] -= w; C[b, a] -= w
+        self._set_C(C)
+
+    def addObservationPoint(self, X):
+        """Add a point at which we will observe but have no observation yet (:502-519): the variance is
+        then taken from the augmented factor chol(augR + pad(inv(C))) while the mean keeps (X, L)."""
+        X = np.array(X, dtype=float, ndmin=2)
+        self.augX = self.X.copy() if self.augX is None else self.augX
+        self.augX = np.r_[self.augX, X]
+        self.model
+        self._attach_aug()
+
+    def addData(self, X, Y, G=None):
+        raise NotImplementedError("can't (yet) add explicit ratings to preference GP")

@@ -122,6 +122,15 @@ int ibo_score_resident(ibo_model* m, ibo_cands* c, int acq, double ymax, double 
 int ibo_get_profile(ibo_model* m, double* out6);
 /* cumulative count of kernels this library launched in this process */
 long ibo_launch_count(void);
+/* measurement helpers (bench.py): live FP64 tensor-pipe peak of `device` in TFLOP/s (DMMA.8x8x4 issue rate);
+ * page-lock / unlock a caller-owned host buffer so the copies of the end-to-end leg run from pinned memory */
+int ibo_fp64_peak(int device, double* tflops);
+int ibo_host_register(void* p, unsigned long bytes);
+int ibo_host_unregister(void* p);
+/* CUDA events on the model's stream (slot 0 = start, 1 = stop) and their elapsed device time */
+int ibo_stream_mark(ibo_model* m, int slot);
+int ibo_stream_elapsed_ms(ibo_model* m, float* ms);
+int ibo_device_synchronize(int device);
 
 /* ---- DIRECT ----------------------------------------------------------------------------------
  * Batched DIRECT following the reference's rectangle rules (cpp/direct.cpp:146-235,372-498).

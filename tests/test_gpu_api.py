@@ -1,0 +1,228 @@
+"""GPU tests of the drop-in Python surface (GaussianProcess / PrefGaussianProcess / EI / gallery) and of
+size-independent properties at BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+
+from oracle import ibo_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _gp(kernel, X, Y, **kw):
+    from ibo_b200.gaussianprocess import GaussianProcess
+    return GaussianProcess(kernel, X, Y, **kw)
+
+
+def test_posterior_api_matches_numpy_path():
+    """GaussianProcess.posterior / posteriors / mu / EI.negf / PI.negf / UCB.negf vs the scalar-faithful oracle"""
+    from ibo_b200.acquisition import EI, PI, UCB
+    from ibo_b200.gaussianprocess.kernel import GaussianKernel_iso
+    bounds = [[0., 10.]] * 4
+    X = np.array(orc.lhc_sample(bounds, 10, seed=0))
+    Y = np.array([-orc.shekel5(x) for x in X])
+    gp = _gp(GaussianKernel_iso([0.3]), X, Y, noise=0.1)
+    o = orc.GPOracle(orc.KernelSpec(orc.K_SE_ISO, [0.3], 4), X, Y, 0.1)
+    pts = np.array(orc.lhc_sample(bounds, 7, seed=3))
+    for x in pts:
+        m, v = gp.posterior(x)
+        mo, vo = o.posterior_scalar(x)
+        assert abs(m - mo) <= 1e-10 * max(abs(mo), 1e-3) and abs(v - vo) <= 1e-10 * vo
+        assert gp.mu(x) == m and gp.negmu(x) == -m
+        ei = EI(gp, xi=0.01)
+        assert abs(-ei.negf(x) - float(orc.ei_py(mo, vo, Y.max(), 0.01))) <= 1e-10 * max(abs(float(orc.ei_py(mo, vo, Y.max(), 0.01))), 1e-5)
+        pi = PI(gp, xi=0.05)
+        assert abs(pi.f(x) - float(orc.pi_py(mo, vo, Y.max(), 0.05))) <= 1e-10
+        ucb = UCB(gp, 4)
+        assert abs(ucb.f(x) - float(orc.ucb_py(mo, vo, orc.ucb_sbeta_py(len(Y), 4)))) <= 1e-10
+    M, V = gp.posteriors(pts)
+    assert M.shape == (7,) and V.shape == (7,)
+    assert (M[0], V[0]) == gp.posterior(pts[0])
+    # R and L attributes
+    assert np.allclose(gp.R, o.R, atol=1e-14) and np.allclose(gp.L, o.L, atol=1e-12)
+
+
+def test_add_data_batch_equals_sequential():
+    """ego/unittest_GP.py:109-156: adding data in one batch or one by one gives the same R and the same posterior"""
+    from ibo_b200.gaussianprocess.kernel import GaussianKernel_ard
+    rs = np.random.RandomState(4)
+    X = rs.rand(40, 3); Y = np.sin(4 * X).sum(axis=1)
+    a = _gp(GaussianKernel_ard([.3, .4, .5]), X, Y)
+    from ibo_b200.gaussianprocess import GaussianProcess
+    b = GaussianProcess(GaussianKernel_ard([.3, .4, .5]))
+    assert b.posterior(X[0]) == (0.0, 1.0)
+    for x, y in zip(X, Y):
+        b.addData(x, y)
+    assert np.array_equal(a.R, b.R)
+    q = rs.rand(9, 3)
+    assert np.array_equal(a.posteriors(q)[0], b.posteriors(q)[0])
+    assert np.array_equal(a.posteriors(q)[1], b.posteriors(q)[1])
+    assert a.getYfromX(X[3]) == Y[3] and a.getYfromX(np.ones(3) * 7) is None
+
+
+def test_training_point_bounds():
+    """ego/unittest_GP.py:94-98: at training points sigma^2 < 1/(1+noise)... here: below noise-level bound, mu near y"""
+    from ibo_b200.gaussianprocess.kernel import GaussianKernel_iso
+    bounds = [[0., 10.]] * 4
+    X = np.array(orc.lhc_sample(bounds, 30, seed=1))
+    Y = np.array([-orc.shekel5(x) for x in X])
+    gp = _gp(GaussianKernel_iso([0.3]), X, Y, noise=0.01)
+    M, V = gp.posteriors(X)
+    assert np.all(V < 1.0 / (1 + 0.01)) and np.all(np.abs(M - Y) < 2 * 0.01 + 0.05)
+
+
+def test_pref_gp_laplace_factor_and_aug_variance():
+    """fitted PrefGaussianProcess (X, Y, C given): L = chol(R + inv(C)); addObservationPoint switches the variance to augL"""
+    from scipy.linalg import solve_triangular
+    from ibo_b200.gaussianprocess import PrefGaussianProcess
+    from ibo_b200.gaussianprocess.kernel import GaussianKernel_ard
+    rs = np.random.RandomState(8)
+    N, d = 60, 4
+    X = rs.rand(N, d) * 10
+    Y = rs.randn(N)
+    A = rs.randn(N, N) * 0.05
+    C = np.eye(N) * 5 + A.dot(A.T)
+    theta = [5.146, 4.189, 4.622, 5.843]
+    gp = PrefGaussianProcess.fromLaplace(GaussianKernel_ard(theta), X, Y, C, noise=0.1)
+    Cinv = np.linalg.inv(C)
+    o = orc.GPOracle(orc.KernelSpec(orc.K_SE_ARD, theta, d), X, Y, 0.1, Cinv=Cinv)
+    assert np.allclose(gp.L, o.L, atol=1e-12)
+    q = rs.rand(50, d) * 10
+    mu, s2 = gp.posteriors(q)
+    mo, so = o.posterior_batch(q)
+    assert np.max(np.abs(mu - mo) / np.maximum(np.abs(mo), 1e-3)) <= 1e-10
+    assert np.max(np.abs(s2 - so) / so) <= 1e-10
+    # observation points (ego/gaussianprocess/__init__.py:502-519)
+    P = rs.rand(3, d) * 10
+    gp.addObservationPoint(P[:2]); gp.addObservationPoint(P[2])
+    augX = np.r_[X, P]
+    augR = orc.build_R(o.kernel, augX, 0.1)
+    pad = np.zeros_like(augR); pad[:N, :N] = Cinv
+    o.augL = np.linalg.cholesky(augR + pad); o.augX = augX
+    mu2, s22 = gp.posteriors(q)
+    mo2, so2 = o.posterior_batch(q)
+    assert np.array_equal(mu2, mu)
+    assert np.max(np.abs(s22 - so2) / so2) <= 1e-10
+    assert np.all(s22 <= s2 + 1e-12)
+    assert np.allclose(gp.augL, o.augL, atol=1e-12)
+
+
+def test_pref_gp_fit_orders_latents():
+    """ego/unittest_GP.py:398-478 property: the latent means respect the preferences"""
+    from ibo_b200.gaussianprocess import PrefGaussianProcess
+    from ibo_b200.gaussianprocess.kernel import GaussianKernel_iso
+    prefs = [(np.array([.2]), np.array([.5]), 0), (np.array([.5]), np.array([.9]), 0), (np.array([.2]), np.array([.9]), 1)]
+    gp = PrefGaussianProcess(GaussianKernel_iso([.3]), prefs)
+    assert gp.mu(np.array([.2])) > gp.mu(np.array([.5])) > gp.mu(np.array([.9]))
+    assert gp.C.shape == (3, 3) and np.allclose(gp.C, gp.C.T)
+    with pytest.raises(NotImplementedError):
+        gp.addData([0.1], [1.0])
+
+
+def test_not_spd_is_reported():
+    from ibo_b200 import _lib
+    X = np.array([[0.0], [1.0], [2.0]]); Y = np.zeros(3)
+    Cinv = -5.0 * np.eye(3)
+    with pytest.raises(np.linalg.LinAlgError) as ei:
+        _lib.Model(_lib.KERNEL_SE_ISO, [1.0], X, Y, 0.1, Cinv=Cinv)
+    assert ei.value.pivot == 1
+
+
+def test_fast_ucb_gallery_properties():
+    """ego/unittest_IBO.py:844-870: gallery points inside the bounds, fixed dimension pinned"""
+    from ibo_b200.acquisition import fastUCBGallery
+    from ibo_b200.gaussianprocess.kernel import GaussianKernel_ard
+    rs = np.random.RandomState(2)
+    bounds = [[0., 0.], [0., 4.], [-1., 3.]]
+    X = np.c_[np.zeros(12), rs.rand(12) * 4, rs.rand(12) * 4 - 1]
+    Y = np.sin(X[:, 1]) + np.cos(X[:, 2])
+    gp = _gp(GaussianKernel_ard([1.0, 1.0, 1.0]), X, Y)
+    gal = fastUCBGallery(gp, bounds, 4, seed=3)
+    assert len(gal) == 4
+    for x in gal:
+        assert x[0] == 0.0 and 0 <= x[1] <= 4 and -1 <= x[2] <= 3
+    for i in range(4):
+        for j in range(i):
+            assert np.linalg.norm(gal[i] - gal[j]) > .5
+    # deterministic with a seed
+    gal2 = fastUCBGallery(gp, bounds, 4, seed=3)
+    assert all(np.array_equal(a, b) for a, b in zip(gal, gal2))
+    # no data, no prior -> starts from the centre
+    from ibo_b200.gaussianprocess import GaussianProcess
+    empty = GaussianProcess(GaussianKernel_ard([1.0, 1.0]))
+    g3 = fastUCBGallery(empty, [[0., 2.], [0., 2.]], 2, seed=1)
+    assert np.array_equal(g3[0], np.array([1.0, 1.0])) and len(g3) == 2
+
+
+def test_python_direct_route_uses_python_arithmetic():
+    from ibo_b200.acquisition import maximizeEI
+    from ibo_b200.gaussianprocess.kernel import GaussianKernel_iso
+    bounds = [[0., 10.]] * 4
+    X = np.array(orc.lhc_sample(bounds, 10, seed=0))
+    Y = np.array([-orc.shekel5(x) for x in X])
+    gp = _gp(GaussianKernel_iso([0.3]), X, Y, noise=0.1)
+    a, ax = maximizeEI(gp, bounds, xi=0.01, maxiter=15, useCDIRECT=True)
+    b, bx = maximizeEI(gp, bounds, xi=0.01, maxiter=15, useCDIRECT=False)
+    # ego/unittest_IBO.py:427-474: the routes agree to 4 decimals (erf approximations differ by ~3e-7)
+    assert abs(a - b) < 5e-5 and np.allclose(ax, bx, atol=1e-4)
+
+
+# ---- full-size properties (BASELINE.json config #2 shape) ------------------------------------
+@pytest.fixture(scope="module")
+def big():
+    from ibo_b200 import _lib
+    rs = np.random.RandomState(0)
+    N, d = 2048, 6
+    X = rs.rand(N, d)
+    Y = orc.hartman6_neg(X)
+    theta = [.53, .57, 2.5, .34, .27, .35]
+    return _lib.Model(_lib.KERNEL_SE_ARD, theta, X, Y, 0.1), X, Y, theta
+
+
+def test_full_size_subsample_vs_oracle(big):
+    from ibo_b200 import _lib
+    m, X, Y, theta = big
+    M = 1 << 17
+    Xs = np.random.RandomState(1).rand(M, 6)
+    sc, mu, s2, best, bidx = m.score(Xs, _lib.ACQ_EI, Y.max(), 0.01, _lib.FLAG_MODE_CPP, want_posterior=True)
+    assert best == sc.max() and bidx == int(np.argmax(sc))
+    sel = np.r_[np.arange(0, M, 509), [bidx], np.argsort(sc)[-16:]]
+    o = orc.GPOracle(orc.KernelSpec(orc.K_SE_ARD, theta, 6), X, Y, 0.1)
+    mo, so = o.posterior_batch(Xs[sel], floor=1e-8)
+    eo = orc.score(orc.ACQ_EI, "cpp", mo, so, Y.max(), 0.01)
+    assert np.max(np.abs(mu[sel] - mo) / np.maximum(np.abs(mo), 1e-3)) <= 1e-10
+    assert np.max(np.abs(np.sqrt(s2[sel]) - np.sqrt(so)) / np.sqrt(so)) <= 1e-10
+    assert np.max(np.abs(sc[sel] - eo) / np.maximum(np.abs(eo), 1e-5)) <= 1e-10
+    assert np.all(s2 >= 1e-8) and np.all(s2 <= 1.1 + 1e-12)
+
+
+def test_scores_do_not_depend_on_batch_shape(big):
+    """a candidate's value is a pure function of (model, x): bit-identical across batch size / position / grouping"""
+    from ibo_b200 import _lib
+    m, X, Y, theta = big
+    Xs = np.random.RandomState(5).rand(70000, 6)
+    full = m.score(Xs, _lib.ACQ_EI, Y.max(), 0.01, _lib.FLAG_MODE_CPP)[0]
+    for lo, hi in [(0, 1), (5, 133), (1000, 1700), (69000, 70000), (300, 41000)]:
+        part = m.score(Xs[lo:hi], _lib.ACQ_EI, Y.max(), 0.01, _lib.FLAG_MODE_CPP)[0]
+        assert np.array_equal(part, full[lo:hi])
+    perm = np.random.RandomState(6).permutation(5000)
+    shuf = m.score(Xs[perm], _lib.ACQ_EI, Y.max(), 0.01, _lib.FLAG_MODE_CPP)[0]
+    assert np.array_equal(shuf, full[perm])
+
+
+def test_resident_candidates_and_ties(big):
+    from ibo_b200 import _lib
+    m, X, Y, theta = big
+    Xs = np.random.RandomState(9).rand(3000, 6)
+    Xs[2000] = Xs[17]; Xs[2999] = Xs[17]            # exact duplicates: lowest index must win any tie
+    c = _lib.ResidentCandidates(m, Xs)
+    out = np.empty(3000)
+    best, bidx, ms = c.score(_lib.ACQ_UCB, Y.max(), 2.0, _lib.FLAG_MODE_CPP, scores_out=out)
+    assert out[17] == out[2000] == out[2999]
+    assert bidx == int(np.argmax(out)) and best == out[bidx] and ms > 0
+    dup = np.repeat(Xs[17:18], 700, axis=0)
+    _, _, _, b2, i2 = m.score(dup, _lib.ACQ_EI, Y.max(), 0.01, _lib.FLAG_MODE_CPP)
+    assert i2 == 0
+    c.close()
+    # empty batch
+    sc, mu, s2, b, i = m.score(np.zeros((0, 6)), _lib.ACQ_EI, Y.max(), 0.01)
+    assert i == -1 and len(sc) == 0
