@@ -207,6 +207,122 @@ def workload_config(args, M):
 
 
 # ------------------------------------------------------------------------------------------------
+# extra measurements: `maximizeEI wall ms` half of the BASELINE metric, model build, other configs
+# ------------------------------------------------------------------------------------------------
+def ref_acqmax(invR, X, Y, hyper, kind, lb, ub, xi, noise, maxiter, maxsample):
+    """the reference's own acqmaxGP (oracle/_ref/libego.so) timed on one host core (it is single-threaded)"""
+    pd = POINTER(c_double)
+    path = os.path.join(ROOT, "oracle", "_ref", "libego.so")
+    if not os.path.exists(path):
+        return None
+    E = ctypes.CDLL(path)
+    E.acqmaxGP.restype = pd
+    E.acqmaxGP.argtypes = [c_int, pd, pd, pd, pd, pd, c_int, c_int, c_int, pd, c_int, pd, pd, c_double, pd, pd,
+                           c_double, c_double, c_int, c_int, c_int]
+    dp = lambda a: a.ctypes.data_as(pd)
+    z = np.zeros(1)
+    t0 = time.perf_counter()
+    res = E.acqmaxGP(X.shape[1], dp(lb), dp(ub), dp(invR), dp(X), dp(Y), X.shape[0], 0, kind, dp(hyper), 0, dp(z), dp(z), 0.0,
+                     dp(z), dp(z), xi, noise, maxiter, 10 ** 6, maxsample)
+    t = time.perf_counter() - t0
+    return {"wall_ms": 1e3 * t, "opt": -res[0], "optx": [res[i + 1] for i in range(X.shape[1])]}
+
+
+def run_suite(args):
+    from ibo_b200 import _lib
+    from ibo_b200.acquisition import cdirectGP, maximizeEI
+    from ibo_b200.gaussianprocess import GaussianProcess
+    from ibo_b200.gaussianprocess.kernel import GaussianKernel_ard, MaternKernel5_ard
+    from oracle import ibo_oracle as orc           # reference-side inputs (inv(R)) for the CPU leg only
+    _lib.require_gpu()
+    out = []
+
+    def emit(d):
+        out.append(d)
+        print(json.dumps(d), flush=True)
+
+    # warm the context / kernels
+    GaussianProcess(GaussianKernel_ard([1.0, 1.0]), np.random.rand(300, 2), np.random.rand(300)).model
+    # ---- config #1: demo.py-style maximizeEI, Branin N=50, d=2, 50 DIRECT iterations ----
+    bounds = [[-5., 10.], [0., 15.]]
+    X = np.array(orc.lhc_sample(bounds, 50, seed=0)); Y = -orc.branin(X) / 100.0
+    t0 = time.perf_counter()
+    gp = GaussianProcess(GaussianKernel_ard([3.4, 10.0]), X, Y, noise=0.1)
+    gp.model
+    t_build = time.perf_counter() - t0
+    ts = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        opt, optx = maximizeEI(gp, bounds, xi=0.01, maxiter=50, maxtime=10 ** 6, maxsample=10000)
+        ts.append(time.perf_counter() - t0)
+    o = orc.GPOracle(orc.KernelSpec(0, [3.4, 10.0], 2), X, Y, 0.1)
+    b = np.array(bounds)
+    ref = ref_acqmax(np.ascontiguousarray(o.invR()), np.ascontiguousarray(X), np.ascontiguousarray(Y), np.array([3.4, 10.0]), 0,
+                     np.ascontiguousarray(b[:, 0]), np.ascontiguousarray(b[:, 1]), 0.01, 0.1, 50, 10000)
+    emit({"suite": "config1_maximizeEI", "N": 50, "d": 2, "maxiter": 50, "wall_ms": 1e3 * min(ts), "model_build_ms": 1e3 * t_build,
+          "nsamples": cdirectGP.last["nsamples"], "opt": opt, "optx": list(optx), "reference_acqmaxGP": ref,
+          "same_point": bool(ref and np.allclose(optx, ref["optx"], atol=1e-12))})
+    # ---- model build (R, Cholesky, W, packing) ----
+    for N in (2048, 4096, 8192):
+        Xb, Yb = synthetic_model(N, 6)
+        best = 1e9
+        for _ in range(2):
+            t0 = time.perf_counter()
+            g = GaussianProcess(GaussianKernel_ard(THETA), Xb, Yb, noise=NOISE)
+            g.model
+            best = min(best, time.perf_counter() - t0)
+            del g
+        emit({"suite": "model_build", "N": N, "d": 6, "wall_ms": 1e3 * best, "gflop": 2 * N ** 3 / 3 / 1e9})
+    # ---- maximizeEI at the headline model size (N=2048, d=6), default budget ----
+    Xb, Yb = synthetic_model(2048, 6)
+    gp = GaussianProcess(GaussianKernel_ard(THETA), Xb, Yb, noise=NOISE)
+    gp.model
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        opt, optx = maximizeEI(gp, [[0., 1.]] * 6, xi=XI, maxiter=50, maxtime=10 ** 6, maxsample=10000)
+        ts.append(time.perf_counter() - t0)
+    ns = cdirectGP.last["nsamples"]
+    o = orc.GPOracle(orc.KernelSpec(0, THETA, 6), Xb, Yb, NOISE)
+    ref = ref_acqmax(np.ascontiguousarray(o.invR()), np.ascontiguousarray(Xb), np.ascontiguousarray(Yb), np.array(THETA), 0,
+                     np.zeros(6), np.ones(6), XI, NOISE, 50, 400)      # bounded: ~400 samples of the reference (4N^2 flops each)
+    emit({"suite": "maximizeEI_N2048", "N": 2048, "d": 6, "maxiter": 50, "maxsample": 10000, "wall_ms": 1e3 * min(ts), "nsamples": ns,
+          "ms_per_1000_samples": 1e6 * min(ts) / ns, "opt": opt,
+          "reference_acqmaxGP_maxsample400": ref})
+    # ---- config #4 slice: Matern-5/2 ARD d=10, N=8192, 2^18 Sobol-like candidates on one GPU ----
+    rs = np.random.RandomState(4)
+    X4 = rs.rand(8192, 10); Y4 = np.sin(2 * X4).sum(axis=1)
+    th4 = [0.5 + 0.05 * j for j in range(10)] + [1.0]
+    gp4 = GaussianProcess(MaternKernel5_ard(th4), X4, Y4, noise=0.1)
+    m4 = gp4.model
+    try:
+        from scipy.stats import qmc
+        C4 = np.ascontiguousarray(qmc.Sobol(d=10, scramble=False).random_base2(18))
+    except Exception:
+        C4 = rs.rand(1 << 18, 10)
+    rc = _lib.ResidentCandidates(m4, C4)
+    rc.score(_lib.ACQ_EI, Y4.max(), 0.01)
+    best4, idx4, ms4 = rc.score(_lib.ACQ_EI, Y4.max(), 0.01, _lib.FLAG_PROFILE)
+    pr = m4.profile()
+    F = 8192.0 ** 2 + 8192 * (2 * 10 + 8)
+    emit({"suite": "config4_slice", "N": 8192, "d": 10, "candidates": len(C4), "ms": ms4, "evals_per_s": len(C4) / (ms4 * 1e-3),
+          "algorithmic_tflops": len(C4) * F / (ms4 * 1e-3) / 1e12, "k1_ms": pr["k1_ms"], "k2_ms": pr["k2_ms"], "k3_ms": pr["k3_ms"]})
+    rc.close()
+    del gp4, m4
+    # ---- config #5: batched-DIRECT maximizeEI d=20, N=4096, 200 iterations ----
+    rs = np.random.RandomState(5)
+    X5 = rs.rand(4096, 20); Y5 = np.sin(2 * X5).sum(axis=1)
+    gp5 = GaussianProcess(GaussianKernel_ard([1.0] * 20), X5, Y5, noise=0.1)
+    gp5.model
+    t0 = time.perf_counter()
+    opt5, optx5 = maximizeEI(gp5, [[0., 1.]] * 20, xi=0.01, maxiter=200, maxtime=10 ** 6, maxsample=10 ** 9)
+    t5 = time.perf_counter() - t0
+    emit({"suite": "config5_direct", "N": 4096, "d": 20, "maxiter": 200, "wall_ms": 1e3 * t5, "nsamples": cdirectGP.last["nsamples"],
+          "iterations": cdirectGP.last["iterations"], "opt": opt5})
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -217,7 +333,10 @@ def main():
     ap.add_argument("--dim", type=int, default=6)
     ap.add_argument("--candidates", type=int, default=1 << 20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--suite", action="store_true", help="extra measurements (maximizeEI wall ms, model build, configs #1/#4/#5)")
     args = ap.parse_args()
+    if args.suite:
+        return run_suite(args)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -18,6 +18,7 @@
 #include <cmath>
 #include <algorithm>
 #include <mutex>
+#include <cstdlib>
 
 namespace ibo {
 
@@ -102,7 +103,7 @@ trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab
     double* sRed = sB + K2_STAGES * BLOB;                       // [2][3][128]
     uint64_t* full = reinterpret_cast<uint64_t*>(sRed + 2 * 3 * 128);
     uint64_t* empty = full + K2_STAGES;
-    const int T = blockIdx.x, g = blockIdx.y;
+    const int g = blockIdx.x, T = blockIdx.y;   // group fastest: the G CTAs of one tile are co-resident and share its slab in L2
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         for (int s = 0; s < K2_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
@@ -145,25 +146,49 @@ trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab
 #pragma unroll
             for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
         const int nkb = (i + 1) * KB_PER_BLOCK;
+        const int nfull = i * KB_PER_BLOCK;     // k-blobs left of the diagonal block: dense
         for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(&full[s], ph);
-            const double2* a2 = reinterpret_cast<const double2*>(sA + s * BLOB) + (wm * 8 * 2) * 32 + lane;
+            // warp wm owns the interleaved m-tiles 2*mt + wm (mt = 0..7) so that the triangular skip below is balanced
+            const double2* a2 = reinterpret_cast<const double2*>(sA + s * BLOB) + (wm * 2) * 32 + lane;
             const double2* b2 = reinterpret_cast<const double2*>(sB + s * BLOB) + (wn * 4 * 2) * 32 + lane;
+            if (kb < nfull) {
 #pragma unroll
-            for (int ks2 = 0; ks2 < 2; ks2++) {
-                double2 af[8], bf[4];
+                for (int ks2 = 0; ks2 < 2; ks2++) {
+                    double2 af[8], bf[4];
 #pragma unroll
-                for (int mt = 0; mt < 8; mt++) af[mt] = a2[(mt * 2 + ks2) * 32];
+                    for (int mt = 0; mt < 8; mt++) af[mt] = a2[(mt * 4 + ks2) * 32];
 #pragma unroll
-                for (int nt = 0; nt < 4; nt++) bf[nt] = b2[(nt * 2 + ks2) * 32];
+                    for (int nt = 0; nt < 4; nt++) bf[nt] = b2[(nt * 2 + ks2) * 32];
 #pragma unroll
-                for (int mt = 0; mt < 8; mt++)
+                    for (int mt = 0; mt < 8; mt++)
 #pragma unroll
-                    for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt].x, bf[nt].x);
+                        for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt].x, bf[nt].x);
 #pragma unroll
-                for (int mt = 0; mt < 8; mt++)
+                    for (int mt = 0; mt < 8; mt++)
 #pragma unroll
-                    for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt].y, bf[nt].y);
+                        for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt].y, bf[nt].y);
+                }
+            } else {
+                // diagonal block of W (lower triangular): in its k-blob kbl the m-tiles 2*mt + wm with mt < kbl are
+                // identically zero (rows 8*(2mt+wm)+7 < 16*kbl) and are skipped
+                const int kbl = kb - nfull;
+#pragma unroll
+                for (int ks2 = 0; ks2 < 2; ks2++) {
+                    double2 bf[4];
+#pragma unroll
+                    for (int nt = 0; nt < 4; nt++) bf[nt] = b2[(nt * 2 + ks2) * 32];
+#pragma unroll
+                    for (int mt = 0; mt < 8; mt++) {
+                        if (mt >= kbl) {
+                            const double2 af = a2[(mt * 4 + ks2) * 32];
+#pragma unroll
+                            for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af.x, bf[nt].x);
+#pragma unroll
+                            for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af.y, bf[nt].y);
+                        }
+                    }
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
@@ -173,7 +198,7 @@ trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab
         double by[8], b1[8];
 #pragma unroll
         for (int mt = 0; mt < 8; mt++) {
-            int r = i * 128 + wm * 64 + mt * 8 + (lane >> 2);
+            int r = i * 128 + (2 * mt + wm) * 8 + (lane >> 2);
             by[mt] = betaY[r];
             b1[mt] = want_p1 ? beta1[r] : 0.0;
         }
@@ -377,6 +402,25 @@ static void set_score_attrs() {
     if (cudaGetDeviceProperties(&pr, dev) == cudaSuccess) g_num_sms = pr.multiProcessorCount;
 }
 
+static long chunk_tiles_default() {
+    static long v = -1;
+    if (v < 0) {
+        const char* e = getenv("IBO_CHUNK_TILES");     // tuning knob (tools/perf_sweep.sh)
+        v = e ? atol(e) : 0;
+        if (v <= 0) v = 2L * g_num_sms;
+    }
+    return v;
+}
+
+// Row-block groups per candidate tile.  (a) L2 residency: the G CTAs of a tile run side by side, so about
+// num_sms / G slab tiles (Np KiB each) are live at once; G = nb/4 keeps that at <= 148 * 4 * 128 KiB = 74 MiB of the
+// 126 MiB L2 for every N.  (b) occupancy: small batches (DIRECT) need tiles * G >= num_sms.
+static int pick_groups(int nb, long tiles) {
+    long G = std::max(1, nb / 4);
+    if (tiles * G < g_num_sms) G = (g_num_sms + tiles - 1) / tiles;
+    return (int)std::min<long>(G, nb);
+}
+
 struct ScoreReq {
     int acq;            // -1: posterior only
     double ymax, parm;
@@ -395,7 +439,7 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
     ibo_model* vm = m->var_model;
     const int nb = m->nb;
     const long tilesTotal = (M + TN - 1) / TN;
-    long chunkTiles = std::min<long>(tilesTotal, 2L * g_num_sms);
+    long chunkTiles = std::min<long>(tilesTotal, chunk_tiles_default());
     // keep the slab below ~6 GiB
     while (chunkTiles > 1 && (double)chunkTiles * nb * KB_PER_BLOCK * BLOB * 8.0 > 6.0e9) chunkTiles = (chunkTiles + 1) / 2;
     const long Mpad = chunkTiles * TN;
@@ -425,8 +469,7 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
         const long tiles = std::min(chunkTiles, tilesTotal - t0);
         const long m0 = t0 * TN;
         const long chunkM = std::min<long>(tiles * TN, M - m0);
-        int G = 1;
-        if (tiles < g_num_sms) G = (int)std::min<long>(nb, (g_num_sms + tiles - 1) / tiles);
+        const int G = pick_groups(nb, tiles);
         if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[1], st));
         kstar_kernel<<<dim3((unsigned)tiles, nb), 256, 2 * 128 * kS * 8, st>>>(m->dXt, dCand, m->dInvTheta, m->dSlab, m->N, m->d, nb, M, m0, m->kind, m->sf2);
         nlaunch++;
@@ -435,12 +478,11 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
             nlaunch++;
         }
         if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[2], st));
-        trigemm_kernel<<<dim3((unsigned)tiles, G), K2_THREADS, K2_SMEM, st>>>(m->dWpack, m->dSlab, m->dBetaY, m->dBeta1, m->dPart, nb, G, Mpad, m->npb > 0);
+        trigemm_kernel<<<dim3(G, (unsigned)tiles), K2_THREADS, K2_SMEM, st>>>(m->dWpack, m->dSlab, m->dBetaY, m->dBeta1, m->dPart, nb, G, Mpad, m->npb > 0);
         nlaunch++; nK2++;
         if (vm) {
-            int Gv = 1;
-            if (tiles < g_num_sms) Gv = (int)std::min<long>(vm->nb, (g_num_sms + tiles - 1) / tiles);
-            trigemm_kernel<<<dim3((unsigned)tiles, Gv), K2_THREADS, K2_SMEM, st>>>(vm->dWpack, vm->dSlab, vm->dBetaY, vm->dBeta1, vm->dPart, vm->nb, Gv, Mpad, 0);
+            const int Gv = pick_groups(vm->nb, tiles);
+            trigemm_kernel<<<dim3(Gv, (unsigned)tiles), K2_THREADS, K2_SMEM, st>>>(vm->dWpack, vm->dSlab, vm->dBetaY, vm->dBeta1, vm->dPart, vm->nb, Gv, Mpad, 0);
             nlaunch++; nK2++;
         }
         if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[3], st));
