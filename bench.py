@@ -450,6 +450,13 @@ def main():
     k2_s = prof["k2_ms"] * 1e-3 / max(prof["k2_launches"], 1)
     cand_per_launch = M / max(prof["k2_launches"], 1)
     achieved = cand_per_launch * flops_per_candidate_k2(N) / k2_s / 1e12
+    traffic = None
+    try:   # dram__bytes_read.sum + dram__bytes_write.sum of K2 from the committed ncu --set full capture, scaled per launch
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k2_traffic.json")))
+        if tj["n_obs"] == N:
+            traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * cand_per_launch / tj["candidates_per_launch"]
+    except Exception:
+        pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -459,7 +466,7 @@ def main():
                 "api": "GaussianProcess.score_batch -> ibo_score_batch (host buffers, pinned)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value if peak.value else None,
-                     "traffic": None, "kernel": "trigemm_kernel (K2)", "flops_per_candidate": flops_per_candidate_k2(N),
+                     "traffic": traffic, "kernel": "trigemm_kernel (K2)", "flops_per_candidate": flops_per_candidate_k2(N),
                      "candidates_per_launch": cand_per_launch, "avg_launch_ms": 1e3 * k2_s,
                      "peak_source": "live DMMA.8x8x4 issue-rate microbenchmark on this GPU (ibo_fp64_peak); MEASURED_PEAKS.json "
                                     "and the profiling guide carry no FP64 figure"},

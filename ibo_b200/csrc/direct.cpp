@@ -6,10 +6,9 @@
 // reference writes them so that, on identical objective values, the trajectory is identical:
 // same samples, same rectangles, same (FMIN, XMIN, nsamples).
 //
-// The potentially-optimal test is evaluated from per-distance-class minima in O(R * #classes)
-// instead of the reference's O(R^2) pair scan; it evaluates the same slope expressions on the
-// extremal member of each class (fl(x - c) and fl(x / c), c > 0, are monotone in x), so accept /
-// reject decisions are bit-identical.
+// The potentially-optimal test is evaluated once per distance class (O(C^2) per iteration) instead of
+// the reference's O(R^2) pair scan, on the same slope expressions, with bit-identical accept / reject
+// decisions (see select()).
 #include "../../include/ibo_b200.h"
 #include <algorithm>
 #include <cmath>
@@ -18,6 +17,8 @@
 #include <ctime>
 #include <limits>
 #include <map>
+#include <set>
+#include <unordered_map>
 #include <string>
 #include <utility>
 #include <vector>
@@ -34,10 +35,40 @@ bool sort_by_val(const ind_val& a, const ind_val& b) { return a.second < b.secon
 const double MAX_DOUBLE = std::numeric_limits<double>::max();
 const double MIN_DOUBLE = std::numeric_limits<double>::min();   // +2.2e-308, as in cpp/direct.h:19
 
-struct Rects {   // structure-of-arrays rectangle store (unit cube coordinates)
+// Append-only rectangle store (unit-cube coordinates).  The reference keeps a std::vector<Rectangle>, erases
+// divided rectangles and appends their children, so the relative order of live rectangles is their creation
+// order -- which is what ids are here.  Rectangles are grouped by their exact centre-to-vertex distance d
+// ("classes"); each class keeps its members ordered by y so that the class minimum and its ties are O(log R).
+struct Store {
     int N = 0;
     std::vector<double> lb, ub, center, d, y;
-    size_t size() const { return d.size(); }
+    std::vector<int> cls;
+    std::vector<char> alive;
+    struct Class { double d; std::multiset<std::pair<double, unsigned> > members; };
+    std::vector<Class> classes;
+    std::unordered_map<unsigned long long, int> cls_of_d;
+    size_t live = 0;
+
+    static double key(double y) { return y != y ? MAX_DOUBLE : y; }   // NaN sorts last
+    unsigned add(const double* l, const double* u, const double* c, double dd, double yy) {
+        unsigned id = (unsigned)d.size();
+        lb.insert(lb.end(), l, l + N); ub.insert(ub.end(), u, u + N); center.insert(center.end(), c, c + N);
+        d.push_back(dd); y.push_back(yy); alive.push_back(1);
+        unsigned long long bits; std::memcpy(&bits, &dd, 8);
+        auto it = cls_of_d.find(bits);
+        int k;
+        if (it == cls_of_d.end()) { k = (int)classes.size(); classes.push_back(Class()); classes.back().d = dd; cls_of_d[bits] = k; }
+        else k = it->second;
+        cls.push_back(k);
+        classes[k].members.insert(std::make_pair(key(yy), id));
+        live++;
+        return id;
+    }
+    void remove(unsigned id) {
+        classes[cls[id]].members.erase(std::make_pair(key(y[id]), id));
+        alive[id] = 0;
+        live--;
+    }
 };
 
 struct Driver {
@@ -48,7 +79,7 @@ struct Driver {
     double FMIN = MAX_DOUBLE;
     std::vector<double> XMIN;
     long nsamples = 0;
-    std::vector<double> xbuf, ybuf;   // batch staging (box coordinates)
+    std::vector<double> xbuf;   // batch staging (box coordinates)
 
     // unit cube -> box (cpp/direct.cpp:113-120)
     void to_box(const double* x, double* out) const {
@@ -82,8 +113,7 @@ inline double center_and_d(const double* lb, const double* ub, double* c, int N)
 }
 
 struct Pending {           // one rectangle being divided
-    size_t src;            // index in the rectangle store
-    double maxlength;
+    unsigned src;          // id in the store
     std::vector<unsigned> dims;     // long, non-fixed dims in ascending order
     long probe0 = 0;       // offset of its 2*k probe values in the phase-A batch
     long child0 = 0;       // offset of its 2*k child values in the phase-B batch
@@ -93,12 +123,12 @@ struct Pending {           // one rectangle being divided
     std::vector<double> old_lb, old_ub; double old_d = 0;
 };
 
-// Divides the given rectangles (already in processing order).  Appends the new rectangles to R in the
-// reference's order and marks sources for removal.  seq: one rectangle per batch pair (reference call order).
-void divide(Driver& D, Rects& R, const std::vector<size_t>& order, bool seq, std::vector<char>& removed) {
+// Divides the given rectangles (already in processing order): appends the new rectangles in the reference's
+// order and retires the sources.  seq: one rectangle per batch pair (the reference's exact call order).
+void divide(Driver& D, Store& R, const std::vector<unsigned>& order, bool seq) {
     const int N = D.N;
     size_t g0 = 0;
-    std::vector<double> pts, yA, yB;
+    std::vector<double> pts, ptsB, yA, yB, lb1, ub1, lb3, ub3, c1(N), c3(N), oc(N);
     while (g0 < order.size()) {
         size_t g1 = seq ? g0 + 1 : order.size();
         std::vector<Pending> P(g1 - g0);
@@ -108,13 +138,12 @@ void divide(Driver& D, Rects& R, const std::vector<size_t>& order, bool seq, std
         for (size_t t = g0; t < g1; t++) {
             Pending& p = P[t - g0];
             p.src = order[t];
-            const double* lb = &R.lb[p.src * N];
-            const double* ub = &R.ub[p.src * N];
-            const double* c = &R.center[p.src * N];
+            const double* lb = &R.lb[(size_t)p.src * N];
+            const double* ub = &R.ub[(size_t)p.src * N];
+            const double* c = &R.center[(size_t)p.src * N];
             double maxlength = ub[0] - lb[0];          // dim 0 even if fixed (reference quirk)
             for (int i = 1; i < N; i++)
                 if (!D.fixed[i] && ub[i] - lb[i] > maxlength) maxlength = ub[i] - lb[i];
-            p.maxlength = maxlength;
             p.probe0 = np;
             for (int i = 0; i < N; i++) {
                 if (!D.fixed[i] && ub[i] - lb[i] == maxlength) {
@@ -130,7 +159,7 @@ void divide(Driver& D, Rects& R, const std::vector<size_t>& order, bool seq, std
         }
         D.eval(pts, np, yA);
         // ---- sort the dims by min(sf1, sf2) and build the children (cpp/direct.cpp:181-232)
-        std::vector<double> ptsB;
+        ptsB.clear();
         long nc = 0;
         for (size_t t = 0; t < P.size(); t++) {
             Pending& p = P[t];
@@ -140,18 +169,17 @@ void divide(Driver& D, Rects& R, const std::vector<size_t>& order, bool seq, std
                 else p.I.push_back(ind_val(p.dims[a], sf2));
             }
             std::sort(p.I.begin(), p.I.end(), sort_by_val);
-            p.old_lb.assign(&R.lb[p.src * N], &R.lb[p.src * N] + N);
-            p.old_ub.assign(&R.ub[p.src * N], &R.ub[p.src * N] + N);
+            p.old_lb.assign(&R.lb[(size_t)p.src * N], &R.lb[(size_t)p.src * N] + N);
+            p.old_ub.assign(&R.ub[(size_t)p.src * N], &R.ub[(size_t)p.src * N] + N);
             p.child0 = nc;
             for (size_t a = 0; a < p.I.size(); a++) {
                 unsigned dd = p.I[a].first;
                 double dwidth = p.old_ub[dd] - p.old_lb[dd];
                 double split1 = p.old_lb[dd] + dwidth / 3.;
                 double split2 = p.old_lb[dd] + 2. * dwidth / 3.;
-                std::vector<double> lb1(p.old_lb), ub1(p.old_ub), lb3(p.old_lb), ub3(p.old_ub);
+                lb1 = p.old_lb; ub1 = p.old_ub; lb3 = p.old_lb; ub3 = p.old_ub;
                 ub1[dd] = split1;
                 lb3[dd] = split2;
-                std::vector<double> c1(N), c3(N);
                 double d1 = center_and_d(lb1.data(), ub1.data(), c1.data(), N);
                 p.old_lb[dd] = split1;
                 p.old_ub[dd] = split2;
@@ -166,8 +194,8 @@ void divide(Driver& D, Rects& R, const std::vector<size_t>& order, bool seq, std
             }
             // the middle third keeps the old centre and y; d is recomputed from the shrunk bounds (:226-231)
             double d = 0.0;
-            const double* oc = &R.center[p.src * N];
-            for (int i = 0; i < N; i++) d += std::pow((p.old_lb[i] - oc[i]), 2);
+            const double* ocp = &R.center[(size_t)p.src * N];
+            for (int i = 0; i < N; i++) d += std::pow((p.old_lb[i] - ocp[i]), 2);
             p.old_d = std::sqrt(d);
         }
         D.eval(ptsB, nc, yB);
@@ -176,61 +204,54 @@ void divide(Driver& D, Rects& R, const std::vector<size_t>& order, bool seq, std
             Pending& p = P[t];
             for (size_t a = 0; a < 2 * p.dims.size(); a++) D.account(&pts[(size_t)(p.probe0 + a) * N], yA[p.probe0 + a]);
             for (size_t a = 0; a < 2 * p.I.size(); a++) D.account(&ptsB[(size_t)(p.child0 + a) * N], yB[p.child0 + a]);
-            for (size_t a = 0; a < 2 * p.I.size(); a++) {
-                R.lb.insert(R.lb.end(), &p.clb[a * N], &p.clb[a * N] + N);
-                R.ub.insert(R.ub.end(), &p.cub[a * N], &p.cub[a * N] + N);
-                R.center.insert(R.center.end(), &p.ccenter[a * N], &p.ccenter[a * N] + N);
-                R.d.push_back(p.cd[a]);
-                R.y.push_back(yB[p.child0 + a]);
-            }
+            for (size_t a = 0; a < 2 * p.I.size(); a++)
+                R.add(&p.clb[a * N], &p.cub[a * N], &p.ccenter[a * N], p.cd[a], yB[p.child0 + a]);
             // middle rectangle (copy of the source with shrunk bounds)
-            std::vector<double> oc(&R.center[p.src * N], &R.center[p.src * N] + N);
+            std::memcpy(oc.data(), &R.center[(size_t)p.src * N], sizeof(double) * N);
             double oy = R.y[p.src];
-            R.lb.insert(R.lb.end(), p.old_lb.begin(), p.old_lb.end());
-            R.ub.insert(R.ub.end(), p.old_ub.begin(), p.old_ub.end());
-            R.center.insert(R.center.end(), oc.begin(), oc.end());
-            R.d.push_back(p.old_d);
-            R.y.push_back(oy);
-            removed.resize(R.size(), 0);
-            removed[p.src] = 1;
+            R.remove(p.src);
+            R.add(p.old_lb.data(), p.old_ub.data(), oc.data(), p.old_d, oy);
         }
         g0 = g1;
     }
 }
 
-void compact(Rects& R, std::vector<char>& removed) {
-    const int N = R.N;
-    size_t w = 0;
-    for (size_t r = 0; r < R.size(); r++) {
-        if (r < removed.size() && removed[r]) continue;
-        if (w != r) {
-            std::memmove(&R.lb[w * N], &R.lb[r * N], sizeof(double) * N);
-            std::memmove(&R.ub[w * N], &R.ub[r * N], sizeof(double) * N);
-            std::memmove(&R.center[w * N], &R.center[r * N], sizeof(double) * N);
-            R.d[w] = R.d[r]; R.y[w] = R.y[r];
-        }
-        w++;
-    }
-    R.lb.resize(w * N); R.ub.resize(w * N); R.center.resize(w * N); R.d.resize(w); R.y.resize(w);
-    removed.assign(w, 0);
-}
-
-// potentially-optimal rectangles, ascending index (cpp/direct.cpp:378-456)
-void select(const Rects& R, double FMIN, std::vector<size_t>& potopts) {
+// potentially-optimal rectangles, ascending creation order (cpp/direct.cpp:378-456).
+// The reference's pair scan decides rectangle j from (d_j, y_j) and the multiset of the others only through
+//   I3: reject if some rectangle of the same size has a smaller y      -> y_j must equal its class minimum
+//   I1/I2: extremal slopes towards smaller / larger classes            -> attained at those classes' minima
+//          (fl(x - c) and fl(x / c), c > 0, are monotone in x, so the extremal slope is the slope of the minimum)
+// so the decision is a function of the class alone and is evaluated once per class: O(C^2 + #selected log R),
+// with accept / reject decisions bit-identical to the O(R^2) scan.
+void select(const Store& R, double FMIN, std::vector<unsigned>& potopts) {
     const double epsilon = 10e-10;
     potopts.clear();
-    // distance classes: exact d -> (min y, second-smallest y is not needed: I3 compares against others)
-    std::map<double, double> cls;   // d -> min y
-    for (size_t r = 0; r < R.size(); r++) {
-        auto it = cls.find(R.d[r]);
-        if (it == cls.end()) cls[R.d[r]] = R.y[r];
-        else if (R.y[r] < it->second) it->second = R.y[r];
-    }
     std::vector<double> cd, cy;
-    for (auto& kv : cls) { cd.push_back(kv.first); cy.push_back(kv.second); }
+    std::vector<int> ck;
+    for (size_t k = 0; k < R.classes.size(); k++) {
+        if (R.classes[k].members.empty()) continue;
+        unsigned id = R.classes[k].members.begin()->second;
+        cd.push_back(R.classes[k].d); cy.push_back(R.y[id]); ck.push_back((int)k);
+    }
     const size_t C = cd.size();
-    for (size_t j = 0; j < R.size(); j++) {
-        const double dj = R.d[j], yj = R.y[j];
+    // Quick reject (exactly the reference's `minI2 <= 0` break): a larger class whose minimum is <= y_j makes the
+    // slope (y_c - y_j)/(d_c - d_j) non-positive.  With classes sorted by d, that is a suffix-minimum lookup, so
+    // only the few classes on the lower-right staircase pay for the full O(C) slope scan.
+    std::vector<size_t> byd(C);
+    for (size_t k = 0; k < C; k++) byd[k] = k;
+    std::sort(byd.begin(), byd.end(), [&](size_t a, size_t b) { return cd[a] < cd[b]; });
+    std::vector<char> dominated(C, 0);
+    {
+        double sufmin = MAX_DOUBLE; bool have = false;
+        for (size_t t = C; t-- > 0;) {
+            size_t k = byd[t];
+            if (have && sufmin - cy[k] <= 0.) dominated[k] = 1;      // sign of fl(y_c - y_j) is exact
+            if (!have || cy[k] < sufmin) { sufmin = cy[k]; have = true; }
+        }
+    }
+    for (size_t k = 0; k < C; k++) {
+        if (dominated[k]) continue;
+        const double dj = cd[k], yj = cy[k];
         double maxI1 = MIN_DOUBLE, minI2 = MAX_DOUBLE;
         bool breaked = false;
         for (size_t c = 0; c < C && !breaked; c++) {
@@ -240,16 +261,21 @@ void select(const Rects& R, double FMIN, std::vector<size_t>& potopts) {
             } else if (cd[c] > dj) {
                 double val = (cy[c] - yj) / (cd[c] - dj);
                 if (val < minI2) { minI2 = val; if (minI2 <= 0.) breaked = true; }
-            } else {
-                if (yj > cy[c]) breaked = true;     // some other rectangle of the same size is better
             }
         }
         if (!breaked && maxI1 != MIN_DOUBLE && minI2 != MAX_DOUBLE && minI2 < maxI1) breaked = true;
         if (breaked) continue;
-        if (minI2 == MAX_DOUBLE) potopts.push_back(j);
-        else if (FMIN == 0.0) { if (yj <= dj * minI2) potopts.push_back(j); }
-        else if (epsilon <= (FMIN - yj) / std::abs(FMIN) + (dj / std::abs(FMIN)) * minI2) potopts.push_back(j);
+        bool ok = false;
+        if (minI2 == MAX_DOUBLE) ok = true;
+        else if (FMIN == 0.0) ok = (yj <= dj * minI2);
+        else ok = (epsilon <= (FMIN - yj) / std::abs(FMIN) + (dj / std::abs(FMIN)) * minI2);
+        if (!ok) continue;
+        // every live member tying the class minimum is potentially optimal
+        const auto& mem = R.classes[ck[k]].members;
+        const double kmin = mem.begin()->first;
+        for (auto it = mem.begin(); it != mem.end() && it->first == kmin; ++it) potopts.push_back(it->second);
     }
+    std::sort(potopts.begin(), potopts.end());
 }
 
 int run_direct(ibo_batch_objective_t f, void* user, int ndim, const double* lb, const double* ub, int maxiter, int maxtime,
@@ -262,7 +288,7 @@ int run_direct(ibo_batch_objective_t f, void* user, int ndim, const double* lb, 
     D.lowerb.assign(lb, lb + ndim); D.upperb.assign(ub, ub + ndim);
     D.fixed.resize(ndim);
     for (int i = 0; i < ndim; i++) D.fixed[i] = (lb[i] == ub[i]);
-    Rects R; R.N = ndim;
+    Store R; R.N = ndim;
     // first rectangle: the unit cube, sampled at its centre (cpp/direct.cpp:349-357)
     {
         std::vector<double> l(ndim, 0.0), u(ndim, 1.0), c(ndim);
@@ -270,17 +296,13 @@ int run_direct(ibo_batch_objective_t f, void* user, int ndim, const double* lb, 
         std::vector<double> y;
         D.eval(c, 1, y);
         D.account(c.data(), y[0]);
-        R.lb = l; R.ub = u; R.center = c; R.d.push_back(d); R.y.push_back(y[0]);
+        R.add(l.data(), u.data(), c.data(), d, y[0]);
     }
-    std::vector<char> removed(1, 0);
-    {
-        std::vector<size_t> order(1, 0);
-        divide(D, R, order, seq, removed);
-        compact(R, removed);
-    }
+    std::vector<unsigned> potopts, order;
+    order.assign(1, 0u);
+    divide(D, R, order, seq);
     int iteration = 0;
     bool done = false;
-    std::vector<size_t> potopts, order;
     while (iteration < maxiter && !done) {
         iteration++;
         select(R, D.FMIN, potopts);
@@ -291,9 +313,9 @@ int run_direct(ibo_batch_objective_t f, void* user, int ndim, const double* lb, 
         order.clear();
         long ns = D.nsamples;
         for (size_t t = potopts.size(); t-- > 0;) {
-            size_t j = potopts[t];
-            const double* l = &R.lb[j * ndim];
-            const double* u = &R.ub[j * ndim];
+            unsigned j = potopts[t];
+            const double* l = &R.lb[(size_t)j * ndim];
+            const double* u = &R.ub[(size_t)j * ndim];
             double maxlength = u[0] - l[0];
             for (int i = 1; i < ndim; i++)
                 if (!D.fixed[i] && u[i] - l[i] > maxlength) maxlength = u[i] - l[i];
@@ -304,8 +326,7 @@ int run_direct(ibo_batch_objective_t f, void* user, int ndim, const double* lb, 
             ns += 4L * k;
             if (ns > (long)(unsigned)maxsample) { done = true; break; }
         }
-        divide(D, R, order, seq, removed);
-        compact(R, removed);
+        divide(D, R, order, seq);
         if (time(NULL) - start > maxtime) break;
         if (D.nsamples > (long)(unsigned)maxsample) break;
     }

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstring>
 #include <mutex>
+#include <map>
 
 namespace ibo {
 
@@ -17,14 +18,81 @@ static thread_local std::string g_err;
 void set_error(const std::string& s) { g_err = s; }
 const char* get_error() { return g_err.c_str(); }
 
+// ---------------------------------------------------------------------------------------------
+// Small caching allocator: sequential BO and fastUCBGallery rebuild the model after every addData, and
+// cudaMalloc / cudaFree of the N x N buffers (plus their implicit device synchronisation) would otherwise dominate
+// the rebuild.  Freed blocks are kept per device and handed back for requests of up to 2x smaller size.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct Pool {
+    std::mutex mu;
+    std::multimap<size_t, void*> free_blocks[16];
+    std::map<void*, size_t> live;
+    size_t cached[16] = {0};
+    static constexpr size_t LIMIT = (size_t)12 << 30;
+} g_pool;
+}
+
+cudaError_t pool_malloc(void** p, size_t bytes) {
+    int dev = 0; cudaGetDevice(&dev); dev &= 15;
+    bytes = (bytes + 511) & ~(size_t)511;
+    std::lock_guard<std::mutex> lk(g_pool.mu);
+    auto& fb = g_pool.free_blocks[dev];
+    auto it = fb.lower_bound(bytes);
+    if (it != fb.end() && it->first <= 2 * bytes + (1 << 20)) {
+        *p = it->second;
+        g_pool.live[*p] = it->first;
+        g_pool.cached[dev] -= it->first;
+        fb.erase(it);
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {     // give cached memory back to the driver and retry once
+        cudaGetLastError();
+        for (auto& kv : fb) cudaFree(kv.second);
+        fb.clear(); g_pool.cached[dev] = 0;
+        e = cudaMalloc(p, bytes);
+    }
+    if (e == cudaSuccess) g_pool.live[*p] = bytes;
+    return e;
+}
+
+// pinned 1 MiB staging buffers (small-batch path of score_host) are recycled too
+static std::vector<double*> g_pinned_free;
+cudaError_t pinned_get(double** p) {
+    {
+        std::lock_guard<std::mutex> lk(g_pool.mu);
+        if (!g_pinned_free.empty()) { *p = g_pinned_free.back(); g_pinned_free.pop_back(); return cudaSuccess; }
+    }
+    return cudaHostAlloc((void**)p, sizeof(double) * (1u << 17), cudaHostAllocDefault);
+}
+void pinned_put(double* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pool.mu);
+    g_pinned_free.push_back(p);
+}
+
+void pool_free(void* p) {
+    if (!p) return;
+    int dev = 0; cudaGetDevice(&dev); dev &= 15;
+    std::lock_guard<std::mutex> lk(g_pool.mu);
+    auto it = g_pool.live.find(p);
+    if (it == g_pool.live.end()) { cudaFree(p); return; }
+    size_t bytes = it->second;
+    g_pool.live.erase(it);
+    if (g_pool.cached[dev] + bytes > Pool::LIMIT) { cudaFree(p); return; }
+    g_pool.free_blocks[dev].insert(std::make_pair(bytes, p));
+    g_pool.cached[dev] += bytes;
+}
+
 int grow(double** p, size_t* cap, size_t need) {
     if (*cap >= need) return IBO_OK;
-    if (*p) cudaFree(*p);
+    if (*p) pool_free(*p);
     *p = nullptr; *cap = 0;
     size_t want = need + need / 8;
-    cudaError_t e = cudaMalloc((void**)p, want * sizeof(double));
+    cudaError_t e = pool_malloc((void**)p, want * sizeof(double));
     if (e != cudaSuccess) {
-        e = cudaMalloc((void**)p, need * sizeof(double));
+        e = pool_malloc((void**)p, need * sizeof(double));
         want = need;
         if (e != cudaSuccess) { set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); cudaGetLastError(); return IBO_E_NOMEM; }
     }
@@ -413,13 +481,14 @@ extern "C" int ibo_device_count(void) {
 static void free_model(ibo_model* m) {
     if (!m) return;
     cudaSetDevice(m->device);
-    double** ptrs[] = {&m->dXt, &m->dInvTheta, &m->dA, &m->dAorig, &m->dW, &m->dD, &m->dWpack, &m->dBetaY, &m->dBeta1, &m->dY,
+    if (m->stream) cudaStreamSynchronize(m->stream);   // blocks go back to the pool: nothing may still be using them
+    double** ptrs[] = {&m->dXt, &m->dInvTheta, &m->dCenter, &m->dA, &m->dAorig, &m->dW, &m->dD, &m->dWpack, &m->dBetaY, &m->dBeta1, &m->dY,
                        &m->dPmeans, &m->dPbeta, &m->dPlb, &m->dPwidth, &m->dCand, &m->dSlab, &m->dPart, &m->dOut, &m->dBlkBest, &m->dBest};
-    for (auto p : ptrs) if (*p) { cudaFree(*p); *p = nullptr; }
+    for (auto p : ptrs) if (*p) { pool_free(*p); *p = nullptr; }
     if (m->dInfo) cudaFree(m->dInfo);
     if (m->dBlkIdx) cudaFree(m->dBlkIdx);
     if (m->dBestIdx) cudaFree(m->dBestIdx);
-    if (m->hPinned) cudaFreeHost(m->hPinned);
+    if (m->hPinned) pinned_put(m->hPinned);
     for (auto& e : m->ev) if (e) cudaEventDestroy(e);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
@@ -470,34 +539,42 @@ static int create_common(int device, int kind, const double* hyper, int nhyper, 
 #define TRYM(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { set_error(std::string(#expr) + ": " + cudaGetErrorString(e__)); cudaGetLastError(); return fail(e__ == cudaErrorMemoryAllocation ? IBO_E_NOMEM : IBO_E_CUDA); } } while (0)
     TRYM(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     for (auto& e : m->ev) TRYM(cudaEventCreate(&e));
-    TRYM(cudaMalloc(&m->dXt, sizeof(double) * (size_t)Np * d));
-    TRYM(cudaMalloc(&m->dInvTheta, sizeof(double) * d));
-    TRYM(cudaMalloc(&m->dA, sizeof(double) * (size_t)Np * Np));
-    TRYM(cudaMalloc(&m->dW, sizeof(double) * (size_t)Np * Np));
-    TRYM(cudaMalloc(&m->dD, sizeof(double) * (size_t)nb * 128 * 128));
-    TRYM(cudaMalloc(&m->dWpack, sizeof(double) * wpack_base(nb) * BLOB));
-    TRYM(cudaMalloc(&m->dBetaY, sizeof(double) * Np));
-    TRYM(cudaMalloc(&m->dBeta1, sizeof(double) * Np));
-    TRYM(cudaMalloc(&m->dY, sizeof(double) * Np));
+    TRYM(pool_malloc((void**)&m->dXt, sizeof(double) * (size_t)Np * d));
+    TRYM(pool_malloc((void**)&m->dInvTheta, sizeof(double) * d));
+    TRYM(pool_malloc((void**)&m->dCenter, sizeof(double) * d));
+    TRYM(pool_malloc((void**)&m->dA, sizeof(double) * (size_t)Np * Np));
+    TRYM(pool_malloc((void**)&m->dW, sizeof(double) * (size_t)Np * Np));
+    TRYM(pool_malloc((void**)&m->dD, sizeof(double) * (size_t)nb * 128 * 128));
+    TRYM(pool_malloc((void**)&m->dWpack, sizeof(double) * wpack_base(nb) * BLOB));
+    TRYM(pool_malloc((void**)&m->dBetaY, sizeof(double) * Np));
+    TRYM(pool_malloc((void**)&m->dBeta1, sizeof(double) * Np));
+    TRYM(pool_malloc((void**)&m->dY, sizeof(double) * Np));
     TRYM(cudaMalloc(&m->dInfo, sizeof(int)));
-    TRYM(cudaMalloc(&m->dBest, sizeof(double)));
+    TRYM(pool_malloc((void**)&m->dBest, sizeof(double)));
     TRYM(cudaMalloc(&m->dBestIdx, sizeof(long long)));
     cudaStream_t st = m->stream;
     // scaled inputs, zero padded
     std::vector<double> xt((size_t)Np * d, 0.0), it(d), yp(Np, 0.0), ones(Np, 0.0);
+    // scaled inputs x * (1/theta), centred on their mean: distances are translation invariant, and centring keeps
+    // |x|^2 small for the |x|^2 + |y|^2 - 2 x.y expansion of K1 (candidates get the same scale and shift there)
+    std::vector<double> ctr(d, 0.0);
     for (int j = 0; j < d; j++) it[j] = 1.0 / theta[j];
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < d; j++) ctr[j] += X[(size_t)i * d + j] * it[j];
+    for (int j = 0; j < d; j++) ctr[j] /= N;
     for (int i = 0; i < N; i++) {
-        for (int j = 0; j < d; j++) xt[(size_t)i * d + j] = X[(size_t)i * d + j] / theta[j];
+        for (int j = 0; j < d; j++) xt[(size_t)i * d + j] = X[(size_t)i * d + j] * it[j] - ctr[j];
         yp[i] = Y[i]; ones[i] = 1.0;
     }
     TRYM(cudaMemcpyAsync(m->dXt, xt.data(), sizeof(double) * xt.size(), cudaMemcpyHostToDevice, st));
     TRYM(cudaMemcpyAsync(m->dInvTheta, it.data(), sizeof(double) * d, cudaMemcpyHostToDevice, st));
+    TRYM(cudaMemcpyAsync(m->dCenter, ctr.data(), sizeof(double) * d, cudaMemcpyHostToDevice, st));
     TRYM(cudaMemcpyAsync(m->dY, yp.data(), sizeof(double) * Np, cudaMemcpyHostToDevice, st));
     if (m->npb > 0) {
-        TRYM(cudaMalloc(&m->dPmeans, sizeof(double) * (size_t)npb * d));
-        TRYM(cudaMalloc(&m->dPbeta, sizeof(double) * npb));
-        TRYM(cudaMalloc(&m->dPlb, sizeof(double) * d));
-        TRYM(cudaMalloc(&m->dPwidth, sizeof(double) * d));
+        TRYM(pool_malloc((void**)&m->dPmeans, sizeof(double) * (size_t)npb * d));
+        TRYM(pool_malloc((void**)&m->dPbeta, sizeof(double) * npb));
+        TRYM(pool_malloc((void**)&m->dPlb, sizeof(double) * d));
+        TRYM(pool_malloc((void**)&m->dPwidth, sizeof(double) * d));
         TRYM(cudaMemcpyAsync(m->dPmeans, pmeans, sizeof(double) * (size_t)npb * d, cudaMemcpyHostToDevice, st));
         TRYM(cudaMemcpyAsync(m->dPbeta, pbeta, sizeof(double) * npb, cudaMemcpyHostToDevice, st));
         TRYM(cudaMemcpyAsync(m->dPlb, plb, sizeof(double) * d, cudaMemcpyHostToDevice, st));
@@ -506,37 +583,37 @@ static int create_common(int device, int kind, const double* hyper, int nhyper, 
     dim3 g2((Np + 255) / 256, Np);
     double* dTmp = nullptr;
     if (invR) {
-        TRYM(cudaMalloc(&dTmp, sizeof(double) * (size_t)N * N));
+        TRYM(pool_malloc((void**)&dTmp, sizeof(double) * (size_t)N * N));
         TRYM(cudaMemcpyAsync(dTmp, invR, sizeof(double) * (size_t)N * N, cudaMemcpyHostToDevice, st));
         build_reversed_kernel<<<g2, 256, 0, st>>>(m->dA, dTmp, N, Np);
     } else {
         if (Cinv) {
-            TRYM(cudaMalloc(&dTmp, sizeof(double) * (size_t)N * N));
+            TRYM(pool_malloc((void**)&dTmp, sizeof(double) * (size_t)N * N));
             TRYM(cudaMemcpyAsync(dTmp, Cinv, sizeof(double) * (size_t)N * N, cudaMemcpyHostToDevice, st));
         }
         build_A_kernel<<<g2, 256, 0, st>>>(m->dA, m->dXt, dTmp, N, Np, d, kind, sf2, noise);
     }
     g_launches++;
     if (Np <= 4096 && !invR) {   // keep A for get_matrix(0)
-        TRYM(cudaMalloc(&m->dAorig, sizeof(double) * (size_t)Np * Np));
+        TRYM(pool_malloc((void**)&m->dAorig, sizeof(double) * (size_t)Np * Np));
         TRYM(cudaMemcpyAsync(m->dAorig, m->dA, sizeof(double) * (size_t)Np * Np, cudaMemcpyDeviceToDevice, st));
     }
     rc = launch_factorize(m, invR != nullptr);
-    if (rc) { if (dTmp) cudaFree(dTmp); return fail(rc); }
+    if (rc) { if (dTmp) pool_free(dTmp); return fail(rc); }
     // beta1 = W 1 (prior-mean correction term)
     TRYM(cudaMemcpyAsync(m->dBeta1, ones.data(), sizeof(double) * Np, cudaMemcpyHostToDevice, st));
     {
         double* dOnes = nullptr;
-        TRYM(cudaMalloc(&dOnes, sizeof(double) * Np));
+        TRYM(pool_malloc((void**)&dOnes, sizeof(double) * Np));
         TRYM(cudaMemcpyAsync(dOnes, m->dBeta1, sizeof(double) * Np, cudaMemcpyDeviceToDevice, st));
         tri_matvec_kernel<<<(Np + 7) / 8, 256, 0, st>>>(m->dW, dOnes, m->dBeta1, Np);
         g_launches++;
         TRYM(cudaStreamSynchronize(st));
-        cudaFree(dOnes);
+        pool_free(dOnes);
     }
     int hinfo = 0;
     TRYM(cudaMemcpy(&hinfo, m->dInfo, sizeof(int), cudaMemcpyDeviceToHost));
-    if (dTmp) cudaFree(dTmp);
+    if (dTmp) pool_free(dTmp);
     TRYM(cudaGetLastError());
     if (hinfo != 0) {
         if (info) *info = hinfo;

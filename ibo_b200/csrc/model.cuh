@@ -15,6 +15,7 @@ struct ibo_model {
     // device arrays
     double* dXt = nullptr;      // scaled training inputs x/theta, [Np][d], rows >= N are zero
     double* dInvTheta = nullptr;// [d]
+    double* dCenter = nullptr;  // [d] mean of the scaled training inputs (dXt is stored centred)
     double* dA = nullptr;       // [Np][Np] row-major: A = R (+Cinv), overwritten by L (lower)
     double* dAorig = nullptr;   // optional copy of A (kept for get_matrix(0)); N<=4096 only
     double* dW = nullptr;       // [Np][Np] row-major: W = inv(L), exact zeros above the diagonal
@@ -54,6 +55,10 @@ struct ibo_cands {
 
 namespace ibo {
 int grow(double** p, size_t* cap, size_t need);
+cudaError_t pool_malloc(void** p, size_t bytes);
+void pool_free(void* p);
+cudaError_t pinned_get(double** p);
+void pinned_put(double* p);
 // launches (all on m->stream)
 int launch_factorize(ibo_model* m, bool from_inverse_reversed);
 }  // namespace ibo

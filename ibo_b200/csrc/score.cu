@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <mutex>
 #include <cstdlib>
+#include <cstring>
 
 namespace ibo {
 
@@ -39,7 +40,8 @@ __device__ __forceinline__ double cov_r2(int kind, double sf2, double r2) {
 // 8-row group -- exactly the two values of its 16-byte slot in the packed B-operand layout.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) kstar_kernel(const double* __restrict__ Xt, const double* __restrict__ cand,
-                                                    const double* __restrict__ inv_theta, double* __restrict__ slab,
+                                                    const double* __restrict__ inv_theta, const double* __restrict__ center,
+                                                    double* __restrict__ slab,
                                                     int N, int d, int nb, long M, long m0, int kind, double sf2) {
     extern __shared__ double sm[];
     const int S = d | 1;
@@ -52,7 +54,7 @@ __global__ void __launch_bounds__(256) kstar_kernel(const double* __restrict__ X
         sX[r * S + j] = Xt[(size_t)(i * 128 + r) * d + j];
         long c = m0 + (long)T * 128 + r;
         if (c >= M) c = M - 1;
-        sC[r * S + j] = cand[(size_t)c * d + j] * inv_theta[j];
+        sC[r * S + j] = cand[(size_t)c * d + j] * inv_theta[j] - center[j];
     }
     __syncthreads();
     const int n8 = lane >> 2, k4 = lane & 3;
@@ -83,17 +85,112 @@ __global__ void __launch_bounds__(256) kstar_kernel(const double* __restrict__ X
 }
 
 // ---------------------------------------------------------------------------------------------
+// K1 (tensor-pipe form): the squared distance through |x|^2 + |y|^2 - 2 x.y with the cross term X* X^T as
+// DMMA.8x8x4 GEMMs over the (zero-padded, centred, 1/theta-scaled) input dimensions, exp / Matern epilogue in
+// registers.  The MMA's column order is permuted (column c <-> training row (c>>1) + 4(c&1) of the 8-row group)
+// so that the accumulator fragment a lane receives -- C[cand = lane/4][cols 2(lane%4), 2(lane%4)+1] -- is exactly
+// the (k4, k4+4) pair of its 16-byte slot in the packed B-operand blob: no shuffle, no shared-memory transpose.
+// Cancellation guard: the expansion's absolute error is ~6 eps (|x|^2 + |y|^2); inputs are centred on the training
+// mean, and any pair with |x|^2 + |y|^2 > EXPAND_LIMIT is recomputed from direct differences in the same thread.
+// ---------------------------------------------------------------------------------------------
+constexpr double EXPAND_LIMIT = 256.0;    // => relative error of k below ~2e-13
+
+template <int DP4>   // number of 4-wide dimension groups, d <= 4*DP4
+__global__ void __launch_bounds__(256) kstar_mma_kernel(const double* __restrict__ Xt, const double* __restrict__ cand,
+                                                        const double* __restrict__ inv_theta, const double* __restrict__ center,
+                                                        double* __restrict__ slab, int N, int d, int nb, long M, long m0,
+                                                        int kind, double sf2) {
+    constexpr int DP = 4 * DP4;
+    constexpr int S = (DP % 16 == 4 || DP % 16 == 12) ? DP : DP + 4;   // (row*S + k) mod 16 distinct over a half-warp
+    extern __shared__ double sm[];
+    double* sX = sm;                  // [128][S] scaled, centred training rows of block i (zero padded dims)
+    double* sC = sX + 128 * S;        // [128][S] scaled, centred candidates of tile T
+    double* sXn = sC + 128 * S;       // [128] squared norms
+    double* sCn = sXn + 128;
+    const int T = blockIdx.x, i = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    for (int idx = tid; idx < 128 * DP; idx += 256) {
+        int r = idx / DP, j = idx - r * DP;
+        double xv = 0.0, cv = 0.0;
+        if (j < d) {
+            xv = Xt[(size_t)(i * 128 + r) * d + j];
+            long c = m0 + (long)T * 128 + r;
+            if (c >= M) c = M - 1;
+            cv = cand[(size_t)c * d + j] * inv_theta[j] - center[j];
+        }
+        sX[r * S + j] = xv;
+        sC[r * S + j] = cv;
+    }
+    __syncthreads();
+    if (tid < 128) {
+        double a = 0, b = 0;
+        for (int j = 0; j < d; j++) { double x = sX[tid * S + j], c = sC[tid * S + j]; a = fma(x, x, a); b = fma(c, c, b); }
+        sXn[tid] = a; sCn[tid] = b;
+    }
+    __syncthreads();
+    const int n8 = lane >> 2, k4 = lane & 3;
+    const int rowmap = (n8 >> 1) + 4 * (n8 & 1);           // training row (within an 8-row group) fed to MMA column n8
+    double* blob = slab + ((size_t)T * (nb * KB_PER_BLOCK) + (size_t)i * KB_PER_BLOCK + w) * BLOB;
+    const int rowbase = i * 128 + w * 16;
+    double bfr[2][DP4], yn[2][2];
+    bool valid[2][2];
+#pragma unroll
+    for (int ks2 = 0; ks2 < 2; ks2++) {
+#pragma unroll
+        for (int s4 = 0; s4 < DP4; s4++) bfr[ks2][s4] = sX[(w * 16 + ks2 * 8 + rowmap) * S + 4 * s4 + k4];
+        yn[ks2][0] = sXn[w * 16 + ks2 * 8 + k4];
+        yn[ks2][1] = sXn[w * 16 + ks2 * 8 + k4 + 4];
+        valid[ks2][0] = (rowbase + ks2 * 8 + k4) < N;
+        valid[ks2][1] = (rowbase + ks2 * 8 + k4 + 4) < N;
+    }
+#pragma unroll 2
+    for (int nt = 0; nt < 16; nt++) {
+        double afr[DP4];
+#pragma unroll
+        for (int s4 = 0; s4 < DP4; s4++) afr[s4] = sC[(nt * 8 + n8) * S + 4 * s4 + k4];
+        const double xn = sCn[nt * 8 + n8];
+#pragma unroll
+        for (int ks2 = 0; ks2 < 2; ks2++) {
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+            for (int s4 = 0; s4 < DP4; s4++) dmma884(c0, c1, afr[s4], bfr[ks2][s4]);
+            double r0 = fma(-2.0, c0, xn + yn[ks2][0]);
+            double r1 = fma(-2.0, c1, xn + yn[ks2][1]);
+            if (xn + fmax(yn[ks2][0], yn[ks2][1]) > EXPAND_LIMIT) {
+                // rare: badly scaled inputs -- direct differences for this pair
+                const double* c = sC + (nt * 8 + n8) * S;
+                const double* xa = sX + (w * 16 + ks2 * 8 + k4) * S;
+                const double* xb = xa + 4 * S;
+                r0 = 0; r1 = 0;
+                for (int j = 0; j < d; j++) {
+                    double da = xa[j] - c[j], db = xb[j] - c[j];
+                    r0 = fma(da, da, r0); r1 = fma(db, db, r1);
+                }
+            }
+            double2 v;
+            v.x = valid[ks2][0] ? cov_r2(kind, sf2, fmax(r0, 0.0)) : 0.0;
+            v.y = valid[ks2][1] ? cov_r2(kind, sf2, fmax(r1, 0.0)) : 0.0;
+            reinterpret_cast<double2*>(blob)[(nt * 2 + ks2) * 32 + lane] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K2: triangular GEMM + fused reduction.
 // ---------------------------------------------------------------------------------------------
 constexpr int K2_STAGES = 6;
 constexpr int K2_THREADS = 384;   // warpgroups 0,1: 8 DMMA warps (240 regs); warpgroup 2: bulk-copy producer (24 regs)
-constexpr int K2_SMEM = K2_STAGES * 2 * BLOB * 8 + 2 * 3 * 128 * 8 + 2 * K2_STAGES * 8;
+constexpr int K2_SMEM = K2_STAGES * 2 * BLOB * 8 + 2 * 3 * 128 * 8 + 2 * K2_STAGES * 8;   // sized for NT = 4; NT = 1 uses less of sB
 
 __device__ __forceinline__ int group_of(int i, int nb, int G) {
     int idx = nb - 1 - i, round = idx / G, pos = idx - round * G;
     return (round & 1) ? (G - 1 - pos) : pos;
 }
 
+// NT = n-tiles (8 candidates each) per warp: the CTA covers 128 rows x 32*NT candidates.  NT = 4 is the throughput
+// shape; NT = 1 serves small batches (DIRECT) where a quarter-width tile gives 4x the CTAs and a 4x shorter k-loop
+// per candidate.  Both shapes own rows and reduce them identically, so a candidate's result is bit-identical.
+template <int NT>
 __global__ void __launch_bounds__(K2_THREADS, 1)
 trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab, const double* __restrict__ betaY,
                const double* __restrict__ beta1, double* __restrict__ part, int nb, int G, long Mpad, int want_p1) {
@@ -103,7 +200,10 @@ trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab
     double* sRed = sB + K2_STAGES * BLOB;                       // [2][3][128]
     uint64_t* full = reinterpret_cast<uint64_t*>(sRed + 2 * 3 * 128);
     uint64_t* empty = full + K2_STAGES;
-    const int g = blockIdx.x, T = blockIdx.y;   // group fastest: the G CTAs of one tile are co-resident and share its slab in L2
+    constexpr int SUB = 4 / NT;                 // CTAs per 128-candidate slab tile
+    constexpr int BBYTES = NT * 4 * 2 * 32 * 2 * 8;   // bytes of one B-operand stage: 4 warps x NT n-tiles x 16 k
+    const int g = blockIdx.x;                   // group fastest: the G CTAs of one tile are co-resident and share its slab in L2
+    const int T = blockIdx.y / SUB, sub = blockIdx.y % SUB;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         for (int s = 0; s < K2_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
@@ -124,9 +224,10 @@ trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab
                 const int nkb = (i + 1) * KB_PER_BLOCK;
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&empty[s], ph ^ 1);
-                    mbar_arrive_expect_tx(&full[s], 2 * BLOB * 8);
+                    mbar_arrive_expect_tx(&full[s], BLOB * 8 + BBYTES);
                     bulk_g2s(sA + s * BLOB, Abase + (size_t)kb * BLOB, BLOB * 8, &full[s]);
-                    bulk_g2s(sB + s * BLOB, Bbase + (size_t)kb * BLOB, BLOB * 8, &full[s]);
+                    // n-tiles are the slowest index of a blob, so this CTA's 4*NT n-tiles are one contiguous slice
+                    bulk_g2s(sB + s * BLOB, Bbase + (size_t)kb * BLOB + sub * (BBYTES / 8), BBYTES, &full[s]);
                     if (++s == K2_STAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -140,34 +241,34 @@ trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab
     int rbcount = 0;
     for (int i = nb - 1; i >= 0; --i) {
         if (group_of(i, nb, G) != g) continue;
-        double acc[8][4][2];
+        double acc[8][NT][2];
 #pragma unroll
         for (int a = 0; a < 8; a++)
 #pragma unroll
-            for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+            for (int b = 0; b < NT; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
         const int nkb = (i + 1) * KB_PER_BLOCK;
         const int nfull = i * KB_PER_BLOCK;     // k-blobs left of the diagonal block: dense
         for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(&full[s], ph);
             // warp wm owns the interleaved m-tiles 2*mt + wm (mt = 0..7) so that the triangular skip below is balanced
             const double2* a2 = reinterpret_cast<const double2*>(sA + s * BLOB) + (wm * 2) * 32 + lane;
-            const double2* b2 = reinterpret_cast<const double2*>(sB + s * BLOB) + (wn * 4 * 2) * 32 + lane;
+            const double2* b2 = reinterpret_cast<const double2*>(sB + s * BLOB) + (wn * NT * 2) * 32 + lane;
             if (kb < nfull) {
 #pragma unroll
                 for (int ks2 = 0; ks2 < 2; ks2++) {
-                    double2 af[8], bf[4];
+                    double2 af[8], bf[NT];
 #pragma unroll
                     for (int mt = 0; mt < 8; mt++) af[mt] = a2[(mt * 4 + ks2) * 32];
 #pragma unroll
-                    for (int nt = 0; nt < 4; nt++) bf[nt] = b2[(nt * 2 + ks2) * 32];
+                    for (int nt = 0; nt < NT; nt++) bf[nt] = b2[(nt * 2 + ks2) * 32];
 #pragma unroll
                     for (int mt = 0; mt < 8; mt++)
 #pragma unroll
-                        for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt].x, bf[nt].x);
+                        for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt].x, bf[nt].x);
 #pragma unroll
                     for (int mt = 0; mt < 8; mt++)
 #pragma unroll
-                        for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt].y, bf[nt].y);
+                        for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt].y, bf[nt].y);
                 }
             } else {
                 // diagonal block of W (lower triangular): in its k-blob kbl the m-tiles 2*mt + wm with mt < kbl are
@@ -175,17 +276,17 @@ trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab
                 const int kbl = kb - nfull;
 #pragma unroll
                 for (int ks2 = 0; ks2 < 2; ks2++) {
-                    double2 bf[4];
+                    double2 bf[NT];
 #pragma unroll
-                    for (int nt = 0; nt < 4; nt++) bf[nt] = b2[(nt * 2 + ks2) * 32];
+                    for (int nt = 0; nt < NT; nt++) bf[nt] = b2[(nt * 2 + ks2) * 32];
 #pragma unroll
                     for (int mt = 0; mt < 8; mt++) {
                         if (mt >= kbl) {
                             const double2 af = a2[(mt * 4 + ks2) * 32];
 #pragma unroll
-                            for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af.x, bf[nt].x);
+                            for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af.x, bf[nt].x);
 #pragma unroll
-                            for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af.y, bf[nt].y);
+                            for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af.y, bf[nt].y);
                         }
                     }
                 }
@@ -202,9 +303,9 @@ trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab
             by[mt] = betaY[r];
             b1[mt] = want_p1 ? beta1[r] : 0.0;
         }
-        double q[4][2], p[4][2], p1[4][2];
+        double q[NT][2], p[NT][2], p1[NT][2];
 #pragma unroll
-        for (int nt = 0; nt < 4; nt++)
+        for (int nt = 0; nt < NT; nt++)
 #pragma unroll
             for (int j = 0; j < 2; j++) {
                 double sq = 0, sp = 0, s1 = 0;
@@ -226,22 +327,22 @@ trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab
         double* red = sRed + (rbcount & 1) * 3 * 128;
         if (wm == 1 && lane < 4) {
 #pragma unroll
-            for (int nt = 0; nt < 4; nt++)
+            for (int nt = 0; nt < NT; nt++)
 #pragma unroll
                 for (int j = 0; j < 2; j++) {
-                    int c = wn * 32 + nt * 8 + 2 * lane + j;
+                    int c = (wn * NT + nt) * 8 + 2 * lane + j;
                     red[c] = q[nt][j]; red[128 + c] = p[nt][j]; red[256 + c] = p1[nt][j];
                 }
         }
         named_bar_sync(1, 256);
         if (wm == 0 && lane < 4) {
             const size_t plane = (size_t)nb * Mpad;
-            double* dst = part + (size_t)i * Mpad + (size_t)T * 128;
+            double* dst = part + (size_t)i * Mpad + (size_t)T * 128 + sub * (32 * NT);
 #pragma unroll
-            for (int nt = 0; nt < 4; nt++)
+            for (int nt = 0; nt < NT; nt++)
 #pragma unroll
                 for (int j = 0; j < 2; j++) {
-                    int c = wn * 32 + nt * 8 + 2 * lane + j;
+                    int c = (wn * NT + nt) * 8 + 2 * lane + j;
                     dst[c] = q[nt][j] + red[c];
                     dst[plane + c] = p[nt][j] + red[128 + c];
                     if (want_p1) dst[2 * plane + c] = p1[nt][j] + red[256 + c];
@@ -394,7 +495,9 @@ static std::once_flag g_score_attr_once;
 static cudaError_t g_score_attr_err = cudaSuccess;
 static int g_num_sms = 148;
 static void set_score_attrs() {
-    g_score_attr_err = cudaFuncSetAttribute(trigemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
+    g_score_attr_err = cudaFuncSetAttribute(trigemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
+    if (g_score_attr_err == cudaSuccess)
+        g_score_attr_err = cudaFuncSetAttribute(trigemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
     if (g_score_attr_err == cudaSuccess)
         g_score_attr_err = cudaFuncSetAttribute(kstar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 65 * 8);
     int dev = 0; cudaGetDevice(&dev);
@@ -412,6 +515,12 @@ static long chunk_tiles_default() {
     return v;
 }
 
+static long narrow_threshold() {
+    static long v = -1;
+    if (v < 0) { const char* e = getenv("IBO_NARROW_MAX"); v = e ? atol(e) : 2048; }
+    return v;
+}
+
 // Row-block groups per candidate tile.  (a) L2 residency: the G CTAs of a tile run side by side, so about
 // num_sms / G slab tiles (Np KiB each) are live at once; G = nb/4 keeps that at <= 148 * 4 * 128 KiB = 74 MiB of the
 // 126 MiB L2 for every N.  (b) occupancy: small batches (DIRECT) need tiles * G >= num_sms.
@@ -419,6 +528,36 @@ static int pick_groups(int nb, long tiles) {
     long G = std::max(1, nb / 4);
     if (tiles * G < g_num_sms) G = (g_num_sms + tiles - 1) / tiles;
     return (int)std::min<long>(G, nb);
+}
+
+template <int DP4>
+static void launch_kstar_mma(dim3 grid, cudaStream_t st, const ibo_model* m, const double* dCand, double* slab, long M, long m0) {
+    constexpr int DP = 4 * DP4;
+    constexpr int S = (DP % 16 == 4 || DP % 16 == 12) ? DP : DP + 4;
+    kstar_mma_kernel<DP4><<<grid, 256, (2 * 128 * S + 256) * 8, st>>>(m->dXt, dCand, m->dInvTheta, m->dCenter, slab, m->N, m->d, m->nb, M, m0, m->kind, m->sf2);
+}
+
+// cross-covariance of one chunk; expansion on the tensor pipe for d <= 32 unless IBO_KSTAR=direct
+static void launch_kstar(const ibo_model* m, const double* dCand, double* slab, long tiles, long M, long m0, cudaStream_t st) {
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("IBO_KSTAR"); mode = (e && !strcmp(e, "direct")) ? 0 : 1; }
+    dim3 grid((unsigned)tiles, m->nb);
+    const int dp4 = (m->d + 3) / 4;
+    if (mode == 0 || dp4 > 8) {
+        const int kS = m->d | 1;
+        kstar_kernel<<<grid, 256, 2 * 128 * kS * 8, st>>>(m->dXt, dCand, m->dInvTheta, m->dCenter, slab, m->N, m->d, m->nb, M, m0, m->kind, m->sf2);
+        return;
+    }
+    switch (dp4) {
+        case 1: launch_kstar_mma<1>(grid, st, m, dCand, slab, M, m0); break;
+        case 2: launch_kstar_mma<2>(grid, st, m, dCand, slab, M, m0); break;
+        case 3: launch_kstar_mma<3>(grid, st, m, dCand, slab, M, m0); break;
+        case 4: launch_kstar_mma<4>(grid, st, m, dCand, slab, M, m0); break;
+        case 5: launch_kstar_mma<5>(grid, st, m, dCand, slab, M, m0); break;
+        case 6: launch_kstar_mma<6>(grid, st, m, dCand, slab, M, m0); break;
+        case 7: launch_kstar_mma<7>(grid, st, m, dCand, slab, M, m0); break;
+        default: launch_kstar_mma<8>(grid, st, m, dCand, slab, M, m0); break;
+    }
 }
 
 struct ScoreReq {
@@ -429,7 +568,7 @@ struct ScoreReq {
 };
 
 // Runs K1..K4 for M candidates resident at dCand; results land in m->dOut ([score|mu|s2][M]) and
-// m->dBest / m->dBestIdx.  Everything is enqueued on m->stream; no host synchronisation here.
+// the (best score, best index) pair at m->dOut[3M], [3M+1].  Everything is enqueued on m->stream; no host sync here.
 static int score_device(ibo_model* m, const double* dCand, long M, const ScoreReq& rq) {
     std::call_once(g_score_attr_once, set_score_attrs);
     if (g_score_attr_err != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(g_score_attr_err)); return IBO_E_CUDA; }
@@ -446,7 +585,7 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
     int rc;
     if ((rc = grow(&m->dSlab, &m->slabCap, (size_t)chunkTiles * nb * KB_PER_BLOCK * BLOB))) return rc;
     if ((rc = grow(&m->dPart, &m->partCap, (size_t)3 * nb * Mpad))) return rc;
-    if ((rc = grow(&m->dOut, &m->outCap, (size_t)3 * M))) return rc;
+    if ((rc = grow(&m->dOut, &m->outCap, (size_t)3 * M + 2))) return rc;
     if (vm) {
         if ((rc = grow(&vm->dSlab, &vm->slabCap, (size_t)chunkTiles * vm->nb * KB_PER_BLOCK * BLOB))) return rc;
         if ((rc = grow(&vm->dPart, &vm->partCap, (size_t)3 * vm->nb * Mpad))) return rc;
@@ -464,25 +603,28 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
     long nlaunch = 0, nK2 = 0;
     if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[0], st));
     long blk0 = 0;
-    const int kS = m->d | 1;
     for (long t0 = 0; t0 < tilesTotal; t0 += chunkTiles) {
         const long tiles = std::min(chunkTiles, tilesTotal - t0);
         const long m0 = t0 * TN;
         const long chunkM = std::min<long>(tiles * TN, M - m0);
-        const int G = pick_groups(nb, tiles);
+        const bool narrow = M <= narrow_threshold();
+        const long ctaTiles = narrow ? (chunkM + 31) / 32 : tiles;      // K2 CTAs along the candidate axis
+        const int G = pick_groups(nb, ctaTiles);
         if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[1], st));
-        kstar_kernel<<<dim3((unsigned)tiles, nb), 256, 2 * 128 * kS * 8, st>>>(m->dXt, dCand, m->dInvTheta, m->dSlab, m->N, m->d, nb, M, m0, m->kind, m->sf2);
+        launch_kstar(m, dCand, m->dSlab, tiles, M, m0, st);
         nlaunch++;
         if (vm) {
-            kstar_kernel<<<dim3((unsigned)tiles, vm->nb), 256, 2 * 128 * kS * 8, st>>>(vm->dXt, dCand, vm->dInvTheta, vm->dSlab, vm->N, vm->d, vm->nb, M, m0, vm->kind, vm->sf2);
+            launch_kstar(vm, dCand, vm->dSlab, tiles, M, m0, st);
             nlaunch++;
         }
         if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[2], st));
-        trigemm_kernel<<<dim3(G, (unsigned)tiles), K2_THREADS, K2_SMEM, st>>>(m->dWpack, m->dSlab, m->dBetaY, m->dBeta1, m->dPart, nb, G, Mpad, m->npb > 0);
+        if (narrow) trigemm_kernel<1><<<dim3(G, (unsigned)ctaTiles), K2_THREADS, K2_SMEM, st>>>(m->dWpack, m->dSlab, m->dBetaY, m->dBeta1, m->dPart, nb, G, Mpad, m->npb > 0);
+        else trigemm_kernel<4><<<dim3(G, (unsigned)tiles), K2_THREADS, K2_SMEM, st>>>(m->dWpack, m->dSlab, m->dBetaY, m->dBeta1, m->dPart, nb, G, Mpad, m->npb > 0);
         nlaunch++; nK2++;
         if (vm) {
-            const int Gv = pick_groups(vm->nb, tiles);
-            trigemm_kernel<<<dim3(Gv, (unsigned)tiles), K2_THREADS, K2_SMEM, st>>>(vm->dWpack, vm->dSlab, vm->dBetaY, vm->dBeta1, vm->dPart, vm->nb, Gv, Mpad, 0);
+            const int Gv = pick_groups(vm->nb, ctaTiles);
+            if (narrow) trigemm_kernel<1><<<dim3(Gv, (unsigned)ctaTiles), K2_THREADS, K2_SMEM, st>>>(vm->dWpack, vm->dSlab, vm->dBetaY, vm->dBeta1, vm->dPart, vm->nb, Gv, Mpad, 0);
+            else trigemm_kernel<4><<<dim3(Gv, (unsigned)tiles), K2_THREADS, K2_SMEM, st>>>(vm->dWpack, vm->dSlab, vm->dBetaY, vm->dBeta1, vm->dPart, vm->nb, Gv, Mpad, 0);
             nlaunch++; nK2++;
         }
         if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[3], st));
@@ -512,7 +654,7 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
         }
     }
     if (rq.acq >= 0) {
-        argmax_final_kernel<<<1, 256, 0, st>>>(m->dBlkBest, m->dBlkIdx, blk0, m->dBest, m->dBestIdx);
+        argmax_final_kernel<<<1, 256, 0, st>>>(m->dBlkBest, m->dBlkIdx, blk0, m->dOut + 3 * M, reinterpret_cast<long long*>(m->dOut + 3 * M + 1));
         nlaunch++;
     }
     g_launches += nlaunch;
@@ -534,17 +676,42 @@ static int score_host(ibo_model* m, const double* Xs, long M, const ScoreReq& rq
     int rc;
     if ((rc = grow(&m->dCand, &m->candCap, (size_t)M * m->d))) return rc;
     cudaStream_t st = m->stream;
-    IBO_CUDA_TRY(cudaMemcpyAsync(m->dCand, Xs, sizeof(double) * (size_t)M * m->d, cudaMemcpyHostToDevice, st));
-    if ((rc = score_device(m, m->dCand, M, rq))) return rc;
-    if (scores) IBO_CUDA_TRY(cudaMemcpyAsync(scores, m->dOut, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
-    if (mu) IBO_CUDA_TRY(cudaMemcpyAsync(mu, m->dOut + M, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
-    if (s2) IBO_CUDA_TRY(cudaMemcpyAsync(s2, m->dOut + 2 * M, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
-    double hb = 0; long long hi = -1;
-    if (rq.acq >= 0) {
-        IBO_CUDA_TRY(cudaMemcpyAsync(&hb, m->dBest, sizeof(double), cudaMemcpyDeviceToHost, st));
-        IBO_CUDA_TRY(cudaMemcpyAsync(&hi, m->dBestIdx, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    // Small batches (DIRECT, gallery) are latency bound: stage through one pinned buffer so that the H2D and the
+    // single D2H are plain DMA transfers instead of pageable copies (each of which costs a staging round trip).
+    const size_t nin = (size_t)M * m->d, nout = 3 * (size_t)M + 2;
+    const bool staged = (nin + nout) <= (1u << 17);
+    if (staged) {
+        if (m->pinnedCap < nin + nout) {
+            IBO_CUDA_TRY(pinned_get(&m->hPinned));
+            m->pinnedCap = 1u << 17;
+        }
+        std::memcpy(m->hPinned, Xs, sizeof(double) * nin);
+        IBO_CUDA_TRY(cudaMemcpyAsync(m->dCand, m->hPinned, sizeof(double) * nin, cudaMemcpyHostToDevice, st));
+    } else {
+        IBO_CUDA_TRY(cudaMemcpyAsync(m->dCand, Xs, sizeof(double) * nin, cudaMemcpyHostToDevice, st));
     }
-    IBO_CUDA_TRY(cudaStreamSynchronize(st));
+    if ((rc = score_device(m, m->dCand, M, rq))) return rc;
+    double hb = 0; long long hi = -1;
+    if (staged) {
+        // dOut is [score | mu | s2][M] followed by the (best, index) pair: one contiguous read-back
+        double* ho = m->hPinned + nin;
+        IBO_CUDA_TRY(cudaMemcpyAsync(ho, m->dOut, sizeof(double) * nout, cudaMemcpyDeviceToHost, st));
+        IBO_CUDA_TRY(cudaStreamSynchronize(st));
+        if (scores) std::memcpy(scores, ho, sizeof(double) * M);
+        if (mu) std::memcpy(mu, ho + M, sizeof(double) * M);
+        if (s2) std::memcpy(s2, ho + 2 * M, sizeof(double) * M);
+        hb = ho[3 * M];
+        std::memcpy(&hi, &ho[3 * M + 1], 8);
+    } else {
+        if (scores) IBO_CUDA_TRY(cudaMemcpyAsync(scores, m->dOut, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
+        if (mu) IBO_CUDA_TRY(cudaMemcpyAsync(mu, m->dOut + M, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
+        if (s2) IBO_CUDA_TRY(cudaMemcpyAsync(s2, m->dOut + 2 * M, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
+        if (rq.acq >= 0) {
+            IBO_CUDA_TRY(cudaMemcpyAsync(&hb, m->dOut + 3 * M, sizeof(double), cudaMemcpyDeviceToHost, st));
+            IBO_CUDA_TRY(cudaMemcpyAsync(&hi, m->dOut + 3 * M + 1, sizeof(long long), cudaMemcpyDeviceToHost, st));
+        }
+        IBO_CUDA_TRY(cudaStreamSynchronize(st));
+    }
     if (best_score) *best_score = hb;
     if (best_idx) *best_idx = (long)hi;
     return IBO_OK;
@@ -608,8 +775,8 @@ extern "C" int ibo_score_resident(ibo_model* m, ibo_cands* c, int acq, double ym
     IBO_CUDA_TRY(cudaEventRecord(m->ev[7], st));
     double hb = 0; long long hi = -1;
     if (scores_host) IBO_CUDA_TRY(cudaMemcpyAsync(scores_host, m->dOut, sizeof(double) * c->M, cudaMemcpyDeviceToHost, st));
-    IBO_CUDA_TRY(cudaMemcpyAsync(&hb, m->dBest, sizeof(double), cudaMemcpyDeviceToHost, st));
-    IBO_CUDA_TRY(cudaMemcpyAsync(&hi, m->dBestIdx, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    IBO_CUDA_TRY(cudaMemcpyAsync(&hb, m->dOut + 3 * c->M, sizeof(double), cudaMemcpyDeviceToHost, st));
+    IBO_CUDA_TRY(cudaMemcpyAsync(&hi, m->dOut + 3 * c->M + 1, sizeof(long long), cudaMemcpyDeviceToHost, st));
     IBO_CUDA_TRY(cudaStreamSynchronize(st));
     if (ms_device) { float ms = 0; cudaEventElapsedTime(&ms, m->ev[6], m->ev[7]); *ms_device = ms; }
     if (best_score) *best_score = hb;
