@@ -309,6 +309,25 @@ def run_suite(args):
           "algorithmic_tflops": len(C4) * F / (ms4 * 1e-3) / 1e12, "k1_ms": pr["k1_ms"], "k2_ms": pr["k2_ms"], "k3_ms": pr["k3_ms"]})
     rc.close()
     del gp4, m4
+    # ---- config #3: PrefGaussianProcess (Laplace) d=4, 500 pairwise preferences, fastUCBGallery of 4 ----
+    from ibo_b200.acquisition import fastUCBGallery
+    from ibo_b200.gaussianprocess import PrefGaussianProcess
+    b3 = [[0., 10.]] * 4
+    P3 = np.array(orc.lhc_sample(b3, 1000, seed=2))
+    prefs = []
+    for i in range(500):
+        a, b_ = P3[2 * i], P3[2 * i + 1]
+        prefs.append((a, b_, 0) if -orc.shekel5(a) > -orc.shekel5(b_) else (b_, a, 0))
+    t0 = time.perf_counter()
+    pg = PrefGaussianProcess(GaussianKernel_ard([5.146, 4.189, 4.622, 5.843]), prefs, noise=0.1)
+    t_fit = time.perf_counter() - t0
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        gal = fastUCBGallery(pg, b3, 4, seed=3)
+        ts.append(time.perf_counter() - t0)
+    emit({"suite": "config3_pref_gallery", "points": len(pg.X), "prefs": 500, "d": 4, "laplace_fit_host_s": t_fit,
+          "fastUCBGallery_wall_ms": 1e3 * min(ts), "gallery": [list(map(float, g)) for g in gal]})
     # ---- config #5: batched-DIRECT maximizeEI d=20, N=4096, 200 iterations ----
     rs = np.random.RandomState(5)
     X5 = rs.rand(4096, 20); Y5 = np.sin(2 * X5).sum(axis=1)

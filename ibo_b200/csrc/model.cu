@@ -165,15 +165,19 @@ __global__ void set_identity_kernel(double* __restrict__ W, int Np) {
 
 // ---------------------------------------------------------------------------------------------
 // Diagonal block: L_kk = chol(A_kk) in place (lower), D_k = inv(L_kk) (dense 128x128, zeros above).
-// One CTA, 512 threads.  info gets the first failing global pivot (1-based) if A is not SPD.
+// One CTA, 512 threads, the block lives in shared memory.
+//   * Cholesky: right-looking with 16-column panels -- inside a panel one column at a time (scale, then update the
+//     rest of the panel), then one rank-16 update of the trailing part (264 barriers instead of 384, and the O(n^2)
+//     work per column of the unblocked form becomes O(16 n)).
+//   * Inverse: recursive doubling from 16x16 diagonal blocks (see below).
+// info gets the first failing global pivot (1-based) if A is not SPD.
 // ---------------------------------------------------------------------------------------------
 constexpr int PS = 129;   // smem row stride of the 128x128 block
 __global__ void __launch_bounds__(512) potrf_diag_kernel(double* __restrict__ A, int ld, int kblk,
                                                          double* __restrict__ Dall, int* __restrict__ info) {
     extern __shared__ double sm[];
     double* S = sm;                    // [128][PS]
-    double* XA = sm + 128 * PS;        // [64][64]  XA[t][col]
-    double* XC = XA + 64 * 64;         // [64][64]
+    double* dinv = sm + 128 * PS;      // [128] 1 / L[i][i]
     const int tid = threadIdx.x;
     double* Ablk = A + (size_t)kblk * 128 * ld + (size_t)kblk * 128;
     for (int idx = tid; idx < 128 * 128; idx += 512) {
@@ -181,24 +185,64 @@ __global__ void __launch_bounds__(512) potrf_diag_kernel(double* __restrict__ A,
         S[r * PS + c] = (c <= r) ? Ablk[(size_t)r * ld + c] : 0.0;
     }
     __syncthreads();
-    for (int j = 0; j < 128; j++) {
-        double piv = S[j * PS + j];
-        if (!(piv > 0.0)) {   // also catches NaN
-            if (tid == 0) atomicCAS(info, 0, kblk * 128 + j + 1);
-            piv = 1.0;        // keep going with garbage; the host checks info
+    for (int c0 = 0; c0 < 128; c0 += 16) {
+        // Panel: eliminate one column at a time on the *unscaled* columns -- S[i][c] -= S[i][j] S[c][j] / piv_j needs only
+        // a reciprocal (one barrier per column); the 1/sqrt(piv) scaling of the 16 columns is deferred to the panel end.
+#pragma unroll
+        for (int jj = 0; jj < 16; jj++) {     // unrolled: nc below is a compile-time constant (no integer division)
+            const int j = c0 + jj;
+            double piv = S[j * PS + j];
+            if (!(piv > 0.0)) {   // also catches NaN
+                if (tid == 0) atomicCAS(info, 0, kblk * 128 + j + 1);
+                piv = 1.0;        // keep going with garbage; the host checks info
+            }
+            const int nc = 15 - jj, nr = 127 - j;
+            if (nc > 0) {
+                const double rp = 1.0 / piv;
+                for (int idx = tid; idx < nr * nc; idx += 512) {
+                    int ri = idx / nc, ci = idx - ri * nc;
+                    int i = j + 1 + ri, c = j + 1 + ci;
+                    if (i >= c) S[i * PS + c] -= S[i * PS + j] * S[c * PS + j] * rp;
+                }
+                __syncthreads();
+            }
         }
-        double inv = 1.0 / sqrt(piv);
-        __syncthreads();
-        if (tid == 0) S[j * PS + j] = sqrt(piv);
-        int i = j + 1 + tid;
-        if (i < 128) S[i * PS + j] *= inv;
-        __syncthreads();
-        int n = 127 - j;
-        for (int idx = tid; idx < n * n; idx += 512) {
-            int a = idx / n, b = idx - a * n;
-            if (b <= a) {
-                int r = j + 1 + a, c = j + 1 + b;
-                S[r * PS + c] -= S[r * PS + j] * S[c * PS + j];
+        // scale the panel: L[i][j] = S[i][j] / sqrt(piv_j), L[j][j] = sqrt(piv_j)
+        {
+            const int nrow = 128 - c0;
+            double myinv = 0.0; int mycol = -1;
+            for (int idx = tid; idx < nrow * 16; idx += 512) {
+                int ri = idx >> 4, jj = idx & 15;
+                int i = c0 + ri, j = c0 + jj;
+                if (i >= j) {
+                    if (jj != mycol) { double pv = S[j * PS + j]; if (!(pv > 0.0)) pv = 1.0; myinv = rsqrt(pv); mycol = jj; }
+                    if (i > j) S[i * PS + j] *= myinv;
+                }
+            }
+            __syncthreads();     // all reads of the unscaled pivots are done
+            if (tid < 16) {
+                int j = c0 + tid;
+                double pv = S[j * PS + j]; if (!(pv > 0.0)) pv = 1.0;
+                double iv = rsqrt(pv);
+                S[j * PS + j] = pv * iv; dinv[j] = iv;
+            }
+            __syncthreads();
+        }
+        // rank-16 update of the trailing block: rows / cols >= c0 + 16
+        const int t0 = c0 + 16, n = 128 - t0;
+        if (n > 0) {
+            // 32 x 16 thread tile walks the n x n square; tiles wholly above the diagonal are skipped
+            const int ty = tid >> 4, tx = tid & 15;
+            for (int rb = 0; rb < n; rb += 32) {
+                for (int cb = 0; cb <= rb + 31 && cb < n; cb += 16) {
+                    int i = t0 + rb + ty, c = t0 + cb + tx;
+                    if (i < 128 && c <= i) {
+                        double acc = 0;
+#pragma unroll
+                        for (int k = 0; k < 16; k++) acc = fma(S[i * PS + c0 + k], S[c * PS + c0 + k], acc);
+                        S[i * PS + c] -= acc;
+                    }
+                }
             }
         }
         __syncthreads();
@@ -207,42 +251,62 @@ __global__ void __launch_bounds__(512) potrf_diag_kernel(double* __restrict__ A,
         int r = idx >> 7, c = idx & 127;
         if (c <= r) Ablk[(size_t)r * ld + c] = S[r * PS + c];
     }
-    // ---- inverse of the lower-triangular block, 2x2 split into 64x64 quadrants ----
-    // XA = inv(L11), XC = inv(L22): one thread per column, forward substitution.
-    if (tid < 128) {
-        const int q = tid >> 6, col = tid & 63;
-        const int o = q * 64;
-        double* X = q ? XC : XA;
-        for (int i = 0; i < 64; i++) {
-            double s = (i == col) ? 1.0 : 0.0;
-            for (int t = 0; t < i; t++) s -= S[(o + i) * PS + o + t] * X[t * 64 + col];
-            X[i * 64 + col] = (i < col) ? 0.0 : s / S[(o + i) * PS + o + i];
+    // ---- X = inv(L) by recursive doubling: inv([[A,0],[B,C]]) = [[inv A, 0], [-inv(C) B inv(A), inv C]].
+    //      Level 0 inverts the eight 16x16 diagonal blocks by forward substitution (4 threads per column); levels
+    //      1..3 (n = 16, 32, 64) are two small triangular matrix products per off-diagonal block, all 512 threads.
+    //      X is kept packed (lower triangle) in shared memory; T = B inv(A) goes to the free upper triangle of S.
+    double* Xp = dinv + 128;                       // packed lower triangle, X[i][c] at i(i+1)/2 + c
+#define XP(i, c) Xp[(((i) * ((i) + 1)) >> 1) + (c)]
+    {
+        const int col = tid >> 2, part = tid & 3;  // global column 0..127, its 16-block and offset
+        const int b0 = col & ~15;
+        for (int i = b0; i < b0 + 16; i++) {       // uniform trip count for all threads
+            double acc = 0;
+            if (i > col)
+                for (int t = col + part; t < i; t += 4) acc = fma(S[i * PS + t], XP(t, col), acc);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            if (part == 0 && i >= col) XP(i, col) = (i == col) ? dinv[i] : -acc * dinv[i];
+            __syncthreads();
         }
     }
-    __syncthreads();
-    // T = L21 * XA  -> stored in the (unused) upper-right quadrant of S
-    for (int idx = tid; idx < 64 * 64; idx += 512) {
-        int r = idx >> 6, c = idx & 63;
-        double s = 0;
-        for (int t = c; t < 64; t++) s += S[(64 + r) * PS + t] * XA[t * 64 + c];
-        S[r * PS + 64 + c] = s;
+    for (int n = 16; n < 128; n <<= 1) {
+        const int npairs = 128 / (2 * n);
+        // T = B * inv(A): T[r][c] = sum_{t=c}^{n-1} L[r0+n+r][r0+t] * X[r0+t][r0+c]  -> S[r0+r][r0+n+c] (upper triangle).
+        // Each thread owns four rows of one column (four independent FMA chains share the X load).
+        const int rg = n / 4, work = npairs * n * rg;
+        for (int idx = tid; idx < work; idx += 512) {
+            int pr = idx / (n * rg), e = idx - pr * (n * rg), c = e / rg, r = (e - c * rg) * 4, r0 = pr * 2 * n;
+            double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+            const double* Lr = S + (r0 + n + r) * PS + r0;
+            for (int t = c; t < n; t++) {
+                double x = XP(r0 + t, r0 + c);
+                a0 = fma(Lr[t], x, a0); a1 = fma(Lr[PS + t], x, a1); a2 = fma(Lr[2 * PS + t], x, a2); a3 = fma(Lr[3 * PS + t], x, a3);
+            }
+            double* Tp = S + (r0 + r) * PS + r0 + n + c;
+            Tp[0] = a0; Tp[PS] = a1; Tp[2 * PS] = a2; Tp[3 * PS] = a3;
+        }
+        __syncthreads();
+        // X21 = -inv(C) * T: X[r0+n+r][r0+c] = -sum_{t=0}^{r} X[r0+n+r][r0+n+t] * T[t][c]; four columns per thread
+        for (int idx = tid; idx < work; idx += 512) {
+            int pr = idx / (n * rg), e = idx - pr * (n * rg), r = e / rg, c = (e - r * rg) * 4, r0 = pr * 2 * n;
+            double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+            const double* Tp = S + r0 * PS + r0 + n + c;
+            for (int t = 0; t <= r; t++) {
+                double x = XP(r0 + n + r, r0 + n + t);
+                a0 = fma(x, Tp[t * PS], a0); a1 = fma(x, Tp[t * PS + 1], a1); a2 = fma(x, Tp[t * PS + 2], a2); a3 = fma(x, Tp[t * PS + 3], a3);
+            }
+            double* Xo = &XP(r0 + n + r, r0 + c);
+            Xo[0] = -a0; Xo[1] = -a1; Xo[2] = -a2; Xo[3] = -a3;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     double* D = Dall + (size_t)kblk * 128 * 128;
     for (int idx = tid; idx < 128 * 128; idx += 512) {
         int r = idx >> 7, c = idx & 127;
-        double v;
-        if (r < 64) v = (c < 64) ? XA[r * 64 + c] : 0.0;
-        else if (c >= 64) v = XC[(r - 64) * 64 + (c - 64)];
-        else {
-            // -(XC * T)[r-64][c]
-            double s = 0;
-            int rr = r - 64;
-            for (int t = 0; t <= rr; t++) s += XC[rr * 64 + t] * S[t * PS + 64 + c];
-            v = -s;
-        }
-        D[r * 128 + c] = v;
+        D[r * 128 + c] = (c <= r) ? XP(r, c) : 0.0;
     }
+#undef XP
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -412,7 +476,7 @@ static int set_kernel_attrs() {
     IBO_CUDA_TRY(cudaFuncSetAttribute(block_step_kernel<MODE_CHOL_TRAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem));
     IBO_CUDA_TRY(cudaFuncSetAttribute(block_step_kernel<MODE_TRTRI_SCALE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem));
     IBO_CUDA_TRY(cudaFuncSetAttribute(block_step_kernel<MODE_TRTRI_UPDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem));
-    IBO_CUDA_TRY(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 * PS + 2 * 64 * 64) * 8));
+    IBO_CUDA_TRY(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 * PS + 128 + 128 * 129 / 2) * 8));
     g_attr_done = true;
     return IBO_OK;
 }
@@ -425,33 +489,48 @@ int launch_factorize(ibo_model* m, bool from_inverse_reversed) {
     cudaStream_t st = m->stream;
     const int Np = m->Np, nb = m->nb;
     const int tile_smem = TILE_SMEM_DOUBLES * 8;
-    const int potrf_smem = (128 * PS + 2 * 64 * 64) * 8;
+    const int potrf_smem = (128 * PS + 128 + 128 * 129 / 2) * 8;
     IBO_CUDA_TRY(cudaMemsetAsync(m->dInfo, 0, sizeof(int), st));
+    dim3 g2((Np + 255) / 256, Np);
+    // The inversion W = inv(L) runs on a second stream, one block step behind the factorisation: step k of the
+    // substitution needs only D_k and the finished block column k of L (potrf + panel of step k), so it overlaps the
+    // trailing update of step k and everything after it.
+    cudaStream_t s2 = from_inverse_reversed ? st : m->stream2;
+    if (!from_inverse_reversed) {
+        IBO_CUDA_TRY(cudaEventRecord(m->evStep, st));            // orders s2 after whatever produced dA / dD users
+        IBO_CUDA_TRY(cudaStreamWaitEvent(s2, m->evStep, 0));
+        set_identity_kernel<<<g2, 256, 0, s2>>>(m->dW, Np);
+        g_launches++;
+    }
     for (int k = 0; k < nb; k++) {
         potrf_diag_kernel<<<1, 512, potrf_smem, st>>>(m->dA, Np, k, m->dD, m->dInfo);
         g_launches++;
         int nrem = nb - 1 - k;
         if (nrem > 0) {
             block_step_kernel<MODE_CHOL_PANEL><<<nrem, 256, tile_smem, st>>>(m->dA, nullptr, m->dD, Np, k);
+            g_launches++;
+        }
+        if (!from_inverse_reversed) {
+            IBO_CUDA_TRY(cudaEventRecord(m->evStep, st));
+            IBO_CUDA_TRY(cudaStreamWaitEvent(s2, m->evStep, 0));
+            block_step_kernel<MODE_TRTRI_SCALE><<<k + 1, 256, tile_smem, s2>>>(m->dA, m->dW, m->dD, Np, k);
+            g_launches++;
+            if (nrem > 0) {
+                block_step_kernel<MODE_TRTRI_UPDATE><<<dim3(k + 1, nrem), 256, tile_smem, s2>>>(m->dA, m->dW, m->dD, Np, k);
+                g_launches++;
+            }
+        }
+        if (nrem > 0) {
             block_step_kernel<MODE_CHOL_TRAIL><<<dim3(nrem, nrem), 256, tile_smem, st>>>(m->dA, nullptr, m->dD, Np, k);
-            g_launches += 2;
+            g_launches++;
         }
     }
-    dim3 g2((Np + 255) / 256, Np);
     if (from_inverse_reversed) {
         reverse_transpose_kernel<<<g2, 256, 0, st>>>(m->dW, m->dA, m->N, Np);
         g_launches++;
     } else {
-        set_identity_kernel<<<g2, 256, 0, st>>>(m->dW, Np);
-        g_launches++;
-        for (int k = 0; k < nb; k++) {
-            block_step_kernel<MODE_TRTRI_SCALE><<<k + 1, 256, tile_smem, st>>>(m->dA, m->dW, m->dD, Np, k);
-            g_launches++;
-            if (k + 1 < nb) {
-                block_step_kernel<MODE_TRTRI_UPDATE><<<dim3(k + 1, nb - 1 - k), 256, tile_smem, st>>>(m->dA, m->dW, m->dD, Np, k);
-                g_launches++;
-            }
-        }
+        IBO_CUDA_TRY(cudaEventRecord(m->evStep, s2));
+        IBO_CUDA_TRY(cudaStreamWaitEvent(st, m->evStep, 0));
     }
     pack_w_kernel<<<dim3(nb * KB_PER_BLOCK, nb), 256, 0, st>>>(m->dW, m->dWpack, Np, nb);
     tri_matvec_kernel<<<(Np + 7) / 8, 256, 0, st>>>(m->dW, m->dY, m->dBetaY, Np);
@@ -481,6 +560,7 @@ extern "C" int ibo_device_count(void) {
 static void free_model(ibo_model* m) {
     if (!m) return;
     cudaSetDevice(m->device);
+    if (m->stream2) cudaStreamSynchronize(m->stream2);
     if (m->stream) cudaStreamSynchronize(m->stream);   // blocks go back to the pool: nothing may still be using them
     double** ptrs[] = {&m->dXt, &m->dInvTheta, &m->dCenter, &m->dA, &m->dAorig, &m->dW, &m->dD, &m->dWpack, &m->dBetaY, &m->dBeta1, &m->dY,
                        &m->dPmeans, &m->dPbeta, &m->dPlb, &m->dPwidth, &m->dCand, &m->dSlab, &m->dPart, &m->dOut, &m->dBlkBest, &m->dBest};
@@ -490,6 +570,8 @@ static void free_model(ibo_model* m) {
     if (m->dBestIdx) cudaFree(m->dBestIdx);
     if (m->hPinned) pinned_put(m->hPinned);
     for (auto& e : m->ev) if (e) cudaEventDestroy(e);
+    if (m->evStep) cudaEventDestroy(m->evStep);
+    if (m->stream2) cudaStreamDestroy(m->stream2);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -538,6 +620,8 @@ static int create_common(int device, int kind, const double* hyper, int nhyper, 
     auto fail = [&](int code) { free_model(m); return code; };
 #define TRYM(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { set_error(std::string(#expr) + ": " + cudaGetErrorString(e__)); cudaGetLastError(); return fail(e__ == cudaErrorMemoryAllocation ? IBO_E_NOMEM : IBO_E_CUDA); } } while (0)
     TRYM(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    TRYM(cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking));
+    TRYM(cudaEventCreateWithFlags(&m->evStep, cudaEventDisableTiming));
     for (auto& e : m->ev) TRYM(cudaEventCreate(&e));
     TRYM(pool_malloc((void**)&m->dXt, sizeof(double) * (size_t)Np * d));
     TRYM(pool_malloc((void**)&m->dInvTheta, sizeof(double) * d));

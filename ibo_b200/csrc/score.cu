@@ -190,10 +190,10 @@ __device__ __forceinline__ int group_of(int i, int nb, int G) {
 // NT = n-tiles (8 candidates each) per warp: the CTA covers 128 rows x 32*NT candidates.  NT = 4 is the throughput
 // shape; NT = 1 serves small batches (DIRECT) where a quarter-width tile gives 4x the CTAs and a 4x shorter k-loop
 // per candidate.  Both shapes own rows and reduce them identically, so a candidate's result is bit-identical.
-template <int NT>
+template <int NT, bool P1>
 __global__ void __launch_bounds__(K2_THREADS, 1)
 trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab, const double* __restrict__ betaY,
-               const double* __restrict__ beta1, double* __restrict__ part, int nb, int G, long Mpad, int want_p1) {
+               const double* __restrict__ beta1, double* __restrict__ part, int nb, int G, long Mpad) {
     extern __shared__ __align__(128) unsigned char smraw[];
     double* sA = reinterpret_cast<double*>(smraw);
     double* sB = sA + K2_STAGES * BLOB;
@@ -301,7 +301,7 @@ trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab
         for (int mt = 0; mt < 8; mt++) {
             int r = i * 128 + (2 * mt + wm) * 8 + (lane >> 2);
             by[mt] = betaY[r];
-            b1[mt] = want_p1 ? beta1[r] : 0.0;
+            b1[mt] = P1 ? beta1[r] : 0.0;
         }
         double q[NT][2], p[NT][2], p1[NT][2];
 #pragma unroll
@@ -314,13 +314,13 @@ trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab
                     double v = acc[mt][nt][j];
                     sq = fma(v, v, sq);
                     sp = fma(v, by[mt], sp);
-                    s1 = fma(v, b1[mt], s1);
+                    if (P1) s1 = fma(v, b1[mt], s1);
                 }
 #pragma unroll
                 for (int o = 4; o < 32; o <<= 1) {
                     sq += __shfl_xor_sync(0xffffffffu, sq, o);
                     sp += __shfl_xor_sync(0xffffffffu, sp, o);
-                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                    if (P1) s1 += __shfl_xor_sync(0xffffffffu, s1, o);
                 }
                 q[nt][j] = sq; p[nt][j] = sp; p1[nt][j] = s1;
             }
@@ -331,7 +331,7 @@ trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab
 #pragma unroll
                 for (int j = 0; j < 2; j++) {
                     int c = (wn * NT + nt) * 8 + 2 * lane + j;
-                    red[c] = q[nt][j]; red[128 + c] = p[nt][j]; red[256 + c] = p1[nt][j];
+                    red[c] = q[nt][j]; red[128 + c] = p[nt][j]; if (P1) red[256 + c] = p1[nt][j];
                 }
         }
         named_bar_sync(1, 256);
@@ -345,7 +345,7 @@ trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab
                     int c = (wn * NT + nt) * 8 + 2 * lane + j;
                     dst[c] = q[nt][j] + red[c];
                     dst[plane + c] = p[nt][j] + red[128 + c];
-                    if (want_p1) dst[2 * plane + c] = p1[nt][j] + red[256 + c];
+                    if (P1) dst[2 * plane + c] = p1[nt][j] + red[256 + c];
                 }
         }
         rbcount++;
@@ -495,9 +495,10 @@ static std::once_flag g_score_attr_once;
 static cudaError_t g_score_attr_err = cudaSuccess;
 static int g_num_sms = 148;
 static void set_score_attrs() {
-    g_score_attr_err = cudaFuncSetAttribute(trigemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
-    if (g_score_attr_err == cudaSuccess)
-        g_score_attr_err = cudaFuncSetAttribute(trigemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
+    g_score_attr_err = cudaFuncSetAttribute(trigemm_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
+    if (g_score_attr_err == cudaSuccess) g_score_attr_err = cudaFuncSetAttribute(trigemm_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
+    if (g_score_attr_err == cudaSuccess) g_score_attr_err = cudaFuncSetAttribute(trigemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
+    if (g_score_attr_err == cudaSuccess) g_score_attr_err = cudaFuncSetAttribute(trigemm_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
     if (g_score_attr_err == cudaSuccess)
         g_score_attr_err = cudaFuncSetAttribute(kstar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 65 * 8);
     int dev = 0; cudaGetDevice(&dev);
@@ -513,6 +514,14 @@ static long chunk_tiles_default() {
         if (v <= 0) v = 2L * g_num_sms;
     }
     return v;
+}
+
+static void launch_trigemm(const ibo_model* m, bool narrow, bool p1, int G, long ytiles, long Mpad, cudaStream_t st) {
+    dim3 grid(G, (unsigned)ytiles);
+#define IBO_K2(NT_, P1_) trigemm_kernel<NT_, P1_><<<grid, K2_THREADS, K2_SMEM, st>>>(m->dWpack, m->dSlab, m->dBetaY, m->dBeta1, m->dPart, m->nb, G, Mpad)
+    if (narrow) { if (p1) IBO_K2(1, true); else IBO_K2(1, false); }
+    else { if (p1) IBO_K2(4, true); else IBO_K2(4, false); }
+#undef IBO_K2
 }
 
 static long narrow_threshold() {
@@ -618,13 +627,11 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
             nlaunch++;
         }
         if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[2], st));
-        if (narrow) trigemm_kernel<1><<<dim3(G, (unsigned)ctaTiles), K2_THREADS, K2_SMEM, st>>>(m->dWpack, m->dSlab, m->dBetaY, m->dBeta1, m->dPart, nb, G, Mpad, m->npb > 0);
-        else trigemm_kernel<4><<<dim3(G, (unsigned)tiles), K2_THREADS, K2_SMEM, st>>>(m->dWpack, m->dSlab, m->dBetaY, m->dBeta1, m->dPart, nb, G, Mpad, m->npb > 0);
+        launch_trigemm(m, narrow, m->npb > 0, G, narrow ? ctaTiles : tiles, Mpad, st);
         nlaunch++; nK2++;
         if (vm) {
             const int Gv = pick_groups(vm->nb, ctaTiles);
-            if (narrow) trigemm_kernel<1><<<dim3(Gv, (unsigned)ctaTiles), K2_THREADS, K2_SMEM, st>>>(vm->dWpack, vm->dSlab, vm->dBetaY, vm->dBeta1, vm->dPart, vm->nb, Gv, Mpad, 0);
-            else trigemm_kernel<4><<<dim3(Gv, (unsigned)tiles), K2_THREADS, K2_SMEM, st>>>(vm->dWpack, vm->dSlab, vm->dBetaY, vm->dBeta1, vm->dPart, vm->nb, Gv, Mpad, 0);
+            launch_trigemm(vm, narrow, false, Gv, narrow ? ctaTiles : tiles, Mpad, st);
             nlaunch++; nK2++;
         }
         if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[3], st));

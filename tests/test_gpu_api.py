@@ -118,6 +118,36 @@ def test_pref_gp_fit_orders_latents():
         gp.addData([0.1], [1.0])
 
 
+def test_config3_shape_preference_gallery():
+    """BASELINE config #3 at reduced size: PrefGaussianProcess (Laplace) d=4 on Shekel5 preferences, gallery of 4"""
+    from ibo_b200.acquisition import fastUCBGallery
+    from ibo_b200.gaussianprocess import PrefGaussianProcess
+    from ibo_b200.gaussianprocess.kernel import GaussianKernel_ard
+    bounds = [[0., 10.]] * 4
+    P = np.array(orc.lhc_sample(bounds, 120, seed=2))
+    prefs = []
+    for i in range(60):
+        a, b = P[2 * i], P[2 * i + 1]
+        fa, fb = -orc.shekel5(a), -orc.shekel5(b)
+        prefs.append((a, b, 0) if fa > fb else (b, a, 0))
+    gp = PrefGaussianProcess(GaussianKernel_ard([5.146, 4.189, 4.622, 5.843]), prefs, noise=0.1)
+    assert gp.X.shape == (120, 4) and gp.C.shape == (120, 120)
+    mu = gp.posteriors(gp.X)[0]
+    idx = dict((tuple(x), i) for i, x in enumerate(gp.X))
+    ok = sum(mu[idx[tuple(v)]] > mu[idx[tuple(u)]] for v, u, _ in prefs)
+    assert ok >= 48                      # the smooth posterior mean respects most preferences (54/60 measured)
+    # L is the factor of R + inv(C)
+    o = orc.GPOracle(orc.KernelSpec(orc.K_SE_ARD, [5.146, 4.189, 4.622, 5.843], 4), gp.X, gp.Y, 0.1, Cinv=np.linalg.inv(gp.C))
+    assert np.allclose(gp.L, o.L, atol=1e-11)
+    gal = fastUCBGallery(gp, bounds, 4, seed=3)
+    assert len(gal) == 4
+    for x in gal:
+        assert all(0 <= v <= 10 for v in x)
+    for i in range(4):
+        for j in range(i):
+            assert np.linalg.norm(gal[i] - gal[j]) > .5
+
+
 def test_not_spd_is_reported():
     from ibo_b200 import _lib
     X = np.array([[0.0], [1.0], [2.0]]); Y = np.zeros(3)

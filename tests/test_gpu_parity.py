@@ -87,3 +87,39 @@ def test_factor_matches_numpy_cholesky():
     assert np.max(np.abs(L - gp.L)) < 1e-12
     assert np.max(np.abs(W.dot(gp.L) - np.eye(N))) < 1e-11
     m.close()
+
+
+EDGE = [
+    # (name, kind, hyper, N, d, M, noise, box)  -- shapes around the 128-row blocks, d = 1, d > 32 (direct-difference K1),
+    # and badly scaled inputs that trip K1's cancellation guard (|x/theta|^2 >> 256 -> per-pair direct differences)
+    ("one_observation", orc.K_SE_ISO, [0.7], 1, 2, 40, 0.1, 1.0),
+    ("n128_exact", orc.K_SE_ARD, [0.4, 0.6, 0.8], 128, 3, 129, 0.1, 1.0),
+    ("n129", orc.K_MATERN3, [0.9, 1.0], 129, 3, 127, 0.1, 1.0),
+    ("d1", orc.K_SE_ISO, [0.15], 90, 1, 333, 0.05, 1.0),
+    ("d40_direct_kernel", orc.K_SE_ARD, [2.0] * 40, 200, 40, 300, 0.1, 1.0),
+    ("d20", orc.K_SE_ARD, [1.0] * 20, 300, 20, 500, 0.1, 1.0),
+    ("badly_scaled_se", orc.K_SE_ISO, [0.05], 150, 3, 400, 0.1, 10.0),
+    ("badly_scaled_matern5", orc.K_MATERN5, [0.04, 1.0], 150, 2, 400, 0.1, 10.0),
+]
+
+
+@pytest.mark.parametrize("case", EDGE, ids=[c[0] for c in EDGE])
+def test_edge_shapes_and_scaling(case):
+    from ibo_b200 import _lib
+    name, kind, hyper, N, d, M, noise, box = case
+    rs = np.random.RandomState(len(name))
+    X = rs.rand(N, d) * box
+    Y = np.cos(3 * X / box).sum(axis=1)
+    Xs = rs.rand(M, d) * box
+    k = min(N, M // 2)
+    Xs[:k] = X[:k] + rs.randn(k, d) * 0.01 * np.min(hyper)      # near training points so that k* is not ~0
+    gp = orc.GPOracle(orc.KernelSpec(kind, hyper, d), X, Y, noise)
+    mu_o, s2_o = gp.posterior_batch(Xs, floor=1e-8)
+    m = _model(kind, hyper, X, Y, noise)
+    sc, mu, s2, best, bidx = m.score(Xs, _lib.ACQ_EI, Y.max(), 0.01, _lib.FLAG_MODE_CPP, want_posterior=True)
+    assert np.max(np.abs(mu - mu_o) / np.maximum(np.abs(mu_o), 1e-3)) <= RTOL
+    assert np.max(np.abs(np.sqrt(s2) - np.sqrt(s2_o)) / np.sqrt(s2_o)) <= RTOL
+    ei_o = orc.score(orc.ACQ_EI, "cpp", mu_o, s2_o, Y.max(), 0.01)
+    _check_scores(sc, ei_o)
+    assert bidx == int(np.argmax(ei_o))
+    m.close()
