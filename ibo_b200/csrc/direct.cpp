@@ -22,6 +22,8 @@
 #include <string>
 #include <utility>
 #include <vector>
+#include <chrono>
+#include <cstdio>
 
 namespace ibo {
 void set_error(const std::string& s);
@@ -38,18 +40,21 @@ const double MIN_DOUBLE = std::numeric_limits<double>::min();   // +2.2e-308, as
 // Append-only rectangle store (unit-cube coordinates).  The reference keeps a std::vector<Rectangle>, erases
 // divided rectangles and appends their children, so the relative order of live rectangles is their creation
 // order -- which is what ids are here.  Rectangles are grouped by their exact centre-to-vertex distance d
-// ("classes"); each class keeps its members ordered by y so that the class minimum and its ties are O(log R).
+// ("classes"); each class keeps its members in a min-heap on y so that the class minimum and its ties are O(log R).
 struct Store {
     int N = 0;
     std::vector<double> lb, ub, center, d, y;
     std::vector<int> cls;
     std::vector<char> alive;
-    struct Class { double d; std::multiset<std::pair<double, unsigned> > members; };
+    // members: binary min-heap on (y, id).  Only class minima are ever taken out (they are the rectangles that get
+    // divided), so a heap -- contiguous, no node allocation -- is all the order structure DIRECT needs.
+    struct Class { double d; std::vector<std::pair<double, unsigned> > heap; };
     std::vector<Class> classes;
     std::unordered_map<unsigned long long, int> cls_of_d;
     size_t live = 0;
 
     static double key(double y) { return y != y ? MAX_DOUBLE : y; }   // NaN sorts last
+    static bool heap_gt(const std::pair<double, unsigned>& a, const std::pair<double, unsigned>& b) { return a > b; }
     unsigned add(const double* l, const double* u, const double* c, double dd, double yy) {
         unsigned id = (unsigned)d.size();
         lb.insert(lb.end(), l, l + N); ub.insert(ub.end(), u, u + N); center.insert(center.end(), c, c + N);
@@ -60,15 +65,23 @@ struct Store {
         if (it == cls_of_d.end()) { k = (int)classes.size(); classes.push_back(Class()); classes.back().d = dd; cls_of_d[bits] = k; }
         else k = it->second;
         cls.push_back(k);
-        classes[k].members.insert(std::make_pair(key(yy), id));
+        auto& h = classes[k].heap;
+        h.push_back(std::make_pair(key(yy), id));
+        std::push_heap(h.begin(), h.end(), heap_gt);
         live++;
         return id;
     }
-    void remove(unsigned id) {
-        classes[cls[id]].members.erase(std::make_pair(key(y[id]), id));
-        alive[id] = 0;
-        live--;
+    // takes every member tying the class minimum out of class k (ascending id not guaranteed)
+    void pop_minima(int k, std::vector<unsigned>& out) {
+        auto& h = classes[k].heap;
+        const double kmin = h.front().first;
+        while (!h.empty() && h.front().first == kmin) {
+            out.push_back(h.front().second);
+            std::pop_heap(h.begin(), h.end(), heap_gt);
+            h.pop_back();
+        }
     }
+    void retire(unsigned id) { alive[id] = 0; live--; }     // the id was taken out of its heap by pop_minima
 };
 
 struct Driver {
@@ -114,29 +127,37 @@ inline double center_and_d(const double* lb, const double* ub, double* c, int N)
 
 struct Pending {           // one rectangle being divided
     unsigned src;          // id in the store
-    std::vector<unsigned> dims;     // long, non-fixed dims in ascending order
+    int ndims = 0;         // number of longest, non-fixed sides
+    long dim0 = 0;         // offset of its dims in the flat dims array
     long probe0 = 0;       // offset of its 2*k probe values in the phase-A batch
-    long child0 = 0;       // offset of its 2*k child values in the phase-B batch
+    long child0 = 0;       // offset of its 2*k children in the phase-B batch / flat child arrays
+    double old_d = 0;      // d of the shrunk middle rectangle
+};
+
+// Scratch reused across iterations (no per-rectangle allocations in the hot loop).
+struct Scratch {
+    std::vector<Pending> P;
+    std::vector<unsigned> dims;
     std::vector<ind_val> I;
-    // children, in the reference's return order [c1_dimA, c3_dimA, c1_dimB, ..., middle]
-    std::vector<double> clb, cub, ccenter, cd;
-    std::vector<double> old_lb, old_ub; double old_d = 0;
+    std::vector<double> pts, ptsB, yA, yB;       // probe points / child centres (unit cube) and their values
+    std::vector<double> clb, cub, cd;            // children, in the reference's return order
+    std::vector<double> mid_lb, mid_ub;          // shrunk middle rectangles, one per Pending
 };
 
 // Divides the given rectangles (already in processing order): appends the new rectangles in the reference's
 // order and retires the sources.  seq: one rectangle per batch pair (the reference's exact call order).
-void divide(Driver& D, Store& R, const std::vector<unsigned>& order, bool seq) {
+void divide(Driver& D, Store& R, const std::vector<unsigned>& order, bool seq, Scratch& W) {
     const int N = D.N;
     size_t g0 = 0;
-    std::vector<double> pts, ptsB, yA, yB, lb1, ub1, lb3, ub3, c1(N), c3(N), oc(N);
     while (g0 < order.size()) {
         size_t g1 = seq ? g0 + 1 : order.size();
-        std::vector<Pending> P(g1 - g0);
+        const size_t np_rect = g1 - g0;
+        W.P.assign(np_rect, Pending());
+        W.dims.clear(); W.pts.clear();
         // ---- phase A: probe points at lb + w/3, lb + 2w/3 along every longest side (cpp/direct.cpp:156-192)
-        pts.clear();
         long np = 0;
         for (size_t t = g0; t < g1; t++) {
-            Pending& p = P[t - g0];
+            Pending& p = W.P[t - g0];
             p.src = order[t];
             const double* lb = &R.lb[(size_t)p.src * N];
             const double* ub = &R.ub[(size_t)p.src * N];
@@ -145,72 +166,81 @@ void divide(Driver& D, Store& R, const std::vector<unsigned>& order, bool seq) {
             for (int i = 1; i < N; i++)
                 if (!D.fixed[i] && ub[i] - lb[i] > maxlength) maxlength = ub[i] - lb[i];
             p.probe0 = np;
+            p.dim0 = (long)W.dims.size();
             for (int i = 0; i < N; i++) {
                 if (!D.fixed[i] && ub[i] - lb[i] == maxlength) {
-                    p.dims.push_back((unsigned)i);
-                    size_t o = pts.size();
-                    pts.insert(pts.end(), c, c + N);
-                    pts.insert(pts.end(), c, c + N);
-                    pts[o + i] = lb[i] + maxlength / 3.;
-                    pts[o + N + i] = lb[i] + 2. * maxlength / 3.;
+                    W.dims.push_back((unsigned)i);
+                    size_t o = W.pts.size();
+                    W.pts.insert(W.pts.end(), c, c + N);
+                    W.pts.insert(W.pts.end(), c, c + N);
+                    W.pts[o + i] = lb[i] + maxlength / 3.;
+                    W.pts[o + N + i] = lb[i] + 2. * maxlength / 3.;
                     np += 2;
+                    p.ndims++;
                 }
             }
         }
-        D.eval(pts, np, yA);
+        D.eval(W.pts, np, W.yA);
         // ---- sort the dims by min(sf1, sf2) and build the children (cpp/direct.cpp:181-232)
-        ptsB.clear();
+        const size_t nchild = (size_t)np;            // two children per probed side
+        W.clb.resize(nchild * N); W.cub.resize(nchild * N); W.ptsB.resize(nchild * N); W.cd.resize(nchild);
+        W.mid_lb.resize(np_rect * N); W.mid_ub.resize(np_rect * N);
         long nc = 0;
-        for (size_t t = 0; t < P.size(); t++) {
-            Pending& p = P[t];
-            for (size_t a = 0; a < p.dims.size(); a++) {
-                double sf1 = yA[p.probe0 + 2 * a], sf2 = yA[p.probe0 + 2 * a + 1];
-                if (sf1 < sf2) p.I.push_back(ind_val(p.dims[a], sf1));
-                else p.I.push_back(ind_val(p.dims[a], sf2));
+        for (size_t t = 0; t < np_rect; t++) {
+            Pending& p = W.P[t];
+            W.I.clear();
+            for (int a = 0; a < p.ndims; a++) {
+                double sf1 = W.yA[p.probe0 + 2 * a], sf2 = W.yA[p.probe0 + 2 * a + 1];
+                unsigned dim = W.dims[p.dim0 + a];
+                if (sf1 < sf2) W.I.push_back(ind_val(dim, sf1));
+                else W.I.push_back(ind_val(dim, sf2));
             }
-            std::sort(p.I.begin(), p.I.end(), sort_by_val);
-            p.old_lb.assign(&R.lb[(size_t)p.src * N], &R.lb[(size_t)p.src * N] + N);
-            p.old_ub.assign(&R.ub[(size_t)p.src * N], &R.ub[(size_t)p.src * N] + N);
+            std::sort(W.I.begin(), W.I.end(), sort_by_val);
+            double* olb = &W.mid_lb[t * N];
+            double* oub = &W.mid_ub[t * N];
+            std::memcpy(olb, &R.lb[(size_t)p.src * N], sizeof(double) * N);
+            std::memcpy(oub, &R.ub[(size_t)p.src * N], sizeof(double) * N);
             p.child0 = nc;
-            for (size_t a = 0; a < p.I.size(); a++) {
-                unsigned dd = p.I[a].first;
-                double dwidth = p.old_ub[dd] - p.old_lb[dd];
-                double split1 = p.old_lb[dd] + dwidth / 3.;
-                double split2 = p.old_lb[dd] + 2. * dwidth / 3.;
-                lb1 = p.old_lb; ub1 = p.old_ub; lb3 = p.old_lb; ub3 = p.old_ub;
+            for (size_t a = 0; a < W.I.size(); a++) {
+                unsigned dd = W.I[a].first;
+                double dwidth = oub[dd] - olb[dd];
+                double split1 = olb[dd] + dwidth / 3.;
+                double split2 = olb[dd] + 2. * dwidth / 3.;
+                double* lb1 = &W.clb[(size_t)nc * N];       double* ub1 = &W.cub[(size_t)nc * N];
+                double* lb3 = &W.clb[(size_t)(nc + 1) * N]; double* ub3 = &W.cub[(size_t)(nc + 1) * N];
+                std::memcpy(lb1, olb, sizeof(double) * N); std::memcpy(ub1, oub, sizeof(double) * N);
+                std::memcpy(lb3, olb, sizeof(double) * N); std::memcpy(ub3, oub, sizeof(double) * N);
                 ub1[dd] = split1;
                 lb3[dd] = split2;
-                double d1 = center_and_d(lb1.data(), ub1.data(), c1.data(), N);
-                p.old_lb[dd] = split1;
-                p.old_ub[dd] = split2;
-                double d3 = center_and_d(lb3.data(), ub3.data(), c3.data(), N);
-                p.clb.insert(p.clb.end(), lb1.begin(), lb1.end()); p.cub.insert(p.cub.end(), ub1.begin(), ub1.end());
-                p.ccenter.insert(p.ccenter.end(), c1.begin(), c1.end()); p.cd.push_back(d1);
-                p.clb.insert(p.clb.end(), lb3.begin(), lb3.end()); p.cub.insert(p.cub.end(), ub3.begin(), ub3.end());
-                p.ccenter.insert(p.ccenter.end(), c3.begin(), c3.end()); p.cd.push_back(d3);
-                ptsB.insert(ptsB.end(), c1.begin(), c1.end());
-                ptsB.insert(ptsB.end(), c3.begin(), c3.end());
+                W.cd[nc] = center_and_d(lb1, ub1, &W.ptsB[(size_t)nc * N], N);
+                olb[dd] = split1;
+                oub[dd] = split2;
+                W.cd[nc + 1] = center_and_d(lb3, ub3, &W.ptsB[(size_t)(nc + 1) * N], N);
                 nc += 2;
             }
             // the middle third keeps the old centre and y; d is recomputed from the shrunk bounds (:226-231)
             double d = 0.0;
             const double* ocp = &R.center[(size_t)p.src * N];
-            for (int i = 0; i < N; i++) d += std::pow((p.old_lb[i] - ocp[i]), 2);
+            for (int i = 0; i < N; i++) d += std::pow((olb[i] - ocp[i]), 2);
             p.old_d = std::sqrt(d);
         }
-        D.eval(ptsB, nc, yB);
+        D.eval(W.ptsB, nc, W.yB);
         // ---- replay the reference's call order for FMIN / nsamples, then append the rectangles
-        for (size_t t = 0; t < P.size(); t++) {
-            Pending& p = P[t];
-            for (size_t a = 0; a < 2 * p.dims.size(); a++) D.account(&pts[(size_t)(p.probe0 + a) * N], yA[p.probe0 + a]);
-            for (size_t a = 0; a < 2 * p.I.size(); a++) D.account(&ptsB[(size_t)(p.child0 + a) * N], yB[p.child0 + a]);
-            for (size_t a = 0; a < 2 * p.I.size(); a++)
-                R.add(&p.clb[a * N], &p.cub[a * N], &p.ccenter[a * N], p.cd[a], yB[p.child0 + a]);
+        std::vector<double> oc(N);
+        for (size_t t = 0; t < np_rect; t++) {
+            Pending& p = W.P[t];
+            const long k2 = 2L * p.ndims;
+            for (long a = 0; a < k2; a++) D.account(&W.pts[(size_t)(p.probe0 + a) * N], W.yA[p.probe0 + a]);
+            for (long a = 0; a < k2; a++) D.account(&W.ptsB[(size_t)(p.child0 + a) * N], W.yB[p.child0 + a]);
+            for (long a = 0; a < k2; a++) {
+                const size_t o = (size_t)(p.child0 + a);
+                R.add(&W.clb[o * N], &W.cub[o * N], &W.ptsB[o * N], W.cd[o], W.yB[o]);
+            }
             // middle rectangle (copy of the source with shrunk bounds)
             std::memcpy(oc.data(), &R.center[(size_t)p.src * N], sizeof(double) * N);
             double oy = R.y[p.src];
-            R.remove(p.src);
-            R.add(p.old_lb.data(), p.old_ub.data(), oc.data(), p.old_d, oy);
+            R.retire(p.src);
+            R.add(&W.mid_lb[t * N], &W.mid_ub[t * N], oc.data(), p.old_d, oy);
         }
         g0 = g1;
     }
@@ -223,14 +253,14 @@ void divide(Driver& D, Store& R, const std::vector<unsigned>& order, bool seq) {
 //          (fl(x - c) and fl(x / c), c > 0, are monotone in x, so the extremal slope is the slope of the minimum)
 // so the decision is a function of the class alone and is evaluated once per class: O(C^2 + #selected log R),
 // with accept / reject decisions bit-identical to the O(R^2) scan.
-void select(const Store& R, double FMIN, std::vector<unsigned>& potopts) {
+void select(Store& R, double FMIN, std::vector<unsigned>& potopts) {
     const double epsilon = 10e-10;
     potopts.clear();
     std::vector<double> cd, cy;
     std::vector<int> ck;
     for (size_t k = 0; k < R.classes.size(); k++) {
-        if (R.classes[k].members.empty()) continue;
-        unsigned id = R.classes[k].members.begin()->second;
+        if (R.classes[k].heap.empty()) continue;
+        unsigned id = R.classes[k].heap.front().second;
         cd.push_back(R.classes[k].d); cy.push_back(R.y[id]); ck.push_back((int)k);
     }
     const size_t C = cd.size();
@@ -270,10 +300,9 @@ void select(const Store& R, double FMIN, std::vector<unsigned>& potopts) {
         else if (FMIN == 0.0) ok = (yj <= dj * minI2);
         else ok = (epsilon <= (FMIN - yj) / std::abs(FMIN) + (dj / std::abs(FMIN)) * minI2);
         if (!ok) continue;
-        // every live member tying the class minimum is potentially optimal
-        const auto& mem = R.classes[ck[k]].members;
-        const double kmin = mem.begin()->first;
-        for (auto it = mem.begin(); it != mem.end() && it->first == kmin; ++it) potopts.push_back(it->second);
+        // every member tying the class minimum is potentially optimal; they leave the heap here and are divided
+        // (or the run ends) before the next selection
+        R.pop_minima(ck[k], potopts);
     }
     std::sort(potopts.begin(), potopts.end());
 }
@@ -299,8 +328,10 @@ int run_direct(ibo_batch_objective_t f, void* user, int ndim, const double* lb, 
         R.add(l.data(), u.data(), c.data(), d, y[0]);
     }
     std::vector<unsigned> potopts, order;
-    order.assign(1, 0u);
-    divide(D, R, order, seq);
+    Scratch W;
+    order.clear();
+    R.pop_minima(R.cls[0], order);      // the unit cube leaves its heap like any rectangle about to be divided
+    divide(D, R, order, seq, W);
     int iteration = 0;
     bool done = false;
     while (iteration < maxiter && !done) {
@@ -326,7 +357,7 @@ int run_direct(ibo_batch_objective_t f, void* user, int ndim, const double* lb, 
             ns += 4L * k;
             if (ns > (long)(unsigned)maxsample) { done = true; break; }
         }
-        divide(D, R, order, seq);
+        divide(D, R, order, seq, W);
         if (time(NULL) - start > maxtime) break;
         if (D.nsamples > (long)(unsigned)maxsample) break;
     }
@@ -347,12 +378,15 @@ void scalar_batch(void* user, long n, int ndim, const double* X, double* y) {
     }
 }
 
-struct GpuObjective { ibo_model* m; int acq; double ymax, parm; int flags; int rc; };
+struct GpuObjective { ibo_model* m; int acq; double ymax, parm; int flags; int rc; double t_eval; long batches, points; };
 void gpu_batch(void* user, long n, int ndim, const double* X, double* y) {
     GpuObjective* g = static_cast<GpuObjective*>(user);
     (void)ndim;
     if (g->rc != IBO_OK) { for (long i = 0; i < n; i++) y[i] = 0.0; return; }
+    auto t0 = std::chrono::steady_clock::now();
     g->rc = eval_neg_acq(g->m, X, n, g->acq, g->ymax, g->parm, g->flags, y);
+    g->t_eval += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    g->batches++; g->points += n;
     if (g->rc != IBO_OK) for (long i = 0; i < n; i++) y[i] = 0.0;
 }
 
@@ -369,9 +403,15 @@ extern "C" int ibo_direct_batched(ibo_batch_objective_t f, void* user, int ndim,
 extern "C" int ibo_acqmax(ibo_model* m, const double* lb, const double* ub, int acq, double ymax, double parm, int flags,
                           int maxiter, int maxtime, int maxsample, double* opt, double* optx, long* nsamples, int* iterations) {
     if (!m || acq < 0 || acq > 2) { set_error("bad argument"); return IBO_E_BADARG; }
-    GpuObjective g{m, acq, ymax, parm, flags, IBO_OK};
+    GpuObjective g{m, acq, ymax, parm, flags, IBO_OK, 0.0, 0, 0};
     double fmin = 0;
+    auto t0 = std::chrono::steady_clock::now();
     int rc = run_direct(gpu_batch, &g, ibo_model_dim(m), lb, ub, maxiter, maxtime, maxsample, flags, &fmin, optx, nsamples, iterations);
+    if (getenv("IBO_DIRECT_TIMING")) {
+        double tt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        fprintf(stderr, "[ibo_acqmax] total %.3f ms, GPU batches %.3f ms (%ld batches, %ld points, %.1f us/batch), host driver %.3f ms\n",
+                1e3 * tt, 1e3 * g.t_eval, g.batches, g.points, g.batches ? 1e6 * g.t_eval / g.batches : 0.0, 1e3 * (tt - g.t_eval));
+    }
     if (rc) return rc;
     if (g.rc) return g.rc;
     if (opt) *opt = -fmin;

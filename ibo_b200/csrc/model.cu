@@ -64,7 +64,7 @@ cudaError_t pinned_get(double** p) {
         std::lock_guard<std::mutex> lk(g_pool.mu);
         if (!g_pinned_free.empty()) { *p = g_pinned_free.back(); g_pinned_free.pop_back(); return cudaSuccess; }
     }
-    return cudaHostAlloc((void**)p, sizeof(double) * (1u << 17), cudaHostAllocDefault);
+    return cudaHostAlloc((void**)p, sizeof(double) * (1u << 17), cudaHostAllocMapped | cudaHostAllocPortable);
 }
 void pinned_put(double* p) {
     if (!p) return;

@@ -356,7 +356,7 @@ trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab
 // K3: per-candidate epilogue.
 // ---------------------------------------------------------------------------------------------
 struct EpiParams {
-    int nb, d, N, acq, mode_py, npb, want_p1;
+    int nb, d, N, acq, mode_py, npb, want_p1, want_argmax;
     long M, m0, chunkM, Mpad;
     double noise, ymax, parm, ptheta;
     const double *part, *partVar, *cand, *pmeans, *pbeta, *plb, *pwidth;
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(256) epilogue_kernel(EpiParams P) {
             else idx = m;
         }
     }
-    if (P.acq < 0) return;
+    if (P.acq < 0 || !P.want_argmax) return;
     // block argmax, lowest index wins ties
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -574,11 +574,12 @@ struct ScoreReq {
     double ymax, parm;
     int flags;
     bool want_score, want_mu, want_s2;
+    bool want_argmax = true;
 };
 
 // Runs K1..K4 for M candidates resident at dCand; results land in m->dOut ([score|mu|s2][M]) and
 // the (best score, best index) pair at m->dOut[3M], [3M+1].  Everything is enqueued on m->stream; no host sync here.
-static int score_device(ibo_model* m, const double* dCand, long M, const ScoreReq& rq) {
+static int score_device(ibo_model* m, const double* dCand, long M, const ScoreReq& rq, double* outBase = nullptr) {
     std::call_once(g_score_attr_once, set_score_attrs);
     if (g_score_attr_err != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(g_score_attr_err)); return IBO_E_CUDA; }
     if (m->d > 64) { set_error("d > 64 not supported"); return IBO_E_BADARG; }
@@ -595,6 +596,7 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
     if ((rc = grow(&m->dSlab, &m->slabCap, (size_t)chunkTiles * nb * KB_PER_BLOCK * BLOB))) return rc;
     if ((rc = grow(&m->dPart, &m->partCap, (size_t)3 * nb * Mpad))) return rc;
     if ((rc = grow(&m->dOut, &m->outCap, (size_t)3 * M + 2))) return rc;
+    double* const out = outBase ? outBase : m->dOut;     // outBase: device-visible pinned host memory (zero-copy results)
     if (vm) {
         if ((rc = grow(&vm->dSlab, &vm->slabCap, (size_t)chunkTiles * vm->nb * KB_PER_BLOCK * BLOB))) return rc;
         if ((rc = grow(&vm->dPart, &vm->partCap, (size_t)3 * vm->nb * Mpad))) return rc;
@@ -642,9 +644,10 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
         P.noise = m->noise; P.ymax = rq.ymax; P.parm = rq.parm; P.ptheta = m->ptheta;
         P.part = m->dPart; P.partVar = vm ? vm->dPart : nullptr; P.nbVar = vm ? vm->nb : 0; P.MpadVar = Mpad;
         P.cand = dCand; P.pmeans = m->dPmeans; P.pbeta = m->dPbeta; P.plb = m->dPlb; P.pwidth = m->dPwidth;
-        P.score = rq.want_score ? m->dOut : nullptr;
-        P.mu = rq.want_mu ? m->dOut + M : nullptr;
-        P.s2 = rq.want_s2 ? m->dOut + 2 * M : nullptr;
+        P.score = rq.want_score ? out : nullptr;
+        P.mu = rq.want_mu ? out + M : nullptr;
+        P.s2 = rq.want_s2 ? out + 2 * M : nullptr;
+        P.want_argmax = rq.want_argmax ? 1 : 0;
         P.blkBest = m->dBlkBest; P.blkIdx = m->dBlkIdx; P.blk0 = blk0;
         const unsigned nblk = (unsigned)((chunkM + 255) / 256);
         epilogue_kernel<<<nblk, 256, 0, st>>>(P);
@@ -660,8 +663,8 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
             tK1 += a; tK2 += b; tK3 += c;
         }
     }
-    if (rq.acq >= 0) {
-        argmax_final_kernel<<<1, 256, 0, st>>>(m->dBlkBest, m->dBlkIdx, blk0, m->dOut + 3 * M, reinterpret_cast<long long*>(m->dOut + 3 * M + 1));
+    if (rq.acq >= 0 && rq.want_argmax) {
+        argmax_final_kernel<<<1, 256, 0, st>>>(m->dBlkBest, m->dBlkIdx, blk0, out + 3 * M, reinterpret_cast<long long*>(out + 3 * M + 1));
         nlaunch++;
     }
     g_launches += nlaunch;
@@ -687,33 +690,36 @@ static int score_host(ibo_model* m, const double* Xs, long M, const ScoreReq& rq
     // single D2H are plain DMA transfers instead of pageable copies (each of which costs a staging round trip).
     const size_t nin = (size_t)M * m->d, nout = 3 * (size_t)M + 2;
     const bool staged = (nin + nout) <= (1u << 17);
+    double hb = 0; long long hi = -1;
     if (staged) {
+        // Zero-copy: the pinned buffer is mapped into the device address space.  K3 / K4 write the results straight
+        // into it, and when few CTAs read the candidates (nb x tiles x 128 x d x 8 B over PCIe) K1 / K3 read them from
+        // it too, so a call is: memcpy into pinned memory, 3-4 launches, one stream synchronisation.
         if (m->pinnedCap < nin + nout) {
             IBO_CUDA_TRY(pinned_get(&m->hPinned));
             m->pinnedCap = 1u << 17;
         }
         std::memcpy(m->hPinned, Xs, sizeof(double) * nin);
-        IBO_CUDA_TRY(cudaMemcpyAsync(m->dCand, m->hPinned, sizeof(double) * nin, cudaMemcpyHostToDevice, st));
-    } else {
-        IBO_CUDA_TRY(cudaMemcpyAsync(m->dCand, Xs, sizeof(double) * nin, cudaMemcpyHostToDevice, st));
-    }
-    if ((rc = score_device(m, m->dCand, M, rq))) return rc;
-    double hb = 0; long long hi = -1;
-    if (staged) {
-        // dOut is [score | mu | s2][M] followed by the (best, index) pair: one contiguous read-back
+        const size_t pcie_reads = (size_t)m->nb * ((M + TN - 1) / TN) * TN * m->d * 8;
+        const double* cand = m->hPinned;
+        if (pcie_reads > (256u << 10) || m->var_model) {
+            IBO_CUDA_TRY(cudaMemcpyAsync(m->dCand, m->hPinned, sizeof(double) * nin, cudaMemcpyHostToDevice, st));
+            cand = m->dCand;
+        }
         double* ho = m->hPinned + nin;
-        IBO_CUDA_TRY(cudaMemcpyAsync(ho, m->dOut, sizeof(double) * nout, cudaMemcpyDeviceToHost, st));
+        if ((rc = score_device(m, cand, M, rq, ho))) return rc;
         IBO_CUDA_TRY(cudaStreamSynchronize(st));
         if (scores) std::memcpy(scores, ho, sizeof(double) * M);
         if (mu) std::memcpy(mu, ho + M, sizeof(double) * M);
         if (s2) std::memcpy(s2, ho + 2 * M, sizeof(double) * M);
-        hb = ho[3 * M];
-        std::memcpy(&hi, &ho[3 * M + 1], 8);
+        if (rq.acq >= 0 && rq.want_argmax) { hb = ho[3 * M]; std::memcpy(&hi, &ho[3 * M + 1], 8); }
     } else {
+        IBO_CUDA_TRY(cudaMemcpyAsync(m->dCand, Xs, sizeof(double) * nin, cudaMemcpyHostToDevice, st));
+        if ((rc = score_device(m, m->dCand, M, rq))) return rc;
         if (scores) IBO_CUDA_TRY(cudaMemcpyAsync(scores, m->dOut, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
         if (mu) IBO_CUDA_TRY(cudaMemcpyAsync(mu, m->dOut + M, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
         if (s2) IBO_CUDA_TRY(cudaMemcpyAsync(s2, m->dOut + 2 * M, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
-        if (rq.acq >= 0) {
+        if (rq.acq >= 0 && rq.want_argmax) {
             IBO_CUDA_TRY(cudaMemcpyAsync(&hb, m->dOut + 3 * M, sizeof(double), cudaMemcpyDeviceToHost, st));
             IBO_CUDA_TRY(cudaMemcpyAsync(&hi, m->dOut + 3 * M + 1, sizeof(long long), cudaMemcpyDeviceToHost, st));
         }
@@ -727,6 +733,7 @@ static int score_host(ibo_model* m, const double* Xs, long M, const ScoreReq& rq
 // used by the DIRECT objective (direct.cpp): negated acquisition for n points
 int eval_neg_acq(ibo_model* m, const double* Xs, long n, int acq, double ymax, double parm, int flags, double* y) {
     ScoreReq rq{acq, ymax, parm, flags, true, false, false};
+    rq.want_argmax = false;      // DIRECT consumes every value; the argmax kernels would be wasted launches
     int rc = score_host(m, Xs, n, rq, y, nullptr, nullptr, nullptr, nullptr);
     if (rc) return rc;
     for (long i = 0; i < n; i++) y[i] = -y[i];
