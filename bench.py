@@ -273,6 +273,21 @@ def run_suite(args):
             best = min(best, time.perf_counter() - t0)
             del g
         emit({"suite": "model_build", "N": N, "d": 6, "wall_ms": 1e3 * best, "gflop": 2 * N ** 3 / 3 / 1e9})
+    # ---- addData on a resident model: device rank-1 append (ibo_model_append) vs rebuilding the factor ----
+    for N in (2048, 8192):
+        Xb, Yb = synthetic_model(N + 32, 6)
+        g = GaussianProcess(GaussianKernel_ard(THETA), Xb[:N], Yb[:N], noise=NOISE)
+        g.model
+        g.addData(Xb[N], Yb[N])                      # warm the append kernels
+        t0 = time.perf_counter()
+        for i in range(N + 1, N + 32):
+            g.addData(Xb[i], Yb[i])
+        t_app = (time.perf_counter() - t0) / 31
+        t0 = time.perf_counter()
+        g._invalidate(); g.model
+        t_reb = time.perf_counter() - t0
+        emit({"suite": "addData_append", "N": N, "d": 6, "append_ms_per_point": 1e3 * t_app, "rebuild_ms": 1e3 * t_reb})
+        del g
     # ---- maximizeEI at the headline model size (N=2048, d=6), default budget ----
     Xb, Yb = synthetic_model(2048, 6)
     gp = GaussianProcess(GaussianKernel_ard(THETA), Xb, Yb, noise=NOISE)

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libibo_b200.so")
 # every symbol include/ibo_b200.h declares (checked by tests/test_abi.py)
 EXPORTED = [
     "ibo_last_error", "ibo_version", "ibo_device_count",
-    "ibo_model_create", "ibo_model_create_from_inverse", "ibo_model_destroy", "ibo_model_n", "ibo_model_dim",
+    "ibo_model_create", "ibo_model_create_from_inverse", "ibo_model_append", "ibo_model_destroy", "ibo_model_n", "ibo_model_dim",
     "ibo_model_get_matrix", "ibo_model_set_variance_model",
     "ibo_posterior_batch", "ibo_score_batch",
     "ibo_cands_create", "ibo_cands_destroy", "ibo_score_resident", "ibo_get_profile", "ibo_launch_count",
@@ -80,6 +80,7 @@ def lib():
     L.ibo_model_create_from_inverse.restype = c_int
     L.ibo_model_create_from_inverse.argtypes = [c_int, c_int, pd, c_int, pd, pd, c_int, c_int, c_double, pd, c_double,
                                                 c_int, pd, pd, c_double, pd, pd, POINTER(c_void_p), pi]
+    L.ibo_model_append.argtypes = [c_void_p, pd, pd, c_int, pi]
     L.ibo_model_destroy.argtypes = [c_void_p]
     L.ibo_model_n.argtypes = [c_void_p]
     L.ibo_model_dim.argtypes = [c_void_p]
@@ -177,6 +178,21 @@ class Model(object):
     @property
     def handle(self):
         return self._h
+
+    def append(self, X, Y):
+        """rank-1 device append of observations (ibo_model_append); raises NotPositiveDefinite like a rebuild would"""
+        X = as_f64(X, 2)
+        Y = as_f64(Y, 1).reshape(-1)
+        if X.shape[1] != self.d or X.shape[0] != Y.shape[0]:
+            raise ValueError("appended X / Y have the wrong shape")
+        info = c_int(0)
+        rc = lib().ibo_model_append(self._h, dptr(X), dptr(Y), X.shape[0], ctypes.byref(info))
+        if rc == E_NOTSPD:       # the handle is unusable now
+            self.close()
+        check(rc, info.value)
+        self.X = np.r_[self.X, X]
+        self.Y = np.r_[self.Y, Y]
+        self.N = self.X.shape[0]
 
     def matrix(self, which):
         out = np.empty((self.N, self.N))

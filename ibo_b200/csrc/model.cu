@@ -466,6 +466,204 @@ __global__ void tri_matvec_kernel(const double* __restrict__ W, const double* __
     if (lane == 0) out[r] = s;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Rank-1 append of an observation (ego/gaussianprocess/__init__.py:300-308 with a one-row block):
+//   k = k(X, x_p), l = W k (= inv(L) k), lambda = sqrt(1 + noise - l.l),
+//   L <- [[L, 0], [l^T, lambda]],  W <- [[W, 0], [-(l^T W) / lambda, 1 / lambda]],  beta_p = W_p . Y
+// O(N^2) instead of the O(N^3) rebuild; the new row lands in the identity padding of the 128-row block, so the
+// scoring kernels see it without any re-layout (only row p's entries of the packed blobs are rewritten).
+// Workspace: x_new[d] | kvec[Np] | l[Np] | u[Np] | lambda, 1/lambda.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) append_kvec_kernel(double* __restrict__ Xt, const double* __restrict__ xnew, double* __restrict__ kvec,
+                                                          double* __restrict__ Aorig, int p, int Np, int d, int kind, double sf2, double noise) {
+    int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= Np) return;
+    double v = 0.0;
+    if (c < p) {
+        double r2 = 0;
+        for (int t = 0; t < d; t++) { double df = Xt[(size_t)c * d + t] - xnew[t]; r2 += df * df; }   // (min, max) order as build_A_kernel
+        v = cov_from_r2(kind, sf2, r2);
+    }
+    kvec[c] = v;
+    if (Aorig) {
+        if (c < p) { Aorig[(size_t)p * Np + c] = v; Aorig[(size_t)c * Np + p] = v; }
+        else if (c == p) Aorig[(size_t)p * Np + p] = 1.0 + noise;
+    }
+    if (c < d) Xt[(size_t)p * d + c] = xnew[c];
+}
+
+// u[c] = sum_{r=c}^{p-1} l[r] W[r][c]: 16 columns x 16 row lanes per CTA, lanes summed in a fixed order
+__global__ void __launch_bounds__(256) append_colsum_kernel(const double* __restrict__ W, const double* __restrict__ l, double* __restrict__ u,
+                                                            int p, int Np) {
+    __shared__ double red[16][17];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int c0 = blockIdx.x * 16, c = c0 + tx;
+    double acc = 0;
+    for (int r = c0 + ty; r < p; r += 16) acc = fma(l[r], W[(size_t)r * Np + c], acc);   // rows above the diagonal hold exact zeros
+    red[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && c < p) {
+        double s = 0;
+#pragma unroll
+        for (int t = 0; t < 16; t++) s += red[t][tx];
+        u[c] = s;
+    }
+}
+
+__device__ __forceinline__ double block_sum_256(double v, double* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) s += sh[w];
+    __syncthreads();
+    return s;
+}
+
+__global__ void __launch_bounds__(256) append_pivot_kernel(const double* __restrict__ l, double* __restrict__ lam, int* __restrict__ info,
+                                                           int p, double diag) {
+    __shared__ double sh[8];
+    double s = 0;
+    for (int r = threadIdx.x; r < p; r += 256) s = fma(l[r], l[r], s);
+    s = block_sum_256(s, sh);
+    if (threadIdx.x == 0) {
+        double piv = diag - s;
+        if (!(piv > 0.0)) { atomicCAS(info, 0, p + 1); piv = 1.0; }
+        double lm = sqrt(piv);
+        lam[0] = lm; lam[1] = 1.0 / lm;
+    }
+}
+
+__global__ void __launch_bounds__(256) append_write_kernel(double* __restrict__ A, double* __restrict__ W, double* __restrict__ Wpack,
+                                                           const double* __restrict__ l, const double* __restrict__ u,
+                                                           const double* __restrict__ lam, int p, int Np) {
+    int c = blockIdx.x * 256 + threadIdx.x;
+    if (c > p) return;
+    const double lm = lam[0], inv = lam[1];
+    const double a = c < p ? l[c] : lm;
+    const double w = c < p ? -u[c] * inv : inv;
+    A[(size_t)p * Np + c] = a;
+    W[(size_t)p * Np + c] = w;
+    const int i = p >> 7, r = p & 127;
+    Wpack[(wpack_base(i) + (c >> 4)) * (size_t)BLOB + blob_offset(r, c & 15)] = w;
+}
+
+// betaY[p] = W[p][:] . Y, beta1[p] = W[p][:] . 1 over the real rows c <= p
+__global__ void __launch_bounds__(256) append_beta_kernel(const double* __restrict__ W, const double* __restrict__ Y,
+                                                          double* __restrict__ betaY, double* __restrict__ beta1, int p, int Np) {
+    __shared__ double sh[8];
+    double sy = 0, s1 = 0;
+    for (int c = threadIdx.x; c <= p; c += 256) { double w = W[(size_t)p * Np + c]; sy = fma(w, Y[c], sy); s1 += w; }
+    sy = block_sum_256(sy, sh);
+    s1 = block_sum_256(s1, sh);
+    if (threadIdx.x == 0) { betaY[p] = sy; beta1[p] = s1; }
+}
+
+// Re-home the model in buffers of NpNew rows (a new 128-row block of identity padding).
+static int grow_model_rows(ibo_model* m, int NpNew) {
+    cudaStream_t st = m->stream;
+    const int Np = m->Np, nbNew = NpNew / TM, d = m->d;
+    double *nA = nullptr, *nW = nullptr, *nAo = nullptr, *nXt = nullptr, *nD = nullptr, *nWp = nullptr, *nBY = nullptr, *nB1 = nullptr, *nY = nullptr;
+    double** fresh[] = {&nA, &nW, &nAo, &nXt, &nD, &nWp, &nBY, &nB1, &nY};
+    auto fail = [&](cudaError_t e, const char* what) {
+        set_error(std::string(what) + ": " + cudaGetErrorString(e)); cudaGetLastError();
+        for (auto q : fresh) if (*q) pool_free(*q);
+        return e == cudaErrorMemoryAllocation ? IBO_E_NOMEM : IBO_E_CUDA;
+    };
+#define TRYG(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return fail(e__, #expr); } while (0)
+    const size_t sq = (size_t)NpNew * NpNew;
+    const bool keepAo = m->dAorig && NpNew <= 4096;
+    TRYG(pool_malloc((void**)&nA, sizeof(double) * sq));
+    TRYG(pool_malloc((void**)&nW, sizeof(double) * sq));
+    if (keepAo) TRYG(pool_malloc((void**)&nAo, sizeof(double) * sq));
+    TRYG(pool_malloc((void**)&nXt, sizeof(double) * (size_t)NpNew * d));
+    TRYG(pool_malloc((void**)&nD, sizeof(double) * (size_t)nbNew * 128 * 128));
+    TRYG(pool_malloc((void**)&nWp, sizeof(double) * wpack_base(nbNew) * BLOB));
+    TRYG(pool_malloc((void**)&nBY, sizeof(double) * NpNew));
+    TRYG(pool_malloc((void**)&nB1, sizeof(double) * NpNew));
+    TRYG(pool_malloc((void**)&nY, sizeof(double) * NpNew));
+    dim3 g2((NpNew + 255) / 256, NpNew);
+    set_identity_kernel<<<g2, 256, 0, st>>>(nA, NpNew);
+    set_identity_kernel<<<g2, 256, 0, st>>>(nW, NpNew);
+    g_launches += 2;
+    const size_t rowB = sizeof(double) * Np, rowBn = sizeof(double) * NpNew;
+    TRYG(cudaMemcpy2DAsync(nA, rowBn, m->dA, rowB, rowB, Np, cudaMemcpyDeviceToDevice, st));
+    TRYG(cudaMemcpy2DAsync(nW, rowBn, m->dW, rowB, rowB, Np, cudaMemcpyDeviceToDevice, st));
+    if (keepAo) {
+        set_identity_kernel<<<g2, 256, 0, st>>>(nAo, NpNew);
+        g_launches++;
+        TRYG(cudaMemcpy2DAsync(nAo, rowBn, m->dAorig, rowB, rowB, Np, cudaMemcpyDeviceToDevice, st));
+    }
+    TRYG(cudaMemsetAsync(nXt, 0, sizeof(double) * (size_t)NpNew * d, st));
+    TRYG(cudaMemcpyAsync(nXt, m->dXt, sizeof(double) * (size_t)Np * d, cudaMemcpyDeviceToDevice, st));
+    TRYG(cudaMemsetAsync(nD, 0, sizeof(double) * (size_t)nbNew * 128 * 128, st));
+    TRYG(cudaMemcpyAsync(nD, m->dD, sizeof(double) * (size_t)m->nb * 128 * 128, cudaMemcpyDeviceToDevice, st));
+    double* vecs[3][2] = {{nBY, m->dBetaY}, {nB1, m->dBeta1}, {nY, m->dY}};
+    for (auto& v : vecs) {
+        TRYG(cudaMemsetAsync(v[0], 0, sizeof(double) * NpNew, st));
+        TRYG(cudaMemcpyAsync(v[0], v[1], sizeof(double) * Np, cudaMemcpyDeviceToDevice, st));
+    }
+    pack_w_kernel<<<dim3(nbNew * KB_PER_BLOCK, nbNew), 256, 0, st>>>(nW, nWp, NpNew, nbNew);
+    g_launches++;
+    TRYG(cudaStreamSynchronize(st));      // the old blocks go back to the pool: nothing may still read them
+    TRYG(cudaGetLastError());
+#undef TRYG
+    double** old[] = {&m->dA, &m->dW, &m->dAorig, &m->dXt, &m->dD, &m->dWpack, &m->dBetaY, &m->dBeta1, &m->dY};
+    double* repl[] = {nA, nW, nAo, nXt, nD, nWp, nBY, nB1, nY};
+    for (int q = 0; q < 9; q++) { if (*old[q]) pool_free(*old[q]); *old[q] = repl[q]; }
+    m->Np = NpNew; m->nb = nbNew;
+    return IBO_OK;
+}
+
+int append_rows(ibo_model* m, const double* X, const double* Y, int k, int* info) {
+    const int d = m->d;
+    IBO_CUDA_TRY(cudaSetDevice(m->device));
+    cudaStream_t st = m->stream;
+    if (m->N + k > m->Np) {
+        int rc = grow_model_rows(m, ((m->N + k + TM - 1) / TM) * TM);
+        if (rc) return rc;
+    }
+    const int Np = m->Np;
+    int rc = grow(&m->dAppend, &m->appendCap, (size_t)k * d + 3 * (size_t)Np + 2);
+    if (rc) return rc;
+    double* dXn = m->dAppend;
+    double* kvec = dXn + (size_t)k * d;
+    double* lvec = kvec + Np;
+    double* uvec = lvec + Np;
+    double* lam = uvec + Np;
+    std::vector<double> xs((size_t)k * d);
+    for (int j = 0; j < k; j++)
+        for (int t = 0; t < d; t++) xs[(size_t)j * d + t] = X[(size_t)j * d + t] * m->hInvTheta[t] - m->hCenter[t];
+    IBO_CUDA_TRY(cudaMemsetAsync(m->dInfo, 0, sizeof(int), st));
+    IBO_CUDA_TRY(cudaMemcpyAsync(dXn, xs.data(), sizeof(double) * xs.size(), cudaMemcpyHostToDevice, st));
+    IBO_CUDA_TRY(cudaMemcpyAsync(m->dY + m->N, Y, sizeof(double) * k, cudaMemcpyHostToDevice, st));
+    const int nblk = (Np + 255) / 256;
+    for (int j = 0; j < k; j++) {
+        const int p = m->N + j;
+        append_kvec_kernel<<<nblk, 256, 0, st>>>(m->dXt, dXn + (size_t)j * d, kvec, m->dAorig, p, Np, d, m->kind, m->sf2, m->noise);
+        tri_matvec_kernel<<<(Np + 7) / 8, 256, 0, st>>>(m->dW, kvec, lvec, Np);      // l = W k (rows >= p: identity x 0)
+        append_pivot_kernel<<<1, 256, 0, st>>>(lvec, lam, m->dInfo, p, 1.0 + m->noise);
+        if (p > 0) append_colsum_kernel<<<(p + 15) / 16, 256, 0, st>>>(m->dW, lvec, uvec, p, Np);
+        append_write_kernel<<<(p + 256) / 256, 256, 0, st>>>(m->dA, m->dW, m->dWpack, lvec, uvec, lam, p, Np);
+        append_beta_kernel<<<1, 256, 0, st>>>(m->dW, m->dY, m->dBetaY, m->dBeta1, p, Np);
+        g_launches += p > 0 ? 6 : 5;
+    }
+    int hinfo = 0;
+    IBO_CUDA_TRY(cudaMemcpyAsync(&hinfo, m->dInfo, sizeof(int), cudaMemcpyDeviceToHost, st));
+    IBO_CUDA_TRY(cudaStreamSynchronize(st));
+    IBO_CUDA_TRY(cudaGetLastError());
+    m->N += k;
+    if (info) *info = hinfo;
+    if (hinfo != 0) {
+        set_error("appended matrix is not positive definite (pivot " + std::to_string(hinfo) + "); the model is no longer valid");
+        return IBO_E_NOTSPD;
+    }
+    return IBO_OK;
+}
+
 static bool g_attr_done = false;
 static std::mutex g_attr_mu;
 static int set_kernel_attrs() {
@@ -563,7 +761,7 @@ static void free_model(ibo_model* m) {
     if (m->stream2) cudaStreamSynchronize(m->stream2);
     if (m->stream) cudaStreamSynchronize(m->stream);   // blocks go back to the pool: nothing may still be using them
     double** ptrs[] = {&m->dXt, &m->dInvTheta, &m->dCenter, &m->dA, &m->dAorig, &m->dW, &m->dD, &m->dWpack, &m->dBetaY, &m->dBeta1, &m->dY,
-                       &m->dPmeans, &m->dPbeta, &m->dPlb, &m->dPwidth, &m->dCand, &m->dSlab, &m->dPart, &m->dOut, &m->dBlkBest, &m->dBest};
+                       &m->dPmeans, &m->dPbeta, &m->dPlb, &m->dPwidth, &m->dCand, &m->dSlab, &m->dPart, &m->dOut, &m->dBlkBest, &m->dBest, &m->dAppend};
     for (auto p : ptrs) if (*p) { pool_free(*p); *p = nullptr; }
     if (m->dInfo) cudaFree(m->dInfo);
     if (m->dBlkIdx) cudaFree(m->dBlkIdx);
@@ -650,6 +848,7 @@ static int create_common(int device, int kind, const double* hyper, int nhyper, 
         for (int j = 0; j < d; j++) xt[(size_t)i * d + j] = X[(size_t)i * d + j] * it[j] - ctr[j];
         yp[i] = Y[i]; ones[i] = 1.0;
     }
+    m->hInvTheta = it; m->hCenter = ctr; m->has_cinv = (Cinv != nullptr);
     TRYM(cudaMemcpyAsync(m->dXt, xt.data(), sizeof(double) * xt.size(), cudaMemcpyHostToDevice, st));
     TRYM(cudaMemcpyAsync(m->dInvTheta, it.data(), sizeof(double) * d, cudaMemcpyHostToDevice, st));
     TRYM(cudaMemcpyAsync(m->dCenter, ctr.data(), sizeof(double) * d, cudaMemcpyHostToDevice, st));
@@ -724,6 +923,16 @@ extern "C" int ibo_model_create_from_inverse(int device, int kerneltype, const d
     if (!invR) { set_error("invR is NULL"); return IBO_E_BADARG; }
     return create_common(device, kerneltype, hyper, nhyper, X, Y, N, d, noise, nullptr, invR, sf2, true,
                          npbases, pmeans, pbeta, ptheta, plowerb, pwidth, out, info);
+}
+
+extern "C" int ibo_model_append(ibo_model* m, const double* X, const double* Y, int k, int* info) {
+    if (info) *info = 0;
+    if (!m || !X || !Y || k < 1) { set_error("bad argument"); return IBO_E_BADARG; }
+    if (m->cpp_prior || m->has_cinv || m->var_model) {
+        set_error("append needs a plain R model (no explicit inverse, no Laplace term, no variance model)");
+        return IBO_E_BADARG;
+    }
+    return ibo::append_rows(m, X, Y, k, info);
 }
 
 extern "C" int ibo_model_destroy(ibo_model* m) { free_model(m); return IBO_OK; }

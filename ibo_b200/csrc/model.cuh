@@ -14,6 +14,9 @@ struct ibo_model {
     int Np = 0;          // nb * 128 (identity padded)
     double noise = 0, sf2 = 1;
     bool cpp_prior = false;
+    bool has_cinv = false;            // A = R + inv(C): no rank-1 append
+    std::vector<double> hInvTheta, hCenter;   // host copies (append scales new points the same way)
+    double* dAppend = nullptr; size_t appendCap = 0;   // append workspace: [x_new (d) | kvec (Np) | l (Np) | u (Np) | lambda]
     // device arrays
     double* dXt = nullptr;      // scaled training inputs x/theta, [Np][d], rows >= N are zero
     double* dInvTheta = nullptr;// [d]

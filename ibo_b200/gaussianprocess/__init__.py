@@ -49,6 +49,9 @@ def PDF(x):
 
 class GaussianProcess(object):
 
+    append_above = 256       # addData appends on the device when the resident model has at least this many points ...
+    append_max_rows = 64     # ... and at most this many rows arrive at once (beyond that a rebuild is cheaper)
+
     def __init__(self, kernel, X=None, Y=None, prior=None, noise=.1, gnoise=1e-4, G=None, device=0):
         """
         @param kernel:  kernel object (ibo_b200.gaussianprocess.kernel)
@@ -168,11 +171,23 @@ class GaussianProcess(object):
             self.gnoise = np.tile(self.gnoise, X.shape[1])
         if len(self.X) == 0:
             self.X, self.Y = X.copy(), Y.copy()
-        else:
-            self.X = np.r_[self.X, X]
-            self.Y = np.r_[self.Y, Y]
-        # the factor of the enlarged matrix has the old factor as its leading block, so rebuilding on the
-        # device is the block append of :300-308 carried out blockwise there
+            self._invalidate()
+            return
+        nold = len(self.X)
+        self.X = np.r_[self.X, X]
+        self.Y = np.r_[self.Y, Y]
+        # The factor of the enlarged matrix has the old factor as its leading block (:300-308).  Large resident
+        # models get the new rows appended on the device (O(N^2) per point, ibo_model_append); small ones are simply
+        # rebuilt (sub-millisecond, and a rebuilt model is a pure function of (X, Y), which keeps the reference's
+        # sequential == batch training property, ego/unittest_GP.py:109-156, exact).
+        if (self._model is not None and self._Cinv is None and self._augmodel is None and self.augX is None
+                and nold >= self.append_above and len(X) <= self.append_max_rows):
+            try:
+                self._model.append(X, Y)
+                return
+            except np.linalg.LinAlgError:
+                self._invalidate()
+                raise
         self._invalidate()
 
     def getYfromX(self, qx):

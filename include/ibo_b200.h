@@ -9,7 +9,7 @@
  *
  *   acqmaxGP      replaces  cpp/optimizeGP.cpp:262-349 (bound by ego/acquisition/__init__.py:343-436)
  *   direct        replaces  cpp/direct.cpp:329-581, cpp/direct.h:57 (bound by ego/utils/optimize.py:310-343)
- *   ibo_model_*   replaces  GaussianProcess._computeCorrelations/addData
+ *   ibo_model_*   replaces  GaussianProcess._computeCorrelations/addData (ibo_model_append: the block append)
  *                           (ego/gaussianprocess/__init__.py:134-149,267-308), the Laplace
  *                           L = chol(R + inv(C)) of PrefGaussianProcess (:487-498), and the explicit
  *                           inv(R) of cdirectGP (ego/acquisition/__init__.py:385-388)
@@ -88,6 +88,12 @@ int ibo_model_create_from_inverse(int device, int kerneltype, const double* hype
                                   const double* plowerb, const double* pwidth,
                                   ibo_model** out, int* info);
 
+/* Rank-1 append of k observations (X: k x d row-major, Y[k]) to a plain model (no Cinv, not from_inverse, no variance
+ * model): the block append of GaussianProcess.addData (ego/gaussianprocess/__init__.py:300-308) one row at a time on
+ * the device -- l = W k, lambda = sqrt(1+noise - l.l), new rows of L and W = inv(L), beta -- O(k N^2) instead of the
+ * O(N^3) rebuild; buffers are re-homed when N crosses a multiple of 128.  On IBO_E_NOTSPD (*info = 1-based pivot)
+ * the model is no longer valid and must be destroyed. */
+int ibo_model_append(ibo_model* m, const double* X, const double* Y, int k, int* info);
 int ibo_model_destroy(ibo_model* m);
 int ibo_model_n(const ibo_model* m);
 int ibo_model_dim(const ibo_model* m);

@@ -188,6 +188,20 @@ class GPOracle(object):
         self.augL = None
         self.augX = None
 
+    def add_data(self, X, Y):
+        """Block append of gaussianprocess/__init__.py:300-308: R grows by [m; r], L by [z^T, chol(r - z^T z)]."""
+        X = np.array(X, dtype=float, ndmin=2)
+        Y = np.array(Y, dtype=float, ndmin=1).flatten()
+        r = build_R(self.kernel, X, self.noise)
+        m = self.kernel.cross(self.X, X)     # same vectorised arithmetic as build_R, so R stays exactly what a batch build gives
+        self.R = np.r_[np.c_[self.R, m], np.c_[m.T, r]]
+        z = np.linalg.solve(self.L, m)
+        dd = np.linalg.cholesky(r - np.dot(z.T, z))
+        self.L = np.r_[np.c_[self.L, np.zeros(z.shape)], np.c_[z.T, dd]]
+        self.A = self.R
+        self.X = np.r_[self.X, X]
+        self.Y = np.r_[self.Y, Y]
+
     # -- NumPy path ---------------------------------------------------------------------------
     def posterior_scalar(self, x):
         """Scalar-faithful gaussianprocess/__init__.py:169-228: two *general* linalg.solve against L."""

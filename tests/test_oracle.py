@@ -171,3 +171,17 @@ def test_live_reference_random_model():
     ei = orc.score(orc.ACQ_EI, "cpp", mu_o, s2_o, Y.max(), 0.01)
     assert rel(-ei, v, 1e-5) < 1e-10
     assert np.argmax(ei) == np.argmin(v)
+
+
+def test_oracle_block_append_equals_batch_build():
+    """ego/gaussianprocess/__init__.py:300-308 restated in GPOracle.add_data: same R (exactly) and same L (rounding)
+    as building from all the data at once -- the property ego/unittest_GP.py:109-156 checks"""
+    rs = np.random.RandomState(0)
+    X = rs.rand(30, 3); Y = rs.randn(30)
+    spec = orc.KernelSpec(orc.K_SE_ARD, [.3, .4, .5], 3)
+    o = orc.GPOracle(spec, X[:20], Y[:20], 0.1)
+    o.add_data(X[20:25], Y[20:25]); o.add_data(X[25], Y[25]); o.add_data(X[26:], Y[26:])
+    f = orc.GPOracle(spec, X, Y, 0.1)
+    assert np.array_equal(o.R, f.R) and np.max(np.abs(o.L - f.L)) < 1e-14
+    q = rs.rand(5, 3)
+    assert np.allclose(o.posterior_batch(q)[0], f.posterior_batch(q)[0], rtol=1e-12)
