@@ -56,6 +56,68 @@ def synthetic_candidates(M, d, rank):
     return np.ascontiguousarray(np.random.RandomState(1 + rank).rand(M, d))
 
 
+def sobol_block(d, start, n):
+    """rows [start, start+n) of the unscrambled Sobol sequence in d dimensions (config #4's candidate set)"""
+    import warnings
+    from scipy.stats import qmc
+    eng = qmc.Sobol(d=d, scramble=False)
+    if start:
+        eng.fast_forward(start)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")          # "n is not a power of 2": shards and CPU samples are index ranges on purpose
+        return np.ascontiguousarray(eng.random(n))
+
+
+class Workload(object):
+    """the two bench lines: BASELINE.json configs[1] (default, weak scaling) and configs[3] (strong scaling)"""
+
+    def __init__(self, args, world):
+        self.id = args.workload
+        if self.id == 4:
+            self.N, self.d = 8192, 10
+            self.total = args.candidates if args.candidates else 1 << 24
+            self.M = self.total // world                   # strong scaling: the 16M Sobol points are sharded by index range
+            self.scaling = "strong"
+            self.theta = [0.5 + 0.05 * j for j in range(10)]
+            self.metric = "EI candidate evals/sec (N=8192, d=10, Matern-5/2 ARD, %d Sobol candidates sharded over the GPUs)" % self.total
+        else:
+            self.N, self.d = args.n_obs, args.dim
+            self.M = args.candidates if args.candidates else 1 << 20
+            self.total = self.M * world
+            self.scaling = "weak"
+            self.theta = THETA[:self.d]
+            self.metric = METRIC
+
+    def model_data(self):
+        if self.id == 4:
+            rs = np.random.RandomState(4)
+            X = rs.rand(self.N, self.d)
+            return X, np.sin(2 * X).sum(axis=1)
+        return synthetic_model(self.N, self.d)
+
+    def kernel(self):
+        from ibo_b200.gaussianprocess.kernel import GaussianKernel_ard, MaternKernel5_ard
+        return MaternKernel5_ard(self.theta + [1.0]) if self.id == 4 else GaussianKernel_ard(self.theta)
+
+    def candidates(self, rank):
+        if self.id == 4:
+            return sobol_block(self.d, rank * self.M, self.M)
+        return synthetic_candidates(self.M, self.d, rank)
+
+    def config(self):
+        if self.id == 4:
+            return {"workload": "config #4: GaussianProcess Matern-5/2 ARD d=10, N=8192 observations, EI xi=0.01 over %d unscrambled Sobol "
+                                "candidates sharded by index range (%d per GPU), NCCL argmax" % (self.total, self.M),
+                    "n_obs": self.N, "dim": self.d, "candidates_per_gpu": self.M, "arithmetic": "libm-erf / floor 1e-8 (libego) mode",
+                    "l2": "inputs larger than L2: each step streams the packed K* slab (N x M x 8 B = %.1f GB per GPU) besides W and "
+                          "the candidates" % (self.N * self.M * 8 / 1e9)}
+        return {"workload": "config #2: GaussianProcess SE-ARD d=%d, N=%d observations (Hartman6), EI xi=%.2f over %d uniform random "
+                            "candidates per GPU" % (self.d, self.N, XI, self.M),
+                "n_obs": self.N, "dim": self.d, "candidates_per_gpu": self.M, "arithmetic": "libm-erf / floor 1e-8 (libego) mode",
+                "l2": "inputs larger than L2: each step streams the packed K* slab (N x M x 8 B = %.1f GB) besides W and the candidates"
+                      % (self.N * self.M * 8 / 1e9)}
+
+
 def flops_per_candidate_k2(N):
     """algorithmic FP64 flops of the dominant kernel per candidate: TRSM N^2 + the two fused N-long
     reductions 4N (F(N,d) = N^2 + N(2d+8); the remaining N(2d+4) belong to K1)."""
@@ -151,59 +213,58 @@ def reference_evaluator():
     return "port", 1, run
 
 
-def reference_inputs(n_obs, d):
-    """model arrays in the layout cdirectGP hands to acqmaxGP (ego/acquisition/__init__.py:365-391)"""
+def reference_inputs(wl):
+    """model arrays in the layout cdirectGP hands to acqmaxGP (ego/acquisition/__init__.py:365-391).
+    The reference's C++ has no Matern-5/2 ARD kernel, so for config #4 its evaluator is timed with its
+    SE-ARD kernel on the same X, Y, theta: its cost -- N kernel values + two dense N x N mat-vecs per candidate
+    (cpp/optimizeGP.cpp:57-191) -- does not depend on the kernel."""
     from oracle import ibo_oracle as orc          # allowed here: cpu_baseline / --impl reference legs only
-    X, Y = synthetic_model(n_obs, d)
+    X, Y = wl.model_data()
     X = np.ascontiguousarray(X); Y = np.ascontiguousarray(Y)
-    gp = orc.GPOracle(orc.KernelSpec(orc.K_SE_ARD, THETA[:d], d), X, Y, NOISE)
-    return np.ascontiguousarray(gp.invR()), X, Y, np.ascontiguousarray(np.array(THETA[:d]))
+    gp = orc.GPOracle(orc.KernelSpec(orc.K_SE_ARD, wl.theta, wl.d), X, Y, NOISE)
+    return np.ascontiguousarray(gp.invR()), X, Y, np.ascontiguousarray(np.array(wl.theta))
 
 
-def cpu_baseline(n_obs, d, seconds=12.0):
+def cpu_baseline(wl, seconds=12.0):
     kind, cores, run = reference_evaluator()
-    invR, X, Y, hyper = reference_inputs(n_obs, d)
-    probe = synthetic_candidates(4 * cores, d, 0)
+    invR, X, Y, hyper = reference_inputs(wl)
+    probe = wl.candidates(0)[:4 * cores] if wl.id != 4 else sobol_block(wl.d, 0, 4 * cores)
     t, _ = run(invR, X, Y, hyper, probe)
     n = int(min(max(len(probe) * seconds / max(t, 1e-6), 4 * cores), 200000))
-    Xs = synthetic_candidates(n, d, 0)
+    Xs = synthetic_candidates(n, wl.d, 0) if wl.id != 4 else sobol_block(wl.d, 0, n)
     t, _ = run(invR, X, Y, hyper, Xs)
+    what = "reference cpp/optimizeGP.cpp GP_Maximizer::negei via oracle/_ref" if kind == "reference" else "oracle/oracle_port.c"
+    if wl.id == 4:
+        what += "; SE-ARD kernel, the reference has no Matern-5/2 ARD"
     return {"value": n / t, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": "%d of the workload's candidates, %.1f s on %d host threads (%s)" % (
-                n, t, cores, "reference cpp/optimizeGP.cpp GP_Maximizer::negei via oracle/_ref" if kind == "reference" else "oracle/oracle_port.c")}
+            "sample": "%d of the workload's candidates, %.1f s on %d host threads (%s)" % (n, t, cores, what)}
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
+    wl = Workload(args, world)
     kind, cores, run = reference_evaluator()
-    invR, X, Y, hyper = reference_inputs(args.n_obs, args.dim)
-    probe = synthetic_candidates(4 * cores, args.dim, 0)
+    invR, X, Y, hyper = reference_inputs(wl)
+    gen = (lambda n: sobol_block(wl.d, 0, n)) if wl.id == 4 else (lambda n: synthetic_candidates(n, wl.d, 0))
+    probe = gen(4 * cores)
     t, _ = run(invR, X, Y, hyper, probe)
     per_step = int(min(max(len(probe) * 4.0 / max(t, 1e-6), 4 * cores), 100000))      # ~4 s of CPU work per step
-    Xs = synthetic_candidates(per_step, args.dim, 0)
+    Xs = gen(per_step)
     for _ in range(args.warmup):
         run(invR, X, Y, hyper, Xs[: max(4 * cores, per_step // 8)])
     times = [run(invR, X, Y, hyper, Xs)[0] for _ in range(args.steps)]
     tt = float(np.sum(times))
     value = per_step * args.steps / tt
     sample = "each step = %d candidates of the workload on %d host threads" % (per_step, cores)
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * tt / args.steps, "higher_is_better": True, "scaling": "weak",
+    line = {"impl": "reference", "metric": wl.metric, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * tt / args.steps, "higher_is_better": True, "scaling": wl.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, args.candidates),
+            "config": wl.config(),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
-
-
-def workload_config(args, M):
-    return {"workload": "config #2: GaussianProcess SE-ARD d=%d, N=%d observations (Hartman6), EI xi=%.2f over %d uniform random "
-                        "candidates per GPU" % (args.dim, args.n_obs, XI, M),
-            "n_obs": args.n_obs, "dim": args.dim, "candidates_per_gpu": M, "arithmetic": "libm-erf / floor 1e-8 (libego) mode",
-            "l2": "inputs larger than L2: each step streams the packed K* slab (N x M x 8 B = %.1f GB) besides W and the candidates"
-                  % (args.n_obs * M * 8 / 1e9)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -365,13 +426,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-obs", type=int, default=2048)
     ap.add_argument("--dim", type=int, default=6)
-    ap.add_argument("--candidates", type=int, default=1 << 20)
+    ap.add_argument("--candidates", type=int, default=0, help="per GPU for the default workload (2^20), total for --workload 4 (2^24)")
+    ap.add_argument("--workload", type=int, default=2, choices=[2, 4],
+                    help="2: BASELINE configs[1] (default, the metric's config); 4: configs[3], N=8192 Matern-5/2 ARD, 16M Sobol, strong scaling")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--suite", action="store_true", help="extra measurements (maximizeEI wall ms, model build, configs #1/#4/#5)")
     args = ap.parse_args()
     if args.suite:
         return run_suite(args)
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    args.warmup = max(args.warmup, 3) if (args.impl == "ours" and args.workload == 2) else max(args.warmup, 1 if args.impl == "ours" else 0)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -380,7 +443,6 @@ def main():
 
     from ibo_b200 import _lib
     from ibo_b200.gaussianprocess import GaussianProcess
-    from ibo_b200.gaussianprocess.kernel import GaussianKernel_ard
     L = _lib.lib()
     ndev = _lib.require_gpu()
     device = local % ndev
@@ -397,14 +459,15 @@ def main():
         dist.broadcast_object_list(uid, src=0)
         _lib.check(L.ibo_comm_init(device, rank, world, uid[0]))
 
-    N, d, M = args.n_obs, args.dim, args.candidates
-    X, Y = synthetic_model(N, d)
+    wl = Workload(args, world)
+    N, d, M = wl.N, wl.d, wl.M
+    X, Y = wl.model_data()
     t0 = time.perf_counter()
-    gp = GaussianProcess(GaussianKernel_ard(THETA[:d]), X, Y, noise=NOISE, device=device)
+    gp = GaussianProcess(wl.kernel(), X, Y, noise=NOISE, device=device)
     model = gp.model                                   # builds R, Cholesky, W = inv(L), packing on the device
     t_factor = time.perf_counter() - t0
     ymax = float(np.max(Y))
-    Xs = synthetic_candidates(M, d, rank)
+    Xs = wl.candidates(rank)
     cands = _lib.ResidentCandidates(model, Xs)
     flags = _lib.FLAG_MODE_CPP
 
@@ -443,7 +506,7 @@ def main():
 
     # ---- dominant kernel (K2) timing from CUDA events on the launching stream, same workload ----
     k2 = []
-    for _ in range(max(2, min(args.steps, 3))):
+    for _ in range(max(2, min(args.steps, 3)) if wl.id == 2 else 1):
         cands.score(_lib.ACQ_EI, ymax, XI, flags | _lib.FLAG_PROFILE)
         k2.append(model.profile())
     prof = min(k2, key=lambda p: p["k2_ms"])
@@ -454,11 +517,11 @@ def main():
     out = np.empty(M)
     L.ibo_host_register(Xs.ctypes.data_as(ctypes.c_void_p), Xs.nbytes)
     L.ibo_host_register(out.ctypes.data_as(ctypes.c_void_p), out.nbytes)
-    for _ in range(2):
+    for _ in range(2 if wl.id == 2 else 1):
         gp.score_batch(Xs, 'ei', xi=XI, mode='cpp', out=out)
     sync_all()
     te0 = time.perf_counter()
-    n_e2e = max(2, min(args.steps, 5))
+    n_e2e = max(2, min(args.steps, 5)) if wl.id == 2 else max(1, min(args.steps, 2))
     for _ in range(n_e2e):
         sc, b, bi = gp.score_batch(Xs, 'ei', xi=XI, mode='cpp', out=out)
         gidx = ctypes.c_long(rank * M + bi); scv = c_double(b)
@@ -492,9 +555,9 @@ def main():
     except Exception:
         pass
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * t_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": workload_config(args, M),
+        "metric": wl.metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_step, "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": wl.config(),
         "clocks": clocks,
         "e2e": {"value": world * M / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(Xs.nbytes), "d2h_bytes_per_step": int(out.nbytes + 16),
                 "api": "GaussianProcess.score_batch -> ibo_score_batch (host buffers, pinned)"},
@@ -509,7 +572,8 @@ def main():
         "model_build_s": t_factor, "best": {"ei": best[0], "index": best[1]},
     }
     # ---- the "maximizeEI wall ms" half of the metric (this rank's GPU; DIRECT is latency bound and is not sharded) ----
-    if rank == 0:
+    if rank == 0 and wl.id == 2:
+        from ibo_b200.gaussianprocess.kernel import GaussianKernel_ard
         from ibo_b200.acquisition import cdirectGP, maximizeEI
         from ibo_b200.utils.latinhypercube import lhcSample
         ts = []
@@ -533,7 +597,7 @@ def main():
         line["maximizeEI_wall_ms"] = mx
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(N, d)
+            line["cpu_baseline"] = cpu_baseline(wl)
         print(json.dumps(line))
     if dist is not None:
         L.ibo_comm_destroy()

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libibo_b200.so")
 EXPORTED = [
     "ibo_last_error", "ibo_version", "ibo_device_count",
     "ibo_model_create", "ibo_model_create_from_inverse", "ibo_model_append", "ibo_model_destroy", "ibo_model_n", "ibo_model_dim",
-    "ibo_model_get_matrix", "ibo_model_set_variance_model",
+    "ibo_model_get_matrix", "ibo_model_set_variance_model", "ibo_pref_fit",
     "ibo_posterior_batch", "ibo_score_batch",
     "ibo_cands_create", "ibo_cands_destroy", "ibo_score_resident", "ibo_get_profile", "ibo_launch_count",
     "ibo_fp64_peak", "ibo_host_register", "ibo_host_unregister", "ibo_stream_mark", "ibo_stream_elapsed_ms",
@@ -86,6 +86,7 @@ def lib():
     L.ibo_model_dim.argtypes = [c_void_p]
     L.ibo_model_get_matrix.argtypes = [c_void_p, c_int, pd]
     L.ibo_model_set_variance_model.argtypes = [c_void_p, c_void_p]
+    L.ibo_pref_fit.argtypes = [c_void_p, c_int, pi, pi, pd, pd, c_int, c_double, pd, pd, pi]
     L.ibo_posterior_batch.argtypes = [c_void_p, pd, c_long, c_int, pd, pd]
     L.ibo_score_batch.argtypes = [c_void_p, pd, c_long, c_int, c_double, c_double, c_int, pd, pd, pd, pd, pl]
     L.ibo_cands_create.argtypes = [c_void_p, pd, c_long, POINTER(c_void_p)]
@@ -193,6 +194,20 @@ class Model(object):
         self.X = np.r_[self.X, X]
         self.Y = np.r_[self.Y, Y]
         self.N = self.X.shape[0]
+
+    def pref_fit(self, v, u, deg, start, maxit=100, gtol=1e-9):
+        """Laplace MAP latents of a preference model (ibo_pref_fit) -> (Y, S(Y), |grad|_inf, Newton iterations)"""
+        v = np.ascontiguousarray(v, dtype=np.int32)
+        u = np.ascontiguousarray(u, dtype=np.int32)
+        deg = as_f64(deg, 1)
+        y = as_f64(start, 1).copy()
+        if y.shape[0] != self.N or len(v) != len(u) or len(v) != len(deg):
+            raise ValueError("preference arrays have the wrong shape")
+        S, g, it = c_double(0), c_double(0), c_int(0)
+        ip = lambda a: a.ctypes.data_as(POINTER(c_int))
+        check(lib().ibo_pref_fit(self._h, len(v), ip(v), ip(u), dptr(deg), dptr(y), int(maxit), float(gtol),
+                                 ctypes.byref(S), ctypes.byref(g), ctypes.byref(it)))
+        return y, S.value, g.value, it.value
 
     def matrix(self, which):
         out = np.empty((self.N, self.N))

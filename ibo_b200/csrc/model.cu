@@ -390,6 +390,33 @@ __device__ __forceinline__ void tile_gemm_core(const double* __restrict__ A, int
 
 enum { MODE_CHOL_PANEL = 0, MODE_CHOL_TRAIL = 1, MODE_TRTRI_SCALE = 2, MODE_TRTRI_UPDATE = 3 };
 
+// C_ij = [i == j] I + G_i G_j^T for the lower tiles j <= i; G is [Np][K] row-major (K a multiple of 16).
+// Used by the Laplace fit (laplace.cu): B = I + L^T Lambda L as a rank-P update.
+__global__ void __launch_bounds__(256, 1) syrk_identity_kernel(double* __restrict__ C, const double* __restrict__ G, int Np, int K) {
+    extern __shared__ double sm[];
+    const int i = blockIdx.y, j = blockIdx.x;
+    if (j > i) return;
+    double acc[8][4][2];
+#pragma unroll
+    for (int a = 0; a < 8; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+    tile_gemm_core<true>(G + (size_t)i * 128 * K, K, G + (size_t)j * 128 * K, K, K, acc, sm);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wm = warp >> 2, wn = warp & 3;
+    double* Ct = C + (size_t)i * 128 * Np + (size_t)j * 128;
+#pragma unroll
+    for (int mt = 0; mt < 8; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+            int r = wm * 64 + mt * 8 + (lane >> 2), c = wn * 32 + nt * 8 + 2 * (lane & 3);
+            double2 v;
+            v.x = acc[mt][nt][0] + ((i == j && r == c) ? 1.0 : 0.0);
+            v.y = acc[mt][nt][1] + ((i == j && r == c + 1) ? 1.0 : 0.0);
+            *reinterpret_cast<double2*>(Ct + (size_t)r * Np + c) = v;
+        }
+}
+
+
 template <int MODE>
 __global__ void __launch_bounds__(256, 1) block_step_kernel(double* __restrict__ A, double* __restrict__ W,
                                                             const double* __restrict__ D, int Np, int k) {
@@ -500,7 +527,8 @@ __global__ void __launch_bounds__(256) append_colsum_kernel(const double* __rest
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int c0 = blockIdx.x * 16, c = c0 + tx;
     double acc = 0;
-    for (int r = c0 + ty; r < p; r += 16) acc = fma(l[r], W[(size_t)r * Np + c], acc);   // rows above the diagonal hold exact zeros
+    for (int r = c0 + ty; r < p; r += 16)
+        if (r >= c) acc = fma(l[r], W[(size_t)r * Np + c], acc);   // lower triangle only (dA keeps stale values above it)
     red[ty][tx] = acc;
     __syncthreads();
     if (ty == 0 && c < p) {
@@ -615,6 +643,9 @@ static int grow_model_rows(ibo_model* m, int NpNew) {
     double* repl[] = {nA, nW, nAo, nXt, nD, nWp, nBY, nB1, nY};
     for (int q = 0; q < 9; q++) { if (*old[q]) pool_free(*old[q]); *old[q] = repl[q]; }
     m->Np = NpNew; m->nb = nbNew;
+    for (auto& kv : m->unitTables) if (kv.second.first) cudaFree(kv.second.first);     // keyed on the old nb
+    m->unitTables.clear();
+    m->planCache.clear();
     return IBO_OK;
 }
 
@@ -674,6 +705,7 @@ static int set_kernel_attrs() {
     IBO_CUDA_TRY(cudaFuncSetAttribute(block_step_kernel<MODE_CHOL_TRAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem));
     IBO_CUDA_TRY(cudaFuncSetAttribute(block_step_kernel<MODE_TRTRI_SCALE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem));
     IBO_CUDA_TRY(cudaFuncSetAttribute(block_step_kernel<MODE_TRTRI_UPDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem));
+    IBO_CUDA_TRY(cudaFuncSetAttribute(syrk_identity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem));
     IBO_CUDA_TRY(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 * PS + 128 + 128 * 129 / 2) * 8));
     g_attr_done = true;
     return IBO_OK;
@@ -681,7 +713,7 @@ static int set_kernel_attrs() {
 
 // Factorise m->dA in place, produce dW, dD, dWpack, dBetaY, dBeta1.
 // from_inverse_reversed: dA holds J invR J; W' = reverse-transpose of its Cholesky factor.
-int launch_factorize(ibo_model* m, bool from_inverse_reversed) {
+int launch_factorize(ibo_model* m, bool from_inverse_reversed, bool pack) {
     int rc = set_kernel_attrs();
     if (rc) return rc;
     cudaStream_t st = m->stream;
@@ -730,10 +762,27 @@ int launch_factorize(ibo_model* m, bool from_inverse_reversed) {
         IBO_CUDA_TRY(cudaEventRecord(m->evStep, s2));
         IBO_CUDA_TRY(cudaStreamWaitEvent(st, m->evStep, 0));
     }
-    pack_w_kernel<<<dim3(nb * KB_PER_BLOCK, nb), 256, 0, st>>>(m->dW, m->dWpack, Np, nb);
+    if (pack) { pack_w_kernel<<<dim3(nb * KB_PER_BLOCK, nb), 256, 0, st>>>(m->dW, m->dWpack, Np, nb); g_launches++; }
     tri_matvec_kernel<<<(Np + 7) / 8, 256, 0, st>>>(m->dW, m->dY, m->dBetaY, Np);
-    g_launches += 2;
+    g_launches++;
     IBO_CUDA_TRY(cudaGetLastError());
+    return IBO_OK;
+}
+
+// launch wrappers for the other translation units (laplace.cu)
+void launch_tri_matvec(const double* T, const double* v, double* out, int Np, cudaStream_t st) {
+    tri_matvec_kernel<<<(Np + 7) / 8, 256, 0, st>>>(T, v, out, Np);
+    g_launches++;
+}
+void launch_tri_matvec_t(const double* T, const double* v, double* out, int n, int Np, cudaStream_t st) {
+    append_colsum_kernel<<<(n + 15) / 16, 256, 0, st>>>(T, v, out, n, Np);      // out[c] = sum_{r >= c} v[r] T[r][c], c < n
+    g_launches++;
+}
+int launch_syrk_identity(double* C, const double* G, int Np, int K, cudaStream_t st) {
+    int rc = set_kernel_attrs();
+    if (rc) return rc;
+    syrk_identity_kernel<<<dim3(Np / 128, Np / 128), 256, TILE_SMEM_DOUBLES * 8, st>>>(C, G, Np, K);
+    g_launches++;
     return IBO_OK;
 }
 
@@ -766,6 +815,8 @@ static void free_model(ibo_model* m) {
     if (m->dInfo) cudaFree(m->dInfo);
     if (m->dBlkIdx) cudaFree(m->dBlkIdx);
     if (m->dBestIdx) cudaFree(m->dBestIdx);
+    for (auto& kv : m->unitTables) if (kv.second.first) cudaFree(kv.second.first);
+    m->unitTables.clear();
     if (m->hPinned) pinned_put(m->hPinned);
     for (auto& e : m->ev) if (e) cudaEventDestroy(e);
     if (m->evStep) cudaEventDestroy(m->evStep);
@@ -881,7 +932,7 @@ static int create_common(int device, int kind, const double* hyper, int nhyper, 
         TRYM(pool_malloc((void**)&m->dAorig, sizeof(double) * (size_t)Np * Np));
         TRYM(cudaMemcpyAsync(m->dAorig, m->dA, sizeof(double) * (size_t)Np * Np, cudaMemcpyDeviceToDevice, st));
     }
-    rc = launch_factorize(m, invR != nullptr);
+    rc = launch_factorize(m, invR != nullptr, true);
     if (rc) { if (dTmp) pool_free(dTmp); return fail(rc); }
     // beta1 = W 1 (prior-mean correction term)
     TRYM(cudaMemcpyAsync(m->dBeta1, ones.data(), sizeof(double) * Np, cudaMemcpyHostToDevice, st));

@@ -2,6 +2,8 @@
 #pragma once
 #include "common.cuh"
 #include "../../include/ibo_b200.h"
+#include <map>
+#include <utility>
 #include <vector>
 
 struct ibo_model {
@@ -47,6 +49,8 @@ struct ibo_model {
     double* dBlkBest = nullptr; long long* dBlkIdx = nullptr; size_t blkCap = 0;
     double* dBest = nullptr;  long long* dBestIdx = nullptr;      // final argmax
     double* hPinned = nullptr; size_t pinnedCap = 0;              // pinned staging for small batches
+    std::map<long, std::pair<int*, int>> unitTables;              // K2 work tables (device), keyed by shape and group count
+    std::map<long, std::pair<int, int>> planCache;                // K2 launch plan (MT, G) per number of 32-candidate CTA tiles
     // profile of the last call
     double prof[6] = {0, 0, 0, 0, 0, 0};
     cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -65,5 +69,9 @@ void pool_free(void* p);
 cudaError_t pinned_get(double** p);
 void pinned_put(double* p);
 // launches (all on m->stream)
-int launch_factorize(ibo_model* m, bool from_inverse_reversed);
+int launch_factorize(ibo_model* m, bool from_inverse_reversed, bool pack);
+void launch_tri_matvec(const double* T, const double* v, double* out, int Np, cudaStream_t st);              // out = T v, T lower [Np][Np]
+void launch_tri_matvec_t(const double* T, const double* v, double* out, int n, int Np, cudaStream_t st);     // out = T^T v over the leading n x n
+int launch_syrk_identity(double* C, const double* G, int Np, int K, cudaStream_t st);                        // C = I + G G^T (lower tiles)
+const char* get_error();
 }  // namespace ibo

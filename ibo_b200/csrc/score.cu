@@ -18,6 +18,8 @@
 #include <cmath>
 #include <algorithm>
 #include <mutex>
+#include <queue>
+#include <functional>
 #include <cstdlib>
 #include <cstring>
 
@@ -32,6 +34,14 @@ __device__ __forceinline__ double cov_r2(int kind, double sf2, double r2) {
     }
     double z = 2.23606797749979 * r;
     return sf2 * (1.0 + z + 5.0 * r2 / 3.0) * exp(-z);
+}
+
+// n-tiles (8 candidates) of tile T that hold at least one real candidate: the last tile of a small batch computes only
+// those (a 24-candidate DIRECT batch evaluates 3 of the 16 n-tiles); the rest of the slab tile keeps stale values that
+// only reach the partial sums of candidates >= M, which K3 never reads (candidate columns are independent in K2).
+__device__ __forceinline__ int valid_ntiles(long M, long m0, int T) {
+    long left = M - m0 - (long)T * 128;
+    return left >= 128 ? 16 : (int)((left + 7) >> 3);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -60,6 +70,7 @@ __global__ void __launch_bounds__(256) kstar_kernel(const double* __restrict__ X
     const int n8 = lane >> 2, k4 = lane & 3;
     double* blob = slab + ((size_t)T * (nb * KB_PER_BLOCK) + (size_t)i * KB_PER_BLOCK + w) * BLOB;
     const int rowbase = i * 128 + w * 16;
+    const int ntv = valid_ntiles(M, m0, T);
 #pragma unroll 1
     for (int ks2 = 0; ks2 < 2; ks2++) {
         const int ka = w * 16 + ks2 * 8 + k4, kb = ka + 4;
@@ -67,7 +78,7 @@ __global__ void __launch_bounds__(256) kstar_kernel(const double* __restrict__ X
         const double* xb = sX + kb * S;
         const bool va = (rowbase + ks2 * 8 + k4) < N, vb = (rowbase + ks2 * 8 + k4 + 4) < N;
 #pragma unroll 2
-        for (int nt = 0; nt < 16; nt++) {
+        for (int nt = 0; nt < ntv; nt++) {
             const double* c = sC + (nt * 8 + n8) * S;
             double ra = 0, rb = 0;
             for (int j = 0; j < d; j++) {
@@ -143,8 +154,9 @@ __global__ void __launch_bounds__(256) kstar_mma_kernel(const double* __restrict
         valid[ks2][0] = (rowbase + ks2 * 8 + k4) < N;
         valid[ks2][1] = (rowbase + ks2 * 8 + k4 + 4) < N;
     }
+    const int ntv = valid_ntiles(M, m0, T);
 #pragma unroll 2
-    for (int nt = 0; nt < 16; nt++) {
+    for (int nt = 0; nt < ntv; nt++) {
         double afr[DP4];
 #pragma unroll
         for (int s4 = 0; s4 < DP4; s4++) afr[s4] = sC[(nt * 8 + n8) * S + 4 * s4 + k4];
@@ -179,127 +191,155 @@ __global__ void __launch_bounds__(256) kstar_mma_kernel(const double* __restrict
 // K2: triangular GEMM + fused reduction.
 // ---------------------------------------------------------------------------------------------
 constexpr int K2_STAGES = 6;
-constexpr int K2_THREADS = 384;   // warpgroups 0,1: 8 DMMA warps (240 regs); warpgroup 2: bulk-copy producer (24 regs)
-constexpr int K2_SMEM = K2_STAGES * 2 * BLOB * 8 + 2 * 3 * 128 * 8 + 2 * K2_STAGES * 8;   // sized for NT = 4; NT = 1 uses less of sB
+constexpr int K2_THREADS = 384;   // warpgroups 0,1: 8 DMMA warps; warpgroup 2: bulk-copy producer
 
-__device__ __forceinline__ int group_of(int i, int nb, int G) {
-    int idx = nb - 1 - i, round = idx / G, pos = idx - round * G;
-    return (round & 1) ? (G - 1 - pos) : pos;
-}
+// NT = n-tiles (8 candidates each) per warp, MT = m-tiles (8 rows each) per warp: a CTA covers 16*MT rows x 32*NT candidates.
+//   <4, 8>  throughput shape: 128 rows x 128 candidates, 64 accumulators / thread (240 regs via setmaxnreg), 1 CTA / SM
+//   <1, MT> small batches (DIRECT, gallery): 32 candidates per CTA and, for MT < 8, a 16*MT-row slice ("sub-block") of a
+//           128-row block, so that a batch of a few dozen candidates still spreads over all SMs and the longest
+//           dependent DMMA chain, not a 128-row block, bounds the latency.
+// The work list of a CTA is a table built on the host (units[gstart[g] .. gstart[g+1]), unit = i * 8 + h: sub-block h of
+// row-block i).  Every accumulator runs over k in ascending order whatever the shape or the grouping, so V is bit-identical
+// across shapes; the row reduction is fixed per shape (results do not depend on the batch size, position or grouping
+// within a shape; across shapes they differ by the association of the row sums only).
+template <int NT, int MT> struct K2Cfg {
+    static constexpr int SUBS = 8 / MT;                      // sub-blocks per 128-row block
+    static constexpr int ADBL = MT * 2 * 128;                // doubles of one k-blob's A-operand slice: 2*MT m-tiles x 16 k
+    static constexpr int BDBL = NT * 4 * 128;                // doubles of one k-blob's B-operand slice: 4*NT n-tiles x 16 k
+    // A pipeline stage holds KS k-blobs: the small shapes would otherwise be bound by the bulk-copy round trip (a 6 KiB stage
+    // is consumed in ~150 ns, the copy takes ~1 us) and by the per-stage mbarrier handshake.
+    static constexpr int KS = (NT == 4 || MT == 8) ? 1 : (MT == 4 ? 2 : 4);
+    static constexpr int NS = (NT == 4 || MT == 8) ? K2_STAGES : (MT == 4 ? 4 : 3);
+    static constexpr int SMEM = NS * KS * (ADBL + BDBL) * 8 + 2 * 3 * 128 * 8 + 2 * NS * 8;
+    static constexpr int MINB = NT == 4 ? 1 : (MT == 8 ? 1 : (MT == 1 ? 3 : 2));
+    static constexpr bool REGSPLIT = (NT == 4);              // setmaxnreg warp specialisation only where registers are tight
+};
 
-// NT = n-tiles (8 candidates each) per warp: the CTA covers 128 rows x 32*NT candidates.  NT = 4 is the throughput
-// shape; NT = 1 serves small batches (DIRECT) where a quarter-width tile gives 4x the CTAs and a 4x shorter k-loop
-// per candidate.  Both shapes own rows and reduce them identically, so a candidate's result is bit-identical.
-template <int NT, bool P1>
-__global__ void __launch_bounds__(K2_THREADS, 1)
+template <int NT, int MT, bool P1>
+__global__ void __launch_bounds__(K2_THREADS, (K2Cfg<NT, MT>::MINB))
 trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab, const double* __restrict__ betaY,
-               const double* __restrict__ beta1, double* __restrict__ part, int nb, int G, long Mpad) {
+               const double* __restrict__ beta1, double* __restrict__ part, const int* __restrict__ units,
+               const int* __restrict__ gstart, int nb, long Mpad) {
+    using Cfg = K2Cfg<NT, MT>;
+    constexpr int ADBL = Cfg::ADBL, BDBL = Cfg::BDBL, SUBS = Cfg::SUBS, KS = Cfg::KS, NS = Cfg::NS;
     extern __shared__ __align__(128) unsigned char smraw[];
     double* sA = reinterpret_cast<double*>(smraw);
-    double* sB = sA + K2_STAGES * BLOB;
-    double* sRed = sB + K2_STAGES * BLOB;                       // [2][3][128]
+    double* sB = sA + NS * KS * ADBL;
+    double* sRed = sB + NS * KS * BDBL;                         // [2][3][128]
     uint64_t* full = reinterpret_cast<uint64_t*>(sRed + 2 * 3 * 128);
-    uint64_t* empty = full + K2_STAGES;
+    uint64_t* empty = full + NS;
     constexpr int SUB = 4 / NT;                 // CTAs per 128-candidate slab tile
-    constexpr int BBYTES = NT * 4 * 2 * 32 * 2 * 8;   // bytes of one B-operand stage: 4 warps x NT n-tiles x 16 k
     const int g = blockIdx.x;                   // group fastest: the G CTAs of one tile are co-resident and share its slab in L2
     const int T = blockIdx.y / SUB, sub = blockIdx.y % SUB;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int u0 = gstart[g], u1 = gstart[g + 1];
     if (tid == 0) {
-        for (int s = 0; s < K2_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
+        for (int s = 0; s < NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
         fence_barrier_init();
         fence_proxy_async();
     }
     __syncthreads();
     if (warp >= 8) {
         // ---------------- producer warpgroup: hands its registers to the DMMA warps ----------------
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        if (Cfg::REGSPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
         // one lane streams the operand blobs with bulk TMA
         if (warp == 8 && lane == 0) {
             int s = 0; uint32_t ph = 0;
-            const double* Bbase = slab + (size_t)T * (nb * KB_PER_BLOCK) * BLOB;
-            for (int i = nb - 1; i >= 0; --i) {
-                if (group_of(i, nb, G) != g) continue;
-                const double* Abase = Wpack + wpack_base(i) * BLOB;
-                const int nkb = (i + 1) * KB_PER_BLOCK;
-                for (int kb = 0; kb < nkb; ++kb) {
+            const double* Bbase = slab + (size_t)T * (nb * KB_PER_BLOCK) * BLOB + sub * BDBL;
+            for (int uu = u0; uu < u1; ++uu) {
+                const int i = units[uu] >> 3, h = units[uu] & 7;
+                // m-tiles are the slowest index of a blob: the sub-block's 2*MT m-tiles are one contiguous slice
+                const double* Abase = Wpack + wpack_base(i) * BLOB + h * ADBL;
+                const int nkb = i * KB_PER_BLOCK + (h + 1) * MT;     // k-blobs right of column 16 (h+1) MT of the diagonal block are zero
+                for (int kb = 0; kb < nkb; kb += KS) {
+                    const int nk = (KS == 1) ? 1 : min(KS, nkb - kb);
                     mbar_wait(&empty[s], ph ^ 1);
-                    mbar_arrive_expect_tx(&full[s], BLOB * 8 + BBYTES);
-                    bulk_g2s(sA + s * BLOB, Abase + (size_t)kb * BLOB, BLOB * 8, &full[s]);
-                    // n-tiles are the slowest index of a blob, so this CTA's 4*NT n-tiles are one contiguous slice
-                    bulk_g2s(sB + s * BLOB, Bbase + (size_t)kb * BLOB + sub * (BBYTES / 8), BBYTES, &full[s]);
-                    if (++s == K2_STAGES) { s = 0; ph ^= 1; }
+                    mbar_arrive_expect_tx(&full[s], nk * (ADBL + BDBL) * 8);
+#pragma unroll
+                    for (int kk = 0; kk < KS; kk++) {
+                        if (kk < nk) {
+                            bulk_g2s(sA + (s * KS + kk) * ADBL, Abase + (size_t)(kb + kk) * BLOB, ADBL * 8, &full[s]);
+                            // n-tiles are the slowest index of a blob, so this CTA's 4*NT n-tiles are one contiguous slice
+                            bulk_g2s(sB + (s * KS + kk) * BDBL, Bbase + (size_t)(kb + kk) * BLOB, BDBL * 8, &full[s]);
+                        }
+                    }
+                    if (++s == NS) { s = 0; ph ^= 1; }
                 }
             }
         }
         return;
     }
-    // ---------------- consumers: 8 warps, warp tile 64 (rows) x 32 (candidates) ----------------
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
+    // ---------------- consumers: 8 warps, warp tile 8*MT (rows) x 8*NT (candidates) ----------------
+    if (Cfg::REGSPLIT) asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
     const int wm = warp >> 2, wn = warp & 3;
     int s = 0; uint32_t ph = 0;
     int rbcount = 0;
-    for (int i = nb - 1; i >= 0; --i) {
-        if (group_of(i, nb, G) != g) continue;
-        double acc[8][NT][2];
+    for (int uu = u0; uu < u1; ++uu) {
+        const int i = units[uu] >> 3, h = units[uu] & 7;
+        double acc[MT][NT][2];
 #pragma unroll
-        for (int a = 0; a < 8; a++)
+        for (int a = 0; a < MT; a++)
 #pragma unroll
             for (int b = 0; b < NT; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
-        const int nkb = (i + 1) * KB_PER_BLOCK;
         const int nfull = i * KB_PER_BLOCK;     // k-blobs left of the diagonal block: dense
-        for (int kb = 0; kb < nkb; ++kb) {
+        const int nkb = nfull + (h + 1) * MT;
+        for (int kb0 = 0; kb0 < nkb; kb0 += KS) {
+            const int nk = (KS == 1) ? 1 : min(KS, nkb - kb0);
             mbar_wait(&full[s], ph);
-            // warp wm owns the interleaved m-tiles 2*mt + wm (mt = 0..7) so that the triangular skip below is balanced
-            const double2* a2 = reinterpret_cast<const double2*>(sA + s * BLOB) + (wm * 2) * 32 + lane;
-            const double2* b2 = reinterpret_cast<const double2*>(sB + s * BLOB) + (wn * NT * 2) * 32 + lane;
-            if (kb < nfull) {
+#pragma unroll 1
+            for (int kk = 0; kk < nk; kk++) {
+                const int kb = kb0 + kk;
+                // warp wm owns the interleaved m-tiles 2*mt + wm of the sub-block so that the triangular skip below is balanced
+                const double2* a2 = reinterpret_cast<const double2*>(sA + (s * KS + kk) * ADBL) + (wm * 2) * 32 + lane;
+                const double2* b2 = reinterpret_cast<const double2*>(sB + (s * KS + kk) * BDBL) + (wn * NT * 2) * 32 + lane;
+                if (kb < nfull) {
 #pragma unroll
-                for (int ks2 = 0; ks2 < 2; ks2++) {
-                    double2 af[8], bf[NT];
+                    for (int ks2 = 0; ks2 < 2; ks2++) {
+                        double2 af[MT], bf[NT];
 #pragma unroll
-                    for (int mt = 0; mt < 8; mt++) af[mt] = a2[(mt * 4 + ks2) * 32];
+                        for (int mt = 0; mt < MT; mt++) af[mt] = a2[(mt * 4 + ks2) * 32];
 #pragma unroll
-                    for (int nt = 0; nt < NT; nt++) bf[nt] = b2[(nt * 2 + ks2) * 32];
+                        for (int nt = 0; nt < NT; nt++) bf[nt] = b2[(nt * 2 + ks2) * 32];
 #pragma unroll
-                    for (int mt = 0; mt < 8; mt++)
+                        for (int mt = 0; mt < MT; mt++)
 #pragma unroll
-                        for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt].x, bf[nt].x);
+                            for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt].x, bf[nt].x);
 #pragma unroll
-                    for (int mt = 0; mt < 8; mt++)
+                        for (int mt = 0; mt < MT; mt++)
 #pragma unroll
-                        for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt].y, bf[nt].y);
-                }
-            } else {
-                // diagonal block of W (lower triangular): in its k-blob kbl the m-tiles 2*mt + wm with mt < kbl are
-                // identically zero (rows 8*(2mt+wm)+7 < 16*kbl) and are skipped
-                const int kbl = kb - nfull;
+                            for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt].y, bf[nt].y);
+                    }
+                } else {
+                    // diagonal block of W (lower triangular): in its k-blob kbl the m-tiles 2*(h*MT+mt) + wm with h*MT+mt < kbl
+                    // are identically zero (their rows end before column 16*kbl) and are skipped
+                    const int kbl = kb - nfull - h * MT;
 #pragma unroll
-                for (int ks2 = 0; ks2 < 2; ks2++) {
-                    double2 bf[NT];
+                    for (int ks2 = 0; ks2 < 2; ks2++) {
+                        double2 bf[NT];
 #pragma unroll
-                    for (int nt = 0; nt < NT; nt++) bf[nt] = b2[(nt * 2 + ks2) * 32];
+                        for (int nt = 0; nt < NT; nt++) bf[nt] = b2[(nt * 2 + ks2) * 32];
 #pragma unroll
-                    for (int mt = 0; mt < 8; mt++) {
-                        if (mt >= kbl) {
-                            const double2 af = a2[(mt * 4 + ks2) * 32];
+                        for (int mt = 0; mt < MT; mt++) {
+                            if (mt >= kbl) {
+                                const double2 af = a2[(mt * 4 + ks2) * 32];
 #pragma unroll
-                            for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af.x, bf[nt].x);
+                                for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af.x, bf[nt].x);
 #pragma unroll
-                            for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af.y, bf[nt].y);
+                                for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af.y, bf[nt].y);
+                            }
                         }
                     }
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
-            if (++s == K2_STAGES) { s = 0; ph ^= 1; }
+            if (++s == NS) { s = 0; ph ^= 1; }
         }
-        // ---- fused reduction of this 128 x 128 block of V over its rows ----
-        double by[8], b1[8];
+        // ---- fused reduction of this (16 MT) x (32 NT) block of V over its rows ----
+        double by[MT], b1[MT];
 #pragma unroll
-        for (int mt = 0; mt < 8; mt++) {
-            int r = i * 128 + (2 * mt + wm) * 8 + (lane >> 2);
+        for (int mt = 0; mt < MT; mt++) {
+            int r = i * 128 + (2 * (h * MT + mt) + wm) * 8 + (lane >> 2);
             by[mt] = betaY[r];
             b1[mt] = P1 ? beta1[r] : 0.0;
         }
@@ -310,7 +350,7 @@ trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab
             for (int j = 0; j < 2; j++) {
                 double sq = 0, sp = 0, s1 = 0;
 #pragma unroll
-                for (int mt = 0; mt < 8; mt++) {
+                for (int mt = 0; mt < MT; mt++) {
                     double v = acc[mt][nt][j];
                     sq = fma(v, v, sq);
                     sp = fma(v, by[mt], sp);
@@ -336,8 +376,8 @@ trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab
         }
         named_bar_sync(1, 256);
         if (wm == 0 && lane < 4) {
-            const size_t plane = (size_t)nb * Mpad;
-            double* dst = part + (size_t)i * Mpad + (size_t)T * 128 + sub * (32 * NT);
+            const size_t plane = (size_t)nb * SUBS * Mpad;
+            double* dst = part + (size_t)(i * SUBS + h) * Mpad + (size_t)T * 128 + sub * (32 * NT);
 #pragma unroll
             for (int nt = 0; nt < NT; nt++)
 #pragma unroll
@@ -356,11 +396,11 @@ trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab
 // K3: per-candidate epilogue.
 // ---------------------------------------------------------------------------------------------
 struct EpiParams {
-    int nb, d, N, acq, mode_py, npb, want_p1, want_argmax;
+    int nbPart, d, N, acq, mode_py, npb, want_p1, want_argmax, rowLanes;   // nbPart: rows of the partial-sum planes (nb * sub-blocks)
     long M, m0, chunkM, Mpad;
     double noise, ymax, parm, ptheta;
     const double *part, *partVar, *cand, *pmeans, *pbeta, *plb, *pwidth;
-    int nbVar; long MpadVar;
+    int nbVarPart; long MpadVar;
     double *score, *mu, *s2;
     double* blkBest; long long* blkIdx; long blk0;
 };
@@ -404,19 +444,54 @@ __device__ __forceinline__ double acq_value(int acq, int mode_py, double mu, dou
 }
 
 __global__ void __launch_bounds__(256) epilogue_kernel(EpiParams P) {
-    const long lm = (long)blockIdx.x * 256 + threadIdx.x;    // index within the chunk
+    // rowLanes = 1: one thread per candidate walks all partial rows (throughput shape: nb rows).
+    // rowLanes = 8 / 32: small batches, whose latency shapes of K2 leave up to 8 nb partial rows: 256 / rowLanes candidates
+    //               per block, rowLanes threads per candidate each sum every rowLanes-th row (loads batched four deep),
+    //               combined in a fixed order through shared memory.
+    __shared__ double shq[3][256];
+    const int RL = P.rowLanes, CPB = 256 / RL;                 // candidates per block
+    const int tl = threadIdx.x / CPB;                          // row lane
+    const int cl = threadIdx.x - tl * CPB;
+    const long lm = (long)blockIdx.x * CPB + cl;               // index within the chunk
     const long m = P.m0 + lm;
     double sc = -INFINITY;
     long long idx = 0x7fffffffffffffffLL;
-    if (lm < P.chunkM && m < P.M) {
-        const size_t plane = (size_t)P.nb * P.Mpad;
-        double q = 0, p = 0, p1 = 0;
-        for (int i = 0; i < P.nb; i++) {
-            p += P.part[plane + (size_t)i * P.Mpad + lm];
-            if (P.want_p1) p1 += P.part[2 * plane + (size_t)i * P.Mpad + lm];
+    const bool live = lm < P.chunkM && m < P.M;
+    double q = 0, p = 0, p1 = 0;
+    if (live) {
+        const size_t plane = (size_t)P.nbPart * P.Mpad;
+        const double* pq = P.partVar ? nullptr : P.part + lm;
+        const double* pp = P.part + plane + lm;
+        const double* p1p = P.want_p1 ? P.part + 2 * plane + lm : nullptr;
+        int i = tl;
+        for (; i + 3 * RL < P.nbPart; i += 4 * RL) {
+            double a0 = pp[(size_t)i * P.Mpad], a1 = pp[(size_t)(i + RL) * P.Mpad], a2 = pp[(size_t)(i + 2 * RL) * P.Mpad], a3 = pp[(size_t)(i + 3 * RL) * P.Mpad];
+            double b0 = 0, b1 = 0, b2 = 0, b3 = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+            if (pq) { b0 = pq[(size_t)i * P.Mpad]; b1 = pq[(size_t)(i + RL) * P.Mpad]; b2 = pq[(size_t)(i + 2 * RL) * P.Mpad]; b3 = pq[(size_t)(i + 3 * RL) * P.Mpad]; }
+            if (p1p) { c0 = p1p[(size_t)i * P.Mpad]; c1 = p1p[(size_t)(i + RL) * P.Mpad]; c2 = p1p[(size_t)(i + 2 * RL) * P.Mpad]; c3 = p1p[(size_t)(i + 3 * RL) * P.Mpad]; }
+            p += a0; p += a1; p += a2; p += a3;          // same ascending order as the scalar tail below
+            q += b0; q += b1; q += b2; q += b3;
+            p1 += c0; p1 += c1; p1 += c2; p1 += c3;
         }
-        if (P.partVar) { for (int i = 0; i < P.nbVar; i++) q += P.partVar[(size_t)i * P.MpadVar + lm]; }
-        else { for (int i = 0; i < P.nb; i++) q += P.part[(size_t)i * P.Mpad + lm]; }
+        for (; i < P.nbPart; i += RL) {
+            p += pp[(size_t)i * P.Mpad];
+            if (pq) q += pq[(size_t)i * P.Mpad];
+            if (p1p) p1 += p1p[(size_t)i * P.Mpad];
+        }
+        if (P.partVar) {
+            const double* pv = P.partVar + lm;
+            for (int iv = tl; iv < P.nbVarPart; iv += RL) q += pv[(size_t)iv * P.MpadVar];
+        }
+    }
+    if (RL > 1) {
+        shq[0][threadIdx.x] = q; shq[1][threadIdx.x] = p; shq[2][threadIdx.x] = p1;
+        __syncthreads();
+        if (tl == 0) {
+            q = 0; p = 0; p1 = 0;
+            for (int t = 0; t < RL; t++) { q += shq[0][t * CPB + cl]; p += shq[1][t * CPB + cl]; p1 += shq[2][t * CPB + cl]; }
+        }
+    }
+    if (live && tl == 0) {
         double m0 = 0.0;
         if (P.npb > 0) {
             // RBF-network mean prior, ego/gaussianprocess/prior.py:60-66 == cpp/optimizeGP.cpp:116-134
@@ -494,11 +569,18 @@ __global__ void __launch_bounds__(256) argmax_final_kernel(const double* __restr
 static std::once_flag g_score_attr_once;
 static cudaError_t g_score_attr_err = cudaSuccess;
 static int g_num_sms = 148;
+template <int NT, int MT>
+static cudaError_t set_k2_attr() {
+    cudaError_t e = cudaFuncSetAttribute(trigemm_kernel<NT, MT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2Cfg<NT, MT>::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(trigemm_kernel<NT, MT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2Cfg<NT, MT>::SMEM);
+    return e;
+}
 static void set_score_attrs() {
-    g_score_attr_err = cudaFuncSetAttribute(trigemm_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
-    if (g_score_attr_err == cudaSuccess) g_score_attr_err = cudaFuncSetAttribute(trigemm_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
-    if (g_score_attr_err == cudaSuccess) g_score_attr_err = cudaFuncSetAttribute(trigemm_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
-    if (g_score_attr_err == cudaSuccess) g_score_attr_err = cudaFuncSetAttribute(trigemm_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
+    g_score_attr_err = set_k2_attr<4, 8>();
+    if (g_score_attr_err == cudaSuccess) g_score_attr_err = set_k2_attr<1, 8>();
+    if (g_score_attr_err == cudaSuccess) g_score_attr_err = set_k2_attr<1, 4>();
+    if (g_score_attr_err == cudaSuccess) g_score_attr_err = set_k2_attr<1, 2>();
+    if (g_score_attr_err == cudaSuccess) g_score_attr_err = set_k2_attr<1, 1>();
     if (g_score_attr_err == cudaSuccess)
         g_score_attr_err = cudaFuncSetAttribute(kstar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 65 * 8);
     int dev = 0; cudaGetDevice(&dev);
@@ -516,27 +598,149 @@ static long chunk_tiles_default() {
     return v;
 }
 
-static void launch_trigemm(const ibo_model* m, bool narrow, bool p1, int G, long ytiles, long Mpad, cudaStream_t st) {
-    dim3 grid(G, (unsigned)ytiles);
-#define IBO_K2(NT_, P1_) trigemm_kernel<NT_, P1_><<<grid, K2_THREADS, K2_SMEM, st>>>(m->dWpack, m->dSlab, m->dBetaY, m->dBeta1, m->dPart, m->nb, G, Mpad)
-    if (narrow) { if (p1) IBO_K2(1, true); else IBO_K2(1, false); }
-    else { if (p1) IBO_K2(4, true); else IBO_K2(4, false); }
-#undef IBO_K2
-}
-
 static long narrow_threshold() {
     static long v = -1;
     if (v < 0) { const char* e = getenv("IBO_NARROW_MAX"); v = e ? atol(e) : 2048; }
     return v;
 }
 
-// Row-block groups per candidate tile.  (a) L2 residency: the G CTAs of a tile run side by side, so about
-// num_sms / G slab tiles (Np KiB each) are live at once; G = nb/4 keeps that at <= 148 * 4 * 128 KiB = 74 MiB of the
-// 126 MiB L2 for every N.  (b) occupancy: small batches (DIRECT) need tiles * G >= num_sms.
-static int pick_groups(int nb, long tiles) {
+// ---------------------------------------------------------------------------------------------
+// K2 launch plans.  A plan fixes the CTA shape (MT), the number G of CTAs that share one candidate tile, and the table
+// that deals the (row-block, sub-block) units of a tile to those G CTAs.
+//   wide (NT = 4): G = nb/4 row-block groups in snake order (work ~ i+1; exactly balanced when 2G | nb).  (a) L2
+//     residency: the G CTAs of a tile run side by side, so about num_sms / G slab tiles (Np KiB each) are live at once --
+//     <= 148 * 4 * 128 KiB = 74 MiB of the 126 MiB L2 for every N; (b) small sets raise G until tiles * G >= num_sms.
+//   narrow (NT = 1, M <= 2048): latency matters.  For each shape MT in {8, 4, 2, 1} and each G that fills whole "rounds" of
+//     the SMs, the units are dealt longest-first to the least loaded CTA (LPT) and the makespan is estimated; the cheapest
+//     (MT, G) wins.  Small MT = more, shorter CTAs (a 24-candidate DIRECT batch at N = 2048 runs as 128 CTAs of 16 rows
+//     instead of 16 CTAs of 128 rows) at the price of less operand reuse (A: 2 MT KiB, B: 4 KiB per stage).
+// ---------------------------------------------------------------------------------------------
+struct UnitTable { int G = 0; int* dUnits = nullptr; int* dStart = nullptr; };   // device copies, owned by the model
+
+static double lpt_deal(int nb, int MT, int G, std::vector<int>* units, std::vector<int>* start) {
+    const int SUBS = 8 / MT;
+    struct U { double c; int code; };
+    std::vector<U> us;
+    us.reserve((size_t)nb * SUBS);
+    for (int i = nb - 1; i >= 0; --i)
+        for (int h = SUBS - 1; h >= 0; --h)
+            us.push_back({(double)((i * 8 + (h + 1) * MT) * MT + 6), i * 8 + h});     // stages x m-tiles per warp + epilogue
+    std::stable_sort(us.begin(), us.end(), [](const U& a, const U& b) { return a.c > b.c; });
+    std::vector<double> load(G, 0.0);
+    std::vector<std::vector<int>> mine(units ? G : 0);
+    typedef std::pair<double, int> LG;                                  // (load, group): least loaded first, lowest group on ties
+    std::priority_queue<LG, std::vector<LG>, std::greater<LG>> heap;
+    for (int gI = 0; gI < G; gI++) heap.push(LG(0.0, gI));
+    for (const U& u : us) {
+        LG top = heap.top(); heap.pop();
+        top.first += u.c; load[top.second] = top.first;
+        if (units) mine[top.second].push_back(u.code);
+        heap.push(top);
+    }
+    double mk = 0;
+    for (int gI = 0; gI < G; gI++) mk = std::max(mk, load[gI]);
+    if (units) {
+        units->clear(); start->assign(G + 1, 0);
+        for (int gI = 0; gI < G; gI++) { for (int c : mine[gI]) units->push_back(c); (*start)[gI + 1] = (int)units->size(); }
+    }
+    return mk;
+}
+
+static void snake_deal(int nb, int G, std::vector<int>* units, std::vector<int>* start) {
+    units->clear(); start->assign(G + 1, 0);
+    for (int gI = 0; gI < G; gI++) {
+        for (int i = nb - 1; i >= 0; --i) {
+            int idx = nb - 1 - i, round = idx / G, pos = idx - round * G;
+            if (((round & 1) ? (G - 1 - pos) : pos) == gI) units->push_back(i * 8);
+        }
+        (*start)[gI + 1] = (int)units->size();
+    }
+}
+
+struct K2Plan { int MT; int G; };
+
+static K2Plan plan_narrow(int nb, long ctaTiles) {
+    static int forceMT = -1;
+    if (forceMT < 0) { const char* e = getenv("IBO_NARROW_MT"); forceMT = e ? atoi(e) : 0; }
+    const int mts[4] = {8, 4, 2, 1};
+    const int resident[4] = {1, 2, 2, 3};
+    const double eff[4] = {1.0, 0.95, 0.75, 0.5};        // achievable share of the DMMA rate (operand traffic per DMMA grows as MT shrinks)
+    K2Plan best{8, 1};
+    double bestT = 1e300;
+    for (int q = 0; q < 4; q++) {
+        const int MT = mts[q];
+        if (forceMT > 0 && MT != forceMT) continue;
+        const int nunits = nb * (8 / MT);
+        const long bins = (long)g_num_sms * resident[q];
+        long Gmax = std::min<long>(nunits, std::max<long>(1, bins / ctaTiles));
+        // candidates: G that fill 1 .. resident rounds of the SMs, and the largest one
+        long cand[6]; int nc = 0;
+        for (int r = 1; r <= resident[q]; r++) { long Gc = (long)g_num_sms * r / ctaTiles; if (Gc >= 1 && Gc <= Gmax) cand[nc++] = Gc; }
+        cand[nc++] = Gmax;
+        if (Gmax > 1) cand[nc++] = 1;
+        for (int c = 0; c < nc; c++) {
+            const int G = (int)cand[c];
+            const double mk = lpt_deal(nb, MT, G, nullptr, nullptr);
+            const long perSM = (ctaTiles * G + g_num_sms - 1) / g_num_sms;     // CTAs sharing one SM's DMMA pipe
+            const double t = perSM * (mk + 16.0) / eff[q];
+            if (t < bestT) { bestT = t; best = K2Plan{MT, G}; }
+        }
+    }
+    return best;
+}
+
+static K2Plan plan_narrow_cached(ibo_model* m, long ctaTiles) {
+    auto it = m->planCache.find(ctaTiles);
+    if (it == m->planCache.end()) {
+        K2Plan pl = plan_narrow(m->nb, ctaTiles);
+        it = m->planCache.emplace(ctaTiles, std::make_pair(pl.MT, pl.G)).first;
+    }
+    return K2Plan{it->second.first, it->second.second};
+}
+
+static int pick_groups_wide(int nb, long tiles) {
     long G = std::max(1, nb / 4);
     if (tiles * G < g_num_sms) G = (g_num_sms + tiles - 1) / tiles;
     return (int)std::min<long>(G, nb);
+}
+
+// device table for (MT, G), cached on the model
+static int get_unit_table(ibo_model* m, bool narrow, int MT, int G, const int** dUnits, const int** dStart) {
+    const long key = ((long)(narrow ? 1 : 0) << 40) | ((long)MT << 32) | (long)G;
+    auto it = m->unitTables.find(key);
+    if (it == m->unitTables.end()) {
+        std::vector<int> units, start;
+        if (narrow) lpt_deal(m->nb, MT, G, &units, &start); else snake_deal(m->nb, G, &units, &start);
+        int* d = nullptr;
+        IBO_CUDA_TRY(cudaMalloc(&d, sizeof(int) * (units.size() + start.size())));
+        IBO_CUDA_TRY(cudaMemcpyAsync(d, units.data(), sizeof(int) * units.size(), cudaMemcpyHostToDevice, m->stream));
+        IBO_CUDA_TRY(cudaMemcpyAsync(d + units.size(), start.data(), sizeof(int) * start.size(), cudaMemcpyHostToDevice, m->stream));
+        IBO_CUDA_TRY(cudaStreamSynchronize(m->stream));      // the host vectors go out of scope
+        it = m->unitTables.emplace(key, std::make_pair(d, (int)units.size())).first;
+    }
+    *dUnits = it->second.first;
+    *dStart = it->second.first + it->second.second;
+    return IBO_OK;
+}
+
+template <int NT, int MT>
+static void launch_k2_shape(const ibo_model* m, bool p1, dim3 grid, const int* dUnits, const int* dStart, long Mpad, cudaStream_t st) {
+    if (p1) trigemm_kernel<NT, MT, true><<<grid, K2_THREADS, K2Cfg<NT, MT>::SMEM, st>>>(m->dWpack, m->dSlab, m->dBetaY, m->dBeta1, m->dPart, dUnits, dStart, m->nb, Mpad);
+    else trigemm_kernel<NT, MT, false><<<grid, K2_THREADS, K2Cfg<NT, MT>::SMEM, st>>>(m->dWpack, m->dSlab, m->dBetaY, m->dBeta1, m->dPart, dUnits, dStart, m->nb, Mpad);
+}
+
+// ytiles: CTAs along the candidate axis (128-candidate tiles when wide, 32-candidate tiles when narrow)
+static int launch_trigemm(ibo_model* m, bool narrow, K2Plan pl, bool p1, long ytiles, long Mpad, cudaStream_t st) {
+    const int *dUnits, *dStart;
+    int rc = get_unit_table(m, narrow, pl.MT, pl.G, &dUnits, &dStart);
+    if (rc) return rc;
+    dim3 grid(pl.G, (unsigned)ytiles);
+    if (!narrow) launch_k2_shape<4, 8>(m, p1, grid, dUnits, dStart, Mpad, st);
+    else if (pl.MT == 8) launch_k2_shape<1, 8>(m, p1, grid, dUnits, dStart, Mpad, st);
+    else if (pl.MT == 4) launch_k2_shape<1, 4>(m, p1, grid, dUnits, dStart, Mpad, st);
+    else if (pl.MT == 2) launch_k2_shape<1, 2>(m, p1, grid, dUnits, dStart, Mpad, st);
+    else launch_k2_shape<1, 1>(m, p1, grid, dUnits, dStart, Mpad, st);
+    return IBO_OK;
 }
 
 template <int DP4>
@@ -594,14 +798,22 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
     const long Mpad = chunkTiles * TN;
     int rc;
     if ((rc = grow(&m->dSlab, &m->slabCap, (size_t)chunkTiles * nb * KB_PER_BLOCK * BLOB))) return rc;
-    if ((rc = grow(&m->dPart, &m->partCap, (size_t)3 * nb * Mpad))) return rc;
+    const bool narrow = M <= narrow_threshold();
+    const long ctaTilesAll = narrow ? (std::min<long>(M, Mpad) + 31) / 32 : chunkTiles;      // K2 CTAs along the candidate axis
+    const K2Plan plan = narrow ? plan_narrow_cached(m, ctaTilesAll) : K2Plan{8, pick_groups_wide(nb, chunkTiles)};
+    const int subs = 8 / plan.MT;
+    if ((rc = grow(&m->dPart, &m->partCap, (size_t)3 * nb * subs * Mpad))) return rc;
     if ((rc = grow(&m->dOut, &m->outCap, (size_t)3 * M + 2))) return rc;
     double* const out = outBase ? outBase : m->dOut;     // outBase: device-visible pinned host memory (zero-copy results)
     if (vm) {
         if ((rc = grow(&vm->dSlab, &vm->slabCap, (size_t)chunkTiles * vm->nb * KB_PER_BLOCK * BLOB))) return rc;
-        if ((rc = grow(&vm->dPart, &vm->partCap, (size_t)3 * vm->nb * Mpad))) return rc;
     }
-    const long nblkTotal = (M + 255) / 256 + tilesTotal;   // generous upper bound (chunk boundaries)
+    K2Plan planV{8, 1};
+    if (vm) {
+        planV = narrow ? plan_narrow_cached(vm, ctaTilesAll) : K2Plan{8, pick_groups_wide(vm->nb, chunkTiles)};
+        if ((rc = grow(&vm->dPart, &vm->partCap, (size_t)3 * vm->nb * (8 / planV.MT) * Mpad))) return rc;
+    }
+    const long nblkTotal = (M + 7) / 8 + tilesTotal;       // generous upper bound (chunk boundaries, 8-candidate blocks of small batches)
     if (m->blkCap < (size_t)nblkTotal) {
         if (m->dBlkBest) cudaFree(m->dBlkBest);
         if (m->dBlkIdx) cudaFree(m->dBlkIdx);
@@ -618,9 +830,9 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
         const long tiles = std::min(chunkTiles, tilesTotal - t0);
         const long m0 = t0 * TN;
         const long chunkM = std::min<long>(tiles * TN, M - m0);
-        const bool narrow = M <= narrow_threshold();
         const long ctaTiles = narrow ? (chunkM + 31) / 32 : tiles;      // K2 CTAs along the candidate axis
-        const int G = pick_groups(nb, ctaTiles);
+        K2Plan pl = plan;
+        if (!narrow && tiles != chunkTiles) pl.G = pick_groups_wide(nb, tiles);      // last, shorter chunk
         if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[1], st));
         launch_kstar(m, dCand, m->dSlab, tiles, M, m0, st);
         nlaunch++;
@@ -629,27 +841,30 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
             nlaunch++;
         }
         if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[2], st));
-        launch_trigemm(m, narrow, m->npb > 0, G, narrow ? ctaTiles : tiles, Mpad, st);
+        if ((rc = launch_trigemm(m, narrow, pl, m->npb > 0, ctaTiles, Mpad, st))) return rc;
         nlaunch++; nK2++;
         if (vm) {
-            const int Gv = pick_groups(vm->nb, ctaTiles);
-            launch_trigemm(vm, narrow, false, Gv, narrow ? ctaTiles : tiles, Mpad, st);
+            K2Plan plv = planV;
+            if (!narrow && tiles != chunkTiles) plv.G = pick_groups_wide(vm->nb, tiles);
+            if ((rc = launch_trigemm(vm, narrow, plv, false, ctaTiles, Mpad, st))) return rc;
             nlaunch++; nK2++;
         }
         if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[3], st));
         EpiParams P;
-        P.nb = nb; P.d = m->d; P.N = m->N; P.acq = rq.acq; P.mode_py = (rq.flags & IBO_FLAG_MODE_PY) ? 1 : 0;
+        P.nbPart = nb * subs; P.d = m->d; P.N = m->N; P.acq = rq.acq; P.mode_py = (rq.flags & IBO_FLAG_MODE_PY) ? 1 : 0;
         P.npb = m->npb; P.want_p1 = m->npb > 0;
         P.M = M; P.m0 = m0; P.chunkM = chunkM; P.Mpad = Mpad;
         P.noise = m->noise; P.ymax = rq.ymax; P.parm = rq.parm; P.ptheta = m->ptheta;
-        P.part = m->dPart; P.partVar = vm ? vm->dPart : nullptr; P.nbVar = vm ? vm->nb : 0; P.MpadVar = Mpad;
+        P.part = m->dPart; P.partVar = vm ? vm->dPart : nullptr; P.nbVarPart = vm ? vm->nb * (8 / planV.MT) : 0; P.MpadVar = Mpad;
         P.cand = dCand; P.pmeans = m->dPmeans; P.pbeta = m->dPbeta; P.plb = m->dPlb; P.pwidth = m->dPwidth;
         P.score = rq.want_score ? out : nullptr;
         P.mu = rq.want_mu ? out + M : nullptr;
         P.s2 = rq.want_s2 ? out + 2 * M : nullptr;
         P.want_argmax = rq.want_argmax ? 1 : 0;
         P.blkBest = m->dBlkBest; P.blkIdx = m->dBlkIdx; P.blk0 = blk0;
-        const unsigned nblk = (unsigned)((chunkM + 255) / 256);
+        P.rowLanes = !narrow ? 1 : (std::max(P.nbPart, P.nbVarPart) >= 64 ? 32 : (P.nbPart > 16 ? 8 : 1));
+        const int cpb = 256 / P.rowLanes;
+        const unsigned nblk = (unsigned)((chunkM + cpb - 1) / cpb);
         epilogue_kernel<<<nblk, 256, 0, st>>>(P);
         nlaunch++;
         blk0 += nblk;
@@ -692,20 +907,17 @@ static int score_host(ibo_model* m, const double* Xs, long M, const ScoreReq& rq
     const bool staged = (nin + nout) <= (1u << 17);
     double hb = 0; long long hi = -1;
     if (staged) {
-        // Zero-copy: the pinned buffer is mapped into the device address space.  K3 / K4 write the results straight
-        // into it, and when few CTAs read the candidates (nb x tiles x 128 x d x 8 B over PCIe) K1 / K3 read them from
-        // it too, so a call is: memcpy into pinned memory, 3-4 launches, one stream synchronisation.
+        // Zero-copy results: the pinned buffer is mapped into the device address space and K3 / K4 write the results
+        // straight into it (posted PCIe writes), so a call is: memcpy into pinned memory, one H2D DMA, 3-4 launches,
+        // one stream synchronisation.
         if (m->pinnedCap < nin + nout) {
             IBO_CUDA_TRY(pinned_get(&m->hPinned));
             m->pinnedCap = 1u << 17;
         }
         std::memcpy(m->hPinned, Xs, sizeof(double) * nin);
-        const size_t pcie_reads = (size_t)m->nb * ((M + TN - 1) / TN) * TN * m->d * 8;
-        const double* cand = m->hPinned;
-        if (pcie_reads > (256u << 10) || m->var_model) {
-            IBO_CUDA_TRY(cudaMemcpyAsync(m->dCand, m->hPinned, sizeof(double) * nin, cudaMemcpyHostToDevice, st));
-            cand = m->dCand;
-        }
+        // candidates go to device memory with one small DMA (K1 reading them over PCIe costs ~15 us of dependent round trips)
+        IBO_CUDA_TRY(cudaMemcpyAsync(m->dCand, m->hPinned, sizeof(double) * nin, cudaMemcpyHostToDevice, st));
+        const double* cand = m->dCand;
         double* ho = m->hPinned + nin;
         if ((rc = score_device(m, cand, M, rq, ho))) return rc;
         IBO_CUDA_TRY(cudaStreamSynchronize(st));

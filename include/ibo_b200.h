@@ -103,6 +103,16 @@ int ibo_model_get_matrix(ibo_model* m, int which, double* out);
  * ego/gaussianprocess/__init__.py:214-223,502-519): sigma^2 comes from `aug`, mu from `m`. */
 int ibo_model_set_variance_model(ibo_model* m, ibo_model* aug);
 
+/* ---- PrefGaussianProcess: Laplace MAP fit -----------------------------------------
+ * Minimises the reference's functional (ego/gaussianprocess/__init__.py:355-386)
+ *     S(y) = - sum_p (deg[p]+1) log(CDF((y[v[p]] - y[u[p]]) / sqrt 2) + 1e-10) + |inv(L) y|^2 / 2
+ * (v[p] preferred to u[p]; indices into the model's points; the reference's Chebyshev-erf CDF) by damped Newton steps
+ * on the device instead of the reference's BFGS on numerical gradients (:441-442).  `m` is the plain R model of the N
+ * distinct preference points.  y[N]: in = starting latents (:410-430), out = minimiser.  maxit <= 0 -> 100, gtol <= 0 ->
+ * 1e-9 (sup-norm of the whitened gradient).  S_out / gnorm_out / iters_out may be NULL. */
+int ibo_pref_fit(ibo_model* m, int P, const int* v, const int* u, const double* deg, double* y,
+                 int maxit, double gtol, double* S_out, double* gnorm_out, int* iters_out);
+
 /* ---- batched posterior / scoring -------------------------------------------------------------
  * Xs: M x d row-major candidates (original coordinates).  Outputs may be NULL when not wanted.
  * mu[M], s2[M]: posterior mean and *clipped* variance (floor by mode, ceiling 10).

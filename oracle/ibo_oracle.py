@@ -264,6 +264,42 @@ class GPOracle(object):
 # ---------------------------------------------------------------------------------------------
 # acquisition functions
 # ---------------------------------------------------------------------------------------------
+# ---------------------------------------------------------------------------------------------
+# PrefGaussianProcess: the MAP functional and its minimisation  (ego/gaussianprocess/__init__.py:355-386,441-442)
+# ---------------------------------------------------------------------------------------------
+def pref_S(x, prefinds, L):
+    """S(x) = -sum_p (d+1) log(CDF((x[v]-x[u]) / (sqrt(2) sigma)) + 1e-10) + |inv(L) x|^2 / 2, sigma = 1 (:373-386);
+    the reference solves with the general linalg.solve (:381)."""
+    x = np.asarray(x, dtype=float)
+    logCDFs = 0.
+    Z = math.sqrt(2) * 1
+    for v, u, d in prefinds:
+        logCDFs += (d + 1) * math.log(float(cdf_py((x[v] - x[u]) / Z)) + 1e-10)
+    Lx = np.linalg.solve(L, x)
+    return -logCDFs + np.dot(Lx, Lx) / 2
+
+
+def pref_fit_bfgs(start, prefinds, L):
+    """the reference's optimiser call, verbatim in meaning: fmin_bfgs on numerical gradients (:442)"""
+    from scipy.optimize import fmin_bfgs
+    return np.asarray(fmin_bfgs(pref_S, np.asarray(start, dtype=float), args=(prefinds, L), disp=0), dtype=float)
+
+
+def pref_S_grad(x, prefinds, L):
+    """analytic gradient of pref_S (Gaussian pdf for dCDF/dz) -- used by the tests to certify a minimiser"""
+    from scipy.linalg import solve_triangular
+    x = np.asarray(x, dtype=float)
+    g = np.zeros_like(x)
+    for v, u, d in prefinds:
+        z = (x[v] - x[u]) / math.sqrt(2)
+        q = math.exp(-z * z / 2) / math.sqrt(2 * math.pi) / (float(cdf_py(z)) + 1e-10)
+        gz = -(d + 1) * q / math.sqrt(2)
+        g[v] += gz
+        g[u] -= gz
+    Lx = solve_triangular(L, x, lower=True)
+    return g + solve_triangular(L, Lx, lower=True, trans='T')
+
+
 def ei_py(mu, s2, ymax, xi):
     """EI.negf negated (ego/acquisition/__init__.py:150-164)."""
     ydiff = mu - ymax - xi

@@ -226,17 +226,28 @@ def test_full_size_subsample_vs_oracle(big):
 
 
 def test_scores_do_not_depend_on_batch_shape(big):
-    """a candidate's value is a pure function of (model, x): bit-identical across batch size / position / grouping"""
+    """a candidate's value is a function of (model, x) only.  Large batches (the throughput shape of K2) are bit-identical
+    across batch size / position / chunking / grouping; a small batch (M <= 2048) runs a latency shape of K2 chosen from its
+    size, whose row sums associate differently: there the value is bit-identical across position and order within the
+    batch size, and equal to the large-batch value to rounding (V itself is bit-identical in every shape)."""
     from ibo_b200 import _lib
     m, X, Y, theta = big
     Xs = np.random.RandomState(5).rand(70000, 6)
     full = m.score(Xs, _lib.ACQ_EI, Y.max(), 0.01, _lib.FLAG_MODE_CPP)[0]
-    for lo, hi in [(0, 1), (5, 133), (1000, 1700), (69000, 70000), (300, 41000)]:
+    for lo, hi in [(300, 41000), (2000, 4100), (60000, 70000)]:
         part = m.score(Xs[lo:hi], _lib.ACQ_EI, Y.max(), 0.01, _lib.FLAG_MODE_CPP)[0]
         assert np.array_equal(part, full[lo:hi])
     perm = np.random.RandomState(6).permutation(5000)
     shuf = m.score(Xs[perm], _lib.ACQ_EI, Y.max(), 0.01, _lib.FLAG_MODE_CPP)[0]
     assert np.array_equal(shuf, full[perm])
+    for lo, hi in [(0, 1), (5, 133), (1000, 1700), (69000, 70000), (7, 40), (100, 164), (0, 2048)]:
+        part = m.score(Xs[lo:hi], _lib.ACQ_EI, Y.max(), 0.01, _lib.FLAG_MODE_CPP)[0]
+        assert np.max(np.abs(part - full[lo:hi]) / np.maximum(np.abs(full[lo:hi]), 1e-5)) <= 1e-11
+        again = m.score(Xs[lo:hi][::-1].copy(), _lib.ACQ_EI, Y.max(), 0.01, _lib.FLAG_MODE_CPP)[0]
+        assert np.array_equal(again[::-1], part)
+        if hi - lo > 1:      # same size, different neighbours
+            other = m.score(np.r_[Xs[lo:lo + 1], Xs[40000:40000 + hi - lo - 1]], _lib.ACQ_EI, Y.max(), 0.01, _lib.FLAG_MODE_CPP)[0]
+            assert other[0] == part[0]
 
 
 def test_resident_candidates_and_ties(big):

@@ -76,11 +76,13 @@ def test_append_not_spd_is_reported():
     """prior variance sf2 = 4 above the diagonal 1 + noise (the reference keeps the diagonal at 1 + noise whatever the
     magnitude, App. A): a near-duplicate of a training point makes the enlarged matrix indefinite"""
     from ibo_b200 import _lib
-    X, Y = _data(300, 3, 7)
-    m = _lib.Model(_lib.KERNEL_MATERN3, [0.01, 2.0], X, Y, 0.1)       # well separated points: SPD
+    g = np.arange(6) / 5.0
+    X = np.array([[a, b, c] for a in g for b in g for c in g])         # 216 grid points 0.2 apart: off-diagonals ~ 0, SPD
+    Y = np.sin(3 * X).sum(axis=1)
+    m = _lib.Model(_lib.KERNEL_MATERN3, [0.01, 2.0], X, Y, 0.1)
     with pytest.raises(np.linalg.LinAlgError) as ei:
         m.append(X[:1] + 1e-9, Y[:1])
-    assert ei.value.pivot == 301
+    assert ei.value.pivot == 217
     with pytest.raises(Exception):
         m.posterior(X[:2])             # the handle was closed
 
