@@ -18,6 +18,7 @@ EXPORTED = [
     "ibo_last_error", "ibo_version", "ibo_device_count",
     "ibo_model_create", "ibo_model_create_from_inverse", "ibo_model_append", "ibo_model_destroy", "ibo_model_n", "ibo_model_dim",
     "ibo_model_get_matrix", "ibo_model_set_variance_model", "ibo_pref_fit",
+    "ibo_nlml", "ibo_kernel_matrix",
     "ibo_posterior_batch", "ibo_score_batch",
     "ibo_cands_create", "ibo_cands_destroy", "ibo_score_resident", "ibo_get_profile", "ibo_launch_count",
     "ibo_fp64_peak", "ibo_host_register", "ibo_host_unregister", "ibo_stream_mark", "ibo_stream_elapsed_ms",
@@ -28,7 +29,7 @@ EXPORTED = [
 
 KERNEL_SE_ARD, KERNEL_SE_ISO, KERNEL_MATERN3, KERNEL_MATERN5, KERNEL_MATERN5_ARD = 0, 1, 2, 3, 4
 ACQ_EI, ACQ_PI, ACQ_UCB = 0, 1, 2
-FLAG_MODE_CPP, FLAG_MODE_PY, FLAG_KSTAR_EXPAND, FLAG_DIRECT_SEQ, FLAG_PROFILE = 0x0, 0x1, 0x2, 0x4, 0x8
+FLAG_MODE_CPP, FLAG_MODE_PY, FLAG_KSTAR_EXPAND, FLAG_DIRECT_SEQ, FLAG_PROFILE, FLAG_GRAD_EXACT = 0x0, 0x1, 0x2, 0x4, 0x8, 0x10
 E_BADARG, E_CUDA, E_NOTSPD, E_NOMEM, E_COMM = -1, -2, -3, -4, -5
 
 BATCH_OBJECTIVE = ctypes.CFUNCTYPE(None, c_void_p, c_long, c_int, POINTER(c_double), POINTER(c_double))
@@ -87,6 +88,8 @@ def lib():
     L.ibo_model_get_matrix.argtypes = [c_void_p, c_int, pd]
     L.ibo_model_set_variance_model.argtypes = [c_void_p, c_void_p]
     L.ibo_pref_fit.argtypes = [c_void_p, c_int, pi, pi, pd, pd, c_int, c_double, pd, pd, pi]
+    L.ibo_nlml.argtypes = [c_int, c_int, pd, c_int, pd, pd, c_int, c_int, c_double, c_int, pd, pd, pi]
+    L.ibo_kernel_matrix.argtypes = [c_int, c_int, pd, c_int, pd, c_int, c_int, c_int, c_int, pd]
     L.ibo_posterior_batch.argtypes = [c_void_p, pd, c_long, c_int, pd, pd]
     L.ibo_score_batch.argtypes = [c_void_p, pd, c_long, c_int, c_double, c_double, c_int, pd, pd, pd, pd, pl]
     L.ibo_cands_create.argtypes = [c_void_p, pd, c_long, POINTER(c_void_p)]
@@ -130,6 +133,31 @@ def require_gpu():
         raise IBOError(E_CUDA, "no CUDA device visible; ibo_b200 has no CPU fallback (%s)"
                        % lib().ibo_last_error().decode("utf-8", "replace"))
     return n
+
+
+def nlml(kind, hyper, X, Y, noise, want_grad=True, flags=0, device=0):
+    """ibo_nlml: (nlml, dnlml or None) of trainhyper.marginalLikelihood on the device."""
+    hyper = as_f64(hyper)
+    X = as_f64(X, 2)
+    Y = as_f64(Y)
+    if X.shape[0] != Y.shape[0]:
+        raise ValueError("X and Y differ in length")
+    val = c_double(0.0)
+    grad = np.zeros(len(hyper)) if want_grad else None
+    info = c_int(0)
+    rc = lib().ibo_nlml(device, kind, dptr(hyper), len(hyper), dptr(X), dptr(Y), X.shape[0], X.shape[1], float(noise), flags,
+                        ctypes.byref(val), dptr(grad) if want_grad else None, ctypes.byref(info))
+    check(rc, info.value)
+    return val.value, grad
+
+
+def kernel_matrix(kind, hyper, X, which=-1, flags=0, device=0):
+    """ibo_kernel_matrix: covMatrix(X) (which < 0) or derivative(X, which) as an N x N array."""
+    hyper = as_f64(hyper)
+    X = as_f64(X, 2)
+    out = np.empty((X.shape[0], X.shape[0]))
+    check(lib().ibo_kernel_matrix(device, kind, dptr(hyper), len(hyper), dptr(X), X.shape[0], X.shape[1], int(which), flags, dptr(out)))
+    return out
 
 
 class Model(object):

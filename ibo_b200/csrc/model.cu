@@ -6,6 +6,7 @@
 // (ego/gaussianprocess/__init__.py:134-149,267-308), linalg.cholesky(R + inv(C)) (:487-498) and
 // the explicit linalg.inv(R) of cdirectGP (ego/acquisition/__init__.py:385-388).
 #include "model.cuh"
+#include "tilegemm.cuh"
 #include <cmath>
 #include <cstring>
 #include <mutex>
@@ -115,15 +116,15 @@ __device__ __forceinline__ double cov_from_r2(int kind, double sf2, double r2) {
     return sf2 * (1.0 + z + 5.0 * r2 / 3.0) * exp(-z);
 }
 
-// A[i][j] = k(x_i, x_j) (i != j), 1 + noise on the diagonal, + Cinv; identity in the padding.
+// A[i][j] = k(x_i, x_j) (i != j), `diag` (1 + noise for the GP's R) on the diagonal, + Cinv; identity in the padding.
 __global__ void build_A_kernel(double* __restrict__ A, const double* __restrict__ Xt, const double* __restrict__ Cinv,
-                               int N, int Np, int d, int kind, double sf2, double noise) {
+                               int N, int Np, int d, int kind, double sf2, double diag) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
     int i = blockIdx.y;
     if (j >= Np) return;
     double v;
     if (i >= N || j >= N) v = (i == j) ? 1.0 : 0.0;
-    else if (i == j) v = 1.0 + noise;
+    else if (i == j) v = diag;
     else {
         // evaluate with (min,max) ordering so that A is exactly symmetric
         int a = i < j ? i : j, b = i < j ? j : i;
@@ -307,85 +308,6 @@ __global__ void __launch_bounds__(512) potrf_diag_kernel(double* __restrict__ A,
         D[r * 128 + c] = (c <= r) ? XP(r, c) : 0.0;
     }
 #undef XP
-}
-
-// ---------------------------------------------------------------------------------------------
-// 128x128x(K) tile GEMM on the DMMA pipe from row-major global operands.
-//   8 warps, warp tile 64x32 (8 x 4 DMMA tiles, 64 FP64 accumulators per thread),
-//   cp.async double-buffered 16-deep k-steps into padded (bank-conflict-free) shared memory.
-// ---------------------------------------------------------------------------------------------
-constexpr int AS_STRIDE = 20;    // [128][20]: (row*20 + k) mod 16 distinct over a half-warp
-constexpr int BN_STRIDE = 132;   // [16][132] for the non-transposed B operand
-constexpr int TILE_SMEM_DOUBLES = 2 * (128 * AS_STRIDE) + 2 * (128 * AS_STRIDE);   // A + B(T) buffers (B(N) fits too)
-
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
-
-// acc[mt][nt][2] += A(128 x K) * op(B); TRANSB: B stored [n][k] (row-major, ldb), else [k][n].
-template <bool TRANSB>
-__device__ __forceinline__ void tile_gemm_core(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
-                                               int K, double (&acc)[8][4][2], double* sm) {
-    double* sA = sm;                         // [2][128*AS_STRIDE]
-    double* sB = sm + 2 * 128 * AS_STRIDE;   // [2][128*AS_STRIDE] or [2][16*BN_STRIDE]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3;
-    const int nk = K / BK;
-    auto load_stage = [&](int kb, int buf) {
-        // A: 128 rows x 16 doubles = 1024 16-byte chunks
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            int idx = tid + c * 256;
-            int r = idx >> 3, ch = idx & 7;
-            cp_async16(sA + buf * 128 * AS_STRIDE + r * AS_STRIDE + ch * 2, A + (size_t)r * lda + kb * BK + ch * 2);
-        }
-        if (TRANSB) {
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                int idx = tid + c * 256;
-                int r = idx >> 3, ch = idx & 7;
-                cp_async16(sB + buf * 128 * AS_STRIDE + r * AS_STRIDE + ch * 2, B + (size_t)r * ldb + kb * BK + ch * 2);
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                int idx = tid + c * 256;
-                int r = idx >> 6, ch = idx & 63;
-                cp_async16(sB + buf * 16 * BN_STRIDE + r * BN_STRIDE + ch * 2, B + (size_t)(kb * BK + r) * ldb + ch * 2);
-            }
-        }
-        cp_async_commit();
-    };
-    load_stage(0, 0);
-    for (int kb = 0; kb < nk; kb++) {
-        const int buf = kb & 1;
-        if (kb + 1 < nk) { load_stage(kb + 1, buf ^ 1); cp_async_wait<1>(); }
-        else cp_async_wait<0>();
-        __syncthreads();
-        const double* a_s = sA + buf * 128 * AS_STRIDE + (wm * 64 + (lane >> 2)) * AS_STRIDE + (lane & 3);
-#pragma unroll
-        for (int ks = 0; ks < 4; ks++) {
-            double af[8], bf[4];
-#pragma unroll
-            for (int mt = 0; mt < 8; mt++) af[mt] = a_s[mt * 8 * AS_STRIDE + ks * 4];
-            if (TRANSB) {
-                const double* b_s = sB + buf * 128 * AS_STRIDE + (wn * 32 + (lane >> 2)) * AS_STRIDE + (lane & 3);
-#pragma unroll
-                for (int nt = 0; nt < 4; nt++) bf[nt] = b_s[nt * 8 * AS_STRIDE + ks * 4];
-            } else {
-                const double* b_s = sB + buf * 16 * BN_STRIDE + (ks * 4 + (lane & 3)) * BN_STRIDE + wn * 32 + (lane >> 2);
-#pragma unroll
-                for (int nt = 0; nt < 4; nt++) bf[nt] = b_s[nt * 8];
-            }
-#pragma unroll
-            for (int mt = 0; mt < 8; mt++)
-#pragma unroll
-                for (int nt = 0; nt < 4; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
-        }
-        __syncthreads();
-    }
 }
 
 enum { MODE_CHOL_PANEL = 0, MODE_CHOL_TRAIL = 1, MODE_TRTRI_SCALE = 2, MODE_TRTRI_UPDATE = 3 };
@@ -845,8 +767,10 @@ static int theta_and_sf2(int kind, const double* hyper, int nhyper, int d, bool 
     return IBO_OK;
 }
 
+// diag < 0: the GP's own diagonal 1 + noise; otherwise the value to put on the diagonal of A (marginal likelihood:
+// covMatrix(X) + noise I has sf2 + noise there).
 static int create_common(int device, int kind, const double* hyper, int nhyper, const double* X, const double* Y, int N, int d,
-                         double noise, const double* Cinv, const double* invR, double sf2_override, bool legacy,
+                         double noise, double diag, const double* Cinv, const double* invR, double sf2_override, bool legacy,
                          int npb, const double* pmeans, const double* pbeta, double ptheta, const double* plb, const double* pwidth,
                          ibo_model** out, int* info) {
     if (info) *info = 0;
@@ -925,7 +849,7 @@ static int create_common(int device, int kind, const double* hyper, int nhyper, 
             TRYM(pool_malloc((void**)&dTmp, sizeof(double) * (size_t)N * N));
             TRYM(cudaMemcpyAsync(dTmp, Cinv, sizeof(double) * (size_t)N * N, cudaMemcpyHostToDevice, st));
         }
-        build_A_kernel<<<g2, 256, 0, st>>>(m->dA, m->dXt, dTmp, N, Np, d, kind, sf2, noise);
+        build_A_kernel<<<g2, 256, 0, st>>>(m->dA, m->dXt, dTmp, N, Np, d, kind, sf2, diag < 0 ? 1.0 + noise : diag);
     }
     g_launches++;
     if (Np <= 4096 && !invR) {   // keep A for get_matrix(0)
@@ -963,7 +887,7 @@ extern "C" int ibo_model_create(int device, int kerneltype, const double* hyper,
                                 int N, int d, double noise, const double* Cinv, int npbases, const double* pmeans,
                                 const double* pbeta, double ptheta, const double* plowerb, const double* pwidth,
                                 ibo_model** out, int* info) {
-    return create_common(device, kerneltype, hyper, nhyper, X, Y, N, d, noise, Cinv, nullptr, 1.0, false,
+    return create_common(device, kerneltype, hyper, nhyper, X, Y, N, d, noise, -1.0, Cinv, nullptr, 1.0, false,
                          npbases, pmeans, pbeta, ptheta, plowerb, pwidth, out, info);
 }
 
@@ -972,9 +896,17 @@ extern "C" int ibo_model_create_from_inverse(int device, int kerneltype, const d
                                              int npbases, const double* pmeans, const double* pbeta, double ptheta,
                                              const double* plowerb, const double* pwidth, ibo_model** out, int* info) {
     if (!invR) { set_error("invR is NULL"); return IBO_E_BADARG; }
-    return create_common(device, kerneltype, hyper, nhyper, X, Y, N, d, noise, nullptr, invR, sf2, true,
+    return create_common(device, kerneltype, hyper, nhyper, X, Y, N, d, noise, -1.0, nullptr, invR, sf2, true,
                          npbases, pmeans, pbeta, ptheta, plowerb, pwidth, out, info);
 }
+
+namespace ibo {
+int create_model_with_diag(int device, int kind, const double* hyper, int nhyper, const double* X, const double* Y, int N, int d,
+                           double noise, double diag, ibo_model** out, int* info) {
+    return create_common(device, kind, hyper, nhyper, X, Y, N, d, noise, diag, nullptr, nullptr, 1.0, false,
+                         0, nullptr, nullptr, 0.0, nullptr, nullptr, out, info);
+}
+}  // namespace ibo
 
 extern "C" int ibo_model_append(ibo_model* m, const double* X, const double* Y, int k, int* info) {
     if (info) *info = 0;

@@ -4,7 +4,9 @@ surface (ego/gaussianprocess/kernel.py).  The classes are light descriptors: `sp
 CUDA library which kernel type and hyperparameter vector to use; scalar `cov` exists for
 host-side bookkeeping (e.g. a 1x1 query) and documentation of the formula, the batched work is
 done on the GPU by K1 (ibo_b200/csrc/score.cu) and the R build (ibo_b200/csrc/model.cu).
-`derivative` (hyper-parameter learning, ego/gaussianprocess/trainhyper.py) is out of scope.
+`covMatrix` and `derivative` (hyper-parameter learning, ego/gaussianprocess/trainhyper.py) are evaluated on the GPU
+by ibo_kernel_matrix (ibo_b200/csrc/hyper.cu); `derivative` follows the reference expressions (kernel.py:92-266),
+including its Matern-3/2 quirk, see include/ibo_b200.h: IBO_FLAG_GRAD_EXACT.
 """
 import math
 
@@ -30,16 +32,27 @@ class Kernel(object):
         raise NotImplementedError('kernel-derived class does not have cov method')
 
     def covMatrix(self, X):
-        X = np.vstack(X)
-        n = X.shape[0]
-        K = np.ones((n, n))
-        for i in range(n):
-            for j in range(i + 1):
-                K[i, j] = K[j, i] = self.cov(X[i], X[j])
-        return K
+        """K[i, j] = cov(X[i], X[j]) (kernel.py:43-52), one device launch instead of N^2/2 interpreted calls"""
+        X = np.vstack(X).astype(float)
+        kind, hyper = self.spec(X.shape[1])
+        return _lib.kernel_matrix(kind, hyper, X, -1)
+
+    def _nhyper_device(self, ndim):
+        """(kind, hyper vector, list mapping the reference's hyperparameter index -> device indices to sum)"""
+        kind, hyper = self.spec(ndim)
+        return kind, hyper, [[h] for h in range(len(hyper))]
 
     def derivative(self, X, hp):
-        raise NotImplementedError('hyper-parameter derivatives are outside the acquisition hot path')
+        """dK / d log hyperparams[hp] as the reference's Kernel.derivative returns it (raises ValueError past the end)"""
+        X = np.vstack(X).astype(float)
+        kind, hyper, hmap = self._nhyper_device(X.shape[1])
+        if hp < 0 or hp >= len(hmap):
+            raise ValueError
+        out = None
+        for h in hmap[hp]:
+            D = _lib.kernel_matrix(kind, hyper, X, h)
+            out = D if out is None else out + D
+        return out
 
 
 class SVKernel(object):
@@ -62,6 +75,10 @@ class GaussianKernel_iso(Kernel):
 
     def spec(self, ndim):
         return _lib.KERNEL_SE_ISO, np.array([self._hyperparams[0]])
+
+    def _nhyper_device(self, ndim):
+        kind, hyper = self.spec(ndim)
+        return kind, hyper, [[0]]          # kernel.py:92-105: hp == 0 only
 
     def cov(self, x1, x2):
         diff = np.asarray(x1, dtype=float) - np.asarray(x2, dtype=float)
@@ -98,6 +115,10 @@ class SVGaussianKernel_iso(SVKernel, GaussianKernel_iso):
     def spec(self, ndim):
         # isotropic SE with a signal variance == ARD with equal length scales + magnitude
         return _lib.KERNEL_SE_ARD, np.array([self._hyperparams[0]] * ndim + [self._magnitude])
+
+    def _nhyper_device(self, ndim):
+        kind, hyper = self.spec(ndim)
+        return kind, hyper, [list(range(ndim)), [ndim]]      # d/dlog theta = sum of the per-dimension derivatives
 
     def cov(self, x1, x2):
         return self.covScale(GaussianKernel_iso.cov(self, x1, x2))

@@ -18,6 +18,9 @@
  *                           EI/PI/UCB.negf (ego/acquisition/__init__.py:60-75,100-114,138-164) and
  *                           GP_Maximizer::posterior/negei/negpi/negucb (cpp/optimizeGP.cpp:57-236)
  *   ibo_acqmax    replaces  cdirectGP + acqmaxGP without the explicit inverse
+ *   ibo_nlml / ibo_kernel_matrix
+ *                 replace   trainhyper.marginalLikelihood/nlml/dnlml (ego/gaussianprocess/trainhyper.py:47-136) and
+ *                           Kernel.covMatrix / Kernel.derivative (ego/gaussianprocess/kernel.py:43-52,92-266)
  *
  * Return convention of the ibo_* functions: 0 = ok, <0 = error (see IBO_E_*); the legacy symbols
  * keep the reference's convention (malloc'd double[ndim+1], NULL on failure; caller frees with
@@ -49,6 +52,8 @@ extern "C" {
 #define IBO_FLAG_KSTAR_EXPAND  0x2  /* cross-covariance through |x|^2+|y|^2-2x.y on the DMMA pipe (default: direct differences) */
 #define IBO_FLAG_DIRECT_SEQ    0x4  /* DIRECT: evaluate rectangle by rectangle in the reference's call order */
 #define IBO_FLAG_PROFILE       0x8  /* record per-kernel CUDA-event times (ibo_get_profile) */
+#define IBO_FLAG_GRAD_EXACT    0x10 /* ibo_nlml / ibo_kernel_matrix: analytic Matern-3/2 length-scale derivative instead of
+                                       the reference's expression with the unscaled distance (kernel.py:217-222) */
 
 /* error codes */
 #define IBO_OK            0
@@ -112,6 +117,21 @@ int ibo_model_set_variance_model(ibo_model* m, ibo_model* aug);
  * 1e-9 (sup-norm of the whitened gradient).  S_out / gnorm_out / iters_out may be NULL. */
 int ibo_pref_fit(ibo_model* m, int P, const int* v, const int* u, const double* deg, double* y,
                  int maxit, double gtol, double* S_out, double* gnorm_out, int* iters_out);
+
+/* ---- hyper-parameter learning --------------------------------------------------------
+ * Negative log marginal likelihood of trainhyper.marginalLikelihood (useCholesky branch, trainhyper.py:47-76):
+ *     K = covMatrix(X) + noise I (diagonal sf2 + noise), nlml = Y.inv(K).Y/2 + sum log diag chol(K) + N log(2 pi)/2
+ * and, when dnlml != NULL, dnlml[h] = sum((inv(K) - alpha alpha^T) o dK/dlog hyper[h]) / 2 for every entry of `hyper`
+ * (length scales first, then the magnitude when the kernel has one: SE-ARD/Matern-5/2-ARD with nhyper == d+1,
+ * Matern-3/2, Matern-5/2 with nhyper == 2).  The derivative matrices are the reference's Kernel.derivative
+ * (kernel.py:92-105,152-166,212-228,250-266) including its Matern-3/2 expression unless IBO_FLAG_GRAD_EXACT.
+ * IBO_E_NOTSPD (*info = failing pivot) when K is not positive definite (the reference catches LinAlgError, :61-67).
+ * X: N x d row-major; nothing stays resident. */
+int ibo_nlml(int device, int kerneltype, const double* hyper, int nhyper, const double* X, const double* Y, int N, int d,
+             double noise, int flags, double* nlml, double* dnlml, int* info);
+/* out (N x N row-major) = Kernel.covMatrix(X) when which < 0 (kernel.py:43-52), else Kernel.derivative(X, which) */
+int ibo_kernel_matrix(int device, int kerneltype, const double* hyper, int nhyper, const double* X, int N, int d,
+                      int which, int flags, double* out);
 
 /* ---- batched posterior / scoring -------------------------------------------------------------
  * Xs: M x d row-major candidates (original coordinates).  Outputs may be NULL when not wanted.

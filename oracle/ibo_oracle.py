@@ -262,8 +262,77 @@ class GPOracle(object):
 
 
 # ---------------------------------------------------------------------------------------------
-# acquisition functions
+# hyper-parameter learning: kernel.derivative and the marginal likelihood
+#   (ego/gaussianprocess/kernel.py:92-105,120-127,152-166,181-188,212-228,250-266; ego/gaussianprocess/trainhyper.py:47-95)
 # ---------------------------------------------------------------------------------------------
+def cov_matrix(kernel, X):
+    """Kernel.covMatrix (kernel.py:43-52): K[i,j] = K[j,i] = cov(X[i], X[j]) for j <= i, *including* the diagonal
+    (cov(x, x) = sf2) -- unlike R (build_R) there is no 1+noise diagonal here."""
+    X = np.array(X, dtype=float, ndmin=2)
+    K = kernel.cross(X, X)
+    K = 0.5 * (K + K.T)
+    np.fill_diagonal(K, kernel.sf2)
+    return K
+
+
+def kernel_derivative(kernel, X, hp, exact_matern3=False):
+    """Kernel.derivative(X, hp): the matrix dK / d log(hyper[hp]) as the reference computes it.
+
+    hp indexes the reference's hyperparameter vector: length scales first, then (SV / Matern kernels) the magnitude.
+      SE iso  hp=0: K o |xi-xj|^2/theta^2                    (kernel.py:92-101)
+      SE ARD  hp<D: K o (xi_hp-xj_hp)^2/theta_hp^2           (kernel.py:152-162); K carries sf2 for the SV classes (:181-185)
+      SV      hp=last: 2 K                                   (kernel.py:124-127,186-188)
+      Matern3 hp=0: sf2 r^2 exp(-r) with r = |xi-xj| *unscaled by theta* (kernel.py:212-223) -- a reference quirk (the
+                    derivative of its own cov is sf2 z^2 exp(-z), z = sqrt3 r/theta: `exact_matern3=True`); hp=1: 2 K
+      Matern5 hp=0: sf2 (z + sqrt(z)^3) exp(-sqrt z)/3, z = 5 r^2/theta^2 (kernel.py:250-262); hp=1: 2 K
+      Matern5-ARD (no reference class): the analytic derivative sf2 (5/3)(1+s) exp(-s) (dx_hp/theta_hp)^2, s = sqrt5 r.
+    """
+    X = np.array(X, dtype=float, ndmin=2)
+    n, D = X.shape
+    K = cov_matrix(kernel, X)
+    kind = kernel.kind
+    nlen = D if kind in (K_SE_ARD, K_MATERN5_ARD) else 1
+    if hp == nlen and kind != K_SE_ISO and len(kernel.hyper) > nlen:
+        return 2.0 * K
+    if hp < 0 or hp >= nlen:
+        raise ValueError("kernel has no hyperparameter %d" % hp)
+    diff = X[:, None, :] - X[None, :, :]
+    if kind == K_SE_ISO:
+        return K * (np.sum(diff ** 2, axis=2) / kernel.hyper[0] ** 2)
+    if kind == K_SE_ARD:
+        return K * (diff[:, :, hp] ** 2 / kernel.theta[hp] ** 2)
+    if kind == K_MATERN3:
+        r = np.sqrt(np.sum(diff ** 2, axis=2))
+        if exact_matern3:
+            z = math.sqrt(3) * r / kernel.hyper[0]
+            return kernel.sf2 * z ** 2 * np.exp(-z)
+        return kernel.sf2 * r ** 2 * np.exp(-r)
+    if kind == K_MATERN5:
+        z = np.sum((math.sqrt(5.0) * diff / kernel.hyper[0]) ** 2.0, axis=2)
+        return kernel.sf2 * (z + np.sqrt(z) ** 3.0) * np.exp(-np.sqrt(z)) / 3.0
+    sc = diff / kernel.theta[None, None, :]
+    s = math.sqrt(5.0) * np.sqrt(np.sum(sc ** 2, axis=2))
+    return kernel.sf2 * (5.0 / 3.0) * (1.0 + s) * np.exp(-s) * sc[:, :, hp] ** 2
+
+
+def marginal_likelihood(kernel, X, Y, nhyper, noise=1e-3, compute_gradient=True, exact_matern3=False):
+    """trainhyper.marginalLikelihood with useCholesky=True (trainhyper.py:47-76):
+    K = covMatrix(X) + noise I; nlml = Y.alpha/2 + sum log diag L + N log(2 pi)/2;
+    dnlml[i] = sum((inv(K) - alpha alpha^T) o derivative(X, i)) / 2."""
+    X = np.array(X, dtype=float, ndmin=2)
+    Y = np.array(Y, dtype=float).reshape(-1)
+    NX = len(X)
+    K = cov_matrix(kernel, X) + np.eye(NX) * noise
+    L = np.linalg.cholesky(K)
+    alpha = np.linalg.solve(L.T, np.linalg.solve(L, Y))
+    nlml = 0.5 * np.dot(Y, alpha) + np.sum(np.log(np.diag(L))) + 0.5 * NX * math.log(2.0 * math.pi)
+    if not compute_gradient:
+        return nlml
+    W = np.linalg.solve(L.T, np.linalg.solve(L, np.eye(NX))) - np.outer(alpha, alpha)
+    dnlml = np.array([np.sum(W * kernel_derivative(kernel, X, i, exact_matern3)) / 2.0 for i in range(nhyper)])
+    return nlml, dnlml
+
+
 # ---------------------------------------------------------------------------------------------
 # PrefGaussianProcess: the MAP functional and its minimisation  (ego/gaussianprocess/__init__.py:355-386,441-442)
 # ---------------------------------------------------------------------------------------------

@@ -185,3 +185,75 @@ def test_oracle_block_append_equals_batch_build():
     assert np.array_equal(o.R, f.R) and np.max(np.abs(o.L - f.L)) < 1e-14
     q = rs.rand(5, 3)
     assert np.allclose(o.posterior_batch(q)[0], f.posterior_batch(q)[0], rtol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------
+# hyper-parameter learning: the reference's known answers, ego/unittest_GP.py:160-266
+# (values "collected from Carl Rasmussen's MATLAB code"; they correspond to noise = 0)
+# ---------------------------------------------------------------------------------------------
+HX = np.array([[.5, .1, .3], [.9, 1.2, .1], [.55, .234, .1], [.234, .547, .675]])
+HY = np.array([.5, 1., .5, 2.])
+
+
+def test_marginal_likelihood_known_answers_ard():
+    k = orc.KernelSpec(orc.K_SE_ARD, [2., 2., .1], 3)
+    t0 = np.array([[0, .0046, .0001, 0], [.0046, 0, .0268, 0], [.0001, .0268, 0, 0], [0, 0, 0, 0]])
+    t1 = np.array([[0, .0345, .0006, 0], [.0345, 0, .2044, 0], [.0006, .2044, 0, 0], [0, 0, 0, 0]])
+    t2 = np.array([[0, .4561, .54, .012], [.4561, 0, 0, 0], [.54, .0, 0, 0], [.012, 0, 0, 0]])
+    for hp, t in enumerate((t0, t1, t2)):                              # unittest_GP.py:179-201, epsilon 1e-4
+        assert np.max(np.abs(orc.kernel_derivative(k, HX, hp) - t)) < 1e-4
+    nl, g = orc.marginal_likelihood(k, HX, HY, 3, noise=0.0)          # unittest_GP.py:204-208
+    assert abs(nl - 5.8404) < 5e-5
+    assert np.max(np.abs(g - [0.0039, 0.0302, -0.1733])) < 5e-5
+    with pytest.raises(ValueError):                                    # kernel.py:163-166
+        orc.kernel_derivative(k, HX, 3)
+
+
+def test_marginal_likelihood_known_answers_sv_iso():
+    # SVGaussianKernel_iso([1.5, 1.1]) == SE-ARD with equal length scales + magnitude; d/dlog theta = sum over dims
+    k = orc.KernelSpec(orc.K_SE_ARD, [1.5, 1.5, 1.5, 1.1], 3)
+    nl, g = orc.marginal_likelihood(k, HX, HY, 4, noise=0.0)          # unittest_GP.py:232-236
+    assert abs(nl - 7.514) < 5e-4
+    assert abs(g[:3].sum() - 11.4659) < 5e-5 and abs(g[3] + 10.0714) < 5e-5
+    t0 = np.array([[0, .5543, .0321, .2018], [.5543, 0, .449, .4945], [.0321, .449, 0, .2527], [.2018, .4945, .2527, 0]])
+    t1 = np.array([[2.42, 1.769, 2.3877, 2.2087], [1.769, 2.42, 1.914, 1.8533], [2.3877, 1.914, 2.42, 2.1519],
+                   [2.2087, 1.8533, 2.1519, 2.42]])
+    d0 = sum(orc.kernel_derivative(k, HX, h) for h in range(3))
+    assert np.max(np.abs(d0 - t0)) < 1e-4                              # unittest_GP.py:239-246
+    assert np.max(np.abs(orc.kernel_derivative(k, HX, 3) - t1)) < 1e-4
+
+
+def test_marginal_likelihood_known_answers_matern():
+    k3 = orc.KernelSpec(orc.K_MATERN3, [1.5, 1.1], 3)
+    nl, g = orc.marginal_likelihood(k3, HX, HY, 2, noise=0.0)         # unittest_GP.py:262-266
+    assert abs(nl - 5.1827) < 5e-5
+    assert abs(g[0] - 1.6947897766) < 1e-9                             # pins the reference's unscaled-distance expression
+    assert abs(g[1] + 2.9350) < 5e-5
+    k5 = orc.KernelSpec(orc.K_MATERN5, [1.5, 1.1], 3)
+    nl, g = orc.marginal_likelihood(k5, HX, HY, 2, noise=0.0)         # unittest_GP.py:268-272 (commented out there)
+    assert abs(nl - 5.6652) < 5e-5 and abs(g[0] - 4.4782) < 5e-5 and abs(g[1] + 4.8737) < 5e-5
+
+
+def test_marginal_likelihood_bfgs_known_answers():
+    """unittest_GP.py:215-217,252-254: BFGS over the log hyperparameters (the first ARD length scale is a flat direction
+    -- the data do not vary along it -- so only the other three coordinates are pinned)"""
+    from scipy import optimize
+    f = lambda lh: orc.marginal_likelihood(orc.KernelSpec(orc.K_SE_ARD, np.exp(lh), 3), HX, HY, 4, noise=0.0, compute_gradient=False)
+    g = lambda lh: orc.marginal_likelihood(orc.KernelSpec(orc.K_SE_ARD, np.exp(lh), 3), HX, HY, 4, noise=0.0)[1]
+    r = optimize.fmin_bfgs(f, np.log([2., 2., .1, 1.]), g, disp=False)
+    assert np.max(np.abs(r[1:] - [0.95405, -0.9769, 0.36469])) < 5e-4
+
+
+@pytest.mark.parametrize("kind", [orc.K_SE_ARD, orc.K_SE_ISO, orc.K_MATERN5, orc.K_MATERN5_ARD])
+def test_kernel_derivative_is_the_gradient_of_cov(kind):
+    """finite differences of covMatrix in log hyperparameters (every kind whose reference derivative is exact)"""
+    rs = np.random.RandomState(11)
+    X = rs.rand(7, 3)
+    hyper = {orc.K_SE_ARD: [.4, .6, .9, 1.3], orc.K_SE_ISO: [.7], orc.K_MATERN5: [.8, 1.2], orc.K_MATERN5_ARD: [.5, .7, .9, 1.1]}[kind]
+    k = orc.KernelSpec(kind, hyper, 3)
+    for hp in range(len(hyper)):
+        e = np.zeros(len(hyper)); e[hp] = 1e-6
+        kp = orc.KernelSpec(kind, np.exp(np.log(hyper) + e), 3)
+        km = orc.KernelSpec(kind, np.exp(np.log(hyper) - e), 3)
+        fd = (orc.cov_matrix(kp, X) - orc.cov_matrix(km, X)) / 2e-6
+        assert np.max(np.abs(fd - orc.kernel_derivative(k, X, hp))) < 1e-8
