@@ -365,6 +365,17 @@ def run_suite(args):
     emit({"suite": "maximizeEI_N2048", "N": 2048, "d": 6, "maxiter": 50, "maxsample": 10000, "wall_ms": 1e3 * min(ts), "nsamples": ns,
           "ms_per_1000_samples": 1e6 * min(ts) / ns, "opt": opt,
           "reference_acqmaxGP_maxsample400": ref})
+    # ---- hyper-parameter learning: one nlml + gradient evaluation (ibo_nlml), SE-ARD + magnitude ----
+    for N in (2048, 4096):
+        Xb, Yb = synthetic_model(N, 6)
+        hy = list(THETA) + [1.0]
+        _lib.nlml(_lib.KERNEL_SE_ARD, hy, Xb, Yb, 1e-3)
+        tv, tg = [], []
+        for _ in range(3):
+            t0 = time.perf_counter(); v = _lib.nlml(_lib.KERNEL_SE_ARD, hy, Xb, Yb, 1e-3, want_grad=False)[0]; tv.append(time.perf_counter() - t0)
+            t0 = time.perf_counter(); v, gr = _lib.nlml(_lib.KERNEL_SE_ARD, hy, Xb, Yb, 1e-3); tg.append(time.perf_counter() - t0)
+        emit({"suite": "nlml", "N": N, "d": 6, "nhyper": 7, "value_ms": 1e3 * min(tv), "value_and_gradient_ms": 1e3 * min(tg),
+              "nlml": v, "gflop_value_and_gradient": N ** 3 / 1e9})
     # ---- config #4 slice: Matern-5/2 ARD d=10, N=8192, 2^18 Sobol-like candidates on one GPU ----
     rs = np.random.RandomState(4)
     X4 = rs.rand(8192, 10); Y4 = np.sin(2 * X4).sum(axis=1)
