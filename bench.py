@@ -429,6 +429,71 @@ def run_suite(args):
 
 
 # ------------------------------------------------------------------------------------------------
+def run_direct_workload(args, rank, world, device, dist):
+    """BASELINE configs[4]: end-to-end batched-DIRECT maximizeEI, d=20, N=4096, 200 iterations.  One process per GPU, every rank
+    drives the same deterministic DIRECT; with N>1 each batch is cut into one slice per rank and the values are all-gathered
+    over NCCL (IBO_FLAG_SHARD).  A step is one whole maximizeEI query; the value is its wall time (max over ranks)."""
+    from ibo_b200 import _lib
+    from ibo_b200.acquisition import cdirectGP, maximizeEI
+    from ibo_b200.gaussianprocess import GaussianProcess
+    from ibo_b200.gaussianprocess.kernel import GaussianKernel_ard
+    L = _lib.lib()
+    N, d, iters = 4096, 20, 200
+    rs = np.random.RandomState(5)
+    X = rs.rand(N, d); Y = np.sin(2 * X).sum(axis=1)
+    gp = GaussianProcess(GaussianKernel_ard([1.0] * d), X, Y, noise=0.1, device=device)
+    gp.model
+    bounds = [[0., 1.]] * d
+
+    def sync_all():
+        if dist is not None:
+            dist.barrier()
+        _lib.check(L.ibo_device_synchronize(device))
+
+    def query(shard):
+        return maximizeEI(gp, bounds, xi=0.01, maxiter=iters, maxtime=10 ** 6, maxsample=10 ** 9, shard=shard)
+
+    for _ in range(max(args.warmup, 1)):
+        opt, optx = query(world > 1)
+    sampler = ClockSampler(device)
+    sync_all()
+    sampler.start()
+    launches0 = L.ibo_launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        opt, optx = query(world > 1)
+    sync_all()
+    t_wall = (time.perf_counter() - t0) / args.steps
+    launches = L.ibo_launch_count() - launches0
+    clocks = sampler.stop()
+    nsamples, its = cdirectGP.last["nsamples"], cdirectGP.last["iterations"]
+    # the unsharded query on this rank's GPU alone (what N=1 gives), for the same-trajectory check and the comparison
+    t0 = time.perf_counter()
+    opt1, optx1 = query(False)
+    t_single = time.perf_counter() - t0
+    same = bool(opt == opt1 and np.array_equal(optx, optx1) and cdirectGP.last["nsamples"] == nsamples)
+    if dist is not None:
+        import torch
+        t = torch.tensor([t_wall, t_single, 0.0 if same else 1.0], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_wall, t_single, same = float(t[0]), float(t[1]), bool(t[2] == 0.0)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "maximizeEI wall ms (batched DIRECT, N=4096, d=20, 200 iterations)", "value": 1e3 * t_wall, "unit": "ms",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * t_wall, "higher_is_better": False,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "config #5: GaussianProcess SE-ARD d=20, N=4096, maximizeEI xi=0.01 through batched DIRECT, 200 iterations, "
+                                   "batches of >= %d points cut into one slice per GPU + NCCL all-gather of the values" % (64 * world),
+                       "n_obs": N, "dim": d, "iterations": its, "nsamples": nsamples, "l2": "latency-bound small batches (10^2-10^3 points)"},
+            "clocks": clocks, "gpu_launches": int(launches), "evals_per_s": nsamples / t_wall,
+            "single_gpu_unsharded_wall_ms": 1e3 * t_single, "same_result_as_unsharded": same, "opt": opt,
+            "e2e": {"value": 1e3 * t_wall, "unit": "ms", "h2d_bytes_per_step": int(nsamples * d * 8), "d2h_bytes_per_step": int(nsamples * 8),
+                    "api": "maximizeEI -> cdirectGP -> ibo_acqmax (host candidates in, values out, every batch)"}}))
+    if dist is not None:
+        L.ibo_comm_destroy()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -438,8 +503,9 @@ def main():
     ap.add_argument("--n-obs", type=int, default=2048)
     ap.add_argument("--dim", type=int, default=6)
     ap.add_argument("--candidates", type=int, default=0, help="per GPU for the default workload (2^20), total for --workload 4 (2^24)")
-    ap.add_argument("--workload", type=int, default=2, choices=[2, 4],
-                    help="2: BASELINE configs[1] (default, the metric's config); 4: configs[3], N=8192 Matern-5/2 ARD, 16M Sobol, strong scaling")
+    ap.add_argument("--workload", type=int, default=2, choices=[2, 4, 5],
+                    help="2: BASELINE configs[1] (default, the metric's config); 4: configs[3], N=8192 Matern-5/2 ARD, 16M Sobol, strong scaling; "
+                         "5: configs[4], batched-DIRECT maximizeEI d=20, N=4096, 200 iterations, batches sharded over the GPUs (wall ms)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--suite", action="store_true", help="extra measurements (maximizeEI wall ms, model build, configs #1/#4/#5)")
     args = ap.parse_args()
@@ -469,6 +535,9 @@ def main():
             uid[0] = buf.raw
         dist.broadcast_object_list(uid, src=0)
         _lib.check(L.ibo_comm_init(device, rank, world, uid[0]))
+
+    if args.workload == 5:
+        return run_direct_workload(args, rank, world, device, dist)
 
     wl = Workload(args, world)
     N, d, M = wl.N, wl.d, wl.M

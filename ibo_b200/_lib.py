@@ -25,11 +25,12 @@ EXPORTED = [
     "ibo_device_synchronize",
     "ibo_direct_batched", "ibo_acqmax", "direct", "acqmaxGP",
     "ibo_comm_unique_id", "ibo_comm_init", "ibo_comm_destroy", "ibo_comm_argmax", "ibo_comm_bcast", "ibo_comm_barrier",
+    "ibo_comm_rank", "ibo_comm_size", "ibo_comm_allgather",
 ]
 
 KERNEL_SE_ARD, KERNEL_SE_ISO, KERNEL_MATERN3, KERNEL_MATERN5, KERNEL_MATERN5_ARD = 0, 1, 2, 3, 4
 ACQ_EI, ACQ_PI, ACQ_UCB = 0, 1, 2
-FLAG_MODE_CPP, FLAG_MODE_PY, FLAG_KSTAR_EXPAND, FLAG_DIRECT_SEQ, FLAG_PROFILE, FLAG_GRAD_EXACT = 0x0, 0x1, 0x2, 0x4, 0x8, 0x10
+FLAG_MODE_CPP, FLAG_MODE_PY, FLAG_KSTAR_EXPAND, FLAG_DIRECT_SEQ, FLAG_PROFILE, FLAG_GRAD_EXACT, FLAG_SHARD = 0x0, 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
 E_BADARG, E_CUDA, E_NOTSPD, E_NOMEM, E_COMM = -1, -2, -3, -4, -5
 
 BATCH_OBJECTIVE = ctypes.CFUNCTYPE(None, c_void_p, c_long, c_int, POINTER(c_double), POINTER(c_double))
@@ -113,6 +114,7 @@ def lib():
     L.ibo_comm_init.argtypes = [c_int, c_int, c_int, ctypes.c_char_p]
     L.ibo_comm_argmax.argtypes = [pd, pl]
     L.ibo_comm_bcast.argtypes = [pd, c_long, c_int]
+    L.ibo_comm_allgather.argtypes = [pd, c_long, pd]
     _lib = L
     return L
 

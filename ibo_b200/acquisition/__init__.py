@@ -118,6 +118,10 @@ def cdirectGP(model, bounds, maxiter, maxtime, maxsample, acqfunc=None, xi=-1, b
     lower = np.array([b[0] for b in bounds], dtype=float)
     upper = np.array([b[1] for b in bounds], dtype=float)
     flags = _lib.FLAG_MODE_CPP | (_lib.FLAG_DIRECT_SEQ if kwargs.get('sequential') else 0)
+    if kwargs.get('shard'):
+        # one process per GPU, communicator set up with ibo_comm_init: every DIRECT batch is cut into one slice per rank
+        # and the values are all-gathered over NVLink; all ranks must call with the same arguments
+        flags |= _lib.FLAG_SHARD
     opt, optx, nsamples, iters = model.model.acqmax(lower, upper, acquisition, np.max(model.Y), parm, flags,
                                                    maxiter=maxiter, maxtime=maxtime, maxsample=maxsample)
     cdirectGP.last = dict(nsamples=nsamples, iterations=iters)

@@ -35,6 +35,10 @@ struct Comm {
     cudaStream_t stream = nullptr;
     unsigned char* dPair = nullptr;    // 16 bytes
     unsigned char* dAll = nullptr;     // 16 * nranks
+    // all-gather of per-rank result slices (sharded DIRECT batches): pinned host staging + device buffers, grown on demand
+    double* hGather = nullptr;         // [count * (nranks + 1)]: own slice, then everybody's
+    double* dGather = nullptr;
+    size_t gatherCap = 0;              // doubles per rank
 } C;
 
 int load_nccl() {
@@ -90,7 +94,44 @@ extern "C" int ibo_comm_destroy(void) {
     if (C.dPair) cudaFree(C.dPair);
     if (C.dAll) cudaFree(C.dAll);
     if (C.stream) cudaStreamDestroy(C.stream);
+    if (C.hGather) cudaFreeHost(C.hGather);
+    if (C.dGather) cudaFree(C.dGather);
+    C.hGather = C.dGather = nullptr; C.gatherCap = 0;
     C.dPair = C.dAll = nullptr; C.stream = nullptr;
+    C.rank = 0; C.nranks = 1;
+    return IBO_OK;
+}
+
+extern "C" int ibo_comm_rank(void) { return C.comm ? C.rank : 0; }
+extern "C" int ibo_comm_size(void) { return C.comm ? C.nranks : 1; }
+
+// all[r * count + i] = rank r's mine[i]; every rank passes the same count (host buffers; one H2D, one NCCL all-gather over
+// NVLink, one D2H on the communicator's stream)
+extern "C" int ibo_comm_allgather(const double* mine, long count, double* all) {
+    if (!mine || !all || count < 0) return IBO_E_BADARG;
+    if (count == 0) return IBO_OK;
+    if (!C.comm) {
+        if (C.nranks == 1) { std::memcpy(all, mine, sizeof(double) * (size_t)count); return IBO_OK; }
+        ibo::set_error("communicator not initialised"); return IBO_E_COMM;
+    }
+    IBO_CUDA_TRY(cudaSetDevice(C.device));
+    const size_t per = (size_t)count, tot = per * (size_t)(C.nranks + 1);
+    if (C.gatherCap < per) {
+        if (C.hGather) cudaFreeHost(C.hGather);
+        if (C.dGather) cudaFree(C.dGather);
+        C.hGather = C.dGather = nullptr; C.gatherCap = 0;
+        size_t cap = per < 4096 ? 4096 : per + per / 2;
+        IBO_CUDA_TRY(cudaHostAlloc((void**)&C.hGather, sizeof(double) * cap * (size_t)(C.nranks + 1), cudaHostAllocPortable));
+        IBO_CUDA_TRY(cudaMalloc((void**)&C.dGather, sizeof(double) * cap * (size_t)(C.nranks + 1)));
+        C.gatherCap = cap;
+    }
+    (void)tot;
+    std::memcpy(C.hGather, mine, sizeof(double) * per);
+    IBO_CUDA_TRY(cudaMemcpyAsync(C.dGather, C.hGather, sizeof(double) * per, cudaMemcpyHostToDevice, C.stream));
+    NCCL_TRY(N.AllGather(C.dGather, C.dGather + per, per, ncclFloat64, C.comm, C.stream));
+    IBO_CUDA_TRY(cudaMemcpyAsync(C.hGather + per, C.dGather + per, sizeof(double) * per * (size_t)C.nranks, cudaMemcpyDeviceToHost, C.stream));
+    IBO_CUDA_TRY(cudaStreamSynchronize(C.stream));
+    std::memcpy(all, C.hGather + per, sizeof(double) * per * (size_t)C.nranks);
     return IBO_OK;
 }
 

@@ -378,13 +378,34 @@ void scalar_batch(void* user, long n, int ndim, const double* X, double* y) {
     }
 }
 
-struct GpuObjective { ibo_model* m; int acq; double ymax, parm; int flags; int rc; double t_eval; long batches, points; };
+struct GpuObjective {
+    ibo_model* m; int acq; double ymax, parm; int flags; int rc; double t_eval; long batches, points;
+    long shard_min = 0; long sharded_batches = 0; std::vector<double> mine, all;
+};
 void gpu_batch(void* user, long n, int ndim, const double* X, double* y) {
     GpuObjective* g = static_cast<GpuObjective*>(user);
-    (void)ndim;
     if (g->rc != IBO_OK) { for (long i = 0; i < n; i++) y[i] = 0.0; return; }
     auto t0 = std::chrono::steady_clock::now();
-    g->rc = eval_neg_acq(g->m, X, n, g->acq, g->ymax, g->parm, g->flags, y);
+    const int world = (g->flags & IBO_FLAG_SHARD) ? ibo_comm_size() : 1;
+    if (world > 1 && n >= g->shard_min) {
+        // Every rank runs the same deterministic driver on the same model; a batch is cut into `world` contiguous slices
+        // of `per` points, rank r evaluates slice r, and the values are all-gathered (NCCL over NVLink).  A candidate's
+        // value does not depend on the batch it is evaluated in (DESIGN.md "Determinism"), so the trajectory is the
+        // single-GPU one bit for bit.
+        const long per = (n + world - 1) / world;
+        const int rank = ibo_comm_rank();
+        const long lo = std::min((long)rank * per, n), hi = std::min(lo + per, n);
+        g->mine.assign((size_t)per, 0.0);
+        g->all.resize((size_t)per * world);
+        if (hi > lo) g->rc = eval_neg_acq(g->m, X + (size_t)lo * ndim, hi - lo, g->acq, g->ymax, g->parm, g->flags, g->mine.data());
+        // the collective is entered even after a local failure so that the other ranks are not left waiting
+        int rc2 = ibo_comm_allgather(g->mine.data(), per, g->all.data());
+        if (g->rc == IBO_OK) g->rc = rc2;
+        if (g->rc == IBO_OK) std::memcpy(y, g->all.data(), sizeof(double) * (size_t)n);
+        g->sharded_batches++;
+    } else {
+        g->rc = eval_neg_acq(g->m, X, n, g->acq, g->ymax, g->parm, g->flags, y);
+    }
     g->t_eval += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     g->batches++; g->points += n;
     if (g->rc != IBO_OK) for (long i = 0; i < n; i++) y[i] = 0.0;
@@ -404,13 +425,17 @@ extern "C" int ibo_acqmax(ibo_model* m, const double* lb, const double* ub, int 
                           int maxiter, int maxtime, int maxsample, double* opt, double* optx, long* nsamples, int* iterations) {
     if (!m || acq < 0 || acq > 2) { set_error("bad argument"); return IBO_E_BADARG; }
     GpuObjective g{m, acq, ymax, parm, flags, IBO_OK, 0.0, 0, 0};
+    if (flags & IBO_FLAG_SHARD) {
+        const char* e = getenv("IBO_SHARD_MIN");       // batches below this many points stay on every rank (latency)
+        g.shard_min = e ? atol(e) : 64L * ibo_comm_size();
+    }
     double fmin = 0;
     auto t0 = std::chrono::steady_clock::now();
     int rc = run_direct(gpu_batch, &g, ibo_model_dim(m), lb, ub, maxiter, maxtime, maxsample, flags, &fmin, optx, nsamples, iterations);
     if (getenv("IBO_DIRECT_TIMING")) {
         double tt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        fprintf(stderr, "[ibo_acqmax] total %.3f ms, GPU batches %.3f ms (%ld batches, %ld points, %.1f us/batch), host driver %.3f ms\n",
-                1e3 * tt, 1e3 * g.t_eval, g.batches, g.points, g.batches ? 1e6 * g.t_eval / g.batches : 0.0, 1e3 * (tt - g.t_eval));
+        fprintf(stderr, "[ibo_acqmax] total %.3f ms, GPU batches %.3f ms (%ld batches, %ld sharded, %ld points, %.1f us/batch), host driver %.3f ms\n",
+                1e3 * tt, 1e3 * g.t_eval, g.batches, g.sharded_batches, g.points, g.batches ? 1e6 * g.t_eval / g.batches : 0.0, 1e3 * (tt - g.t_eval));
     }
     if (rc) return rc;
     if (g.rc) return g.rc;

@@ -52,6 +52,8 @@ extern "C" {
 #define IBO_FLAG_KSTAR_EXPAND  0x2  /* cross-covariance through |x|^2+|y|^2-2x.y on the DMMA pipe (default: direct differences) */
 #define IBO_FLAG_DIRECT_SEQ    0x4  /* DIRECT: evaluate rectangle by rectangle in the reference's call order */
 #define IBO_FLAG_PROFILE       0x8  /* record per-kernel CUDA-event times (ibo_get_profile) */
+#define IBO_FLAG_SHARD         0x20 /* ibo_acqmax: cut every DIRECT batch into one slice per rank of the communicator
+                                       (ibo_comm_init) and all-gather the values; all ranks must make the same call */
 #define IBO_FLAG_GRAD_EXACT    0x10 /* ibo_nlml / ibo_kernel_matrix: analytic Matern-3/2 length-scale derivative instead of
                                        the reference's expression with the unscaled distance (kernel.py:217-222) */
 
@@ -203,6 +205,10 @@ int ibo_comm_argmax(double* score, long* index);
 /* broadcast `count` doubles in HOST memory from root through device buffers over NVLink */
 int ibo_comm_bcast(double* buf, long count, int root);
 int ibo_comm_barrier(void);
+int ibo_comm_rank(void);                                       /* 0 when no communicator */
+int ibo_comm_size(void);                                       /* 1 when no communicator */
+/* all[r * count + i] = rank r's mine[i] (host buffers, same count on every rank) */
+int ibo_comm_allgather(const double* mine, long count, double* all);
 
 #ifdef __cplusplus
 }

@@ -86,3 +86,65 @@ def test_two_rank_gloo_argmax():
             assert (s, i) == (-1.0, 5)
         else:
             assert i == int(np.argmax(scores)) and s == scores.max()
+
+
+DIRECT_WORKER = r'''
+import os, sys, json
+import numpy as np
+sys.path.insert(0, %(root)r)
+import torch.distributed as dist
+from ibo_b200.utils.optimize import direct
+from ibo_b200.utils.sharding import sharded_batch_objective
+from oracle import ibo_oracle as orc
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rs = np.random.RandomState(7)
+X = rs.rand(40, 3); Y = np.sin(3 * X).sum(axis=1)
+gp = orc.GPOracle(orc.KernelSpec(orc.K_SE_ARD, [.3, .4, .5], 3), X, Y, 0.1)
+calls = []
+def negei(P):
+    calls.append(len(P))
+    mu, s2 = gp.posterior_batch(P)
+    return -orc.score(orc.ACQ_EI, "py", mu, s2, Y.max(), 0.01)
+f = sharded_batch_objective(negei, dist, min_points=int(os.environ["MINPTS"]))
+fmin, xmin = direct(None, [[0., 1.]] * 3, maxiter=12, batch_objective=f)
+print("RESULT" + json.dumps([fmin, list(xmin), sum(calls), len(calls)]))
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_gloo_sharded_direct_follows_the_single_rank_trajectory():
+    """config #5's multi-GPU scheme on CPU: both ranks drive the same batched DIRECT (host C++ of libibo_b200), each
+    evaluates half of every batch (here with the oracle as objective), values are all-gathered; result and trajectory must be
+    those of the unsharded run"""
+    import json
+    from ibo_b200.utils.optimize import direct
+    from oracle import ibo_oracle as orc
+    rs = np.random.RandomState(7)
+    X = rs.rand(40, 3); Y = np.sin(3 * X).sum(axis=1)
+    gp = orc.GPOracle(orc.KernelSpec(orc.K_SE_ARD, [.3, .4, .5], 3), X, Y, 0.1)
+    npts = []
+
+    def negei(P):
+        npts.append(len(P))
+        mu, s2 = gp.posterior_batch(P)
+        return -orc.score(orc.ACQ_EI, "py", mu, s2, Y.max(), 0.01)
+    fmin1, xmin1 = direct(None, [[0., 1.]] * 3, maxiter=12, batch_objective=negei)
+    for minpts in (0, 16):
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        procs = []
+        for rank in range(2):
+            env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), MINPTS=str(minpts))
+            procs.append(subprocess.Popen([sys.executable, "-c", DIRECT_WORKER % {"root": ROOT}], env=env, stdout=subprocess.PIPE,
+                                          stderr=subprocess.PIPE, text=True))
+        outs = [p.communicate(timeout=240) for p in procs]
+        res = []
+        for (o, e), p in zip(outs, procs):
+            assert p.returncode == 0, e[-2000:]
+            res.append(json.loads([ln for ln in o.splitlines() if ln.startswith("RESULT")][0][6:]))
+        for r in res:
+            assert abs(r[0] - fmin1) <= 1e-12 * abs(fmin1) and np.allclose(r[1], xmin1, rtol=0, atol=0)
+        assert res[0][3] == len(npts)                                  # same batches (rank 1 skips the 1-point first batch)
+        if minpts == 0:
+            assert res[0][2] + res[1][2] == sum(npts)                  # every point evaluated exactly once across ranks
