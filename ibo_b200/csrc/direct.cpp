@@ -49,9 +49,25 @@ struct Store {
     // members: binary min-heap on (y, id).  Only class minima are ever taken out (they are the rectangles that get
     // divided), so a heap -- contiguous, no node allocation -- is all the order structure DIRECT needs.
     struct Class { double d; std::vector<std::pair<double, unsigned> > heap; };
-    std::vector<Class> classes;
+    std::vector<Class> classes;          // only the first `ncls` entries are in use (the rest keep their heap capacity)
+    size_t ncls = 0;
     std::unordered_map<unsigned long long, int> cls_of_d;
     size_t live = 0;
+
+    // The store is kept per host thread and reused by successive queries (sequential BO / the gallery issue one DIRECT
+    // run per step): clearing keeps the capacity, so only the first query pays for growing ~25 MB of rectangle
+    // geometry through fresh pages (that growth was ~40 % of the host driver time at d = 20, 200 iterations).
+    void reset(int ndim) {
+        N = ndim;
+        if (lb.capacity() > ((size_t)1 << 27)) {      // > 1 GiB per array: give the memory back
+            std::vector<double>().swap(lb); std::vector<double>().swap(ub); std::vector<double>().swap(center);
+        }
+        lb.clear(); ub.clear(); center.clear(); d.clear(); y.clear(); cls.clear(); alive.clear();
+        for (size_t k = 0; k < ncls; k++) classes[k].heap.clear();
+        ncls = 0;
+        cls_of_d.clear();
+        live = 0;
+    }
 
     static double key(double y) { return y != y ? MAX_DOUBLE : y; }   // NaN sorts last
     static bool heap_gt(const std::pair<double, unsigned>& a, const std::pair<double, unsigned>& b) { return a > b; }
@@ -62,7 +78,11 @@ struct Store {
         unsigned long long bits; std::memcpy(&bits, &dd, 8);
         auto it = cls_of_d.find(bits);
         int k;
-        if (it == cls_of_d.end()) { k = (int)classes.size(); classes.push_back(Class()); classes.back().d = dd; cls_of_d[bits] = k; }
+        if (it == cls_of_d.end()) {
+            k = (int)ncls++;
+            if (classes.size() < ncls) classes.push_back(Class());
+            classes[k].d = dd; cls_of_d[bits] = k;
+        }
         else k = it->second;
         cls.push_back(k);
         auto& h = classes[k].heap;
@@ -144,6 +164,11 @@ struct Scratch {
     std::vector<double> mid_lb, mid_ub;          // shrunk middle rectangles, one per Pending
 };
 
+// phase timers of the host driver (printed by run_direct when IBO_DIRECT_TIMING is set)
+struct PhaseTimes { double select = 0, probes = 0, children = 0, replay = 0; };
+static thread_local PhaseTimes g_pt;
+static inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 // Divides the given rectangles (already in processing order): appends the new rectangles in the reference's
 // order and retires the sources.  seq: one rectangle per batch pair (the reference's exact call order).
 void divide(Driver& D, Store& R, const std::vector<unsigned>& order, bool seq, Scratch& W) {
@@ -155,6 +180,7 @@ void divide(Driver& D, Store& R, const std::vector<unsigned>& order, bool seq, S
         W.P.assign(np_rect, Pending());
         W.dims.clear(); W.pts.clear();
         // ---- phase A: probe points at lb + w/3, lb + 2w/3 along every longest side (cpp/direct.cpp:156-192)
+        double tA = now_s();
         long np = 0;
         for (size_t t = g0; t < g1; t++) {
             Pending& p = W.P[t - g0];
@@ -180,7 +206,9 @@ void divide(Driver& D, Store& R, const std::vector<unsigned>& order, bool seq, S
                 }
             }
         }
+        g_pt.probes += now_s() - tA;
         D.eval(W.pts, np, W.yA);
+        double tB = now_s();
         // ---- sort the dims by min(sf1, sf2) and build the children (cpp/direct.cpp:181-232)
         const size_t nchild = (size_t)np;            // two children per probed side
         W.clb.resize(nchild * N); W.cub.resize(nchild * N); W.ptsB.resize(nchild * N); W.cd.resize(nchild);
@@ -224,7 +252,9 @@ void divide(Driver& D, Store& R, const std::vector<unsigned>& order, bool seq, S
             for (int i = 0; i < N; i++) d += std::pow((olb[i] - ocp[i]), 2);
             p.old_d = std::sqrt(d);
         }
+        g_pt.children += now_s() - tB;
         D.eval(W.ptsB, nc, W.yB);
+        double tC = now_s();
         // ---- replay the reference's call order for FMIN / nsamples, then append the rectangles
         std::vector<double> oc(N);
         for (size_t t = 0; t < np_rect; t++) {
@@ -242,6 +272,7 @@ void divide(Driver& D, Store& R, const std::vector<unsigned>& order, bool seq, S
             R.retire(p.src);
             R.add(&W.mid_lb[t * N], &W.mid_ub[t * N], oc.data(), p.old_d, oy);
         }
+        g_pt.replay += now_s() - tC;
         g0 = g1;
     }
 }
@@ -258,7 +289,7 @@ void select(Store& R, double FMIN, std::vector<unsigned>& potopts) {
     potopts.clear();
     std::vector<double> cd, cy;
     std::vector<int> ck;
-    for (size_t k = 0; k < R.classes.size(); k++) {
+    for (size_t k = 0; k < R.ncls; k++) {
         if (R.classes[k].heap.empty()) continue;
         unsigned id = R.classes[k].heap.front().second;
         cd.push_back(R.classes[k].d); cy.push_back(R.y[id]); ck.push_back((int)k);
@@ -279,21 +310,36 @@ void select(Store& R, double FMIN, std::vector<unsigned>& potopts) {
             if (!have || cy[k] < sufmin) { sufmin = cy[k]; have = true; }
         }
     }
+    // classes in ascending d (distinct by construction): sd / sy are the sorted copies the slope scans stream through
+    std::vector<double> sd(C), sy(C);
+    for (size_t t = 0; t < C; t++) { sd[t] = cd[byd[t]]; sy[t] = cy[byd[t]]; }
+    std::vector<size_t> pos(C);
+    for (size_t t = 0; t < C; t++) pos[byd[t]] = t;
     for (size_t k = 0; k < C; k++) {
         if (dominated[k]) continue;
         const double dj = cd[k], yj = cy[k];
         double maxI1 = MIN_DOUBLE, minI2 = MAX_DOUBLE;
         bool breaked = false;
-        for (size_t c = 0; c < C && !breaked; c++) {
-            if (cd[c] < dj) {
-                double val = (yj - cy[c]) / (dj - cd[c]);
+        // maxI1 = max over smaller classes of (yj - yc)/(dj - dc), minI2 = min over larger classes of (yc - yj)/(dc - dj):
+        // max / min do not depend on the visiting order, so the scan walks outwards from the class's own position, where
+        // the steepest slopes usually are, and stops at the first moment the reference's final test `minI2 < maxI1` is
+        // already decided (maxI1 only grows, minI2 only shrinks) -- same accept / reject, a fraction of the divisions.
+        // (`minI2 <= 0` cannot occur here: that is the `dominated` case above.)
+        const size_t t = pos[k];
+        size_t l = t, r = t + 1;
+        while ((l > 0 || r < C) && !breaked) {
+            if (l > 0) {
+                --l;
+                double val = (yj - sy[l]) / (dj - sd[l]);
                 if (val > maxI1) maxI1 = val;
-            } else if (cd[c] > dj) {
-                double val = (cy[c] - yj) / (cd[c] - dj);
-                if (val < minI2) { minI2 = val; if (minI2 <= 0.) breaked = true; }
             }
+            if (r < C) {
+                double val = (sy[r] - yj) / (sd[r] - dj);
+                if (val < minI2) minI2 = val;
+                ++r;
+            }
+            if (maxI1 != MIN_DOUBLE && minI2 != MAX_DOUBLE && minI2 < maxI1) breaked = true;
         }
-        if (!breaked && maxI1 != MIN_DOUBLE && minI2 != MAX_DOUBLE && minI2 < maxI1) breaked = true;
         if (breaked) continue;
         bool ok = false;
         if (minI2 == MAX_DOUBLE) ok = true;
@@ -317,7 +363,8 @@ int run_direct(ibo_batch_objective_t f, void* user, int ndim, const double* lb, 
     D.lowerb.assign(lb, lb + ndim); D.upperb.assign(ub, ub + ndim);
     D.fixed.resize(ndim);
     for (int i = 0; i < ndim; i++) D.fixed[i] = (lb[i] == ub[i]);
-    Store R; R.N = ndim;
+    static thread_local Store R;
+    R.reset(ndim);
     // first rectangle: the unit cube, sampled at its centre (cpp/direct.cpp:349-357)
     {
         std::vector<double> l(ndim, 0.0), u(ndim, 1.0), c(ndim);
@@ -328,7 +375,7 @@ int run_direct(ibo_batch_objective_t f, void* user, int ndim, const double* lb, 
         R.add(l.data(), u.data(), c.data(), d, y[0]);
     }
     std::vector<unsigned> potopts, order;
-    Scratch W;
+    static thread_local Scratch W;
     order.clear();
     R.pop_minima(R.cls[0], order);      // the unit cube leaves its heap like any rectangle about to be divided
     divide(D, R, order, seq, W);
@@ -336,7 +383,9 @@ int run_direct(ibo_batch_objective_t f, void* user, int ndim, const double* lb, 
     bool done = false;
     while (iteration < maxiter && !done) {
         iteration++;
+        double tS = now_s();
         select(R, D.FMIN, potopts);
+        g_pt.select += now_s() - tS;
         if (potopts.empty()) break;    // "could not divide any more" (cpp/direct.cpp:473-477)
         // division order: highest index first; stop after the rectangle that pushes nsamples past
         // maxsample (cpp/direct.cpp:479-492).  Each rectangle costs 4 samples per longest side, which is
@@ -361,6 +410,11 @@ int run_direct(ibo_batch_objective_t f, void* user, int ndim, const double* lb, 
         if (time(NULL) - start > maxtime) break;
         if (D.nsamples > (long)(unsigned)maxsample) break;
     }
+    if (getenv("IBO_DIRECT_TIMING"))
+        fprintf(stderr, "[run_direct] host phases: select %.3f ms, probe build %.3f ms, child build %.3f ms, replay+append %.3f ms; "
+                        "%zu rectangles, %zu classes\n", 1e3 * g_pt.select, 1e3 * g_pt.probes, 1e3 * g_pt.children, 1e3 * g_pt.replay,
+                R.d.size(), R.ncls);
+    g_pt = PhaseTimes();
     if (fmin) *fmin = D.FMIN;
     if (xmin) for (int i = 0; i < ndim; i++) xmin[i] = D.XMIN.empty() ? lb[i] : D.XMIN[i];
     if (nsamples) *nsamples = D.nsamples;
