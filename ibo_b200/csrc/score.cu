@@ -154,9 +154,12 @@ __global__ void __launch_bounds__(256) kstar_mma_kernel(const double* __restrict
         valid[ks2][0] = (rowbase + ks2 * 8 + k4) < N;
         valid[ks2][1] = (rowbase + ks2 * 8 + k4 + 4) < N;
     }
-    const int ntv = valid_ntiles(M, m0, T);
+    // small batches split the 16 n-tiles of a candidate tile over gridDim.z CTAs (4x the CTAs, a quarter of the dependent
+    // exp chain each): K1 of a 162-point DIRECT batch at N = 4096 otherwise runs 64 CTAs of 64 exps per thread
+    const int ntPer = 16 / (int)gridDim.z;
+    const int ntv = min(valid_ntiles(M, m0, T), ((int)blockIdx.z + 1) * ntPer);
 #pragma unroll 2
-    for (int nt = 0; nt < ntv; nt++) {
+    for (int nt = (int)blockIdx.z * ntPer; nt < ntv; nt++) {
         double afr[DP4];
 #pragma unroll
         for (int s4 = 0; s4 < DP4; s4++) afr[s4] = sC[(nt * 8 + n8) * S + 4 * s4 + k4];
@@ -761,6 +764,10 @@ static void launch_kstar(const ibo_model* m, const double* dCand, double* slab, 
         kstar_kernel<<<grid, 256, 2 * 128 * kS * 8, st>>>(m->dXt, dCand, m->dInvTheta, m->dCenter, slab, m->N, m->d, m->nb, M, m0, m->kind, m->sf2);
         return;
     }
+    // few CTAs (DIRECT / gallery batches): split each candidate tile's n-tiles over grid.z until the grid covers the SMs
+    unsigned z = 1;
+    while (z < 16 && (long)tiles * m->nb * z < g_num_sms) z *= 2;
+    grid.z = z;
     switch (dp4) {
         case 1: launch_kstar_mma<1>(grid, st, m, dCand, slab, M, m0); break;
         case 2: launch_kstar_mma<2>(grid, st, m, dCand, slab, M, m0); break;
