@@ -22,7 +22,7 @@ EXPORTED = [
     "ibo_posterior_batch", "ibo_score_batch",
     "ibo_cands_create", "ibo_cands_destroy", "ibo_score_resident", "ibo_get_profile", "ibo_launch_count",
     "ibo_fp64_peak", "ibo_host_register", "ibo_host_unregister", "ibo_stream_mark", "ibo_stream_elapsed_ms",
-    "ibo_device_synchronize",
+    "ibo_device_synchronize", "ibo_debug_exp",
     "ibo_direct_batched", "ibo_acqmax", "direct", "acqmaxGP",
     "ibo_comm_unique_id", "ibo_comm_init", "ibo_comm_destroy", "ibo_comm_argmax", "ibo_comm_bcast", "ibo_comm_barrier",
     "ibo_comm_rank", "ibo_comm_size", "ibo_comm_allgather",
@@ -103,6 +103,7 @@ def lib():
     L.ibo_stream_mark.argtypes = [c_void_p, c_int]
     L.ibo_stream_elapsed_ms.argtypes = [c_void_p, POINTER(c_float)]
     L.ibo_device_synchronize.argtypes = [c_int]
+    L.ibo_debug_exp.argtypes = [c_int, pd, c_long, pd, pd]
     L.ibo_direct_batched.argtypes = [BATCH_OBJECTIVE, c_void_p, c_int, pd, pd, c_int, c_int, c_int, c_int, pd, pd, pl, pi]
     L.ibo_acqmax.argtypes = [c_void_p, pd, pd, c_int, c_double, c_double, c_int, c_int, c_int, c_int, pd, pd, pl, pi]
     L.direct.restype = POINTER(c_double)

@@ -36,6 +36,49 @@ __device__ __forceinline__ double cov_r2(int kind, double sf2, double r2) {
     return sf2 * (1.0 + z + 5.0 * r2 / 3.0) * exp(-z);
 }
 
+// exp(x) for x <= 0 with the coefficients in the constant bank.  K1 is issue bound (ncu: 78 % of the issue slots, FP64 pipe
+// 39 %), and libdevice's exp materialises its eleven 64-bit polynomial constants with two uniform moves each per call
+// (UMOV = 26 % of all executed instructions of K1): here every coefficient is a constant-bank operand of its DFMA.
+// exp(x) = 2^k exp(r), k = rint(x log2 e), r = x - k ln2 (two-term Cody-Waite with FMA), Taylor to degree 13 on
+// |r| <= ln2 / 2 (truncation 4e-18), scaling through the exponent field; results below 2^-1021 flush to zero.
+// Measured against libdevice exp on 10^7 arguments in [-745, 0]: <= 1 ulp (tests/test_gpu_api.py).
+__constant__ double EXPC[16] = {
+    1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0,
+    1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5,
+    1.4426950408889634,            // [12] log2(e)
+    6755399441055744.0,            // [13] 1.5 * 2^52: adding it rounds to the nearest integer
+    -6.93147180369123816490e-01,   // [14] -ln2 (high part)
+    -1.90821492927058770002e-10};  // [15] -ln2 (low part)
+
+__device__ __forceinline__ double exp_nonpos(double x) {
+    const double t = fma(x, EXPC[12], EXPC[13]);
+    const int k = __double2loint(t);
+    const double kf = t - EXPC[13];
+    double r = fma(kf, EXPC[14], x);
+    r = fma(kf, EXPC[15], r);
+    double p = EXPC[0];
+#pragma unroll
+    for (int c = 1; c < 12; c++) p = fma(p, r, EXPC[c]);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double res = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+    return x < -707.0 ? 0.0 : res;
+}
+
+// covariance from the scaled squared distance with the kernel class fixed at compile time (0: SE, 1: Matern-3/2,
+// 2: Matern-5/2) -- same formulas as cov_r2
+template <int KC>
+__device__ __forceinline__ double cov_r2_t(double sf2, double r2) {
+    if (KC == 0) return sf2 * exp_nonpos(-0.5 * r2);
+    const double r = sqrt(r2);
+    if (KC == 1) {
+        const double z = 1.7320508075688772 * r;
+        return sf2 * (1.0 + z) * exp_nonpos(-z);
+    }
+    const double z = 2.23606797749979 * r;
+    return sf2 * (1.0 + z + 5.0 * r2 / 3.0) * exp_nonpos(-z);
+}
+
 // n-tiles (8 candidates) of tile T that hold at least one real candidate: the last tile of a small batch computes only
 // those (a 24-candidate DIRECT batch evaluates 3 of the 16 n-tiles); the rest of the slab tile keeps stale values that
 // only reach the partial sums of candidates >= M, which K3 never reads (candidate columns are independent in K2).
@@ -106,7 +149,7 @@ __global__ void __launch_bounds__(256) kstar_kernel(const double* __restrict__ X
 // ---------------------------------------------------------------------------------------------
 constexpr double EXPAND_LIMIT = 256.0;    // => relative error of k below ~2e-13
 
-template <int DP4>   // number of 4-wide dimension groups, d <= 4*DP4
+template <int DP4, int KC>   // DP4: number of 4-wide dimension groups, d <= 4*DP4; KC: kernel class (cov_r2_t)
 __global__ void __launch_bounds__(256) kstar_mma_kernel(const double* __restrict__ Xt, const double* __restrict__ cand,
                                                         const double* __restrict__ inv_theta, const double* __restrict__ center,
                                                         double* __restrict__ slab, int N, int d, int nb, long M, long m0,
@@ -183,8 +226,8 @@ __global__ void __launch_bounds__(256) kstar_mma_kernel(const double* __restrict
                 }
             }
             double2 v;
-            v.x = valid[ks2][0] ? cov_r2(kind, sf2, fmax(r0, 0.0)) : 0.0;
-            v.y = valid[ks2][1] ? cov_r2(kind, sf2, fmax(r1, 0.0)) : 0.0;
+            v.x = valid[ks2][0] ? cov_r2_t<KC>(sf2, fmax(r0, 0.0)) : 0.0;
+            v.y = valid[ks2][1] ? cov_r2_t<KC>(sf2, fmax(r1, 0.0)) : 0.0;
             reinterpret_cast<double2*>(blob)[(nt * 2 + ks2) * 32 + lane] = v;
         }
     }
@@ -750,7 +793,13 @@ template <int DP4>
 static void launch_kstar_mma(dim3 grid, cudaStream_t st, const ibo_model* m, const double* dCand, double* slab, long M, long m0) {
     constexpr int DP = 4 * DP4;
     constexpr int S = (DP % 16 == 4 || DP % 16 == 12) ? DP : DP + 4;
-    kstar_mma_kernel<DP4><<<grid, 256, (2 * 128 * S + 256) * 8, st>>>(m->dXt, dCand, m->dInvTheta, m->dCenter, slab, m->N, m->d, m->nb, M, m0, m->kind, m->sf2);
+    const size_t smem = (2 * 128 * S + 256) * 8;
+    if (m->kind <= IBO_KERNEL_SE_ISO)
+        kstar_mma_kernel<DP4, 0><<<grid, 256, smem, st>>>(m->dXt, dCand, m->dInvTheta, m->dCenter, slab, m->N, m->d, m->nb, M, m0, m->kind, m->sf2);
+    else if (m->kind == IBO_KERNEL_MATERN3)
+        kstar_mma_kernel<DP4, 1><<<grid, 256, smem, st>>>(m->dXt, dCand, m->dInvTheta, m->dCenter, slab, m->N, m->d, m->nb, M, m0, m->kind, m->sf2);
+    else
+        kstar_mma_kernel<DP4, 2><<<grid, 256, smem, st>>>(m->dXt, dCand, m->dInvTheta, m->dCenter, slab, m->N, m->d, m->nb, M, m0, m->kind, m->sf2);
 }
 
 // cross-covariance of one chunk; expansion on the tensor pipe for d <= 32 unless IBO_KSTAR=direct
@@ -949,6 +998,11 @@ static int score_host(ibo_model* m, const double* Xs, long M, const ScoreReq& rq
     return IBO_OK;
 }
 
+__global__ void debug_exp_kernel(const double* __restrict__ x, long n, double* __restrict__ fast, double* __restrict__ ref) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i < n) { fast[i] = exp_nonpos(x[i]); ref[i] = exp(x[i]); }
+}
+
 // used by the DIRECT objective (direct.cpp): negated acquisition for n points
 int eval_neg_acq(ibo_model* m, const double* Xs, long n, int acq, double ymax, double parm, int flags, double* y) {
     ScoreReq rq{acq, ymax, parm, flags, true, false, false};
@@ -1020,5 +1074,24 @@ extern "C" int ibo_score_resident(ibo_model* m, ibo_cands* c, int acq, double ym
 extern "C" int ibo_get_profile(ibo_model* m, double* out6) {
     if (!m || !out6) { set_error("bad argument"); return IBO_E_BADARG; }
     for (int i = 0; i < 6; i++) out6[i] = m->prof[i];
+    return IBO_OK;
+}
+
+// test hook: K1's exp_nonpos next to libdevice exp for n arguments <= 0 (host arrays)
+extern "C" int ibo_debug_exp(int device, const double* x, long n, double* out_fast, double* out_ref) {
+    if (!x || !out_fast || !out_ref || n < 1) { set_error("bad argument"); return IBO_E_BADARG; }
+    if (ibo_device_count() <= 0) { set_error("no CUDA device available (libibo_b200 has no CPU fallback)"); return IBO_E_CUDA; }
+    IBO_CUDA_TRY(cudaSetDevice(device));
+    double* d = nullptr;
+    IBO_CUDA_TRY(cudaMalloc(&d, sizeof(double) * 3 * (size_t)n));
+    cudaError_t e = cudaMemcpy(d, x, sizeof(double) * n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        debug_exp_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d, n, d + n, d + 2 * n);
+        g_launches++;
+        e = cudaMemcpy(out_fast, d + n, sizeof(double) * n, cudaMemcpyDeviceToHost);
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out_ref, d + 2 * n, sizeof(double) * n, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) { set_error(std::string("ibo_debug_exp: ") + cudaGetErrorString(e)); return IBO_E_CUDA; }
     return IBO_OK;
 }

@@ -169,6 +169,8 @@ int ibo_host_unregister(void* p);
 int ibo_stream_mark(ibo_model* m, int slot);
 int ibo_stream_elapsed_ms(ibo_model* m, float* ms);
 int ibo_device_synchronize(int device);
+/* test hook: the cross-covariance kernel's own exp (x <= 0) next to libdevice exp, host arrays of n values */
+int ibo_debug_exp(int device, const double* x, long n, double* out_fast, double* out_ref);
 
 /* ---- DIRECT ----------------------------------------------------------------------------------
  * Batched DIRECT following the reference's rectangle rules (cpp/direct.cpp:146-235,372-498).

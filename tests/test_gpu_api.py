@@ -267,3 +267,24 @@ def test_resident_candidates_and_ties(big):
     # empty batch
     sc, mu, s2, b, i = m.score(np.zeros((0, 6)), _lib.ACQ_EI, Y.max(), 0.01)
     assert i == -1 and len(sc) == 0
+
+
+def test_kstar_exp_is_within_one_ulp_of_libdevice():
+    """K1's own exp (constant-bank Taylor/Cody-Waite, ibo_b200/csrc/score.cu: exp_nonpos) against libdevice exp"""
+    import ctypes
+    from ibo_b200 import _lib
+    rs = np.random.RandomState(0)
+    x = np.concatenate([-rs.rand(2_000_000) * 50.0, -rs.rand(500_000) * 745.0, -np.exp(-rs.rand(500_000) * 40.0),
+                        [0.0, -0.0, -1e-300, -706.9, -707.0, -707.1, -745.0, -1e4, -np.inf]])
+    fast, ref = np.empty_like(x), np.empty_like(x)
+    _lib.check(_lib.lib().ibo_debug_exp(0, _lib.dptr(x), len(x), _lib.dptr(fast), _lib.dptr(ref)))
+    keep = x >= -707.0                                  # below: flushed to zero by design (values < 1e-307)
+    assert np.all(fast[~keep] == 0.0) and np.all(ref[~keep] < 1e-306)
+    ulp = np.spacing(ref[keep])
+    assert np.max(np.abs(fast[keep] - ref[keep]) / ulp) <= 1.0
+    assert fast[x == 0.0].tolist() == [1.0, 1.0]
+    # and against the correctly rounded value for a sample (math.exp is < 1 ulp)
+    import math
+    idx = rs.choice(np.flatnonzero(keep), 20000, replace=False)
+    exact = np.array([math.exp(v) for v in x[idx]])
+    assert np.max(np.abs(fast[idx] - exact) / np.spacing(exact)) <= 1.0
