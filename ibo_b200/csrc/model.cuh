@@ -63,6 +63,10 @@ struct ibo_cands {
 };
 
 namespace ibo {
+struct ScoreReq;
+// fused single-launch path for models of one row-block (tiny.cu)
+bool tiny_eligible(const ibo_model* m);
+int score_tiny(ibo_model* m, const double* cand, long M, const ScoreReq& rq, double* out);
 int grow(double** p, size_t* cap, size_t need);
 cudaError_t pool_malloc(void** p, size_t bytes);
 void pool_free(void* p);

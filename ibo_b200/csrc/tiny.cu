@@ -1,0 +1,233 @@
+// Fused scoring kernel for small models (N <= 128: one 128-row block) -- the reference's own operating point
+// (demo.py, the unit tests and interactive galleries work with tens of observations, BASELINE.json config #1).
+//
+// Replaces, in one launch, GaussianProcess.posterior + EI/PI/UCB.negf per candidate (ego/gaussianprocess/__init__.py:169-228,
+// ego/acquisition/__init__.py:60-164) / GP_Maximizer::posterior + negei/negpi/negucb (cpp/optimizeGP.cpp:57-236).
+//
+// For such models the general path (K1 -> K2 -> K3, score.cu) is pure latency: three dependent launches, an H2D DMA and
+// a slab round trip for ~N^2/2 = a few thousand FMAs per candidate.  Here one CTA keeps W = inv(L) transposed in shared
+// memory and walks tiles of 8 candidates: k* by direct differences (no expansion, no cancellation), v = W k* with one
+// thread per training row (ascending-k FMA chains, 8 candidates in flight per thread), the three row reductions in a
+// fixed order, then the epilogue.  For a DIRECT batch the candidates are read straight from mapped pinned host memory
+// and the values are written straight back to it: one launch and one stream synchronisation per batch.
+// A candidate's value is a function of (model, x) only (fixed summation orders), so DIRECT trajectories stay reproducible.
+#include "model.cuh"
+#include "scoremath.cuh"
+#include <mutex>
+
+namespace ibo {
+namespace {
+
+constexpr int TC = 8;        // candidates per tile
+constexpr int WS = 129;      // row stride of the transposed W in shared memory (conflict-free both ways)
+
+struct TinyParams {
+    const double *W, *Xt, *betaY, *beta1, *invTheta, *center, *cand;
+    const double *pmeans, *pbeta, *plb, *pwidth;
+    double *score, *mu, *s2;
+    double* blkBest; long long* blkIdx;
+    long M;
+    int N, d, acq, mode_py, npb, want_argmax;
+    double sf2, noise, ymax, parm, ptheta;
+};
+
+template <int KC>
+__global__ void __launch_bounds__(128) tiny_fused_kernel(TinyParams P) {
+    extern __shared__ double sm[];
+    double* sW = sm;                         // [N][WS]: sW[c * WS + r] = W[r][c]
+    double* sK = sW + (size_t)P.N * WS;      // [TC][128] cross-covariances of the tile
+    double* sC = sK + TC * 128;              // [TC][d] scaled, centred candidates
+    double* sR = sC + TC * P.d;              // [3][4 warps][TC] reduction scratch
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = P.N, d = P.d;
+    // W (row-major, ld 128) -> shared, transposed: coalesced along c, conflict-free stores
+    for (int idx = tid; idx < N * 128; idx += 128) {
+        const int r = idx >> 7, c = idx & 127;
+        if (c < N) sW[c * WS + r] = (c <= r) ? P.W[(size_t)r * 128 + c] : 0.0;
+    }
+    const double by = tid < N ? P.betaY[tid] : 0.0;
+    const double b1 = (tid < N && P.npb > 0) ? P.beta1[tid] : 0.0;
+    double best = -INFINITY;
+    long long bestIdx = 0x7fffffffffffffffLL;
+    const long ntile = (P.M + TC - 1) / TC;
+    for (long t = blockIdx.x; t < ntile; t += gridDim.x) {
+        const long m0 = t * TC;
+        __syncthreads();                     // previous tile's sK / sC / sR are free (and sW is complete on the first pass)
+        for (int idx = tid; idx < TC * d; idx += 128) {
+            const int j = idx / d, q = idx - j * d;
+            long m = m0 + j; if (m >= P.M) m = P.M - 1;
+            sC[idx] = P.cand[(size_t)m * d + q] * P.invTheta[q] - P.center[q];
+        }
+        __syncthreads();
+        // k*[j][c], thread c: direct differences against its own training row
+        {
+            double r2[TC];
+#pragma unroll
+            for (int j = 0; j < TC; j++) r2[j] = 0.0;
+            if (tid < N) {
+                const double* x = P.Xt + (size_t)tid * d;
+                for (int q = 0; q < d; q++) {
+                    const double xv = x[q];
+#pragma unroll
+                    for (int j = 0; j < TC; j++) { const double df = xv - sC[j * d + q]; r2[j] = fma(df, df, r2[j]); }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < TC; j++) sK[j * 128 + tid] = tid < N ? cov_r2_t<KC>(P.sf2, r2[j]) : 0.0;
+        }
+        __syncthreads();
+        // v_r[j] = sum_{c <= r} W[r][c] k*[j][c], thread r
+        double v[TC];
+#pragma unroll
+        for (int j = 0; j < TC; j++) v[j] = 0.0;
+        if (tid < N) {
+            for (int c = 0; c <= tid; c++) {
+                const double w = sW[c * WS + tid];
+#pragma unroll
+                for (int j = 0; j < TC; j++) v[j] = fma(w, sK[j * 128 + c], v[j]);
+            }
+        }
+        // row reductions: xor tree inside the warp, then the four warps in ascending order
+#pragma unroll
+        for (int j = 0; j < TC; j++) {
+            double q = v[j] * v[j], p = v[j] * by, p1 = v[j] * b1;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                q += __shfl_xor_sync(0xffffffffu, q, o);
+                p += __shfl_xor_sync(0xffffffffu, p, o);
+                p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+            }
+            if (lane == 0) { sR[(0 * 4 + warp) * TC + j] = q; sR[(1 * 4 + warp) * TC + j] = p; sR[(2 * 4 + warp) * TC + j] = p1; }
+        }
+        __syncthreads();
+        if (tid < TC && m0 + tid < P.M) {
+            const long m = m0 + tid;
+            double q = 0, p = 0, p1 = 0;
+#pragma unroll
+            for (int w = 0; w < 4; w++) { q += sR[(0 * 4 + w) * TC + tid]; p += sR[(1 * 4 + w) * TC + tid]; p1 += sR[(2 * 4 + w) * TC + tid]; }
+            double mean0 = 0.0;
+            if (P.npb > 0) mean0 = prior_mean(P.cand + (size_t)m * d, d, P.npb, P.pmeans, P.pbeta, P.ptheta, P.plb, P.pwidth);
+            const double mu = mean0 + p - mean0 * p1;
+            double s2 = (1.0 + P.noise) - q;
+            const double floor_ = P.mode_py ? 10e-8 : 1e-8;   // gaussianprocess/__init__.py:224 vs cpp/optimizeGP.cpp:150
+            s2 = s2 < floor_ ? floor_ : (s2 > 10.0 ? 10.0 : s2);
+            if (P.mu) P.mu[m] = mu;
+            if (P.s2) P.s2[m] = s2;
+            if (P.acq >= 0) {
+                const double val = acq_value(P.acq, P.mode_py, mu, s2, P.ymax, P.parm);
+                if (P.score) P.score[m] = val;
+                if (val == val) { if (val > best || (val == best && m < bestIdx)) { best = val; bestIdx = m; } }
+                else if (bestIdx == 0x7fffffffffffffffLL) bestIdx = m;      // NaN never wins, but an all-NaN set still names an index
+            }
+        }
+    }
+    if (P.acq < 0 || !P.want_argmax) return;
+    // the tile owners (threads 0..7, all in warp 0) combine: lowest index wins ties
+    if (warp == 0) {
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            const double os = __shfl_xor_sync(0xffffffffu, best, o);
+            const long long oi = __shfl_xor_sync(0xffffffffu, bestIdx, o);
+            if (os > best || (os == best && oi < bestIdx)) { best = os; bestIdx = oi; }
+        }
+        if (lane == 0) { P.blkBest[blockIdx.x] = best; P.blkIdx[blockIdx.x] = bestIdx; }
+    }
+}
+
+__global__ void __launch_bounds__(256) tiny_argmax_kernel(const double* __restrict__ blkBest, const long long* __restrict__ blkIdx,
+                                                          int nblk, double* __restrict__ best, long long* __restrict__ bestIdx) {
+    __shared__ double ws[256];
+    __shared__ long long wi[256];
+    double sc = -INFINITY;
+    long long idx = 0x7fffffffffffffffLL;
+    for (int b = threadIdx.x; b < nblk; b += 256) {
+        const double os = blkBest[b]; const long long oi = blkIdx[b];
+        if (os > sc || (os == sc && oi < idx)) { sc = os; idx = oi; }
+    }
+    ws[threadIdx.x] = sc; wi[threadIdx.x] = idx;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            const double os = ws[threadIdx.x + o]; const long long oi = wi[threadIdx.x + o];
+            if (os > ws[threadIdx.x] || (os == ws[threadIdx.x] && oi < wi[threadIdx.x])) { ws[threadIdx.x] = os; wi[threadIdx.x] = oi; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { *best = ws[0]; *bestIdx = wi[0]; }
+}
+
+std::once_flag g_tiny_once;
+cudaError_t g_tiny_err = cudaSuccess;
+int g_tiny_sms = 148;
+
+size_t tiny_smem(int N, int d) { return sizeof(double) * ((size_t)N * WS + TC * 128 + (size_t)TC * d + 3 * 4 * TC); }
+
+}  // namespace
+
+// models the fused kernel serves: a single row-block, no separate variance model (PrefGP's aug factor), IBO_TINY=0 disables
+bool tiny_eligible(const ibo_model* m) {
+    if (m->nb != 1 || m->var_model != nullptr || m->d > 64) return false;
+    const char* e = getenv("IBO_TINY");          // read per call: the tests compare both paths in one process
+    return !(e && e[0] == '0');
+}
+
+// Scores M candidates at `cand` (device memory, or mapped pinned host memory) into out = [score | mu | s2][M] (+ the argmax
+// pair at out[3M], out[3M+1]); everything is enqueued on m->stream.
+int score_tiny(ibo_model* m, const double* cand, long M, const ScoreReq& rq, double* out) {
+    std::call_once(g_tiny_once, [] {
+        const int maxsm = (int)tiny_smem(128, 64);
+        g_tiny_err = cudaFuncSetAttribute(tiny_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
+        if (g_tiny_err == cudaSuccess) g_tiny_err = cudaFuncSetAttribute(tiny_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
+        if (g_tiny_err == cudaSuccess) g_tiny_err = cudaFuncSetAttribute(tiny_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
+        int dev = 0; cudaGetDevice(&dev);
+        cudaDeviceProp pr;
+        if (cudaGetDeviceProperties(&pr, dev) == cudaSuccess) g_tiny_sms = pr.multiProcessorCount;
+    });
+    if (g_tiny_err != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(g_tiny_err)); return IBO_E_CUDA; }
+    cudaStream_t st = m->stream;
+    const bool prof = (rq.flags & IBO_FLAG_PROFILE) != 0;
+    const long ntile = (M + TC - 1) / TC;
+    // one CTA per tile up to a few waves; beyond that CTAs walk tiles so that W is staged once per CTA
+    const size_t smem = tiny_smem(m->N, m->d);
+    const int perSM = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / smem));
+    const int grid = (int)std::min<long>(ntile, (long)g_tiny_sms * perSM);
+    if (m->blkCap < (size_t)grid) {
+        if (m->dBlkBest) cudaFree(m->dBlkBest);
+        if (m->dBlkIdx) cudaFree(m->dBlkIdx);
+        m->dBlkBest = nullptr; m->dBlkIdx = nullptr; m->blkCap = 0;
+        const size_t cap = (size_t)g_tiny_sms * 8;
+        IBO_CUDA_TRY(cudaMalloc(&m->dBlkBest, sizeof(double) * cap));
+        IBO_CUDA_TRY(cudaMalloc(&m->dBlkIdx, sizeof(long long) * cap));
+        m->blkCap = cap;
+    }
+    TinyParams P;
+    P.W = m->dW; P.Xt = m->dXt; P.betaY = m->dBetaY; P.beta1 = m->dBeta1; P.invTheta = m->dInvTheta; P.center = m->dCenter; P.cand = cand;
+    P.pmeans = m->dPmeans; P.pbeta = m->dPbeta; P.plb = m->dPlb; P.pwidth = m->dPwidth;
+    P.score = rq.want_score ? out : nullptr;
+    P.mu = rq.want_mu ? out + M : nullptr;
+    P.s2 = rq.want_s2 ? out + 2 * M : nullptr;
+    P.blkBest = m->dBlkBest; P.blkIdx = m->dBlkIdx;
+    P.M = M; P.N = m->N; P.d = m->d; P.acq = rq.acq; P.mode_py = (rq.flags & IBO_FLAG_MODE_PY) ? 1 : 0; P.npb = m->npb;
+    P.want_argmax = (rq.acq >= 0 && rq.want_argmax) ? 1 : 0;
+    P.sf2 = m->sf2; P.noise = m->noise; P.ymax = rq.ymax; P.parm = rq.parm; P.ptheta = m->ptheta;
+    if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[0], st));
+    if (m->kind <= IBO_KERNEL_SE_ISO) tiny_fused_kernel<0><<<grid, 128, smem, st>>>(P);
+    else if (m->kind == IBO_KERNEL_MATERN3) tiny_fused_kernel<1><<<grid, 128, smem, st>>>(P);
+    else tiny_fused_kernel<2><<<grid, 128, smem, st>>>(P);
+    long nlaunch = 1;
+    if (P.want_argmax) {
+        tiny_argmax_kernel<<<1, 256, 0, st>>>(m->dBlkBest, m->dBlkIdx, grid, out + 3 * M, reinterpret_cast<long long*>(out + 3 * M + 1));
+        nlaunch++;
+    }
+    g_launches += nlaunch;
+    if (prof) {
+        IBO_CUDA_TRY(cudaEventRecord(m->ev[5], st));
+        IBO_CUDA_TRY(cudaEventSynchronize(m->ev[5]));
+        float tot; cudaEventElapsedTime(&tot, m->ev[0], m->ev[5]);
+        m->prof[0] = 0; m->prof[1] = tot; m->prof[2] = 0; m->prof[3] = tot; m->prof[4] = (double)nlaunch; m->prof[5] = 1;
+    }
+    IBO_CUDA_TRY(cudaGetLastError());
+    return IBO_OK;
+}
+
+}  // namespace ibo
