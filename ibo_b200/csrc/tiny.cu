@@ -19,96 +19,133 @@ namespace ibo {
 namespace {
 
 constexpr int TC = 8;        // candidates per tile
-constexpr int WS = 129;      // row stride of the transposed W in shared memory (conflict-free both ways)
+constexpr int WS = 129;      // row stride of W in shared memory: odd, so that thread r walking row r is conflict free
+
+struct TinySide {            // one factor: the model itself, or the variance model of PrefGaussianProcess.addObservationPoint
+    const double *W, *Xt, *center;
+    int N;
+};
 
 struct TinyParams {
-    const double *W, *Xt, *betaY, *beta1, *invTheta, *center, *cand;
+    TinySide side[2];        // [1].N == 0 when there is no variance model
+    const double *betaY, *beta1, *invTheta, *cand;
     const double *pmeans, *pbeta, *plb, *pwidth;
     double *score, *mu, *s2;
     double* blkBest; long long* blkIdx;
     long M;
-    int N, d, acq, mode_py, npb, want_argmax;
+    int d, acq, mode_py, npb, want_argmax;
     double sf2, noise, ymax, parm, ptheta;
 };
+
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src));
+}
 
 template <int KC>
 __global__ void __launch_bounds__(128) tiny_fused_kernel(TinyParams P) {
     extern __shared__ double sm[];
-    double* sW = sm;                         // [N][WS]: sW[c * WS + r] = W[r][c]
-    double* sK = sW + (size_t)P.N * WS;      // [TC][128] cross-covariances of the tile
-    double* sC = sK + TC * 128;              // [TC][d] scaled, centred candidates
-    double* sR = sC + TC * P.d;              // [3][4 warps][TC] reduction scratch
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int N = P.N, d = P.d;
-    // W (row-major, ld 128) -> shared, transposed: coalesced along c, conflict-free stores
-    for (int idx = tid; idx < N * 128; idx += 128) {
-        const int r = idx >> 7, c = idx & 127;
-        if (c < N) sW[c * WS + r] = (c <= r) ? P.W[(size_t)r * 128 + c] : 0.0;
+    const int d = P.d, XS = d | 1;                   // odd row stride of the training inputs
+    const int nside = P.side[1].N > 0 ? 2 : 1;
+    // shared-memory carve-up: per side W [N][WS] (lower triangle) and X [N][XS]; then k* [TC][128], the raw candidates of
+    // the tile [TC][d], 1/theta [d], and the reduction scratch [3][4][TC]
+    double* sW[2]; double* sX[2];
+    double* ptr = sm;
+    for (int s = 0; s < nside; s++) { sW[s] = ptr; ptr += (size_t)P.side[s].N * WS; sX[s] = ptr; ptr += (size_t)P.side[s].N * XS; }
+    double* sK = ptr;  ptr += TC * 128;
+    double* sC = ptr;  ptr += TC * d;
+    double* sT = ptr;  ptr += d;
+    double* sR = ptr;
+    // stage the factors with 8-byte async copies: every element is in flight at once (a register-staged copy of W costs one
+    // L2 round trip per row and was most of the kernel's time)
+    for (int s = 0; s < nside; s++) {
+        const int N = P.side[s].N;
+        for (int idx = tid; idx < N * 128; idx += 128) {
+            const int r = idx >> 7, c = idx & 127;
+            if (c <= r) cp_async8(sW[s] + r * WS + c, P.side[s].W + (size_t)r * 128 + c);
+        }
+        for (int idx = tid; idx < N * d; idx += 128) {
+            const int r = idx / d, q = idx - r * d;
+            cp_async8(sX[s] + r * XS + q, P.side[s].Xt + idx);
+        }
     }
-    const double by = tid < N ? P.betaY[tid] : 0.0;
-    const double b1 = (tid < N && P.npb > 0) ? P.beta1[tid] : 0.0;
+    asm volatile("cp.async.commit_group;");
+    for (int q = tid; q < d; q += 128) sT[q] = P.invTheta[q];
+    const int N0 = P.side[0].N;
+    const double by = tid < N0 ? P.betaY[tid] : 0.0;
+    const double b1 = (tid < N0 && P.npb > 0) ? P.beta1[tid] : 0.0;
     double best = -INFINITY;
     long long bestIdx = 0x7fffffffffffffffLL;
     const long ntile = (P.M + TC - 1) / TC;
+    asm volatile("cp.async.wait_group 0;");
     for (long t = blockIdx.x; t < ntile; t += gridDim.x) {
         const long m0 = t * TC;
-        __syncthreads();                     // previous tile's sK / sC / sR are free (and sW is complete on the first pass)
+        __syncthreads();                     // previous tile's scratch is free; the staged factors are visible on the first pass
         for (int idx = tid; idx < TC * d; idx += 128) {
             const int j = idx / d, q = idx - j * d;
             long m = m0 + j; if (m >= P.M) m = P.M - 1;
-            sC[idx] = P.cand[(size_t)m * d + q] * P.invTheta[q] - P.center[q];
+            sC[idx] = P.cand[(size_t)m * d + q];           // one parallel round trip when the candidates live in mapped host memory
         }
-        __syncthreads();
-        // k*[j][c], thread c: direct differences against its own training row
-        {
-            double r2[TC];
+        double q_sum = 0, p_sum = 0, p1_sum = 0;           // of candidate m0 + tid (threads 0..7)
+        for (int s = 0; s < nside; s++) {
+            const int N = P.side[s].N;
+            __syncthreads();
+            // k*[j][c], thread c: direct differences between its training row and the scaled, centred candidates
+            {
+                double r2[TC];
 #pragma unroll
-            for (int j = 0; j < TC; j++) r2[j] = 0.0;
+                for (int j = 0; j < TC; j++) r2[j] = 0.0;
+                if (tid < N) {
+                    const double* x = sX[s] + tid * XS;
+                    for (int q = 0; q < d; q++) {
+                        const double xv = x[q], it = sT[q], ctr = P.side[s].center[q];     // rows are stored scaled and centred
+#pragma unroll
+                        for (int j = 0; j < TC; j++) { const double df = xv - (sC[j * d + q] * it - ctr); r2[j] = fma(df, df, r2[j]); }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < TC; j++) sK[j * 128 + tid] = tid < N ? cov_r2_t<KC>(P.sf2, r2[j]) : 0.0;
+            }
+            __syncthreads();
+            // v_r[j] = sum_{c <= r} W[r][c] k*[j][c], thread r
+            double v[TC];
+#pragma unroll
+            for (int j = 0; j < TC; j++) v[j] = 0.0;
             if (tid < N) {
-                const double* x = P.Xt + (size_t)tid * d;
-                for (int q = 0; q < d; q++) {
-                    const double xv = x[q];
+                const double* w = sW[s] + tid * WS;
+                for (int c = 0; c <= tid; c++) {
+                    const double wv = w[c];
 #pragma unroll
-                    for (int j = 0; j < TC; j++) { const double df = xv - sC[j * d + q]; r2[j] = fma(df, df, r2[j]); }
+                    for (int j = 0; j < TC; j++) v[j] = fma(wv, sK[j * 128 + c], v[j]);
                 }
             }
+            // row reductions: xor tree inside the warp, then the four warps in ascending order
 #pragma unroll
-            for (int j = 0; j < TC; j++) sK[j * 128 + tid] = tid < N ? cov_r2_t<KC>(P.sf2, r2[j]) : 0.0;
-        }
-        __syncthreads();
-        // v_r[j] = sum_{c <= r} W[r][c] k*[j][c], thread r
-        double v[TC];
+            for (int j = 0; j < TC; j++) {
+                double q = v[j] * v[j], p = v[j] * by, p1 = v[j] * b1;
 #pragma unroll
-        for (int j = 0; j < TC; j++) v[j] = 0.0;
-        if (tid < N) {
-            for (int c = 0; c <= tid; c++) {
-                const double w = sW[c * WS + tid];
+                for (int o = 16; o > 0; o >>= 1) {
+                    q += __shfl_xor_sync(0xffffffffu, q, o);
+                    p += __shfl_xor_sync(0xffffffffu, p, o);
+                    p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+                }
+                if (lane == 0) { sR[(0 * 4 + warp) * TC + j] = q; sR[(1 * 4 + warp) * TC + j] = p; sR[(2 * 4 + warp) * TC + j] = p1; }
+            }
+            __syncthreads();
+            if (tid < TC) {
+                double q = 0, p = 0, p1 = 0;
 #pragma unroll
-                for (int j = 0; j < TC; j++) v[j] = fma(w, sK[j * 128 + c], v[j]);
+                for (int w = 0; w < 4; w++) { q += sR[(0 * 4 + w) * TC + tid]; p += sR[(1 * 4 + w) * TC + tid]; p1 += sR[(2 * 4 + w) * TC + tid]; }
+                q_sum = q;                                  // the variance comes from the last side (the aug factor if there is one)
+                if (s == 0) { p_sum = p; p1_sum = p1; }     // the mean always from the model itself (gaussianprocess/__init__.py:214-223)
             }
         }
-        // row reductions: xor tree inside the warp, then the four warps in ascending order
-#pragma unroll
-        for (int j = 0; j < TC; j++) {
-            double q = v[j] * v[j], p = v[j] * by, p1 = v[j] * b1;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                q += __shfl_xor_sync(0xffffffffu, q, o);
-                p += __shfl_xor_sync(0xffffffffu, p, o);
-                p1 += __shfl_xor_sync(0xffffffffu, p1, o);
-            }
-            if (lane == 0) { sR[(0 * 4 + warp) * TC + j] = q; sR[(1 * 4 + warp) * TC + j] = p; sR[(2 * 4 + warp) * TC + j] = p1; }
-        }
-        __syncthreads();
         if (tid < TC && m0 + tid < P.M) {
             const long m = m0 + tid;
-            double q = 0, p = 0, p1 = 0;
-#pragma unroll
-            for (int w = 0; w < 4; w++) { q += sR[(0 * 4 + w) * TC + tid]; p += sR[(1 * 4 + w) * TC + tid]; p1 += sR[(2 * 4 + w) * TC + tid]; }
             double mean0 = 0.0;
-            if (P.npb > 0) mean0 = prior_mean(P.cand + (size_t)m * d, d, P.npb, P.pmeans, P.pbeta, P.ptheta, P.plb, P.pwidth);
-            const double mu = mean0 + p - mean0 * p1;
-            double s2 = (1.0 + P.noise) - q;
+            if (P.npb > 0) mean0 = prior_mean(sC + tid * d, d, P.npb, P.pmeans, P.pbeta, P.ptheta, P.plb, P.pwidth);
+            const double mu = mean0 + p_sum - mean0 * p1_sum;
+            double s2 = (1.0 + P.noise) - q_sum;
             const double floor_ = P.mode_py ? 10e-8 : 1e-8;   // gaussianprocess/__init__.py:224 vs cpp/optimizeGP.cpp:150
             s2 = s2 < floor_ ? floor_ : (s2 > 10.0 ? 10.0 : s2);
             if (P.mu) P.mu[m] = mu;
@@ -160,13 +197,20 @@ std::once_flag g_tiny_once;
 cudaError_t g_tiny_err = cudaSuccess;
 int g_tiny_sms = 148;
 
-size_t tiny_smem(int N, int d) { return sizeof(double) * ((size_t)N * WS + TC * 128 + (size_t)TC * d + 3 * 4 * TC); }
+size_t tiny_smem(int N, int Nvar, int d) {
+    return sizeof(double) * ((size_t)(N + Nvar) * (WS + (d | 1)) + TC * 128 + (size_t)TC * d + d + 3 * 4 * TC);
+}
+constexpr size_t TINY_SMEM_MAX = 200 * 1024;
 
 }  // namespace
 
-// models the fused kernel serves: a single row-block, no separate variance model (PrefGP's aug factor), IBO_TINY=0 disables
+// models the fused kernel serves: a single row-block (also for the variance model of PrefGP's aug factor, if any) that
+// fits shared memory; IBO_TINY=0 disables
 bool tiny_eligible(const ibo_model* m) {
-    if (m->nb != 1 || m->var_model != nullptr || m->d > 64) return false;
+    if (m->nb != 1 || m->d > 64) return false;
+    const ibo_model* vm = m->var_model;
+    if (vm && (vm->nb != 1 || vm->kind != m->kind || vm->sf2 != m->sf2)) return false;
+    if (tiny_smem(m->N, vm ? vm->N : 0, m->d) > TINY_SMEM_MAX) return false;
     const char* e = getenv("IBO_TINY");          // read per call: the tests compare both paths in one process
     return !(e && e[0] == '0');
 }
@@ -175,7 +219,7 @@ bool tiny_eligible(const ibo_model* m) {
 // pair at out[3M], out[3M+1]); everything is enqueued on m->stream.
 int score_tiny(ibo_model* m, const double* cand, long M, const ScoreReq& rq, double* out) {
     std::call_once(g_tiny_once, [] {
-        const int maxsm = (int)tiny_smem(128, 64);
+        const int maxsm = (int)TINY_SMEM_MAX;
         g_tiny_err = cudaFuncSetAttribute(tiny_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
         if (g_tiny_err == cudaSuccess) g_tiny_err = cudaFuncSetAttribute(tiny_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
         if (g_tiny_err == cudaSuccess) g_tiny_err = cudaFuncSetAttribute(tiny_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
@@ -188,7 +232,8 @@ int score_tiny(ibo_model* m, const double* cand, long M, const ScoreReq& rq, dou
     const bool prof = (rq.flags & IBO_FLAG_PROFILE) != 0;
     const long ntile = (M + TC - 1) / TC;
     // one CTA per tile up to a few waves; beyond that CTAs walk tiles so that W is staged once per CTA
-    const size_t smem = tiny_smem(m->N, m->d);
+    const ibo_model* vm = m->var_model;
+    const size_t smem = tiny_smem(m->N, vm ? vm->N : 0, m->d);
     const int perSM = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / smem));
     const int grid = (int)std::min<long>(ntile, (long)g_tiny_sms * perSM);
     if (m->blkCap < (size_t)grid) {
@@ -201,13 +246,15 @@ int score_tiny(ibo_model* m, const double* cand, long M, const ScoreReq& rq, dou
         m->blkCap = cap;
     }
     TinyParams P;
-    P.W = m->dW; P.Xt = m->dXt; P.betaY = m->dBetaY; P.beta1 = m->dBeta1; P.invTheta = m->dInvTheta; P.center = m->dCenter; P.cand = cand;
+    P.side[0] = TinySide{m->dW, m->dXt, m->dCenter, m->N};
+    P.side[1] = vm ? TinySide{vm->dW, vm->dXt, vm->dCenter, vm->N} : TinySide{nullptr, nullptr, nullptr, 0};
+    P.betaY = m->dBetaY; P.beta1 = m->dBeta1; P.invTheta = m->dInvTheta; P.cand = cand;
     P.pmeans = m->dPmeans; P.pbeta = m->dPbeta; P.plb = m->dPlb; P.pwidth = m->dPwidth;
     P.score = rq.want_score ? out : nullptr;
     P.mu = rq.want_mu ? out + M : nullptr;
     P.s2 = rq.want_s2 ? out + 2 * M : nullptr;
     P.blkBest = m->dBlkBest; P.blkIdx = m->dBlkIdx;
-    P.M = M; P.N = m->N; P.d = m->d; P.acq = rq.acq; P.mode_py = (rq.flags & IBO_FLAG_MODE_PY) ? 1 : 0; P.npb = m->npb;
+    P.M = M; P.d = m->d; P.acq = rq.acq; P.mode_py = (rq.flags & IBO_FLAG_MODE_PY) ? 1 : 0; P.npb = m->npb;
     P.want_argmax = (rq.acq >= 0 && rq.want_argmax) ? 1 : 0;
     P.sf2 = m->sf2; P.noise = m->noise; P.ymax = rq.ymax; P.parm = rq.parm; P.ptheta = m->ptheta;
     if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[0], st));
