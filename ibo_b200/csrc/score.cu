@@ -730,14 +730,15 @@ static void launch_kstar(const ibo_model* m, const double* dCand, double* slab, 
 
 // Runs K1..K4 for M candidates resident at dCand; results land in m->dOut ([score|mu|s2][M]) and
 // the (best score, best index) pair at m->dOut[3M], [3M+1].  Everything is enqueued on m->stream; no host sync here.
-static int score_device(ibo_model* m, const double* dCand, long M, const ScoreReq& rq, double* outBase = nullptr) {
+static int score_device(ibo_model* m, const double* dCand, long M, const ScoreReq& rq, double* outBase = nullptr,
+                        const double* hostCand = nullptr) {
     std::call_once(g_score_attr_once, set_score_attrs);
     if (g_score_attr_err != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(g_score_attr_err)); return IBO_E_CUDA; }
     if (m->d > 64) { set_error("d > 64 not supported"); return IBO_E_BADARG; }
     if (tiny_eligible(m)) {       // N <= 128: one fused launch (tiny.cu)
         int rc0;
         if (!outBase && (rc0 = grow(&m->dOut, &m->outCap, (size_t)3 * M + 2))) return rc0;
-        return score_tiny(m, dCand, M, rq, outBase ? outBase : m->dOut);
+        return score_tiny(m, dCand, M, rq, outBase ? outBase : m->dOut, hostCand);
     }
     cudaStream_t st = m->stream;
     const bool prof = (rq.flags & IBO_FLAG_PROFILE) != 0;
@@ -873,7 +874,7 @@ static int score_host(ibo_model* m, const double* Xs, long M, const ScoreReq& rq
         if (tiny_eligible(m)) cand = m->hPinned;
         else IBO_CUDA_TRY(cudaMemcpyAsync(m->dCand, m->hPinned, sizeof(double) * nin, cudaMemcpyHostToDevice, st));
         double* ho = m->hPinned + nin;
-        if ((rc = score_device(m, cand, M, rq, ho))) return rc;
+        if ((rc = score_device(m, cand, M, rq, ho, m->hPinned))) return rc;
         IBO_CUDA_TRY(cudaStreamSynchronize(st));
         if (scores) std::memcpy(scores, ho, sizeof(double) * M);
         if (mu) std::memcpy(mu, ho + M, sizeof(double) * M);

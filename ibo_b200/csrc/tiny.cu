@@ -13,6 +13,7 @@
 // A candidate's value is a function of (model, x) only (fixed summation orders), so DIRECT trajectories stay reproducible.
 #include "model.cuh"
 #include "scoremath.cuh"
+#include <cstring>
 #include <mutex>
 
 namespace ibo {
@@ -37,13 +38,20 @@ struct TinyParams {
     double sf2, noise, ymax, parm, ptheta;
 };
 
+// A small batch travels in the kernel's parameter buffer: the launch itself delivers the candidates, and the kernel's
+// longest latency -- a PCIe read of mapped host memory, several microseconds -- disappears.  448 doubles keep the two
+// parameter structs inside the classic 4 KiB limit.
+constexpr int TINY_INLINE = 448;
+struct TinyInline { double x[TINY_INLINE]; };
+
 __device__ __forceinline__ void cp_async8(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src));
 }
 
 template <int KC>
-__global__ void __launch_bounds__(128) tiny_fused_kernel(TinyParams P) {
+__global__ void __launch_bounds__(128) tiny_fused_kernel(const __grid_constant__ TinyParams P, const __grid_constant__ TinyInline I) {
     extern __shared__ double sm[];
+    const double* __restrict__ cands = P.cand ? P.cand : I.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = P.d, XS = d | 1;                   // odd row stride of the training inputs
     const int nside = P.side[1].N > 0 ? 2 : 1;
@@ -54,7 +62,8 @@ __global__ void __launch_bounds__(128) tiny_fused_kernel(TinyParams P) {
     for (int s = 0; s < nside; s++) { sW[s] = ptr; ptr += (size_t)P.side[s].N * WS; sX[s] = ptr; ptr += (size_t)P.side[s].N * XS; }
     double* sK = ptr;  ptr += TC * 128;
     double* sC = ptr;  ptr += TC * d;
-    double* sT = ptr;  ptr += d;
+    double* sT = ptr;  ptr += d;             // 1 / theta
+    double* sCtr = ptr; ptr += 2 * d;        // centres of the two sides
     double* sR = ptr;
     // stage the factors with 8-byte async copies: every element is in flight at once (a register-staged copy of W costs one
     // L2 round trip per row and was most of the kernel's time)
@@ -69,22 +78,34 @@ __global__ void __launch_bounds__(128) tiny_fused_kernel(TinyParams P) {
             cp_async8(sX[s] + r * XS + q, P.side[s].Xt + idx);
         }
     }
+    for (int q = tid; q < d; q += 128) {
+        cp_async8(sT + q, P.invTheta + q);
+        for (int s = 0; s < nside; s++) cp_async8(sCtr + s * d + q, P.side[s].center + q);
+    }
     asm volatile("cp.async.commit_group;");
-    for (int q = tid; q < d; q += 128) sT[q] = P.invTheta[q];
+    // The first tile's candidates are fetched while the copies above are in flight: for a DIRECT batch they come over PCIe
+    // (mapped host memory), the longest latency in the kernel -- everything else hides behind it.
+    const long ntile = (P.M + TC - 1) / TC;
+    for (int idx = tid; idx < TC * d; idx += 128) {
+        const int j = idx / d, q = idx - j * d;
+        long m = (long)blockIdx.x * TC + j; if (m >= P.M) m = P.M - 1;
+        sC[idx] = cands[(size_t)m * d + q];
+    }
     const int N0 = P.side[0].N;
     const double by = tid < N0 ? P.betaY[tid] : 0.0;
     const double b1 = (tid < N0 && P.npb > 0) ? P.beta1[tid] : 0.0;
     double best = -INFINITY;
     long long bestIdx = 0x7fffffffffffffffLL;
-    const long ntile = (P.M + TC - 1) / TC;
     asm volatile("cp.async.wait_group 0;");
     for (long t = blockIdx.x; t < ntile; t += gridDim.x) {
         const long m0 = t * TC;
-        __syncthreads();                     // previous tile's scratch is free; the staged factors are visible on the first pass
-        for (int idx = tid; idx < TC * d; idx += 128) {
-            const int j = idx / d, q = idx - j * d;
-            long m = m0 + j; if (m >= P.M) m = P.M - 1;
-            sC[idx] = P.cand[(size_t)m * d + q];           // one parallel round trip when the candidates live in mapped host memory
+        if (t != blockIdx.x) {
+            __syncthreads();                 // previous tile's scratch is free
+            for (int idx = tid; idx < TC * d; idx += 128) {
+                const int j = idx / d, q = idx - j * d;
+                long m = m0 + j; if (m >= P.M) m = P.M - 1;
+                sC[idx] = cands[(size_t)m * d + q];
+            }
         }
         double q_sum = 0, p_sum = 0, p1_sum = 0;           // of candidate m0 + tid (threads 0..7)
         for (int s = 0; s < nside; s++) {
@@ -98,7 +119,7 @@ __global__ void __launch_bounds__(128) tiny_fused_kernel(TinyParams P) {
                 if (tid < N) {
                     const double* x = sX[s] + tid * XS;
                     for (int q = 0; q < d; q++) {
-                        const double xv = x[q], it = sT[q], ctr = P.side[s].center[q];     // rows are stored scaled and centred
+                        const double xv = x[q], it = sT[q], ctr = sCtr[s * d + q];     // rows are stored scaled and centred
 #pragma unroll
                         for (int j = 0; j < TC; j++) { const double df = xv - (sC[j * d + q] * it - ctr); r2[j] = fma(df, df, r2[j]); }
                     }
@@ -198,7 +219,7 @@ cudaError_t g_tiny_err = cudaSuccess;
 int g_tiny_sms = 148;
 
 size_t tiny_smem(int N, int Nvar, int d) {
-    return sizeof(double) * ((size_t)(N + Nvar) * (WS + (d | 1)) + TC * 128 + (size_t)TC * d + d + 3 * 4 * TC);
+    return sizeof(double) * ((size_t)(N + Nvar) * (WS + (d | 1)) + TC * 128 + (size_t)TC * d + 3 * d + 3 * 4 * TC);
 }
 constexpr size_t TINY_SMEM_MAX = 200 * 1024;
 
@@ -217,7 +238,8 @@ bool tiny_eligible(const ibo_model* m) {
 
 // Scores M candidates at `cand` (device memory, or mapped pinned host memory) into out = [score | mu | s2][M] (+ the argmax
 // pair at out[3M], out[3M+1]); everything is enqueued on m->stream.
-int score_tiny(ibo_model* m, const double* cand, long M, const ScoreReq& rq, double* out) {
+// `host_cand`: the same candidates in host memory when the caller has them there (small batches ride in the parameter buffer)
+int score_tiny(ibo_model* m, const double* cand, long M, const ScoreReq& rq, double* out, const double* host_cand) {
     std::call_once(g_tiny_once, [] {
         const int maxsm = (int)TINY_SMEM_MAX;
         g_tiny_err = cudaFuncSetAttribute(tiny_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
@@ -257,10 +279,18 @@ int score_tiny(ibo_model* m, const double* cand, long M, const ScoreReq& rq, dou
     P.M = M; P.d = m->d; P.acq = rq.acq; P.mode_py = (rq.flags & IBO_FLAG_MODE_PY) ? 1 : 0; P.npb = m->npb;
     P.want_argmax = (rq.acq >= 0 && rq.want_argmax) ? 1 : 0;
     P.sf2 = m->sf2; P.noise = m->noise; P.ymax = rq.ymax; P.parm = rq.parm; P.ptheta = m->ptheta;
+    static TinyInline I;        // launches copy the parameter buffer synchronously; one host thread per model
+    TinyInline Ilocal;
+    TinyInline* Ip = &I;
+    if (host_cand && (size_t)M * m->d <= (size_t)TINY_INLINE) {
+        std::memcpy(Ilocal.x, host_cand, sizeof(double) * (size_t)M * m->d);
+        P.cand = nullptr;
+        Ip = &Ilocal;
+    }
     if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[0], st));
-    if (m->kind <= IBO_KERNEL_SE_ISO) tiny_fused_kernel<0><<<grid, 128, smem, st>>>(P);
-    else if (m->kind == IBO_KERNEL_MATERN3) tiny_fused_kernel<1><<<grid, 128, smem, st>>>(P);
-    else tiny_fused_kernel<2><<<grid, 128, smem, st>>>(P);
+    if (m->kind <= IBO_KERNEL_SE_ISO) tiny_fused_kernel<0><<<grid, 128, smem, st>>>(P, *Ip);
+    else if (m->kind == IBO_KERNEL_MATERN3) tiny_fused_kernel<1><<<grid, 128, smem, st>>>(P, *Ip);
+    else tiny_fused_kernel<2><<<grid, 128, smem, st>>>(P, *Ip);
     long nlaunch = 1;
     if (P.want_argmax) {
         tiny_argmax_kernel<<<1, 256, 0, st>>>(m->dBlkBest, m->dBlkIdx, grid, out + 3 * M, reinterpret_cast<long long*>(out + 3 * M + 1));
