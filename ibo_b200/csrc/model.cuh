@@ -65,7 +65,7 @@ struct ibo_cands {
 namespace ibo {
 struct ScoreReq;
 // fused single-launch path for models of one row-block (tiny.cu)
-bool tiny_eligible(const ibo_model* m);
+bool tiny_eligible(const ibo_model* m, long M);
 int score_tiny(ibo_model* m, const double* cand, long M, const ScoreReq& rq, double* out, const double* host_cand);
 int grow(double** p, size_t* cap, size_t need);
 cudaError_t pool_malloc(void** p, size_t bytes);

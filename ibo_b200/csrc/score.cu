@@ -735,7 +735,7 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
     std::call_once(g_score_attr_once, set_score_attrs);
     if (g_score_attr_err != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(g_score_attr_err)); return IBO_E_CUDA; }
     if (m->d > 64) { set_error("d > 64 not supported"); return IBO_E_BADARG; }
-    if (tiny_eligible(m)) {       // N <= 128: one fused launch (tiny.cu)
+    if (tiny_eligible(m, M)) {       // N <= 128, small batch: one fused launch (tiny.cu)
         int rc0;
         if (!outBase && (rc0 = grow(&m->dOut, &m->outCap, (size_t)3 * M + 2))) return rc0;
         return score_tiny(m, dCand, M, rq, outBase ? outBase : m->dOut, hostCand);
@@ -871,7 +871,7 @@ static int score_host(ibo_model* m, const double* Xs, long M, const ScoreReq& rq
         // candidates go to device memory with one small DMA (K1 reading them over PCIe costs ~15 us of dependent round trips);
         // the fused small-model kernel stages its tile with one parallel load and reads the mapped buffer directly
         const double* cand = m->dCand;
-        if (tiny_eligible(m)) cand = m->hPinned;
+        if (tiny_eligible(m, M)) cand = m->hPinned;
         else IBO_CUDA_TRY(cudaMemcpyAsync(m->dCand, m->hPinned, sizeof(double) * nin, cudaMemcpyHostToDevice, st));
         double* ho = m->hPinned + nin;
         if ((rc = score_device(m, cand, M, rq, ho, m->hPinned))) return rc;
