@@ -45,6 +45,11 @@ void set_error(const std::string& s);
 
 extern long g_launches;   // kernels launched by this library (bench.py's gpu_launches)
 
+// A small candidate batch can travel in a kernel's parameter buffer: the launch itself delivers it, no H2D DMA and no PCIe
+// read inside the kernel.  448 doubles keep the parameter block inside the classic 4 KiB limit.
+constexpr int CAND_INLINE = 448;
+struct CandInline { double x[CAND_INLINE]; };
+
 // ---------------------------------------------------------------------------------------------
 // device primitives
 // ---------------------------------------------------------------------------------------------
@@ -86,6 +91,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may be
+// scheduled while its predecessor in the stream is still running; pdl_wait() blocks until that predecessor has completed and
+// its writes are visible (a no-op for a normal launch), pdl_launch_dependents() lets the successor be scheduled early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

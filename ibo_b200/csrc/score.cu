@@ -97,10 +97,12 @@ __global__ void __launch_bounds__(256) kstar_kernel(const double* __restrict__ X
 constexpr double EXPAND_LIMIT = 256.0;    // => relative error of k below ~2e-13
 
 template <int DP4, int KC>   // DP4: number of 4-wide dimension groups, d <= 4*DP4; KC: kernel class (cov_r2_t)
-__global__ void __launch_bounds__(256) kstar_mma_kernel(const double* __restrict__ Xt, const double* __restrict__ cand,
+__global__ void __launch_bounds__(256) kstar_mma_kernel(const double* __restrict__ Xt, const double* __restrict__ cand_dev,
                                                         const double* __restrict__ inv_theta, const double* __restrict__ center,
                                                         double* __restrict__ slab, int N, int d, int nb, long M, long m0,
-                                                        int kind, double sf2) {
+                                                        int kind, double sf2, const __grid_constant__ CandInline inl) {
+    pdl_launch_dependents();                 // small batches: K2 is launched programmatically and may be scheduled now
+    const double* __restrict__ cand = cand_dev ? cand_dev : inl.x;      // small batches ride in the parameter buffer
     constexpr int DP = 4 * DP4;
     constexpr int S = (DP % 16 == 4 || DP % 16 == 12) ? DP : DP + 4;   // (row*S + k) mod 16 distinct over a half-warp
     extern __shared__ double sm[];
@@ -232,11 +234,13 @@ trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab
         fence_proxy_async();
     }
     __syncthreads();
+    if (NT == 1) pdl_launch_dependents();        // small batches: K3 may be scheduled now (it waits for this grid to finish)
     if (warp >= 8) {
         // ---------------- producer warpgroup: hands its registers to the DMMA warps ----------------
         if (Cfg::REGSPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
         // one lane streams the operand blobs with bulk TMA
         if (warp == 8 && lane == 0) {
+            if (NT == 1) pdl_wait();             // the K* slab comes from K1 (programmatic launch: K1 may still be running)
             int s = 0; uint32_t ph = 0;
             const double* Bbase = slab + (size_t)T * (nb * KB_PER_BLOCK) * BLOB + sub * BDBL;
             for (int uu = u0; uu < u1; ++uu) {
@@ -404,6 +408,7 @@ __global__ void __launch_bounds__(256) epilogue_kernel(EpiParams P) {
     //               per block, rowLanes threads per candidate each sum every rowLanes-th row (loads batched four deep),
     //               combined in a fixed order through shared memory.
     __shared__ double shq[3][256];
+    pdl_wait();                                                // programmatic launch behind K2 (small batches); no-op otherwise
     const int RL = P.rowLanes, CPB = 256 / RL;                 // candidates per block
     const int tl = threadIdx.x / CPB;                          // row lane
     const int cl = threadIdx.x - tl * CPB;
@@ -667,10 +672,30 @@ static int get_unit_table(ibo_model* m, bool narrow, int MT, int G, const int** 
     return IBO_OK;
 }
 
+// launch with (pdl) or without the programmatic-stream-serialization attribute
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+static bool pdl_enabled() {
+    const char* e = getenv("IBO_PDL");
+    return !(e && e[0] == '0');
+}
+
 template <int NT, int MT>
 static void launch_k2_shape(const ibo_model* m, bool p1, dim3 grid, const int* dUnits, const int* dStart, long Mpad, cudaStream_t st) {
-    if (p1) trigemm_kernel<NT, MT, true><<<grid, K2_THREADS, K2Cfg<NT, MT>::SMEM, st>>>(m->dWpack, m->dSlab, m->dBetaY, m->dBeta1, m->dPart, dUnits, dStart, m->nb, Mpad);
-    else trigemm_kernel<NT, MT, false><<<grid, K2_THREADS, K2Cfg<NT, MT>::SMEM, st>>>(m->dWpack, m->dSlab, m->dBetaY, m->dBeta1, m->dPart, dUnits, dStart, m->nb, Mpad);
+    const bool pdl = (NT == 1) && pdl_enabled();     // small batches only: the throughput shape must not sit on SMs K1 is using
+    if (p1) launch_ex(trigemm_kernel<NT, MT, true>, grid, dim3(K2_THREADS), K2Cfg<NT, MT>::SMEM, st, pdl,
+                      m->dWpack, m->dSlab, m->dBetaY, m->dBeta1, m->dPart, dUnits, dStart, m->nb, Mpad);
+    else launch_ex(trigemm_kernel<NT, MT, false>, grid, dim3(K2_THREADS), K2Cfg<NT, MT>::SMEM, st, pdl,
+                   m->dWpack, m->dSlab, m->dBetaY, m->dBeta1, m->dPart, dUnits, dStart, m->nb, Mpad);
 }
 
 // ytiles: CTAs along the candidate axis (128-candidate tiles when wide, 32-candidate tiles when narrow)
@@ -688,25 +713,35 @@ static int launch_trigemm(ibo_model* m, bool narrow, K2Plan pl, bool p1, long yt
 }
 
 template <int DP4>
-static void launch_kstar_mma(dim3 grid, cudaStream_t st, const ibo_model* m, const double* dCand, double* slab, long M, long m0) {
+static void launch_kstar_mma(dim3 grid, cudaStream_t st, const ibo_model* m, const double* dCand, double* slab, long M, long m0,
+                             const CandInline& inl) {
     constexpr int DP = 4 * DP4;
     constexpr int S = (DP % 16 == 4 || DP % 16 == 12) ? DP : DP + 4;
     const size_t smem = (2 * 128 * S + 256) * 8;
     if (m->kind <= IBO_KERNEL_SE_ISO)
-        kstar_mma_kernel<DP4, 0><<<grid, 256, smem, st>>>(m->dXt, dCand, m->dInvTheta, m->dCenter, slab, m->N, m->d, m->nb, M, m0, m->kind, m->sf2);
+        kstar_mma_kernel<DP4, 0><<<grid, 256, smem, st>>>(m->dXt, dCand, m->dInvTheta, m->dCenter, slab, m->N, m->d, m->nb, M, m0, m->kind, m->sf2, inl);
     else if (m->kind == IBO_KERNEL_MATERN3)
-        kstar_mma_kernel<DP4, 1><<<grid, 256, smem, st>>>(m->dXt, dCand, m->dInvTheta, m->dCenter, slab, m->N, m->d, m->nb, M, m0, m->kind, m->sf2);
+        kstar_mma_kernel<DP4, 1><<<grid, 256, smem, st>>>(m->dXt, dCand, m->dInvTheta, m->dCenter, slab, m->N, m->d, m->nb, M, m0, m->kind, m->sf2, inl);
     else
-        kstar_mma_kernel<DP4, 2><<<grid, 256, smem, st>>>(m->dXt, dCand, m->dInvTheta, m->dCenter, slab, m->N, m->d, m->nb, M, m0, m->kind, m->sf2);
+        kstar_mma_kernel<DP4, 2><<<grid, 256, smem, st>>>(m->dXt, dCand, m->dInvTheta, m->dCenter, slab, m->N, m->d, m->nb, M, m0, m->kind, m->sf2, inl);
+}
+
+static bool kstar_uses_mma(const ibo_model* m) {
+    static int mode = -1;
+    if (mode < 0) { const char* e = getenv("IBO_KSTAR"); mode = (e && !strcmp(e, "direct")) ? 0 : 1; }
+    return mode == 1 && (m->d + 3) / 4 <= 8;
 }
 
 // cross-covariance of one chunk; expansion on the tensor pipe for d <= 32 unless IBO_KSTAR=direct
-static void launch_kstar(const ibo_model* m, const double* dCand, double* slab, long tiles, long M, long m0, cudaStream_t st) {
-    static int mode = -1;
-    if (mode < 0) { const char* e = getenv("IBO_KSTAR"); mode = (e && !strcmp(e, "direct")) ? 0 : 1; }
+// inl != nullptr: the candidates are in *inl (host copy for the parameter buffer) and dCand is not valid
+static void launch_kstar(const ibo_model* m, const double* dCand, double* slab, long tiles, long M, long m0, cudaStream_t st,
+                         const CandInline* inl = nullptr) {
+    static CandInline none;
+    const CandInline& I = inl ? *inl : none;
+    if (inl) dCand = nullptr;
     dim3 grid((unsigned)tiles, m->nb);
     const int dp4 = (m->d + 3) / 4;
-    if (mode == 0 || dp4 > 8) {
+    if (!kstar_uses_mma(m)) {
         const int kS = m->d | 1;
         kstar_kernel<<<grid, 256, 2 * 128 * kS * 8, st>>>(m->dXt, dCand, m->dInvTheta, m->dCenter, slab, m->N, m->d, m->nb, M, m0, m->kind, m->sf2);
         return;
@@ -716,14 +751,14 @@ static void launch_kstar(const ibo_model* m, const double* dCand, double* slab, 
     while (z < 16 && (long)tiles * m->nb * z < g_num_sms) z *= 2;
     grid.z = z;
     switch (dp4) {
-        case 1: launch_kstar_mma<1>(grid, st, m, dCand, slab, M, m0); break;
-        case 2: launch_kstar_mma<2>(grid, st, m, dCand, slab, M, m0); break;
-        case 3: launch_kstar_mma<3>(grid, st, m, dCand, slab, M, m0); break;
-        case 4: launch_kstar_mma<4>(grid, st, m, dCand, slab, M, m0); break;
-        case 5: launch_kstar_mma<5>(grid, st, m, dCand, slab, M, m0); break;
-        case 6: launch_kstar_mma<6>(grid, st, m, dCand, slab, M, m0); break;
-        case 7: launch_kstar_mma<7>(grid, st, m, dCand, slab, M, m0); break;
-        default: launch_kstar_mma<8>(grid, st, m, dCand, slab, M, m0); break;
+        case 1: launch_kstar_mma<1>(grid, st, m, dCand, slab, M, m0, I); break;
+        case 2: launch_kstar_mma<2>(grid, st, m, dCand, slab, M, m0, I); break;
+        case 3: launch_kstar_mma<3>(grid, st, m, dCand, slab, M, m0, I); break;
+        case 4: launch_kstar_mma<4>(grid, st, m, dCand, slab, M, m0, I); break;
+        case 5: launch_kstar_mma<5>(grid, st, m, dCand, slab, M, m0, I); break;
+        case 6: launch_kstar_mma<6>(grid, st, m, dCand, slab, M, m0, I); break;
+        case 7: launch_kstar_mma<7>(grid, st, m, dCand, slab, M, m0, I); break;
+        default: launch_kstar_mma<8>(grid, st, m, dCand, slab, M, m0, I); break;
     }
 }
 
@@ -744,6 +779,13 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
     const bool prof = (rq.flags & IBO_FLAG_PROFILE) != 0;
     ibo_model* vm = m->var_model;
     const int nb = m->nb;
+    // hostCand given and dCand null: the batch is small enough to ride in K1's parameter buffer (score_host decided)
+    CandInline inlBuf;
+    const CandInline* inl = nullptr;
+    if (hostCand && !dCand) {
+        std::memcpy(inlBuf.x, hostCand, sizeof(double) * (size_t)M * m->d);
+        inl = &inlBuf;
+    }
     const long tilesTotal = (M + TN - 1) / TN;
     long chunkTiles = std::min<long>(tilesTotal, chunk_tiles_default());
     // keep the slab below ~6 GiB
@@ -787,10 +829,10 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
         K2Plan pl = plan;
         if (!narrow && tiles != chunkTiles) pl.G = pick_groups_wide(nb, tiles);      // last, shorter chunk
         if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[1], st));
-        launch_kstar(m, dCand, m->dSlab, tiles, M, m0, st);
+        launch_kstar(m, dCand, m->dSlab, tiles, M, m0, st, inl);
         nlaunch++;
         if (vm) {
-            launch_kstar(vm, dCand, vm->dSlab, tiles, M, m0, st);
+            launch_kstar(vm, dCand, vm->dSlab, tiles, M, m0, st, inl);
             nlaunch++;
         }
         if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[2], st));
@@ -818,7 +860,7 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
         P.rowLanes = !narrow ? 1 : (std::max(P.nbPart, P.nbVarPart) >= 64 ? 32 : (P.nbPart > 16 ? 8 : 1));
         const int cpb = 256 / P.rowLanes;
         const unsigned nblk = (unsigned)((chunkM + cpb - 1) / cpb);
-        epilogue_kernel<<<nblk, 256, 0, st>>>(P);
+        launch_ex(epilogue_kernel, dim3(nblk), dim3(256), 0, st, narrow && pdl_enabled() && !prof, P);
         nlaunch++;
         blk0 += nblk;
         if (prof) {
@@ -871,7 +913,10 @@ static int score_host(ibo_model* m, const double* Xs, long M, const ScoreReq& rq
         // candidates go to device memory with one small DMA (K1 reading them over PCIe costs ~15 us of dependent round trips);
         // the fused small-model kernel stages its tile with one parallel load and reads the mapped buffer directly
         const double* cand = m->dCand;
+        const ibo_model* vmh = m->var_model;
         if (tiny_eligible(m, M)) cand = m->hPinned;
+        else if (nin <= (size_t)CAND_INLINE && m->npb == 0 && kstar_uses_mma(m) && (!vmh || kstar_uses_mma(vmh)))
+            cand = nullptr;          // K1 takes the batch from its parameter buffer (K3 reads candidates only for a prior mean)
         else IBO_CUDA_TRY(cudaMemcpyAsync(m->dCand, m->hPinned, sizeof(double) * nin, cudaMemcpyHostToDevice, st));
         double* ho = m->hPinned + nin;
         if ((rc = score_device(m, cand, M, rq, ho, m->hPinned))) return rc;

@@ -38,18 +38,12 @@ struct TinyParams {
     double sf2, noise, ymax, parm, ptheta;
 };
 
-// A small batch travels in the kernel's parameter buffer: the launch itself delivers the candidates, and the kernel's
-// longest latency -- a PCIe read of mapped host memory, several microseconds -- disappears.  448 doubles keep the two
-// parameter structs inside the classic 4 KiB limit.
-constexpr int TINY_INLINE = 448;
-struct TinyInline { double x[TINY_INLINE]; };
-
 __device__ __forceinline__ void cp_async8(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src));
 }
 
 template <int KC>
-__global__ void __launch_bounds__(128) tiny_fused_kernel(const __grid_constant__ TinyParams P, const __grid_constant__ TinyInline I) {
+__global__ void __launch_bounds__(128) tiny_fused_kernel(const __grid_constant__ TinyParams P, const __grid_constant__ CandInline I) {
     extern __shared__ double sm[];
     const double* __restrict__ cands = P.cand ? P.cand : I.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -284,10 +278,10 @@ int score_tiny(ibo_model* m, const double* cand, long M, const ScoreReq& rq, dou
     P.M = M; P.d = m->d; P.acq = rq.acq; P.mode_py = (rq.flags & IBO_FLAG_MODE_PY) ? 1 : 0; P.npb = m->npb;
     P.want_argmax = (rq.acq >= 0 && rq.want_argmax) ? 1 : 0;
     P.sf2 = m->sf2; P.noise = m->noise; P.ymax = rq.ymax; P.parm = rq.parm; P.ptheta = m->ptheta;
-    static TinyInline I;        // launches copy the parameter buffer synchronously; one host thread per model
-    TinyInline Ilocal;
-    TinyInline* Ip = &I;
-    if (host_cand && (size_t)M * m->d <= (size_t)TINY_INLINE) {
+    static CandInline I;        // launches copy the parameter buffer synchronously; one host thread per model
+    CandInline Ilocal;
+    CandInline* Ip = &I;
+    if (host_cand && (size_t)M * m->d <= (size_t)CAND_INLINE) {
         std::memcpy(Ilocal.x, host_cand, sizeof(double) * (size_t)M * m->d);
         P.cand = nullptr;
         Ip = &Ilocal;
