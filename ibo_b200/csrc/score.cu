@@ -101,7 +101,6 @@ __global__ void __launch_bounds__(256) kstar_mma_kernel(const double* __restrict
                                                         const double* __restrict__ inv_theta, const double* __restrict__ center,
                                                         double* __restrict__ slab, int N, int d, int nb, long M, long m0,
                                                         int kind, double sf2, const __grid_constant__ CandInline inl) {
-    pdl_launch_dependents();                 // small batches: K2 is launched programmatically and may be scheduled now
     const double* __restrict__ cand = cand_dev ? cand_dev : inl.x;      // small batches ride in the parameter buffer
     constexpr int DP = 4 * DP4;
     constexpr int S = (DP % 16 == 4 || DP % 16 == 12) ? DP : DP + 4;   // (row*S + k) mod 16 distinct over a half-warp
@@ -180,6 +179,9 @@ __global__ void __launch_bounds__(256) kstar_mma_kernel(const double* __restrict
             reinterpret_cast<double2*>(blob)[(nt * 2 + ks2) * 32 + lane] = v;
         }
     }
+    // Small batches launch K2 programmatically: it may be scheduled once every CTA of this grid is here.  (Triggering at the
+    // top instead lets K2's CTAs occupy SMs this grid still needs -- measured: a 162-point batch at N = 4096 went 181 -> 274 us.)
+    pdl_launch_dependents();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -234,7 +236,6 @@ trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab
         fence_proxy_async();
     }
     __syncthreads();
-    if (NT == 1) pdl_launch_dependents();        // small batches: K3 may be scheduled now (it waits for this grid to finish)
     if (warp >= 8) {
         // ---------------- producer warpgroup: hands its registers to the DMMA warps ----------------
         if (Cfg::REGSPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
@@ -387,6 +388,7 @@ trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab
         }
         rbcount++;
     }
+    if (NT == 1) pdl_launch_dependents();        // small batches: K3 (programmatic launch) may be scheduled as this grid drains
 }
 
 // ---------------------------------------------------------------------------------------------
