@@ -199,25 +199,29 @@ constexpr int K2_THREADS = 384;   // warpgroups 0,1: 8 DMMA warps; warpgroup 2: 
 // row-block i).  Every accumulator runs over k in ascending order whatever the shape or the grouping, so V is bit-identical
 // across shapes; the row reduction is fixed per shape (results do not depend on the batch size, position or grouping
 // within a shape; across shapes they differ by the association of the row sums only).
-template <int NT, int MT> struct K2Cfg {
+// DEEP: the small shapes with as many pipeline stages as shared memory allows (one CTA per SM).  A batch whose CTAs all fit
+// side by side (grid <= number of SMs: a few dozen candidates) is bound by the bulk-copy round trip of its longest unit --
+// 32 stages of 4 k-blobs for the last 16-row sub-block at N = 2048, three in flight -- not by the DMMA pipe.
+template <int NT, int MT, bool DEEP = false> struct K2Cfg {
     static constexpr int SUBS = 8 / MT;                      // sub-blocks per 128-row block
     static constexpr int ADBL = MT * 2 * 128;                // doubles of one k-blob's A-operand slice: 2*MT m-tiles x 16 k
     static constexpr int BDBL = NT * 4 * 128;                // doubles of one k-blob's B-operand slice: 4*NT n-tiles x 16 k
     // A pipeline stage holds KS k-blobs: the small shapes would otherwise be bound by the bulk-copy round trip (a 6 KiB stage
     // is consumed in ~150 ns, the copy takes ~1 us) and by the per-stage mbarrier handshake.
     static constexpr int KS = (NT == 4 || MT == 8) ? 1 : (MT == 4 ? 2 : 4);
-    static constexpr int NS = (NT == 4 || MT == 8) ? K2_STAGES : (MT == 4 ? 4 : 3);
+    static constexpr int NS = DEEP ? (MT == 8 ? 9 : (MT == 2 ? 6 : 8))
+                                   : ((NT == 4 || MT == 8) ? K2_STAGES : (MT == 4 ? 4 : 3));
     static constexpr int SMEM = NS * KS * (ADBL + BDBL) * 8 + 2 * 3 * 128 * 8 + 2 * NS * 8;
-    static constexpr int MINB = NT == 4 ? 1 : (MT == 8 ? 1 : (MT == 1 ? 3 : 2));
+    static constexpr int MINB = (DEEP || NT == 4) ? 1 : (MT == 8 ? 1 : (MT == 1 ? 3 : 2));
     static constexpr bool REGSPLIT = (NT == 4);              // setmaxnreg warp specialisation only where registers are tight
 };
 
-template <int NT, int MT, bool P1>
-__global__ void __launch_bounds__(K2_THREADS, (K2Cfg<NT, MT>::MINB))
+template <int NT, int MT, bool P1, bool DEEP = false>
+__global__ void __launch_bounds__(K2_THREADS, (K2Cfg<NT, MT, DEEP>::MINB))
 trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab, const double* __restrict__ betaY,
                const double* __restrict__ beta1, double* __restrict__ part, const int* __restrict__ units,
-               const int* __restrict__ gstart, int nb, long Mpad) {
-    using Cfg = K2Cfg<NT, MT>;
+               const int* __restrict__ gstart, int nb, long Mpad, long Mvalid) {
+    using Cfg = K2Cfg<NT, MT, DEEP>;
     constexpr int ADBL = Cfg::ADBL, BDBL = Cfg::BDBL, SUBS = Cfg::SUBS, KS = Cfg::KS, NS = Cfg::NS;
     extern __shared__ __align__(128) unsigned char smraw[];
     double* sA = reinterpret_cast<double*>(smraw);
@@ -270,22 +274,33 @@ trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab
     // ---------------- consumers: 8 warps, warp tile 8*MT (rows) x 8*NT (candidates) ----------------
     if (Cfg::REGSPLIT) asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
     const int wm = warp >> 2, wn = warp & 3;
+    // Small batches: a warp whose 8 candidates lie beyond the batch (a 9-point DIRECT batch fills 2 of the 4 n-tiles of its
+    // 32-candidate CTA tile) issues no DMMAs -- it only keeps the pipeline handshake going -- so the SM's DMMA pipe serves
+    // the warps that carry candidates; the longest unit of such a batch is bound by that pipe.
+    const bool active = (NT != 1) || ((long)T * 128 + sub * 32 + wn * 8 < Mvalid);
     int s = 0; uint32_t ph = 0;
     int rbcount = 0;
     for (int uu = u0; uu < u1; ++uu) {
         const int i = units[uu] >> 3, h = units[uu] & 7;
-        double acc[MT][NT][2];
+        // SPLIT independent accumulator chains per (m-tile, n-tile): a warp of the smallest shapes owns one or two DMMA tiles,
+        // and a single chain of dependent DMMAs (4 per k-blob, ~60 cycles each) was the floor of a small batch -- 16 us for the
+        // last sub-block at N = 2048.  Chain c takes the k-steps with (2 ks2 + half) % SPLIT == c; the chains are summed once
+        // at the end (in a fixed order: V is deterministic per shape).
+        constexpr int SPLIT = (MT * NT >= 4) ? 1 : 4 / (MT * NT);
+        double accs[SPLIT][MT][NT][2];
 #pragma unroll
-        for (int a = 0; a < MT; a++)
+        for (int c = 0; c < SPLIT; c++)
 #pragma unroll
-            for (int b = 0; b < NT; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+            for (int a = 0; a < MT; a++)
+#pragma unroll
+                for (int b = 0; b < NT; b++) accs[c][a][b][0] = accs[c][a][b][1] = 0.0;
         const int nfull = i * KB_PER_BLOCK;     // k-blobs left of the diagonal block: dense
         const int nkb = nfull + (h + 1) * MT;
         for (int kb0 = 0; kb0 < nkb; kb0 += KS) {
             const int nk = (KS == 1) ? 1 : min(KS, nkb - kb0);
             mbar_wait(&full[s], ph);
 #pragma unroll 1
-            for (int kk = 0; kk < nk; kk++) {
+            for (int kk = 0; kk < (active ? nk : 0); kk++) {
                 const int kb = kb0 + kk;
                 // warp wm owns the interleaved m-tiles 2*mt + wm of the sub-block so that the triangular skip below is balanced
                 const double2* a2 = reinterpret_cast<const double2*>(sA + (s * KS + kk) * ADBL) + (wm * 2) * 32 + lane;
@@ -301,11 +316,13 @@ trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab
 #pragma unroll
                         for (int mt = 0; mt < MT; mt++)
 #pragma unroll
-                            for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt].x, bf[nt].x);
+                            for (int nt = 0; nt < NT; nt++)
+                                dmma884(accs[(2 * ks2) % SPLIT][mt][nt][0], accs[(2 * ks2) % SPLIT][mt][nt][1], af[mt].x, bf[nt].x);
 #pragma unroll
                         for (int mt = 0; mt < MT; mt++)
 #pragma unroll
-                            for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt].y, bf[nt].y);
+                            for (int nt = 0; nt < NT; nt++)
+                                dmma884(accs[(2 * ks2 + 1) % SPLIT][mt][nt][0], accs[(2 * ks2 + 1) % SPLIT][mt][nt][1], af[mt].y, bf[nt].y);
                     }
                 } else {
                     // diagonal block of W (lower triangular): in its k-blob kbl the m-tiles 2*(h*MT+mt) + wm with h*MT+mt < kbl
@@ -321,9 +338,11 @@ trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab
                             if (mt >= kbl) {
                                 const double2 af = a2[(mt * 4 + ks2) * 32];
 #pragma unroll
-                                for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af.x, bf[nt].x);
+                                for (int nt = 0; nt < NT; nt++)
+                                    dmma884(accs[(2 * ks2) % SPLIT][mt][nt][0], accs[(2 * ks2) % SPLIT][mt][nt][1], af.x, bf[nt].x);
 #pragma unroll
-                                for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], af.y, bf[nt].y);
+                                for (int nt = 0; nt < NT; nt++)
+                                    dmma884(accs[(2 * ks2 + 1) % SPLIT][mt][nt][0], accs[(2 * ks2 + 1) % SPLIT][mt][nt][1], af.y, bf[nt].y);
                             }
                         }
                     }
@@ -333,6 +352,17 @@ trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab
             if (lane == 0) mbar_arrive(&empty[s]);
             if (++s == NS) { s = 0; ph ^= 1; }
         }
+        double acc[MT][NT][2];
+#pragma unroll
+        for (int a = 0; a < MT; a++)
+#pragma unroll
+            for (int b = 0; b < NT; b++)
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    if (SPLIT == 1) acc[a][b][j] = accs[0][a][b][j];
+                    else if (SPLIT == 2) acc[a][b][j] = accs[0][a][b][j] + accs[1 % SPLIT][a][b][j];
+                    else acc[a][b][j] = (accs[0][a][b][j] + accs[1 % SPLIT][a][b][j]) + (accs[2 % SPLIT][a][b][j] + accs[3 % SPLIT][a][b][j]);
+                }
         // ---- fused reduction of this (16 MT) x (32 NT) block of V over its rows ----
         double by[MT], b1[MT];
 #pragma unroll
@@ -524,6 +554,10 @@ template <int NT, int MT>
 static cudaError_t set_k2_attr() {
     cudaError_t e = cudaFuncSetAttribute(trigemm_kernel<NT, MT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2Cfg<NT, MT>::SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(trigemm_kernel<NT, MT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2Cfg<NT, MT>::SMEM);
+    if constexpr (NT == 1) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(trigemm_kernel<NT, MT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2Cfg<NT, MT, true>::SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(trigemm_kernel<NT, MT, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2Cfg<NT, MT, true>::SMEM);
+    }
     return e;
 }
 static void set_score_attrs() {
@@ -691,26 +725,41 @@ static bool pdl_enabled() {
     return !(e && e[0] == '0');
 }
 
+static int deep_mode() {       // IBO_K2_DEEP: 0 = never, 1 = whenever the shape is a small one, unset = when the grid fits the SMs
+    const char* e = getenv("IBO_K2_DEEP");
+    return e ? atoi(e) : -1;
+}
+
 template <int NT, int MT>
-static void launch_k2_shape(const ibo_model* m, bool p1, dim3 grid, const int* dUnits, const int* dStart, long Mpad, cudaStream_t st) {
+static void launch_k2_shape(const ibo_model* m, bool p1, dim3 grid, const int* dUnits, const int* dStart, long Mpad, long Mvalid, cudaStream_t st) {
     const bool pdl = (NT == 1) && pdl_enabled();     // small batches only: the throughput shape must not sit on SMs K1 is using
+    if constexpr (NT == 1) {
+        const int dm = deep_mode();
+        if (dm == 1 || (dm < 0 && (long)grid.x * grid.y <= g_num_sms)) {
+            if (p1) launch_ex(trigemm_kernel<NT, MT, true, NT == 1>, grid, dim3(K2_THREADS), K2Cfg<NT, MT, NT == 1>::SMEM, st, pdl,
+                              m->dWpack, m->dSlab, m->dBetaY, m->dBeta1, m->dPart, dUnits, dStart, m->nb, Mpad, Mvalid);
+            else launch_ex(trigemm_kernel<NT, MT, false, NT == 1>, grid, dim3(K2_THREADS), K2Cfg<NT, MT, NT == 1>::SMEM, st, pdl,
+                           m->dWpack, m->dSlab, m->dBetaY, m->dBeta1, m->dPart, dUnits, dStart, m->nb, Mpad, Mvalid);
+            return;
+        }
+    }
     if (p1) launch_ex(trigemm_kernel<NT, MT, true>, grid, dim3(K2_THREADS), K2Cfg<NT, MT>::SMEM, st, pdl,
-                      m->dWpack, m->dSlab, m->dBetaY, m->dBeta1, m->dPart, dUnits, dStart, m->nb, Mpad);
+                      m->dWpack, m->dSlab, m->dBetaY, m->dBeta1, m->dPart, dUnits, dStart, m->nb, Mpad, Mvalid);
     else launch_ex(trigemm_kernel<NT, MT, false>, grid, dim3(K2_THREADS), K2Cfg<NT, MT>::SMEM, st, pdl,
-                   m->dWpack, m->dSlab, m->dBetaY, m->dBeta1, m->dPart, dUnits, dStart, m->nb, Mpad);
+                   m->dWpack, m->dSlab, m->dBetaY, m->dBeta1, m->dPart, dUnits, dStart, m->nb, Mpad, Mvalid);
 }
 
 // ytiles: CTAs along the candidate axis (128-candidate tiles when wide, 32-candidate tiles when narrow)
-static int launch_trigemm(ibo_model* m, bool narrow, K2Plan pl, bool p1, long ytiles, long Mpad, cudaStream_t st) {
+static int launch_trigemm(ibo_model* m, bool narrow, K2Plan pl, bool p1, long ytiles, long Mpad, long Mvalid, cudaStream_t st) {
     const int *dUnits, *dStart;
     int rc = get_unit_table(m, narrow, pl.MT, pl.G, &dUnits, &dStart);
     if (rc) return rc;
     dim3 grid(pl.G, (unsigned)ytiles);
-    if (!narrow) launch_k2_shape<4, 8>(m, p1, grid, dUnits, dStart, Mpad, st);
-    else if (pl.MT == 8) launch_k2_shape<1, 8>(m, p1, grid, dUnits, dStart, Mpad, st);
-    else if (pl.MT == 4) launch_k2_shape<1, 4>(m, p1, grid, dUnits, dStart, Mpad, st);
-    else if (pl.MT == 2) launch_k2_shape<1, 2>(m, p1, grid, dUnits, dStart, Mpad, st);
-    else launch_k2_shape<1, 1>(m, p1, grid, dUnits, dStart, Mpad, st);
+    if (!narrow) launch_k2_shape<4, 8>(m, p1, grid, dUnits, dStart, Mpad, Mvalid, st);
+    else if (pl.MT == 8) launch_k2_shape<1, 8>(m, p1, grid, dUnits, dStart, Mpad, Mvalid, st);
+    else if (pl.MT == 4) launch_k2_shape<1, 4>(m, p1, grid, dUnits, dStart, Mpad, Mvalid, st);
+    else if (pl.MT == 2) launch_k2_shape<1, 2>(m, p1, grid, dUnits, dStart, Mpad, Mvalid, st);
+    else launch_k2_shape<1, 1>(m, p1, grid, dUnits, dStart, Mpad, Mvalid, st);
     return IBO_OK;
 }
 
@@ -838,12 +887,12 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
             nlaunch++;
         }
         if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[2], st));
-        if ((rc = launch_trigemm(m, narrow, pl, m->npb > 0, ctaTiles, Mpad, st))) return rc;
+        if ((rc = launch_trigemm(m, narrow, pl, m->npb > 0, ctaTiles, Mpad, chunkM, st))) return rc;
         nlaunch++; nK2++;
         if (vm) {
             K2Plan plv = planV;
             if (!narrow && tiles != chunkTiles) plv.G = pick_groups_wide(vm->nb, tiles);
-            if ((rc = launch_trigemm(vm, narrow, plv, false, ctaTiles, Mpad, st))) return rc;
+            if ((rc = launch_trigemm(vm, narrow, plv, false, ctaTiles, Mpad, chunkM, st))) return rc;
             nlaunch++; nK2++;
         }
         if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[3], st));
