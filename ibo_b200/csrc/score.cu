@@ -234,8 +234,11 @@ trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab
     const int T = blockIdx.y / SUB, sub = blockIdx.y % SUB;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int u0 = gstart[g], u1 = gstart[g + 1];
+    // The multi-blob stages of the small shapes are fed by KS producer lanes (one per producer warp, lane p moves blob p of
+    // every stage): a single lane issuing the 2 KS small bulk copies of a stage was the floor of a small batch.
+    constexpr int NPROD = KS;
     if (tid == 0) {
-        for (int s = 0; s < NS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 8); }
+        for (int s = 0; s < NS; s++) { mbar_init(&full[s], NPROD); mbar_init(&empty[s], 8); }
         fence_barrier_init();
         fence_proxy_async();
     }
@@ -243,8 +246,9 @@ trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab
     if (warp >= 8) {
         // ---------------- producer warpgroup: hands its registers to the DMMA warps ----------------
         if (Cfg::REGSPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-        // one lane streams the operand blobs with bulk TMA
-        if (warp == 8 && lane == 0) {
+        // one lane per stage blob streams the operand slices with bulk TMA
+        const int pk = warp - 8;
+        if (pk < NPROD && lane == 0) {
             if (NT == 1) pdl_wait();             // the K* slab comes from K1 (programmatic launch: K1 may still be running)
             int s = 0; uint32_t ph = 0;
             const double* Bbase = slab + (size_t)T * (nb * KB_PER_BLOCK) * BLOB + sub * BDBL;
@@ -254,16 +258,14 @@ trigemm_kernel(const double* __restrict__ Wpack, const double* __restrict__ slab
                 const double* Abase = Wpack + wpack_base(i) * BLOB + h * ADBL;
                 const int nkb = i * KB_PER_BLOCK + (h + 1) * MT;     // k-blobs right of column 16 (h+1) MT of the diagonal block are zero
                 for (int kb = 0; kb < nkb; kb += KS) {
-                    const int nk = (KS == 1) ? 1 : min(KS, nkb - kb);
                     mbar_wait(&empty[s], ph ^ 1);
-                    mbar_arrive_expect_tx(&full[s], nk * (ADBL + BDBL) * 8);
-#pragma unroll
-                    for (int kk = 0; kk < KS; kk++) {
-                        if (kk < nk) {
-                            bulk_g2s(sA + (s * KS + kk) * ADBL, Abase + (size_t)(kb + kk) * BLOB, ADBL * 8, &full[s]);
-                            // n-tiles are the slowest index of a blob, so this CTA's 4*NT n-tiles are one contiguous slice
-                            bulk_g2s(sB + (s * KS + kk) * BDBL, Bbase + (size_t)(kb + kk) * BLOB, BDBL * 8, &full[s]);
-                        }
+                    if (kb + pk < nkb) {
+                        mbar_arrive_expect_tx(&full[s], (ADBL + BDBL) * 8);
+                        bulk_g2s(sA + (s * KS + pk) * ADBL, Abase + (size_t)(kb + pk) * BLOB, ADBL * 8, &full[s]);
+                        // n-tiles are the slowest index of a blob, so this CTA's 4*NT n-tiles are one contiguous slice
+                        bulk_g2s(sB + (s * KS + pk) * BDBL, Bbase + (size_t)(kb + pk) * BLOB, BDBL * 8, &full[s]);
+                    } else {
+                        mbar_arrive(&full[s]);   // short last stage: nothing to move for this lane
                     }
                     if (++s == NS) { s = 0; ph ^= 1; }
                 }
