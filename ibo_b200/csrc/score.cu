@@ -680,6 +680,7 @@ static K2Plan plan_narrow_cached(ibo_model* m, long ctaTiles) {
     auto it = m->planCache.find(ctaTiles);
     if (it == m->planCache.end()) {
         K2Plan pl = plan_narrow(m->nb, ctaTiles);
+        if (getenv("IBO_DEBUG_PLAN")) fprintf(stderr, "[plan_narrow] nb=%d ctaTiles=%ld -> MT=%d G=%d (%ld CTAs)\n", m->nb, ctaTiles, pl.MT, pl.G, ctaTiles * pl.G);
         it = m->planCache.emplace(ctaTiles, std::make_pair(pl.MT, pl.G)).first;
     }
     return K2Plan{it->second.first, it->second.second};
