@@ -17,6 +17,7 @@
 #include <ctime>
 #include <limits>
 #include <map>
+#include <memory>
 #include <set>
 #include <unordered_map>
 #include <string>
@@ -52,6 +53,7 @@ struct Store {
     std::vector<Class> classes;          // only the first `ncls` entries are in use (the rest keep their heap capacity)
     size_t ncls = 0;
     std::unordered_map<unsigned long long, int> cls_of_d;
+    std::vector<int> by_d;               // class ids in ascending d (select() walks them in this order)
     size_t live = 0;
 
     // The store is kept per host thread and reused by successive queries (sequential BO / the gallery issue one DIRECT
@@ -66,6 +68,7 @@ struct Store {
         for (size_t k = 0; k < ncls; k++) classes[k].heap.clear();
         ncls = 0;
         cls_of_d.clear();
+        by_d.clear();
         live = 0;
     }
 
@@ -82,6 +85,7 @@ struct Store {
             k = (int)ncls++;
             if (classes.size() < ncls) classes.push_back(Class());
             classes[k].d = dd; cls_of_d[bits] = k;
+            by_d.insert(std::upper_bound(by_d.begin(), by_d.end(), dd, [this](double v, int c) { return v < classes[c].d; }), k);
         }
         else k = it->second;
         cls.push_back(k);
@@ -287,37 +291,32 @@ void divide(Driver& D, Store& R, const std::vector<unsigned>& order, bool seq, S
 void select(Store& R, double FMIN, std::vector<unsigned>& potopts) {
     const double epsilon = 10e-10;
     potopts.clear();
-    std::vector<double> cd, cy;
-    std::vector<int> ck;
-    for (size_t k = 0; k < R.ncls; k++) {
+    // live classes in ascending d (distinct by construction; the store keeps the order up to date as classes appear, a few
+    // per iteration, so nothing is sorted here): sd / sy / sk are what the slope scans stream through
+    static thread_local std::vector<double> sd, sy;
+    static thread_local std::vector<int> sk;
+    static thread_local std::vector<char> dominated;
+    sd.clear(); sy.clear(); sk.clear();
+    for (int k : R.by_d) {
         if (R.classes[k].heap.empty()) continue;
         unsigned id = R.classes[k].heap.front().second;
-        cd.push_back(R.classes[k].d); cy.push_back(R.y[id]); ck.push_back((int)k);
+        sd.push_back(R.classes[k].d); sy.push_back(R.y[id]); sk.push_back(k);
     }
-    const size_t C = cd.size();
+    const size_t C = sd.size();
     // Quick reject (exactly the reference's `minI2 <= 0` break): a larger class whose minimum is <= y_j makes the
     // slope (y_c - y_j)/(d_c - d_j) non-positive.  With classes sorted by d, that is a suffix-minimum lookup, so
-    // only the few classes on the lower-right staircase pay for the full O(C) slope scan.
-    std::vector<size_t> byd(C);
-    for (size_t k = 0; k < C; k++) byd[k] = k;
-    std::sort(byd.begin(), byd.end(), [&](size_t a, size_t b) { return cd[a] < cd[b]; });
-    std::vector<char> dominated(C, 0);
+    // only the few classes on the lower-right staircase pay for a slope scan.
+    dominated.assign(C, 0);
     {
         double sufmin = MAX_DOUBLE; bool have = false;
         for (size_t t = C; t-- > 0;) {
-            size_t k = byd[t];
-            if (have && sufmin - cy[k] <= 0.) dominated[k] = 1;      // sign of fl(y_c - y_j) is exact
-            if (!have || cy[k] < sufmin) { sufmin = cy[k]; have = true; }
+            if (have && sufmin - sy[t] <= 0.) dominated[t] = 1;      // sign of fl(y_c - y_j) is exact
+            if (!have || sy[t] < sufmin) { sufmin = sy[t]; have = true; }
         }
     }
-    // classes in ascending d (distinct by construction): sd / sy are the sorted copies the slope scans stream through
-    std::vector<double> sd(C), sy(C);
-    for (size_t t = 0; t < C; t++) { sd[t] = cd[byd[t]]; sy[t] = cy[byd[t]]; }
-    std::vector<size_t> pos(C);
-    for (size_t t = 0; t < C; t++) pos[byd[t]] = t;
-    for (size_t k = 0; k < C; k++) {
-        if (dominated[k]) continue;
-        const double dj = cd[k], yj = cy[k];
+    for (size_t t = 0; t < C; t++) {
+        if (dominated[t]) continue;
+        const double dj = sd[t], yj = sy[t];
         double maxI1 = MIN_DOUBLE, minI2 = MAX_DOUBLE;
         bool breaked = false;
         // maxI1 = max over smaller classes of (yj - yc)/(dj - dc), minI2 = min over larger classes of (yc - yj)/(dc - dj):
@@ -325,7 +324,6 @@ void select(Store& R, double FMIN, std::vector<unsigned>& potopts) {
         // the steepest slopes usually are, and stops at the first moment the reference's final test `minI2 < maxI1` is
         // already decided (maxI1 only grows, minI2 only shrinks) -- same accept / reject, a fraction of the divisions.
         // (`minI2 <= 0` cannot occur here: that is the `dominated` case above.)
-        const size_t t = pos[k];
         size_t l = t, r = t + 1;
         while ((l > 0 || r < C) && !breaked) {
             if (l > 0) {
@@ -348,7 +346,7 @@ void select(Store& R, double FMIN, std::vector<unsigned>& potopts) {
         if (!ok) continue;
         // every member tying the class minimum is potentially optimal; they leave the heap here and are divided
         // (or the run ends) before the next selection
-        R.pop_minima(ck[k], potopts);
+        R.pop_minima(sk[t], potopts);
     }
     std::sort(potopts.begin(), potopts.end());
 }
@@ -363,7 +361,18 @@ int run_direct(ibo_batch_objective_t f, void* user, int ndim, const double* lb, 
     D.lowerb.assign(lb, lb + ndim); D.upperb.assign(ub, ub + ndim);
     D.fixed.resize(ndim);
     for (int i = 0; i < ndim; i++) D.fixed[i] = (lb[i] == ub[i]);
-    static thread_local Store R;
+    // The per-thread store is reused by successive queries; a nested query (an objective callback that itself runs
+    // DIRECT on this thread) gets a private one.
+    static thread_local Store tlsR;
+    static thread_local Scratch tlsW;
+    static thread_local bool tlsBusy = false;
+    const bool nested = tlsBusy;
+    std::unique_ptr<Store> ownR(nested ? new Store() : nullptr);
+    std::unique_ptr<Scratch> ownW(nested ? new Scratch() : nullptr);
+    Store& R = nested ? *ownR : tlsR;
+    Scratch& W = nested ? *ownW : tlsW;
+    struct BusyGuard { bool& b; bool set; ~BusyGuard() { if (set) b = false; } } guard{tlsBusy, !nested};
+    if (!nested) tlsBusy = true;
     R.reset(ndim);
     // first rectangle: the unit cube, sampled at its centre (cpp/direct.cpp:349-357)
     {
@@ -375,7 +384,6 @@ int run_direct(ibo_batch_objective_t f, void* user, int ndim, const double* lb, 
         R.add(l.data(), u.data(), c.data(), d, y[0]);
     }
     std::vector<unsigned> potopts, order;
-    static thread_local Scratch W;
     order.clear();
     R.pop_minima(R.cls[0], order);      // the unit cube leaves its heap like any rectangle about to be divided
     divide(D, R, order, seq, W);

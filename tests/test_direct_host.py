@@ -92,3 +92,23 @@ def test_maxsample_zero_and_degenerate_boxes():
                               ctypes.byref(fmin), _lib.dptr(xmin), ctypes.byref(ns), ctypes.byref(it))
     assert rc == 0 and xmin[1] == 1.0 and ns.value >= 5
     assert L.ibo_direct_batched(_lib.BATCH_OBJECTIVE(cb), None, 0, None, None, 1, 1, 1, 0, None, None, None, None) == _lib.E_BADARG
+
+
+def test_nested_direct_on_one_thread_is_safe():
+    """an objective that itself runs DIRECT (same host thread): the inner run must not disturb the outer one's rectangle store"""
+    from ibo_b200.utils.optimize import direct
+
+    def inner(x):
+        return float(np.sum((np.asarray(x) - 0.3) ** 2))
+
+    def outer_plain(x):
+        return float(np.sum((np.asarray(x) - 0.6) ** 2))
+
+    def outer_nested(x):
+        v, _ = direct(inner, [[0., 1.]] * 2, maxiter=5)
+        assert abs(v - 2 * (0.5 - 0.3) ** 2) < 0.1
+        return outer_plain(x)
+
+    a = direct(outer_plain, [[0., 1.]] * 2, maxiter=15)
+    b = direct(outer_nested, [[0., 1.]] * 2, maxiter=15)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])
