@@ -20,9 +20,10 @@ class Kernel(object):
         self._hyperparams = np.array(hyperparams, dtype=float)
         self._hyperparams.setflags(write=False)      # read-only, as kernel.py:34-40
 
-    @property
-    def hyperparams(self):
+    def getHyperparams(self):
         return self._hyperparams
+
+    hyperparams = property(getHyperparams)
 
     def spec(self, ndim):
         """-> (kernel type id, hyperparameter vector) for the C ABI."""

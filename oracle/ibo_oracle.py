@@ -576,6 +576,70 @@ def direct_cpp(f, lb, ub, maxiter, maxsample, record=None):
 
 
 # ---------------------------------------------------------------------------------------------
+# maximizeEI / cdirectGP and fastUCBGallery
+#   (ego/acquisition/__init__.py:174-197,307-447; ego/acquisition/gallery.py:42-135)
+# ---------------------------------------------------------------------------------------------
+def acqmax_cpp(gp, bounds, acq, parm, maxiter=50, maxsample=10000):
+    """cdirectGP + acqmaxGP restated: inv(R) is formed once (ego/acquisition/__init__.py:385-388), DIRECT
+    (cpp/direct.cpp) minimises the libego-arithmetic negative acquisition (cpp/optimizeGP.cpp:194-236), and the
+    result comes back as (-min, argmin) (:443-447).  maxtime is not modelled."""
+    b = np.array(bounds, dtype=float)
+    invR = gp.invR()
+    ymax = gp.Y.max()
+
+    def f(x):
+        mu, sig = gp.posterior_cpp(x[None, :], invR=invR)
+        return -float(score(acq, "cpp", mu, sig ** 2, ymax, parm)[0])
+    fmin, xmin, ns = direct_cpp(f, b[:, 0], b[:, 1], maxiter, maxsample)
+    return -fmin, np.array(xmin, dtype=float)
+
+
+def fast_ucb_gallery(kernel, X, Y, bounds, N, prior=None, use_best=True, samples=300, seed=None,
+                     maxiter=50, maxsample=10000):
+    """ego/acquisition/gallery.py:42-135 for a model that has data (the no-data branches, :68-90, need BFGS on the
+    prior mean and are host logic only).  hallucGP is a plain GP with the default noise 0.1 whatever the source model
+    was (:67); per slot: maximizeEI(xi=.3) through libego's DIRECT (:101), the 0.5 distance rule (:102-105), `samples`
+    latin-hypercube points scored with the Python-arithmetic EI(xi=.4) (:98,111-116), the prior means (:119-130),
+    then hallucGP.addData(best, hallucGP.mu(best)) (:134).  `seed` pins the reference's unseeded lhcSample the same way
+    the product's `seed` extension does (seed + slot index)."""
+    gallery = []
+    X = np.array(X, dtype=float, ndmin=2)
+    Y = np.array(Y, dtype=float).reshape(-1)
+    if use_best:                                                                # :50-63
+        bestY, bestX = -np.inf, None
+        for x, y in zip(X, Y):
+            if y > bestY and all(b[0] <= v <= b[1] for v, b in zip(x, bounds)):
+                bestY, bestX = y, x
+        if bestX is not None:
+            gallery.append(bestX)
+    halluc = GPOracle(kernel, X, Y, noise=0.1, prior=prior)                     # :67
+    slot = 0
+    while len(gallery) < N:                                                     # :93
+        bestU, bestX = -np.inf, None
+        opt, optx = acqmax_cpp(halluc, bounds, ACQ_EI, .3, maxiter, maxsample)  # :101
+        if len(gallery) == 0 or min(np.linalg.norm(optx - gx) for gx in gallery) > .5:
+            bestU, bestX = opt, optx
+        cand = np.array(lhc_sample(bounds, samples, seed=None if seed is None else seed + slot))
+        mu, s2 = halluc.posterior_batch(cand)
+        u = ei_py(mu, s2, halluc.Y.max(), .4)                                   # :98 ut = EI(hallucGP, xi=.4)
+        for x, ux in zip(cand, u):                                              # :111-116
+            if ux > bestU and min(np.linalg.norm(x - gx) for gx in gallery) > .5:
+                bestU, bestX = ux, x
+        if prior is not None:                                                   # :119-130
+            pm = np.array([[np.clip(x[i], bounds[i][0], bounds[i][1]) for i in range(len(x))] for x in prior.means])
+            pm = pm * prior.width + prior.lowerb
+            mu, s2 = halluc.posterior_batch(pm)
+            for x, ux in zip(pm, ei_py(mu, s2, halluc.Y.max(), .4)):
+                if ux > bestU and (len(gallery) == 0 or min(np.linalg.norm(x - gx) for gx in gallery) > .5):
+                    bestU, bestX = ux, x
+        gallery.append(bestX)
+        mub, _ = halluc.posterior_batch(bestX[None, :])                         # :134
+        halluc.add_data(bestX, mub[0])
+        slot += 1
+    return gallery
+
+
+# ---------------------------------------------------------------------------------------------
 # test functions used as fixture data (ego/utils/testfunctions.py:171-182,244-250,289-304)
 # ---------------------------------------------------------------------------------------------
 def branin(x):

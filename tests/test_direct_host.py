@@ -112,3 +112,112 @@ def test_nested_direct_on_one_thread_is_safe():
     a = direct(outer_plain, [[0., 1.]] * 2, maxiter=15)
     b = direct(outer_nested, [[0., 1.]] * 2, maxiter=15)
     assert a[0] == b[0] and np.array_equal(a[1], b[1])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# randomized differential test against the reference's own `direct` (oracle/_ref/libego.so, compiled from the
+# untouched cpp/direct.cpp) and against the oracle restatement: random boxes (some dims fixed), objectives built to
+# hit the selection rules' corner cases -- exact y ties (quantised / constant objectives), FMIN == 0 (cpp/direct.cpp:
+# 430-442), negative and huge values, `maxsample` cuts in the middle of an iteration (:487-492)
+# ---------------------------------------------------------------------------------------------------------------
+REF_LIBEGO = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libego.so")
+
+
+def _random_case(seed):
+    rs = np.random.RandomState(1000 + seed)
+    d = int(rs.randint(1, 7))
+    lb = np.round(rs.uniform(-3, 1, d), 2)
+    ub = lb + np.round(rs.uniform(0.5, 4, d), 2)
+    for i in range(1 if d > 1 else 0, d):        # dim 0 fixed stalls DIRECT by design, covered by the golden traces
+        if rs.rand() < 0.15:
+            ub[i] = lb[i]
+    c = lb + rs.rand(d) * (ub - lb + 1e-9)
+    w = rs.uniform(0.2, 3.0, d)
+    kind = seed % 6
+    if kind == 0:
+        f = lambda x: float(np.sum(w * (x - c) ** 2))                              # smooth
+    elif kind == 1:
+        f = lambda x: float(np.floor(4 * np.sum(w * (x - c) ** 2)) / 4)            # plateaus: many exact ties
+    elif kind == 2:
+        f = lambda x: 1.25                                                         # everything ties
+    elif kind == 3:
+        f = lambda x: float(np.sum(np.abs(np.round(x - lb, 12))))                  # reaches FMIN == 0 only at the corner
+    elif kind == 4:
+        f = lambda x: float(-1e6 * np.exp(-np.sum(w * (x - c) ** 2)) + np.sum(np.sin(5 * x)))   # large negative
+    else:
+        f = lambda x: float(np.max(np.abs(x - c)) > 0.4)                           # 0/1 valued: FMIN == 0 with ties
+    maxiter = int(rs.randint(1, 22))
+    maxsample = int(rs.choice([7, 50, 333, 100000]))
+    return d, lb, ub, f, maxiter, maxsample
+
+
+def _run_ours(d, lb, ub, f, maxiter, maxsample, flags):
+    pts = []
+
+    def cb(user, n, ndim, X, y):
+        A = np.ctypeslib.as_array(X, shape=(n, ndim)).copy()
+        pts.append(A)
+        for i in range(n):
+            y[i] = f(A[i])
+    fmin = c_double(0); xmin = np.empty(d); ns = c_long(0); it = c_int(0)
+    rc = _lib.lib().ibo_direct_batched(_lib.BATCH_OBJECTIVE(cb), None, d, _lib.dptr(lb), _lib.dptr(ub), maxiter, 100000, maxsample,
+                                       flags, ctypes.byref(fmin), _lib.dptr(xmin), ctypes.byref(ns), ctypes.byref(it))
+    assert rc == 0
+    return fmin.value, xmin.copy(), ns.value, np.vstack(pts)
+
+
+def _run_reference(d, lb, ub, f, maxiter, maxsample):
+    ref = ctypes.CDLL(REF_LIBEGO)
+    ref.direct.restype = ctypes.POINTER(c_double)
+    trace = []
+
+    def cb(n, x):
+        xx = np.array([x[i] for i in range(n)])
+        trace.append(xx)
+        return f(xx)
+    res = ref.direct(_lib.OBJECTIVE(cb), d, _lib.dptr(lb), _lib.dptr(ub), maxiter, 100000, maxsample)
+    return res[0], np.array([res[i + 1] for i in range(d)]), len(trace), np.array(trace)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_LIBEGO), reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed", range(48))
+def test_batched_direct_equals_live_reference_on_random_problems(seed, capfd):
+    d, lb, ub, f, maxiter, maxsample = _random_case(seed)
+    rf, rx, rn, rtrace = _run_reference(d, lb, ub, f, maxiter, maxsample)
+    capfd.readouterr()                      # the reference prints its termination reason
+    for flags in (0, _lib.FLAG_DIRECT_SEQ):
+        of, ox, on, opts = _run_ours(d, lb, ub, f, maxiter, maxsample, flags)
+        assert of == rf and np.array_equal(ox, rx) and on == rn, (seed, flags)
+        if flags:
+            assert np.array_equal(opts, rtrace)                       # same call sequence, sample by sample
+        else:
+            # same multiset of samples (the batched driver reorders them inside an iteration)
+            assert np.array_equal(np.sort(opts.view([('', opts.dtype)] * d), axis=0), np.sort(rtrace.view([('', rtrace.dtype)] * d), axis=0))
+
+
+@pytest.mark.parametrize("seed", range(0, 48, 5))
+def test_batched_direct_equals_oracle_restatement_on_random_problems(seed):
+    """the same cases against oracle.direct_cpp -- runs on the GPU box too, where only the prebuilt oracle/_ref travels"""
+    d, lb, ub, f, maxiter, maxsample = _random_case(seed)
+    maxiter = min(maxiter, 10)
+    rec = []
+    rf, rx, rn = orc.direct_cpp(f, lb, ub, maxiter, maxsample, record=rec)
+    of, ox, on, opts = _run_ours(d, lb, ub, f, maxiter, maxsample, _lib.FLAG_DIRECT_SEQ)
+    assert of == rf and np.array_equal(ox, rx) and on == rn
+    assert np.array_equal(opts, np.array(rec))
+
+
+@pytest.mark.skipif(not os.path.exists(REF_LIBEGO), reason="oracle/_ref not built")
+@pytest.mark.parametrize("d", [17, 20, 24])
+def test_batched_direct_equals_live_reference_beyond_16_dims(d, capfd):
+    """more than 16 equally long sides: std::sort is no longer an insertion sort (cpp/direct.cpp:194), tie order of the
+    dimension sort must still be the reference's -- a symmetric objective makes every probe value tie"""
+    lb = np.zeros(d); ub = np.ones(d)
+    for f in (lambda x: float(np.sum((x - 0.5) ** 2)), lambda x: float(np.sum(np.cos(7 * x)) + x[3])):
+        rf, rx, rn, rtrace = _run_reference(d, lb, ub, f, 6, 100000)
+        capfd.readouterr()
+        of, ox, on, opts = _run_ours(d, lb, ub, f, 6, 100000, _lib.FLAG_DIRECT_SEQ)
+        assert of == rf and np.array_equal(ox, rx) and on == rn
+        assert np.array_equal(opts, rtrace)
+        of, ox, on, opts = _run_ours(d, lb, ub, f, 6, 100000, 0)
+        assert of == rf and np.array_equal(ox, rx) and on == rn

@@ -288,3 +288,34 @@ def test_kstar_exp_is_within_one_ulp_of_libdevice():
     idx = rs.choice(np.flatnonzero(keep), 20000, replace=False)
     exact = np.array([math.exp(v) for v in x[idx]])
     assert np.max(np.abs(fast[idx] - exact) / np.spacing(exact)) <= 1.0
+
+
+# ---- fastUCBGallery against the oracle restatement of ego/acquisition/gallery.py:42-135 ---------------------
+@pytest.mark.parametrize("with_prior", [False, True])
+def test_fast_ucb_gallery_matches_oracle_restatement(with_prior, monkeypatch):
+    """same model, bounds and latin-hypercube seed -> the same gallery, slot by slot: DIRECT (xi=.3) point, the 0.5
+    distance rule, the EI(xi=.4) scan over the LHS candidates / prior means, and the hallucinated append."""
+    import functools
+    import ibo_b200.acquisition as acq
+    from ibo_b200.gaussianprocess.kernel import GaussianKernel_ard
+    from ibo_b200.gaussianprocess.prior import RBFNMeanPrior
+    rs = np.random.RandomState(11)
+    bounds = [[0., 4.], [-1., 3.], [0., 2.]]
+    X = np.c_[rs.rand(14) * 4, rs.rand(14) * 4 - 1, rs.rand(14) * 2]
+    Y = np.sin(X[:, 0]) + np.cos(X[:, 1]) - (X[:, 2] - 1) ** 2
+    theta = [1.0, 0.8, 0.6]
+    prior = oprior = None
+    if with_prior:
+        means = rs.rand(4, 3); beta = rs.randn(4) * 0.3
+        lowerb = np.array([b[0] for b in bounds]); width = np.array([b[1] - b[0] for b in bounds])
+        prior = RBFNMeanPrior(means=means, beta=beta, theta=10., lowerb=lowerb, width=width)
+        oprior = orc.PriorSpec(means, beta, 10., lowerb, width)
+    gp = _gp(GaussianKernel_ard(theta), X, Y, prior=prior) if with_prior else _gp(GaussianKernel_ard(theta), X, Y)
+    # the oracle's DIRECT is pure Python: both sides run 12 iterations instead of maximizeEI's default 50
+    monkeypatch.setattr(acq, "maximizeEI", functools.partial(acq.maximizeEI, maxiter=12))
+    gal = acq.fastUCBGallery(gp, bounds, 4, samples=100, seed=5)
+    ref = orc.fast_ucb_gallery(orc.KernelSpec(orc.K_SE_ARD, theta, 3), X, Y, bounds, 4, prior=oprior, samples=100, seed=5,
+                               maxiter=12)
+    assert len(gal) == len(ref) == 4
+    for a, b in zip(gal, ref):
+        assert np.allclose(a, b, rtol=0, atol=1e-9), (gal, ref)

@@ -257,3 +257,56 @@ def test_kernel_derivative_is_the_gradient_of_cov(kind):
         km = orc.KernelSpec(kind, np.exp(np.log(hyper) - e), 3)
         fd = (orc.cov_matrix(kp, X) - orc.cov_matrix(km, X)) / 2e-6
         assert np.max(np.abs(fd - orc.kernel_derivative(k, X, hp))) < 1e-8
+
+
+# ---- fastUCBGallery restatement (ego/acquisition/gallery.py:42-135) -------------------------------------------
+def _gallery_case():
+    rs = np.random.RandomState(11)
+    bounds = [[0., 4.], [-1., 3.], [0., 2.]]
+    X = np.c_[rs.rand(14) * 4, rs.rand(14) * 4 - 1, rs.rand(14) * 2]
+    Y = np.sin(X[:, 0]) + np.cos(X[:, 1]) - (X[:, 2] - 1) ** 2
+    return bounds, X, Y, [1.0, 0.8, 0.6]
+
+
+def test_oracle_gallery_properties():
+    """ego/unittest_IBO.py:844-870: nothing out of bounds, a fixed dimension stays pinned; plus the 0.5 distance rule
+    (gallery.py:102,113), the seeded determinism, and useBest putting the best in-bounds observation first (:50-63)"""
+    bounds, X, Y, theta = _gallery_case()
+    k = orc.KernelSpec(orc.K_SE_ARD, theta, 3)
+    gal = orc.fast_ucb_gallery(k, X, Y, bounds, 4, samples=100, seed=5, maxiter=12)
+    assert len(gal) == 4 and np.array_equal(gal[0], X[np.argmax(Y)])
+    for i, x in enumerate(gal):
+        assert all(b[0] <= v <= b[1] for v, b in zip(x, bounds))
+        assert all(np.linalg.norm(x - gal[j]) > .5 for j in range(i))
+    again = orc.fast_ucb_gallery(k, X, Y, bounds, 4, samples=100, seed=5, maxiter=12)
+    assert all(np.array_equal(a, b) for a, b in zip(gal, again))
+    pinned = [[0., 4.], [-1., 3.], [1., 1.]]                      # unittest_IBO.py:864 pins a dimension
+    for x in orc.fast_ucb_gallery(k, X, Y, pinned, 3, samples=60, seed=1, maxiter=8):
+        # the seeded best observation (slot 0) may lie outside a pinned box only if it passed the in-bounds filter
+        assert all(b[0] <= v <= b[1] for v, b in zip(x, pinned))
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libego.so")),
+                    reason="oracle/_ref not built")
+def test_oracle_gallery_direct_step_equals_live_acqmaxGP(capfd):
+    """the DIRECT step of a gallery slot (maximizeEI(hallucGP, xi=.3), gallery.py:101) is libego's acqmaxGP on inv(R)"""
+    import ctypes
+    from ctypes import POINTER, c_double, c_int
+    bounds, X, Y, theta = _gallery_case()
+    gp = orc.GPOracle(orc.KernelSpec(orc.K_SE_ARD, theta, 3), X, Y, noise=0.1)
+    opt, optx = orc.acqmax_cpp(gp, bounds, orc.ACQ_EI, .3, maxiter=12)
+    ego = ctypes.CDLL(os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libego.so"))
+    pd = POINTER(c_double)
+    ego.acqmaxGP.restype = pd
+    ego.acqmaxGP.argtypes = [c_int, pd, pd, pd, pd, pd, c_int, c_int, c_int, pd, c_int, pd, pd, c_double, pd, pd,
+                             c_double, c_double, c_int, c_int, c_int]
+    dp = lambda a: a.ctypes.data_as(pd)
+    b = np.array(bounds)
+    lb = np.ascontiguousarray(b[:, 0]); ub = np.ascontiguousarray(b[:, 1])
+    invR = np.ascontiguousarray(gp.invR()); Xc = np.ascontiguousarray(X); Yc = np.ascontiguousarray(Y)
+    hyper = np.array(theta); dummy = np.zeros(1)
+    res = ego.acqmaxGP(3, dp(lb), dp(ub), dp(invR), dp(Xc), dp(Yc), len(Y), 0, 0, dp(hyper), 0, dp(dummy), dp(dummy), 0.0,
+                       dp(dummy), dp(dummy), .3, 0.1, 12, 100000, 10000)
+    capfd.readouterr()
+    assert abs(-res[0] - opt) <= 1e-12 * max(abs(opt), 1e-3)
+    assert np.array_equal(optx, [res[1], res[2], res[3]])
