@@ -1,6 +1,7 @@
 // Batched DIRECT: the reference's rectangle rules (cpp/direct.cpp:49-65 Rectangle, :111-141 samplef,
 // :146-235 divrec, :372-498 selection + division order) restructured so that every iteration issues
-// two batches -- all probe points of all potentially-optimal rectangles, then all child centres --
+// one batch -- all probe points of all potentially-optimal rectangles together with every child centre that does
+// not depend on the division order (all but a few per thousand), the rest in a second, small batch --
 // instead of one objective call per sample.  Floating-point expressions that decide control flow
 // (side lengths, centre-to-vertex distances, slopes, the epsilon test) are written exactly as the
 // reference writes them so that, on identical objective values, the trajectory is identical:
@@ -154,7 +155,8 @@ struct Pending {           // one rectangle being divided
     int ndims = 0;         // number of longest, non-fixed sides
     long dim0 = 0;         // offset of its dims in the flat dims array
     long probe0 = 0;       // offset of its 2*k probe values in the phase-A batch
-    long child0 = 0;       // offset of its 2*k children in the phase-B batch / flat child arrays
+    long child0 = 0;       // offset of its 2*k children in the flat child arrays
+    long spec0 = -1;       // offset of its 2*k speculative child values in the phase-A batch (-1: children wait for phase B)
     double old_d = 0;      // d of the shrunk middle rectangle
 };
 
@@ -164,6 +166,9 @@ struct Scratch {
     std::vector<unsigned> dims;
     std::vector<ind_val> I;
     std::vector<double> pts, ptsB, yA, yB;       // probe points / child centres (unit cube) and their values
+    std::vector<double> spec, ptsB2, yB2;        // speculative child centres (phase A) / children left for phase B
+    std::vector<long> lateIdx;                   // child index of every point of the phase-B batch
+    std::vector<int> posOfDim;                   // dim -> position among the rectangle's long dims
     std::vector<double> clb, cub, cd;            // children, in the reference's return order
     std::vector<double> mid_lb, mid_ub;          // shrunk middle rectangles, one per Pending
 };
@@ -210,17 +215,61 @@ void divide(Driver& D, Store& R, const std::vector<unsigned>& order, bool seq, S
                 }
             }
         }
+        // ---- child centres that do not depend on the division order ride in the same batch.  A child of side A is
+        // centred at lb + (ub - lb)/2 of ITS bounds (cpp/direct.cpp:54-58): along A that is the centre of the outer third,
+        // along every other long side B it is the centre of B's full extent if B is split after A and of B's middle third
+        // if B was split before A (:201-232) -- the order is only known once the probe values are back.  The two
+        // expressions agree bit for bit for all but ~2e-4 of the DIRECT intervals; a rectangle all of whose long sides
+        // agree gets its 2k child centres evaluated now, the others wait for phase B as before.  The evaluated set, the
+        // values and the replay order are the reference's either way; an iteration costs one GPU batch instead of two.
+        long nspec = 0;
+        W.spec.clear();
+        if (!seq) {
+            static thread_local std::vector<double> cb;
+            cb.resize(N);
+            for (size_t t = 0; t < np_rect; t++) {
+                Pending& p = W.P[t];
+                const double* lb = &R.lb[(size_t)p.src * N];
+                const double* ub = &R.ub[(size_t)p.src * N];
+                bool clean = true;
+                for (int a = 0; a < p.ndims && clean; a++) {
+                    const unsigned i = W.dims[p.dim0 + a];
+                    const double w = ub[i] - lb[i];
+                    const double s1 = lb[i] + w / 3., s2 = lb[i] + 2. * w / 3.;
+                    clean = (lb[i] + (ub[i] - lb[i]) / 2.) == (s1 + (s2 - s1) / 2.);
+                }
+                if (!clean) continue;
+                for (int i = 0; i < N; i++) cb[i] = lb[i] + (ub[i] - lb[i]) / 2.;
+                p.spec0 = nspec;
+                for (int a = 0; a < p.ndims; a++) {
+                    const unsigned i = W.dims[p.dim0 + a];
+                    const double w = ub[i] - lb[i];
+                    const double s1 = lb[i] + w / 3., s2 = lb[i] + 2. * w / 3.;
+                    size_t o = W.spec.size();
+                    W.spec.insert(W.spec.end(), cb.begin(), cb.end());
+                    W.spec.insert(W.spec.end(), cb.begin(), cb.end());
+                    W.spec[o + i] = lb[i] + (s1 - lb[i]) / 2.;
+                    W.spec[o + N + i] = s2 + (ub[i] - s2) / 2.;
+                    nspec += 2;
+                }
+            }
+            W.pts.insert(W.pts.end(), W.spec.begin(), W.spec.end());
+        }
         g_pt.probes += now_s() - tA;
-        D.eval(W.pts, np, W.yA);
+        D.eval(W.pts, np + nspec, W.yA);
         double tB = now_s();
         // ---- sort the dims by min(sf1, sf2) and build the children (cpp/direct.cpp:181-232)
         const size_t nchild = (size_t)np;            // two children per probed side
         W.clb.resize(nchild * N); W.cub.resize(nchild * N); W.ptsB.resize(nchild * N); W.cd.resize(nchild);
         W.mid_lb.resize(np_rect * N); W.mid_ub.resize(np_rect * N);
         long nc = 0;
+        W.yB.resize(nchild);
+        W.lateIdx.clear();
+        W.posOfDim.resize(N);
         for (size_t t = 0; t < np_rect; t++) {
             Pending& p = W.P[t];
             W.I.clear();
+            for (int a = 0; a < p.ndims; a++) W.posOfDim[W.dims[p.dim0 + a]] = a;
             for (int a = 0; a < p.ndims; a++) {
                 double sf1 = W.yA[p.probe0 + 2 * a], sf2 = W.yA[p.probe0 + 2 * a + 1];
                 unsigned dim = W.dims[p.dim0 + a];
@@ -248,6 +297,13 @@ void divide(Driver& D, Store& R, const std::vector<unsigned>& order, bool seq, S
                 olb[dd] = split1;
                 oub[dd] = split2;
                 W.cd[nc + 1] = center_and_d(lb3, ub3, &W.ptsB[(size_t)(nc + 1) * N], N);
+                for (int c2 = 0; c2 < 2; c2++) {
+                    // value from the phase-A batch when the child's centre is bit for bit the one evaluated there
+                    const long sp = p.spec0 < 0 ? -1 : p.spec0 + 2 * W.posOfDim[dd] + c2;
+                    if (sp >= 0 && !std::memcmp(&W.ptsB[(size_t)(nc + c2) * N], &W.spec[(size_t)sp * N], sizeof(double) * N))
+                        W.yB[nc + c2] = W.yA[np + sp];
+                    else W.lateIdx.push_back(nc + c2);
+                }
                 nc += 2;
             }
             // the middle third keeps the old centre and y; d is recomputed from the shrunk bounds (:226-231)
@@ -257,7 +313,14 @@ void divide(Driver& D, Store& R, const std::vector<unsigned>& order, bool seq, S
             p.old_d = std::sqrt(d);
         }
         g_pt.children += now_s() - tB;
-        D.eval(W.ptsB, nc, W.yB);
+        if ((long)W.lateIdx.size() == nc) D.eval(W.ptsB, nc, W.yB);
+        else if (!W.lateIdx.empty()) {
+            const size_t nl = W.lateIdx.size();
+            W.ptsB2.resize(nl * N);
+            for (size_t q = 0; q < nl; q++) std::memcpy(&W.ptsB2[q * N], &W.ptsB[(size_t)W.lateIdx[q] * N], sizeof(double) * N);
+            D.eval(W.ptsB2, (long)nl, W.yB2);
+            for (size_t q = 0; q < nl; q++) W.yB[W.lateIdx[q]] = W.yB2[q];
+        }
         double tC = now_s();
         // ---- replay the reference's call order for FMIN / nsamples, then append the rectangles
         std::vector<double> oc(N);
