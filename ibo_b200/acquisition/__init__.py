@@ -130,7 +130,7 @@ def cdirectGP(model, bounds, maxiter, maxtime, maxsample, acqfunc=None, xi=-1, b
 
 def _python_direct(obj, bounds, **kw):
     """useCDIRECT=False route: the same DIRECT driver over the Python-path objective (batched)."""
-    opt, optx = direct(obj.negf, bounds, batch_objective=lambda P: -obj.f_batch(P), **kw)
+    opt, optx = direct(obj.negf, bounds, batch_objective=lambda P: -obj.f_batch(P), pure=True, **kw)
     return -opt, optx
 
 

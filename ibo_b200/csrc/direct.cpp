@@ -156,7 +156,9 @@ struct Pending {           // one rectangle being divided
     long dim0 = 0;         // offset of its dims in the flat dims array
     long probe0 = 0;       // offset of its 2*k probe values in the phase-A batch
     long child0 = 0;       // offset of its 2*k children in the flat child arrays
-    long spec0 = -1;       // offset of its 2*k speculative child values in the phase-A batch (-1: children wait for phase B)
+    long spec0 = -1;       // first entry of its (long side, variant) table in Scratch::specMap (-1: children wait for phase B)
+    int nu = 0;            // number of unclean long sides (<= 2 when spec0 >= 0), see divide()
+    int udim[2] = {0, 0};
     double old_d = 0;      // d of the shrunk middle rectangle
 };
 
@@ -168,6 +170,7 @@ struct Scratch {
     std::vector<double> pts, ptsB, yA, yB;       // probe points / child centres (unit cube) and their values
     std::vector<double> spec, ptsB2, yB2;        // speculative child centres (phase A) / children left for phase B
     std::vector<long> lateIdx;                   // child index of every point of the phase-B batch
+    std::vector<long> specMap;                   // (rectangle, long side, variant) -> first of its two points in `spec`, or -1
     std::vector<int> posOfDim;                   // dim -> position among the rectangle's long dims
     std::vector<double> clb, cub, cd;            // children, in the reference's return order
     std::vector<double> mid_lb, mid_ub;          // shrunk middle rectangles, one per Pending
@@ -180,7 +183,7 @@ static inline double now_s() { return std::chrono::duration<double>(std::chrono:
 
 // Divides the given rectangles (already in processing order): appends the new rectangles in the reference's
 // order and retires the sources.  seq: one rectangle per batch pair (the reference's exact call order).
-void divide(Driver& D, Store& R, const std::vector<unsigned>& order, bool seq, Scratch& W) {
+void divide(Driver& D, Store& R, const std::vector<unsigned>& order, bool seq, bool speculate, Scratch& W) {
     const int N = D.N;
     size_t g0 = 0;
     while (g0 < order.size()) {
@@ -215,42 +218,60 @@ void divide(Driver& D, Store& R, const std::vector<unsigned>& order, bool seq, S
                 }
             }
         }
-        // ---- child centres that do not depend on the division order ride in the same batch.  A child of side A is
-        // centred at lb + (ub - lb)/2 of ITS bounds (cpp/direct.cpp:54-58): along A that is the centre of the outer third,
-        // along every other long side B it is the centre of B's full extent if B is split after A and of B's middle third
-        // if B was split before A (:201-232) -- the order is only known once the probe values are back.  The two
-        // expressions agree bit for bit for all but ~2e-4 of the DIRECT intervals; a rectangle all of whose long sides
-        // agree gets its 2k child centres evaluated now, the others wait for phase B as before.  The evaluated set, the
-        // values and the replay order are the reference's either way; an iteration costs one GPU batch instead of two.
+        // ---- child centres ride in the same batch.  A child of side A is centred at lb + (ub - lb)/2 of ITS bounds
+        // (cpp/direct.cpp:54-58): along A that is the centre of the outer third, along every other long side B it is the
+        // centre of B's full extent if B is split after A and of B's middle third if B was split before A (:201-232) --
+        // and the order is only known once the probe values are back.  The two expressions agree bit for bit for almost
+        // every DIRECT interval that does not start at 0 (a few per ten thousand differ); intervals touching the lower
+        // face of the box (lb = 0: full relative precision) often differ in the last place.  Sides where they differ are
+        // the rectangle's "unclean" sides U.
+        //   U empty            -> the 2k child centres are order independent and are evaluated now;
+        //   |U| <= 2, spec     -> every child is evaluated now for each subset of U \ {A} that may precede A (<= 4
+        //                         variants; the values of the variants that did not occur are discarded);
+        //   otherwise          -> the children wait for phase B as before.
+        // `spec` (IBO_FLAG_DIRECT_SPECULATE) is for pure objectives only: the callback sees points the reference never
+        // samples.  The samples that count, their values and the replay order are the reference's in every case; an
+        // iteration costs one GPU batch instead of two.
         long nspec = 0;
-        W.spec.clear();
+        W.spec.clear(); W.specMap.clear();
         if (!seq) {
-            static thread_local std::vector<double> cb;
-            cb.resize(N);
+            static thread_local std::vector<double> cu, cs;
+            cu.resize(N); cs.resize(N);
             for (size_t t = 0; t < np_rect; t++) {
                 Pending& p = W.P[t];
                 const double* lb = &R.lb[(size_t)p.src * N];
                 const double* ub = &R.ub[(size_t)p.src * N];
-                bool clean = true;
-                for (int a = 0; a < p.ndims && clean; a++) {
-                    const unsigned i = W.dims[p.dim0 + a];
-                    const double w = ub[i] - lb[i];
-                    const double s1 = lb[i] + w / 3., s2 = lb[i] + 2. * w / 3.;
-                    clean = (lb[i] + (ub[i] - lb[i]) / 2.) == (s1 + (s2 - s1) / 2.);
-                }
-                if (!clean) continue;
-                for (int i = 0; i < N; i++) cb[i] = lb[i] + (ub[i] - lb[i]) / 2.;
-                p.spec0 = nspec;
+                for (int i = 0; i < N; i++) cu[i] = lb[i] + (ub[i] - lb[i]) / 2.;
+                int nu = 0;
                 for (int a = 0; a < p.ndims; a++) {
                     const unsigned i = W.dims[p.dim0 + a];
                     const double w = ub[i] - lb[i];
                     const double s1 = lb[i] + w / 3., s2 = lb[i] + 2. * w / 3.;
-                    size_t o = W.spec.size();
-                    W.spec.insert(W.spec.end(), cb.begin(), cb.end());
-                    W.spec.insert(W.spec.end(), cb.begin(), cb.end());
-                    W.spec[o + i] = lb[i] + (s1 - lb[i]) / 2.;
-                    W.spec[o + N + i] = s2 + (ub[i] - s2) / 2.;
-                    nspec += 2;
+                    cs[i] = s1 + (s2 - s1) / 2.;
+                    if (cu[i] != cs[i]) { if (nu < 2) p.udim[nu] = (int)i; nu++; }
+                }
+                if (nu > (speculate ? 2 : 0)) continue;
+                p.nu = nu;
+                p.spec0 = (long)W.specMap.size();
+                const int nvar = 1 << nu;
+                for (int a = 0; a < p.ndims; a++) {
+                    const unsigned i = W.dims[p.dim0 + a];
+                    const double w = ub[i] - lb[i];
+                    const double s1 = lb[i] + w / 3., s2 = lb[i] + 2. * w / 3.;
+                    for (int mask = 0; mask < nvar; mask++) {
+                        // bit j of mask: unclean side udim[j] was split before this one (its own bit is never set)
+                        bool own = false;
+                        for (int j2 = 0; j2 < nu; j2++) own = own || (((mask >> j2) & 1) && p.udim[j2] == (int)i);
+                        if (own) { W.specMap.push_back(-1); continue; }
+                        W.specMap.push_back(nspec);
+                        size_t o = W.spec.size();
+                        W.spec.insert(W.spec.end(), cu.begin(), cu.end());
+                        for (int j2 = 0; j2 < nu; j2++) if ((mask >> j2) & 1) W.spec[o + p.udim[j2]] = cs[p.udim[j2]];
+                        W.spec.insert(W.spec.end(), W.spec.begin() + o, W.spec.begin() + o + N);
+                        W.spec[o + i] = lb[i] + (s1 - lb[i]) / 2.;
+                        W.spec[o + N + i] = s2 + (ub[i] - s2) / 2.;
+                        nspec += 2;
+                    }
                 }
             }
             W.pts.insert(W.pts.end(), W.spec.begin(), W.spec.end());
@@ -282,6 +303,7 @@ void divide(Driver& D, Store& R, const std::vector<unsigned>& order, bool seq, S
             std::memcpy(olb, &R.lb[(size_t)p.src * N], sizeof(double) * N);
             std::memcpy(oub, &R.ub[(size_t)p.src * N], sizeof(double) * N);
             p.child0 = nc;
+            int doneMask = 0;      // unclean sides already split
             for (size_t a = 0; a < W.I.size(); a++) {
                 unsigned dd = W.I[a].first;
                 double dwidth = oub[dd] - olb[dd];
@@ -297,13 +319,15 @@ void divide(Driver& D, Store& R, const std::vector<unsigned>& order, bool seq, S
                 olb[dd] = split1;
                 oub[dd] = split2;
                 W.cd[nc + 1] = center_and_d(lb3, ub3, &W.ptsB[(size_t)(nc + 1) * N], N);
+                // value from the phase-A batch when the child's centre is bit for bit one of those evaluated there
+                long sp = -1;
+                if (p.spec0 >= 0) sp = W.specMap[(size_t)p.spec0 + ((size_t)W.posOfDim[dd] << p.nu) + doneMask];
                 for (int c2 = 0; c2 < 2; c2++) {
-                    // value from the phase-A batch when the child's centre is bit for bit the one evaluated there
-                    const long sp = p.spec0 < 0 ? -1 : p.spec0 + 2 * W.posOfDim[dd] + c2;
-                    if (sp >= 0 && !std::memcmp(&W.ptsB[(size_t)(nc + c2) * N], &W.spec[(size_t)sp * N], sizeof(double) * N))
-                        W.yB[nc + c2] = W.yA[np + sp];
+                    if (sp >= 0 && !std::memcmp(&W.ptsB[(size_t)(nc + c2) * N], &W.spec[(size_t)(sp + c2) * N], sizeof(double) * N))
+                        W.yB[nc + c2] = W.yA[np + sp + c2];
                     else W.lateIdx.push_back(nc + c2);
                 }
+                for (int j2 = 0; j2 < p.nu; j2++) if (p.udim[j2] == (int)dd) doneMask |= 1 << j2;
                 nc += 2;
             }
             // the middle third keeps the old centre and y; d is recomputed from the shrunk bounds (:226-231)
@@ -418,6 +442,7 @@ int run_direct(ibo_batch_objective_t f, void* user, int ndim, const double* lb, 
                int maxsample, int flags, double* fmin, double* xmin, long* nsamples, int* iterations) {
     if (!f || ndim < 1 || !lb || !ub) { set_error("bad argument"); return IBO_E_BADARG; }
     const bool seq = (flags & IBO_FLAG_DIRECT_SEQ) != 0;
+    const bool speculate = !seq && (flags & IBO_FLAG_DIRECT_SPECULATE) != 0;
     time_t start = time(NULL);
     Driver D;
     D.f = f; D.user = user; D.N = ndim;
@@ -449,7 +474,7 @@ int run_direct(ibo_batch_objective_t f, void* user, int ndim, const double* lb, 
     std::vector<unsigned> potopts, order;
     order.clear();
     R.pop_minima(R.cls[0], order);      // the unit cube leaves its heap like any rectangle about to be divided
-    divide(D, R, order, seq, W);
+    divide(D, R, order, seq, speculate, W);
     int iteration = 0;
     bool done = false;
     while (iteration < maxiter && !done) {
@@ -477,7 +502,7 @@ int run_direct(ibo_batch_objective_t f, void* user, int ndim, const double* lb, 
             ns += 4L * k;
             if (ns > (long)(unsigned)maxsample) { done = true; break; }
         }
-        divide(D, R, order, seq, W);
+        divide(D, R, order, seq, speculate, W);
         if (time(NULL) - start > maxtime) break;
         if (D.nsamples > (long)(unsigned)maxsample) break;
     }
@@ -556,7 +581,8 @@ extern "C" int ibo_acqmax(ibo_model* m, const double* lb, const double* ub, int 
     }
     double fmin = 0;
     auto t0 = std::chrono::steady_clock::now();
-    int rc = run_direct(gpu_batch, &g, ibo_model_dim(m), lb, ub, maxiter, maxtime, maxsample, flags, &fmin, optx, nsamples, iterations);
+    // the GPU objective is a pure function of the point (DESIGN.md "Determinism"): the driver may speculate
+    int rc = run_direct(gpu_batch, &g, ibo_model_dim(m), lb, ub, maxiter, maxtime, maxsample, flags | IBO_FLAG_DIRECT_SPECULATE, &fmin, optx, nsamples, iterations);
     if (getenv("IBO_DIRECT_TIMING")) {
         double tt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         fprintf(stderr, "[ibo_acqmax] total %.3f ms, GPU batches %.3f ms (%ld batches, %ld sharded, %ld points, %.1f us/batch), host driver %.3f ms\n",

@@ -47,18 +47,21 @@ def _run(batch_cb, bounds, maxiter, maxtime, maxsample, flags):
     return fmin.value, xmin, ns.value
 
 
-def direct(f, bounds, args=None, debug=False, maxiter=None, maxsample=None, maxtime=None, batch_objective=None):
+def direct(f, bounds, args=None, debug=False, maxiter=None, maxsample=None, maxtime=None, batch_objective=None, pure=False):
     """Minimise f over the box `bounds` (sequence of (min, max)); returns (value, location).
 
     y = f(x, *args).  At least one of maxiter / maxsample / maxtime must be given (optimize.py:99-100).
-    `batch_objective(P)` (optional) evaluates an (n, d) array of points at once."""
+    `batch_objective(P)` (optional) evaluates an (n, d) array of points at once; `pure=True` additionally tells the
+    driver that the batch objective has no state, so that it may evaluate a few extra points per batch whose values
+    it discards (IBO_FLAG_DIRECT_SPECULATE: one batch per iteration even where a child centre depends on the
+    division order in its last bit; same result and sample count)."""
     if not (maxiter or maxsample or maxtime):
         raise ValueError("No termination criterion set!")
     args = [] if args is None else args
     if batch_objective is None:
         batch, flags = (lambda P: [f(np.array(p), *args) for p in P]), _lib.FLAG_DIRECT_SEQ
     else:
-        batch, flags = batch_objective, 0
+        batch, flags = batch_objective, (_lib.FLAG_DIRECT_SPECULATE if pure else 0)
     fmin, xmin, _ = _run(batch, bounds, maxiter if maxiter else _BIG, maxtime if maxtime else _BIG,
                          (maxsample - 1) if maxsample else _BIG, flags)
     return fmin, xmin

@@ -54,6 +54,11 @@ extern "C" {
 #define IBO_FLAG_PROFILE       0x8  /* record per-kernel CUDA-event times (ibo_get_profile) */
 #define IBO_FLAG_SHARD         0x20 /* ibo_acqmax: cut every DIRECT batch into one slice per rank of the communicator
                                        (ibo_comm_init) and all-gather the values; all ranks must make the same call */
+#define IBO_FLAG_DIRECT_SPECULATE 0x40 /* DIRECT over a PURE batch objective: where a child centre depends on the division order
+                                       only in its last bit, evaluate its (<= 4) possible values together with the probe points
+                                       instead of in a second batch.  The callback then sees a few points the reference never
+                                       samples; their values are discarded, so FMIN/XMIN/nsamples and the trajectory are unchanged.
+                                       ibo_acqmax sets it (the GPU objective is pure). */
 #define IBO_FLAG_GRAD_EXACT    0x10 /* ibo_nlml / ibo_kernel_matrix: analytic Matern-3/2 length-scale derivative instead of
                                        the reference's expression with the unscaled distance (kernel.py:217-222) */
 

@@ -221,3 +221,51 @@ def test_batched_direct_equals_live_reference_beyond_16_dims(d, capfd):
         assert np.array_equal(opts, rtrace)
         of, ox, on, opts = _run_ours(d, lb, ub, f, 6, 100000, 0)
         assert of == rf and np.array_equal(ox, rx) and on == rn
+
+
+@pytest.mark.skipif(not os.path.exists(REF_LIBEGO), reason="oracle/_ref not built")
+@pytest.mark.parametrize("seed", range(48))
+def test_speculating_direct_equals_live_reference(seed, capfd):
+    """IBO_FLAG_DIRECT_SPECULATE (what ibo_acqmax runs with): same FMIN / XMIN / sample count as the reference; every
+    reference sample is evaluated, in at most a few more points, and -- the point of it -- in fewer batches"""
+    d, lb, ub, f, maxiter, maxsample = _random_case(seed)
+    rf, rx, rn, rtrace = _run_reference(d, lb, ub, f, maxiter, maxsample)
+    capfd.readouterr()
+    of, ox, on, opts = _run_ours(d, lb, ub, f, maxiter, maxsample, _lib.FLAG_DIRECT_SPECULATE)
+    assert of == rf and np.array_equal(ox, rx) and on == rn, seed
+    ref_set = set(map(bytes, np.ascontiguousarray(rtrace)))
+    our_set = set(map(bytes, np.ascontiguousarray(opts)))
+    assert ref_set <= our_set
+    assert len(opts) <= 3 * rn + 8
+
+
+def test_one_batch_per_iteration():
+    """an optimum in a corner of the box: intervals starting at 0 keep full relative precision, so the centre of a middle
+    third and the centre of the full side differ in the last place (the 'unclean' sides of divide()); speculation keeps
+    such iterations at one batch for up to two unclean sides"""
+    def count(d, flags, maxiter=40):
+        batches = []
+
+        def cb(user, n, ndim, X, y):
+            A = np.ctypeslib.as_array(X, shape=(n, ndim))
+            batches.append(n)
+            v = np.sum(np.sin(3 * A) + (A - .4) ** 2, axis=1)
+            for i in range(n):
+                y[i] = v[i]
+        lb = np.zeros(d); ub = np.ones(d)
+        fmin = c_double(0); xmin = np.empty(d); ns = c_long(0); it = c_int(0)
+        rc = _lib.lib().ibo_direct_batched(_lib.BATCH_OBJECTIVE(cb), None, d, _lib.dptr(lb), _lib.dptr(ub), maxiter, 100000, 10 ** 7,
+                                           flags, ctypes.byref(fmin), _lib.dptr(xmin), ctypes.byref(ns), ctypes.byref(it))
+        assert rc == 0
+        return fmin.value, xmin.copy(), ns.value, it.value, batches
+    for d in (2, 3, 6):
+        plain = count(d, 0)
+        spec = count(d, _lib.FLAG_DIRECT_SPECULATE)
+        assert plain[0] == spec[0] and np.array_equal(plain[1], spec[1]) and plain[2] == spec[2] and plain[3] == spec[3]
+        assert sum(plain[4]) == plain[2]                      # without the flag exactly the reference's samples are evaluated
+        assert len(spec[4]) <= len(plain[4]) <= 2 * plain[3] + 3
+        if d == 2:
+            assert len(spec[4]) == spec[3] + 2                # centre, first division, one batch per iteration
+    # interior optimum: already one batch per iteration without speculation (within a few late batches)
+    interior = count(4, 0, maxiter=30)
+    assert len(interior[4]) <= interior[3] + 2 + 3
