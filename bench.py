@@ -645,6 +645,10 @@ def main():
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value if peak.value else None,
                      "traffic": traffic, "kernel": "trigemm_kernel (K2)", "flops_per_candidate": flops_per_candidate_k2(N),
                      "candidates_per_launch": cand_per_launch, "avg_launch_ms": 1e3 * k2_s,
+                     # the whole step (K1 + K2 + K3 + argmax) against the same peak: F(N,d) = N^2 + N(2d+8) flops per candidate
+                     "step": {"flops_per_candidate": float(N) * N + N * (2.0 * d + 8.0),
+                              "achieved": M * (float(N) * N + N * (2.0 * d + 8.0)) / t_step / 1e12,
+                              "frac": (M * (float(N) * N + N * (2.0 * d + 8.0)) / t_step / 1e12 / peak.value) if peak.value else None},
                      "peak_source": "live DMMA.8x8x4 issue-rate microbenchmark on this GPU (ibo_fp64_peak); MEASURED_PEAKS.json "
                                     "and the profiling guide carry no FP64 figure"},
         "kernel_ms_per_step": {"k1_kstar": prof["k1_ms"], "k2_trigemm": prof["k2_ms"], "k3_epilogue": prof["k3_ms"], "total": prof["total_ms"]},
