@@ -507,6 +507,8 @@ def main():
                     help="2: BASELINE configs[1] (default, the metric's config); 4: configs[3], N=8192 Matern-5/2 ARD, 16M Sobol, strong scaling; "
                          "5: configs[4], batched-DIRECT maximizeEI d=20, N=4096, 200 iterations, batches sharded over the GPUs (wall ms)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--int8", action="store_true",
+                    help="time the experimental INT8-tensor-core emulation of K2 (IBO_FLAG_INT8) as the main arm instead of the FP64 DMMA path")
     ap.add_argument("--suite", action="store_true", help="extra measurements (maximizeEI wall ms, model build, configs #1/#4/#5)")
     args = ap.parse_args()
     if args.suite:
@@ -549,7 +551,7 @@ def main():
     ymax = float(np.max(Y))
     Xs = wl.candidates(rank)
     cands = _lib.ResidentCandidates(model, Xs)
-    flags = _lib.FLAG_MODE_CPP
+    flags = _lib.FLAG_MODE_CPP | (_lib.FLAG_INT8 if args.int8 else 0)
 
     def step_resident():
         best, bidx, ms = cands.score(_lib.ACQ_EI, ymax, XI, flags)
@@ -592,6 +594,34 @@ def main():
     prof = min(k2, key=lambda p: p["k2_ms"])
     peak = c_double(0)
     _lib.check(L.ibo_fp64_peak(device, ctypes.byref(peak)))
+
+    # ---- experimental INT8-emulated K2 on the same resident candidates (untimed region of the main arm): rate + agreement ----
+    int8_leg = None
+    if wl.id == 2 and N > 128:
+        try:
+            f8 = _lib.FLAG_MODE_CPP | _lib.FLAG_INT8
+            s_ref, s_i8 = np.empty(M), np.empty(M)
+            b_ref = cands.score(_lib.ACQ_EI, ymax, XI, _lib.FLAG_MODE_CPP, scores_out=s_ref)
+            b_i8 = cands.score(_lib.ACQ_EI, ymax, XI, f8, scores_out=s_i8)
+            ts8 = []
+            for _ in range(3):
+                ts8.append(cands.score(_lib.ACQ_EI, ymax, XI, f8)[2])
+            cands.score(_lib.ACQ_EI, ymax, XI, f8 | _lib.FLAG_PROFILE)
+            p8 = model.profile()
+            pk8 = c_double(0)
+            _lib.check(L.ibo_i8_peak(device, ctypes.byref(pk8)))
+            nbk = (N + 127) // 128
+            ops = 2.0 * 28 * 128 * 32 * 4 * (nbk * (nbk + 1) // 2)           # int8 ops per candidate: 28 slice pairs per k-step
+            int8_leg = {"value": M / (min(ts8) * 1e-3), "unit": UNIT, "ms_per_step": min(ts8),
+                        "k1_ms": p8["k1_ms"], "k2_ms": p8["k2_ms"], "k3_ms": p8["k3_ms"],
+                        "k2_int8_tops": M * ops / (p8["k2_ms"] * 1e-3) / 1e12, "int8_peak_tops": pk8.value,
+                        "k2_frac_of_int8_peak": (M * ops / (p8["k2_ms"] * 1e-3) / 1e12 / pk8.value) if pk8.value else None,
+                        "max_rel_dEI_vs_fp64_path": float(np.max(np.abs(s_i8 - s_ref) / np.maximum(np.abs(s_ref), 1e-5))),
+                        "same_argmax": bool(b_ref[1] == b_i8[1]),
+                        "note": "IBO_FLAG_INT8: sigma^2 through 7 x 7-bit Ozaki slices on tcgen05.mma kind::i8 (28 exact INT32 slice products "
+                                "per FP64 product, FP64 assembly), mu as k*.alpha; K1 of chunk c+1 overlaps K2 of chunk c; off by default"}
+        except Exception as e:       # the experimental leg must never take the main arm down
+            int8_leg = {"error": str(e)}
 
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region ----
     out = np.empty(M)
@@ -655,6 +685,10 @@ def main():
         "wall_ms_per_step": 1e3 * t_wall / args.steps,
         "model_build_s": t_factor, "best": {"ei": best[0], "index": best[1]},
     }
+    if int8_leg is not None:
+        line["int8_emulation"] = int8_leg
+    if args.int8:
+        line["config"]["arithmetic"] += " + IBO_FLAG_INT8 (sigma^2 via INT8 tensor-core emulation of the FP64 GEMM)"
     # ---- the "maximizeEI wall ms" half of the metric (this rank's GPU; DIRECT is latency bound and is not sharded) ----
     if rank == 0 and wl.id == 2:
         from ibo_b200.gaussianprocess.kernel import GaussianKernel_ard

@@ -21,7 +21,7 @@ EXPORTED = [
     "ibo_nlml", "ibo_kernel_matrix",
     "ibo_posterior_batch", "ibo_score_batch",
     "ibo_cands_create", "ibo_cands_destroy", "ibo_score_resident", "ibo_get_profile", "ibo_launch_count",
-    "ibo_fp64_peak", "ibo_host_register", "ibo_host_unregister", "ibo_stream_mark", "ibo_stream_elapsed_ms",
+    "ibo_fp64_peak", "ibo_i8_peak", "ibo_host_register", "ibo_host_unregister", "ibo_stream_mark", "ibo_stream_elapsed_ms",
     "ibo_device_synchronize", "ibo_debug_exp",
     "ibo_direct_batched", "ibo_acqmax", "direct", "acqmaxGP",
     "ibo_comm_unique_id", "ibo_comm_init", "ibo_comm_destroy", "ibo_comm_argmax", "ibo_comm_bcast", "ibo_comm_barrier",
@@ -32,6 +32,7 @@ KERNEL_SE_ARD, KERNEL_SE_ISO, KERNEL_MATERN3, KERNEL_MATERN5, KERNEL_MATERN5_ARD
 ACQ_EI, ACQ_PI, ACQ_UCB = 0, 1, 2
 FLAG_MODE_CPP, FLAG_MODE_PY, FLAG_KSTAR_EXPAND, FLAG_DIRECT_SEQ, FLAG_PROFILE, FLAG_GRAD_EXACT, FLAG_SHARD = 0x0, 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
 FLAG_DIRECT_SPECULATE = 0x40
+FLAG_INT8 = 0x80
 E_BADARG, E_CUDA, E_NOTSPD, E_NOMEM, E_COMM = -1, -2, -3, -4, -5
 
 BATCH_OBJECTIVE = ctypes.CFUNCTYPE(None, c_void_p, c_long, c_int, POINTER(c_double), POINTER(c_double))
@@ -99,6 +100,7 @@ def lib():
     L.ibo_score_resident.argtypes = [c_void_p, c_void_p, c_int, c_double, c_double, c_int, pd, pd, pl, POINTER(c_float)]
     L.ibo_get_profile.argtypes = [c_void_p, pd]
     L.ibo_fp64_peak.argtypes = [c_int, pd]
+    L.ibo_i8_peak.argtypes = [c_int, pd]
     L.ibo_host_register.argtypes = [c_void_p, ctypes.c_ulong]
     L.ibo_host_unregister.argtypes = [c_void_p]
     L.ibo_stream_mark.argtypes = [c_void_p, c_int]

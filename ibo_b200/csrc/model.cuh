@@ -32,6 +32,11 @@ struct ibo_model {
     double* dBeta1 = nullptr;   // [Np]  W 1
     double* dY = nullptr;       // [Np]
     int* dInfo = nullptr;
+    // experimental int8-emulated K2 (score_i8.cuh), built on first use: packed 7-bit slices of W, per-row scales
+    // ([Np] slicing scale, [Np] scale * sf2), alpha = W^T W Y and W^T W 1
+    double* dWi8 = nullptr; double* dRowScale = nullptr; double* dAlphaY = nullptr; double* dAlpha1 = nullptr;
+    bool i8Valid = false;
+    cudaEvent_t evI8[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // K1 done [2], K2+K3 done [2], fork
     // prior (RBF network), device copies
     int npb = 0;
     double ptheta = 0;

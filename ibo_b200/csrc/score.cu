@@ -817,6 +817,10 @@ static void launch_kstar(const ibo_model* m, const double* dCand, double* slab, 
 }
 
 
+}  // namespace ibo
+#include "score_i8.cuh"
+namespace ibo {
+
 // Runs K1..K4 for M candidates resident at dCand; results land in m->dOut ([score|mu|s2][M]) and
 // the (best score, best index) pair at m->dOut[3M], [3M+1].  Everything is enqueued on m->stream; no host sync here.
 static int score_device(ibo_model* m, const double* dCand, long M, const ScoreReq& rq, double* outBase = nullptr,
@@ -851,6 +855,21 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
     const long ctaTilesAll = narrow ? (std::min<long>(M, Mpad) + 31) / 32 : chunkTiles;      // K2 CTAs along the candidate axis
     const K2Plan plan = narrow ? plan_narrow_cached(m, ctaTilesAll) : K2Plan{8, pick_groups_wide(nb, chunkTiles)};
     const int subs = 8 / plan.MT;
+    const bool i8 = !narrow && !vm && m->d <= 32 && i8_requested(rq.flags);      // experimental int8-emulated K2 (score_i8.cuh)
+    if (i8 && (rc = ensure_i8(m))) return rc;
+    // int8 path: K1 of chunk c+1 (FP64 / integer pipes, stream2) runs under K2 of chunk c (tensor pipe, main stream); slab and
+    // partial-sum planes are double buffered.  With IBO_FLAG_PROFILE the chunks run back to back so that K1 / K2 can be timed.
+    const bool i8pipe = i8 && !prof;
+    const size_t i8SlabBytes = (size_t)chunkTiles * 2 * nb * 4 * I8_B_STAGE, i8PartDbl = (size_t)3 * nb * Mpad;
+    if (i8) {
+        if ((rc = grow(&m->dSlab, &m->slabCap, 2 * ((i8SlabBytes + 7) / 8)))) return rc;
+        if ((rc = grow(&m->dPart, &m->partCap, 2 * i8PartDbl))) return rc;
+        if (i8pipe) {
+            IBO_CUDA_TRY(cudaEventRecord(m->evI8[4], st));
+            IBO_CUDA_TRY(cudaStreamWaitEvent(m->stream2, m->evI8[4], 0));
+        }
+    }
+    long ci = 0;
     if ((rc = grow(&m->dPart, &m->partCap, (size_t)3 * nb * subs * Mpad))) return rc;
     if ((rc = grow(&m->dOut, &m->outCap, (size_t)3 * M + 2))) return rc;
     double* const out = outBase ? outBase : m->dOut;     // outBase: device-visible pinned host memory (zero-copy results)
@@ -883,14 +902,25 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
         K2Plan pl = plan;
         if (!narrow && tiles != chunkTiles) pl.G = pick_groups_wide(nb, tiles);      // last, shorter chunk
         if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[1], st));
-        launch_kstar(m, dCand, m->dSlab, tiles, M, m0, st, inl);
+        const int buf = (int)(ci & 1);
+        uint8_t* const i8Slab = reinterpret_cast<uint8_t*>(m->dSlab) + (size_t)buf * (((i8SlabBytes + 7) / 8) * 8);
+        double* const chunkPart = i8 ? m->dPart + (size_t)buf * i8PartDbl : m->dPart;
+        if (i8pipe) {
+            if (ci >= 2) IBO_CUDA_TRY(cudaStreamWaitEvent(m->stream2, m->evI8[2 + buf], 0));     // chunk ci-2 is done with this buffer
+            launch_kstar_i8(m, dCand, tiles, M, m0, Mpad, i8Slab, chunkPart, m->stream2);
+            IBO_CUDA_TRY(cudaEventRecord(m->evI8[buf], m->stream2));
+            IBO_CUDA_TRY(cudaStreamWaitEvent(st, m->evI8[buf], 0));
+        }
+        else if (i8) launch_kstar_i8(m, dCand, tiles, M, m0, Mpad, i8Slab, chunkPart, st);
+        else launch_kstar(m, dCand, m->dSlab, tiles, M, m0, st, inl);
         nlaunch++;
         if (vm) {
             launch_kstar(vm, dCand, vm->dSlab, tiles, M, m0, st, inl);
             nlaunch++;
         }
         if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[2], st));
-        if ((rc = launch_trigemm(m, narrow, pl, m->npb > 0, ctaTiles, Mpad, chunkM, st))) return rc;
+        if (i8) launch_trigemm_i8(m, tiles, Mpad, i8Slab, chunkPart, st);
+        else if ((rc = launch_trigemm(m, narrow, pl, m->npb > 0, ctaTiles, Mpad, chunkM, st))) return rc;
         nlaunch++; nK2++;
         if (vm) {
             K2Plan plv = planV;
@@ -904,7 +934,7 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
         P.npb = m->npb; P.want_p1 = m->npb > 0;
         P.M = M; P.m0 = m0; P.chunkM = chunkM; P.Mpad = Mpad;
         P.noise = m->noise; P.ymax = rq.ymax; P.parm = rq.parm; P.ptheta = m->ptheta;
-        P.part = m->dPart; P.partVar = vm ? vm->dPart : nullptr; P.nbVarPart = vm ? vm->nb * (8 / planV.MT) : 0; P.MpadVar = Mpad;
+        P.part = chunkPart; P.partVar = vm ? vm->dPart : nullptr; P.nbVarPart = vm ? vm->nb * (8 / planV.MT) : 0; P.MpadVar = Mpad;
         P.cand = dCand; P.pmeans = m->dPmeans; P.pbeta = m->dPbeta; P.plb = m->dPlb; P.pwidth = m->dPwidth;
         P.score = rq.want_score ? out : nullptr;
         P.mu = rq.want_mu ? out + M : nullptr;
@@ -917,6 +947,8 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
         launch_ex(epilogue_kernel, dim3(nblk), dim3(256), 0, st, narrow && pdl_enabled() && !prof, P);
         nlaunch++;
         blk0 += nblk;
+        if (i8pipe) IBO_CUDA_TRY(cudaEventRecord(m->evI8[2 + buf], st));
+        ci++;
         if (prof) {
             IBO_CUDA_TRY(cudaEventRecord(m->ev[4], st));
             IBO_CUDA_TRY(cudaEventSynchronize(m->ev[4]));
@@ -1072,6 +1104,38 @@ extern "C" int ibo_score_resident(ibo_model* m, ibo_cands* c, int acq, double ym
 extern "C" int ibo_get_profile(ibo_model* m, double* out6) {
     if (!m || !out6) { set_error("bad argument"); return IBO_E_BADARG; }
     for (int i = 0; i < 6; i++) out6[i] = m->prof[i];
+    return IBO_OK;
+}
+
+// live INT8 tensor-pipe peak of `device` in TOP/s (int8 multiply-adds x 2), tcgen05.mma kind::i8 issue rate
+extern "C" int ibo_i8_peak(int device, double* tops) {
+    if (!tops) { set_error("bad argument"); return IBO_E_BADARG; }
+    if (ibo_device_count() <= 0) { set_error("no CUDA device available (libibo_b200 has no CPU fallback)"); return IBO_E_CUDA; }
+    IBO_CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp pr;
+    IBO_CUDA_TRY(cudaGetDeviceProperties(&pr, device));
+    const int sms = pr.multiProcessorCount, iters = 4000, smem = (128 + 256) * 128;
+    IBO_CUDA_TRY(cudaFuncSetAttribute(i8_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int* sink = nullptr;
+    IBO_CUDA_TRY(cudaMalloc(&sink, sizeof(int) * 128 * sms));
+    cudaEvent_t e0, e1;
+    IBO_CUDA_TRY(cudaEventCreate(&e0));
+    IBO_CUDA_TRY(cudaEventCreate(&e1));
+    double best = 0;
+    for (int r = 0; r < 5; r++) {
+        IBO_CUDA_TRY(cudaEventRecord(e0));
+        i8_peak_kernel<<<sms, 128, smem>>>(iters, sink);
+        IBO_CUDA_TRY(cudaEventRecord(e1));
+        IBO_CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double t = 2.0 * 128 * 256 * 128 * (double)iters * sms / (ms * 1e-3) / 1e12;
+        if (r >= 1 && t > best) best = t;
+        g_launches++;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    IBO_CUDA_TRY(cudaGetLastError());
+    *tops = best;
     return IBO_OK;
 }
 

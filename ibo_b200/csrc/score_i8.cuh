@@ -1,0 +1,436 @@
+// EXPERIMENTAL (IBO_FLAG_INT8 / IBO_INT8=1, wide batches only): K2's FP64 triangular GEMM V = W K* emulated on the INT8 tensor
+// cores (tcgen05.mma kind::i8, INT32 accumulators in TMEM) with an Ozaki-style slicing, and the K1 / model-side kernels that
+// feed it.  The B200's INT8 tensor rate is 4.5 POP/s (tools/research/umma_i8_probe.cu: 4.49 measured) against 37 TF/s of
+// DMMA; 28 slice products per FP64 product leave a ~4x higher ceiling for sigma^2 at the parity bound
+// (tools/research/ozaki_int8_study.py: 7 slices of 7 bits -> sigma^2 within 5e-12 relative at N = 1024..2048).
+//
+//   W  (row r)       = 2^e_r * sum_{t=1..7} 2^(-7t) A_t      A_t balanced digits in [-64, 64] of rint(w 2^(49 - e_r))
+//   K* (any element) =         sum_{u=1..7} 2^(-7u) B_u      B_u in [0, 127], digits of rint(k 2^49) (k / sf2 lies in [0, 1])
+//   V = 2^e_r * sum_{g=2..8} 2^(-7g) D_g,   D_g = sum_{t+u=g} A_t B_u^T  (exact INT32; pairs with t + u > 8 are dropped)
+//
+// One MMA covers several pairs: the B slices of a candidate tile are consecutive 64-row blocks of one K-major operand, so
+// A_t x [B_u0 .. B_u0+n-1] is a single 128 x 64n x 32 instruction whose 64-column output blocks land on the accumulators of
+// groups g = t+u0 .. t+u0+n-1 (TMEM columns 64 (g - 2)): 10 instructions per 32-deep k-step instead of 28.
+// sigma^2 only needs sum_r V_r^2 per candidate; the posterior mean is taken as k* . alpha (alpha = W^T W Y, plain FP64 dot
+// products inside K1, same partial-sum planes as K2's V . beta), which K3 consumes unchanged.
+//
+// Operand layout (both in HBM and in shared memory): the no-swizzle K-major canonical layout of the UMMA shared-memory
+// descriptor -- 8 x 16-byte core matrices, the two 16-byte k chunks of a row group 128 B apart (LBO), row groups 256 B apart
+// (SBO) -- so that a pipeline stage is two contiguous bulk copies (28 KiB of W slices + 14 KiB of K* slices).
+#pragma once
+
+namespace ibo {
+
+constexpr int I8_S = 7;                          // slices per operand
+constexpr int I8_FRAC = 49;                      // 7 * I8_S fixed-point bits
+constexpr int I8_NT = 64;                        // candidates per tile
+constexpr int I8_A_SLICE = 128 * 32;             // bytes: 128 rows x 32 k
+constexpr int I8_B_SLICE = I8_NT * 32;           // bytes: 64 candidates x 32 k
+constexpr int I8_A_STAGE = I8_S * I8_A_SLICE;    // 28672
+constexpr int I8_B_STAGE = I8_S * I8_B_SLICE;    // 14336
+constexpr int I8_STAGES = 4;
+constexpr int I8_THREADS = 192;                  // warp 0: bulk-copy producer, warp 1: TMEM owner + MMA issuer, warps 2-5: epilogue
+constexpr int I8_SMEM = I8_STAGES * (I8_A_STAGE + I8_B_STAGE) + 4 * 64 * 8 + 16 * 8;
+
+// byte offset of element (row r, k) in a [rows x 32] canonical tile
+__host__ __device__ inline uint32_t i8_canon(int r, int k) { return (uint32_t)((((r >> 3) * 2 + (k >> 4)) << 7) + ((r & 7) << 4) + (k & 15)); }
+// first k-step of row-block i in the packed W slices (row-block i owns 4 (i + 1) steps of I8_A_STAGE bytes)
+__host__ __device__ inline size_t wi8_base(int i) { return (size_t)4 * ((size_t)i * (i + 1) / 2) * I8_A_STAGE; }
+
+// ---- tcgen05 / TMEM primitives (encodings checked on the device by tools/research/umma_i8_probe.cu) ----------------------
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t addr) {        // LBO = 128 B, SBO = 256 B, version 1, no swizzle
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ constexpr uint32_t umma_idesc_i8(int M, int N) { // S32 accumulator, signed 8-bit A / B, K-major
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {               // arrives on `bar` once every MMA issued so far has completed
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// model side: per-row power-of-two scale of W and the seven slices, packed per (row-block, k-step)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) i8_rowscale_kernel(const double* __restrict__ W, int Np, double sf2, double* __restrict__ rowScale) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= Np) return;
+    double mx = 0.0;
+    for (int k = lane; k <= row; k += 32) mx = fmax(mx, fabs(W[(size_t)row * Np + k]));
+    for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    // 2^e with |w| / 2^e < 1/2 for the whole row (balanced digits: the top one must stay within [-64, 64]); slot 0: the scale used for slicing, slot 1: the same times sf2 (K* is sliced
+    // as k / sf2 in [0, 1]) which the epilogue multiplies back
+    if (lane == 0) {
+        const double sc = mx > 0.0 ? scalbn(1.0, ilogb(mx) + 2) : 1.0;
+        rowScale[row] = sc;
+        rowScale[Np + row] = sc * sf2;
+    }
+}
+
+__global__ void __launch_bounds__(256) i8_slice_w_kernel(const double* __restrict__ W, const double* __restrict__ rowScale, int Np,
+                                                         uint8_t* __restrict__ Wi8) {
+    const int j = blockIdx.x, i = blockIdx.y;                 // k-step, row-block
+    if (j >= (i + 1) * 4) return;
+    const int r = threadIdx.x & 127, c16 = threadIdx.x >> 7;  // row of the block, 16-byte k chunk of the step
+    const int row = i * 128 + r, k0 = j * 32 + c16 * 16;
+    const double inv = 1.0 / rowScale[row];                   // power of two: exact
+    long long q[16];
+#pragma unroll
+    for (int kk = 0; kk < 16; kk++) {
+        const double w = W[(size_t)row * Np + k0 + kk];        // exact zeros above the diagonal
+        q[kk] = __double2ll_rn(w * inv * 562949953421312.0);   // 2^49, round to nearest; |w| * inv < 1/2 -> |q| <= 2^48
+    }
+    uint8_t* dst = Wi8 + wi8_base(i) + (size_t)j * I8_A_STAGE + i8_canon(r, c16 * 16);
+    // balanced digits, least significant first: d_t in [-64, 63] for t = 7 .. 2, the rest (|d_1| <= 64) is the top digit.
+    // Zero-mean digits make the dropped slice pairs (t + u > 8) a zero-mean error that grows like sqrt(N), not N.
+#pragma unroll
+    for (int t = I8_S; t >= 1; t--) {
+        uint32_t w4[4];
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            uint32_t word = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                const int kk = v * 4 + b;
+                long long dgt;
+                if (t > 1) { dgt = ((q[kk] + 64) & 127) - 64; q[kk] = (q[kk] - dgt) >> 7; }
+                else dgt = q[kk];
+                word |= ((uint32_t)(int)dgt & 0xffu) << (8 * b);
+            }
+            w4[v] = word;
+        }
+        *reinterpret_cast<uint4*>(dst + (size_t)(t - 1) * I8_A_SLICE) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 (int8): one CTA = (64-candidate tile T, row-block i); thread = (candidate c, k-step of the block).  Kernel values from
+// direct differences, sliced from a 49-bit fixed-point image, 16 bytes (one core-matrix row) per store; the partial dot
+// products k* . alphaY / k* . alpha1 of the block go to planes 1 / 2 of `part` (what K2 writes as V . beta).
+// ---------------------------------------------------------------------------------------------
+template <int KC, int DMAX>
+__global__ void __launch_bounds__(256) kstar_i8_kernel(const double* __restrict__ Xt, const double* __restrict__ cand,
+                                                       const double* __restrict__ inv_theta, const double* __restrict__ center,
+                                                       const double* __restrict__ alphaY, const double* __restrict__ alpha1,
+                                                       uint8_t* __restrict__ Ki8, double* __restrict__ part,
+                                                       int N, int d, int nb, long M, long m0, long Mpad, double sf2, int want_p1) {
+    // DMAX >= d (even): the dimension loops have a compile-time length, the thread's candidate lives in registers and the
+    // training rows (zero padded to DMAX) are read with 16-byte broadcast loads
+    __shared__ __align__(16) double sX[128 * DMAX];
+    __shared__ double sAy[128], sA1[128], red[512];
+    const int T = blockIdx.x, i = blockIdx.y, tid = threadIdx.x;
+    for (int idx = tid; idx < 128 * DMAX; idx += 256) {
+        const int r = idx / DMAX, j = idx - r * DMAX;
+        sX[idx] = j < d ? Xt[(size_t)(i * 128 + r) * d + j] : 0.0;
+    }
+    if (tid < 128) { sAy[tid] = alphaY[i * 128 + tid]; sA1[tid] = alpha1[i * 128 + tid]; }
+    const int c = tid & 63, kg = tid >> 6;
+    double xc[DMAX];
+    {
+        long cg = m0 + (long)T * 64 + c;
+        if (cg >= M) cg = M - 1;
+#pragma unroll
+        for (int j = 0; j < DMAX; j++) xc[j] = j < d ? cand[(size_t)cg * d + j] * inv_theta[j] - center[j] : 0.0;
+    }
+    __syncthreads();
+    double sy = 0.0, s1 = 0.0;
+    uint8_t* dst0 = Ki8 + ((size_t)T * (nb * 4) + (size_t)i * 4 + kg) * I8_B_STAGE;
+#pragma unroll 1
+    for (int c16 = 0; c16 < 2; c16++) {
+        unsigned long long q[16];
+#pragma unroll
+        for (int kk = 0; kk < 16; kk++) {
+            const int k = kg * 32 + c16 * 16 + kk;
+            const double2* xr = reinterpret_cast<const double2*>(sX + k * DMAX);
+            double r2a = 0.0, r2b = 0.0;
+#pragma unroll
+            for (int j2 = 0; j2 < DMAX / 2; j2++) {
+                const double2 x2 = xr[j2];
+                const double da = x2.x - xc[2 * j2], db = x2.y - xc[2 * j2 + 1];
+                r2a = fma(da, da, r2a);
+                r2b = fma(db, db, r2b);
+            }
+            const double v = (i * 128 + k) < N ? cov_r2_t<KC>(1.0, r2a + r2b) : 0.0;   // in [0, 1]
+            sy = fma(v, sAy[k], sy);
+            s1 = fma(v, sA1[k], s1);
+            unsigned long long qq = (unsigned long long)__double2ll_rn(v * 562949953421312.0);      // 2^49, round to nearest
+            q[kk] = qq > 562949953421311ull ? 562949953421311ull : qq;                 // v == 1 (candidate on a training point)
+        }
+        uint8_t* dst = dst0 + i8_canon(c, c16 * 16);
+#pragma unroll
+        for (int t = 1; t <= I8_S; t++) {
+            uint32_t w4[4];
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                uint32_t word = 0;
+#pragma unroll
+                for (int b = 0; b < 4; b++) word |= (uint32_t)((q[v * 4 + b] >> (I8_FRAC - 7 * t)) & 127ull) << (8 * b);
+                w4[v] = word;
+            }
+            *reinterpret_cast<uint4*>(dst + (size_t)(t - 1) * I8_B_SLICE) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        }
+    }
+    red[kg * 64 + c] = sy;
+    red[256 + kg * 64 + c] = s1;
+    __syncthreads();
+    if (tid < 64) {
+        const size_t plane = (size_t)nb * Mpad;
+        const size_t o = (size_t)i * Mpad + (size_t)T * 64 + tid;
+        part[plane + o] = sf2 * (((red[tid] + red[64 + tid]) + red[128 + tid]) + red[192 + tid]);
+        if (want_p1) part[2 * plane + o] = sf2 * (((red[256 + tid] + red[320 + tid]) + red[384 + tid]) + red[448 + tid]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2 (int8): CTA = (row-block group g of G, 64-candidate tile T).  Row-blocks are dealt to the groups in snake order
+// (work ~ i + 1), each one a full sweep over its 4 (i + 1) k-steps into the seven group accumulators, then the epilogue
+// warps assemble V in FP64 and reduce sum_r V_r^2 per candidate in a fixed order.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(I8_THREADS, 1) trigemm_i8_kernel(const uint8_t* __restrict__ Wi8, const uint8_t* __restrict__ Ki8,
+                                                                    const double* __restrict__ rowScaleSf, double* __restrict__ part,
+                                                                    int nb, long Mpad) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sA = smem;                                          // [stage][7][128 x 32]
+    uint8_t* sB = smem + I8_STAGES * I8_A_STAGE;                 // [stage][7][64 x 32]
+    double* red = reinterpret_cast<double*>(smem + I8_STAGES * (I8_A_STAGE + I8_B_STAGE));     // [4][64]
+    uint64_t* full = reinterpret_cast<uint64_t*>(red + 4 * 64);
+    uint64_t* empty = full + I8_STAGES;
+    uint64_t* tfull = empty + I8_STAGES;
+    uint64_t* tempty = tfull + 1;
+    uint32_t* tbase = reinterpret_cast<uint32_t*>(tempty + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = blockIdx.x, G = gridDim.x, T = blockIdx.y;
+    if (tid == 0) {
+        for (int s = 0; s < I8_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tfull, 1);
+        mbar_init(tempty, 128);
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tbase)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tb = *tbase;
+    const int rounds = (nb + G - 1) / G;
+
+    if (warp == 0) {
+        // ---------------- producer: two contiguous bulk copies per k-step ----------------
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            const uint8_t* Bb = Ki8 + (size_t)T * (nb * 4) * I8_B_STAGE;
+            for (int r = 0; r < rounds; r++) {
+                const int idx = r * G + ((r & 1) ? (G - 1 - g) : g);
+                if (idx >= nb) continue;
+                const int i = nb - 1 - idx;
+                const uint8_t* Ab = Wi8 + wi8_base(i);
+                for (int j = 0; j < (i + 1) * 4; j++) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&full[s], I8_A_STAGE + I8_B_STAGE);
+                    bulk_g2s(sA + s * I8_A_STAGE, Ab + (size_t)j * I8_A_STAGE, I8_A_STAGE, &full[s]);
+                    bulk_g2s(sB + s * I8_B_STAGE, Bb + (size_t)j * I8_B_STAGE, I8_B_STAGE, &full[s]);
+                    if (++s == I8_STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer (one lane) ----------------
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0; int rb = 0;
+            for (int r = 0; r < rounds; r++) {
+                const int idx = r * G + ((r & 1) ? (G - 1 - g) : g);
+                if (idx >= nb) continue;
+                const int i = nb - 1 - idx;
+                mbar_wait(tempty, (uint32_t)(rb & 1) ^ 1);          // the epilogue has drained the previous row-block's accumulators
+                tc_fence_after();
+                for (int j = 0; j < (i + 1) * 4; j++) {
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(sA + s * I8_A_STAGE), b0 = smem_u32(sB + s * I8_B_STAGE);
+                    const uint32_t first = j == 0 ? 0u : 1u;
+                    // slice t of W against B slices u0 .. u0+n-1: columns 64 (t + u0 - 2), N = 64 n
+#define I8_MMA(t, u0, n, acc) umma_i8(tb + 64u * ((t) + (u0) - 2), umma_smem_desc(a0 + ((t) - 1) * I8_A_SLICE), \
+                                      umma_smem_desc(b0 + ((u0) - 1) * I8_B_SLICE), umma_idesc_i8(128, 64 * (n)), acc)
+                    I8_MMA(1, 1, 4, first); I8_MMA(1, 5, 3, first);          // the two t = 1 instructions touch every group first
+                    I8_MMA(2, 1, 4, 1u);    I8_MMA(2, 5, 2, 1u);
+                    I8_MMA(3, 1, 4, 1u);    I8_MMA(3, 5, 1, 1u);
+                    I8_MMA(4, 1, 4, 1u);
+                    I8_MMA(5, 1, 3, 1u);
+                    I8_MMA(6, 1, 2, 1u);
+                    I8_MMA(7, 1, 1, 1u);
+#undef I8_MMA
+                    umma_commit(&empty[s]);                          // the stage is free once these MMAs have read it
+                    if (++s == I8_STAGES) { s = 0; ph ^= 1; }
+                }
+                umma_commit(tfull);                                  // accumulators of row-block i complete
+                rb++;
+            }
+        }
+    } else {
+        // ---------------- epilogue: warps 2..5 own TMEM lanes 32 (warp % 4) .. + 31 ----------------
+        const int qd = warp & 3, et = (warp - 2) * 32 + lane;
+        int rb = 0;
+        for (int r = 0; r < rounds; r++) {
+            const int idx = r * G + ((r & 1) ? (G - 1 - g) : g);
+            if (idx >= nb) continue;
+            const int i = nb - 1 - idx;
+            const double rs = rowScaleSf[i * 128 + qd * 32 + lane];
+            mbar_wait(tfull, (uint32_t)(rb & 1));
+            tc_fence_after();
+#pragma unroll 1
+            for (int c8 = 0; c8 < 8; c8++) {
+                uint32_t D[I8_S][8];
+#pragma unroll
+                for (int gq = 0; gq < I8_S; gq++) tmem_ld8_nowait(tb + ((uint32_t)(qd * 32) << 16) + 64u * gq + 8u * c8, D[gq]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    const long long hi = (long long)(int)D[0][e] * 16384 + (long long)(int)D[1][e] * 128 + (long long)(int)D[2][e];
+                    const long long mid = (long long)(int)D[3][e] * 16384 + (long long)(int)D[4][e] * 128 + (long long)(int)D[5][e];
+                    const double lo = (double)(int)D[6][e];
+                    double v = fma((double)hi, 3.7252902984619140625e-09,                     // 2^-28
+                                   fma((double)mid, 1.7763568394002504646778106689453125e-15, // 2^-49
+                                       lo * 1.387778780781445675529539585113525390625e-17));  // 2^-56
+                    v *= rs;
+                    double sq = v * v;
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                    if (lane == 0) red[qd * 64 + c8 * 8 + e] = sq;
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty);                                     // 128 arrivals: the accumulators may be overwritten
+            named_bar_sync(1, 128);
+            if (et < 64) {
+                // TMEM lane quarter q holds rows 32 q .. 32 q + 31: ascending row order
+                part[(size_t)i * Mpad + (size_t)T * 64 + et] = ((red[et] + red[64 + et]) + red[128 + et]) + red[192 + et];
+            }
+            named_bar_sync(1, 128);
+            rb++;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tb), "r"(512u) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int ensure_i8(ibo_model* m) {
+    if (m->i8Valid) return IBO_OK;
+    cudaStream_t st = m->stream;
+    const int Np = m->Np, nb = m->nb;
+    for (double** p : {&m->dWi8, &m->dRowScale, &m->dAlphaY, &m->dAlpha1}) if (*p) { pool_free(*p); *p = nullptr; }
+    IBO_CUDA_TRY(pool_malloc((void**)&m->dWi8, wi8_base(nb)));
+    IBO_CUDA_TRY(pool_malloc((void**)&m->dRowScale, sizeof(double) * 2 * Np));
+    IBO_CUDA_TRY(pool_malloc((void**)&m->dAlphaY, sizeof(double) * Np));
+    IBO_CUDA_TRY(pool_malloc((void**)&m->dAlpha1, sizeof(double) * Np));
+    i8_rowscale_kernel<<<(Np + 7) / 8, 256, 0, st>>>(m->dW, Np, m->sf2, m->dRowScale);
+    i8_slice_w_kernel<<<dim3(nb * 4, nb), 256, 0, st>>>(m->dW, m->dRowScale, Np, reinterpret_cast<uint8_t*>(m->dWi8));
+    g_launches += 2;
+    launch_tri_matvec_t(m->dW, m->dBetaY, m->dAlphaY, Np, Np, st);       // alpha = W^T (W Y)
+    launch_tri_matvec_t(m->dW, m->dBeta1, m->dAlpha1, Np, Np, st);
+    IBO_CUDA_TRY(cudaFuncSetAttribute(trigemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
+    // K1 CTAs of the next chunk are meant to run next to a resident K2 CTA (174 KiB): ask for the largest shared-memory
+    // carve-out so that the 21 KiB a smaller configuration would leave do not limit them to one per SM
+    IBO_CUDA_TRY(cudaFuncSetAttribute(trigemm_i8_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    IBO_CUDA_TRY(cudaGetLastError());
+    for (auto& e : m->evI8) if (!e) IBO_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    m->i8Valid = true;
+    return IBO_OK;
+}
+
+// d <= 32 (K1's register-resident candidate), no variance model
+static bool i8_requested(int flags) {
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("IBO_INT8"); env = (e && e[0] == '1') ? 1 : 0; }
+    return env == 1 || (flags & IBO_FLAG_INT8) != 0;
+}
+
+template <int DMAX>
+static void launch_kstar_i8_d(ibo_model* m, const double* dCand, dim3 g1, long M, long m0, long Mpad, uint8_t* Ki8, double* part, cudaStream_t st) {
+    const int p1 = m->npb > 0 ? 1 : 0;
+    if (m->kind <= IBO_KERNEL_SE_ISO)
+        kstar_i8_kernel<0, DMAX><<<g1, 256, 0, st>>>(m->dXt, dCand, m->dInvTheta, m->dCenter, m->dAlphaY, m->dAlpha1, Ki8, part, m->N, m->d, m->nb, M, m0, Mpad, m->sf2, p1);
+    else if (m->kind == IBO_KERNEL_MATERN3)
+        kstar_i8_kernel<1, DMAX><<<g1, 256, 0, st>>>(m->dXt, dCand, m->dInvTheta, m->dCenter, m->dAlphaY, m->dAlpha1, Ki8, part, m->N, m->d, m->nb, M, m0, Mpad, m->sf2, p1);
+    else
+        kstar_i8_kernel<2, DMAX><<<g1, 256, 0, st>>>(m->dXt, dCand, m->dInvTheta, m->dCenter, m->dAlphaY, m->dAlpha1, Ki8, part, m->N, m->d, m->nb, M, m0, Mpad, m->sf2, p1);
+}
+
+// K1 of one chunk on the int8 path; tiles = 128-candidate tiles of the chunk (the slab holds 2 * tiles 64-candidate tiles)
+static void launch_kstar_i8(ibo_model* m, const double* dCand, long tiles, long M, long m0, long Mpad, uint8_t* Ki8, double* part, cudaStream_t st) {
+    dim3 g1((unsigned)(tiles * 2), m->nb);
+    const int d = m->d;
+    if (d <= 2) launch_kstar_i8_d<2>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
+    else if (d <= 4) launch_kstar_i8_d<4>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
+    else if (d <= 6) launch_kstar_i8_d<6>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
+    else if (d <= 8) launch_kstar_i8_d<8>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
+    else if (d <= 12) launch_kstar_i8_d<12>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
+    else if (d <= 16) launch_kstar_i8_d<16>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
+    else if (d <= 24) launch_kstar_i8_d<24>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
+    else launch_kstar_i8_d<32>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
+}
+
+// K2 of one chunk on the int8 path
+static void launch_trigemm_i8(ibo_model* m, long tiles, long Mpad, const uint8_t* Ki8, double* part, cudaStream_t st) {
+    int G = std::max(1, m->nb / 4);
+    if (tiles * 2 * G < g_num_sms) G = (int)std::min<long>(m->nb, (g_num_sms + tiles * 2 - 1) / (tiles * 2));
+    trigemm_i8_kernel<<<dim3(G, (unsigned)(tiles * 2)), I8_THREADS, I8_SMEM, st>>>(reinterpret_cast<const uint8_t*>(m->dWi8), Ki8,
+                                                                                  m->dRowScale + m->Np, part, m->nb, Mpad);
+}
+
+// ---- live INT8 tensor peak (bench.py): back-to-back 128 x 256 x 32 MMAs from resident operands, one CTA per SM ----
+__global__ void __launch_bounds__(128) i8_peak_kernel(int iters, int* __restrict__ sink) {
+    extern __shared__ __align__(1024) uint8_t smem[];      // A: 128 x 128 B, B: 256 x 128 B (four k-steps of 32)
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tbase;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (128 + 256) * 128; i += 128) smem[i] = (uint8_t)((i * 7 + 3) & 3);
+    if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tbase)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t td = tbase;
+    if (tid == 0) {
+        // 128-byte-deep tiles: the k chunks of a row group are 128 B apart, row groups 8 * 128 B apart
+        auto desc = [](uint32_t addr) {
+            return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46);
+        };
+        const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 128 * 128);
+        for (int it = 0; it < iters; it++)
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++) umma_i8(td + (uint32_t)(it & 1) * 256u, desc(a0 + kk * 256), desc(b0 + kk * 256), umma_idesc_i8(128, 256), 1u);
+        umma_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    uint32_t v[8];
+    tmem_ld8_nowait(td + ((uint32_t)(warp * 32) << 16), v);
+    tmem_ld_wait();
+    if (v[0] == 0x7fffffffu) sink[blockIdx.x * 128 + tid] = (int)v[1];
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(td), "r"(512u) : "memory");
+}
+
+}  // namespace ibo

@@ -59,6 +59,10 @@ extern "C" {
                                        instead of in a second batch.  The callback then sees a few points the reference never
                                        samples; their values are discarded, so FMIN/XMIN/nsamples and the trajectory are unchanged.
                                        ibo_acqmax sets it (the GPU objective is pure). */
+#define IBO_FLAG_INT8          0x80 /* EXPERIMENTAL, scoring calls with more than 2048 candidates on models without a variance model:
+                                       sigma^2 through an INT8 tensor-core emulation of the FP64 triangular GEMM (7 x 7-bit Ozaki
+                                       slices, exact INT32 accumulation, FP64 assembly; ibo_b200/csrc/score_i8.cuh) and mu as
+                                       k* . alpha.  Off by default; IBO_INT8=1 in the environment forces it. */
 #define IBO_FLAG_GRAD_EXACT    0x10 /* ibo_nlml / ibo_kernel_matrix: analytic Matern-3/2 length-scale derivative instead of
                                        the reference's expression with the unscaled distance (kernel.py:217-222) */
 
@@ -168,6 +172,8 @@ long ibo_launch_count(void);
 /* measurement helpers (bench.py): live FP64 tensor-pipe peak of `device` in TFLOP/s (DMMA.8x8x4 issue rate);
  * page-lock / unlock a caller-owned host buffer so the copies of the end-to-end leg run from pinned memory */
 int ibo_fp64_peak(int device, double* tflops);
+/* live INT8 tensor-pipe peak in TOP/s (tcgen05.mma kind::i8 issue rate): the roofline of the experimental IBO_FLAG_INT8 path */
+int ibo_i8_peak(int device, double* tops);
 int ibo_host_register(void* p, unsigned long bytes);
 int ibo_host_unregister(void* p);
 /* CUDA events on the model's stream (slot 0 = start, 1 = stop) and their elapsed device time */
