@@ -688,7 +688,18 @@ def main():
     if int8_leg is not None:
         line["int8_emulation"] = int8_leg
     if args.int8:
+        # main arm on the INT8 path: the dominant kernel is trigemm_i8_kernel, bounded by the INT8 tensor pipe
         line["config"]["arithmetic"] += " + IBO_FLAG_INT8 (sigma^2 via INT8 tensor-core emulation of the FP64 GEMM)"
+        pk8 = c_double(0)
+        _lib.check(L.ibo_i8_peak(device, ctypes.byref(pk8)))
+        nbk = (N + 127) // 128
+        ops = 2.0 * 28 * 128 * 32 * 4 * (nbk * (nbk + 1) // 2)
+        ach = M * ops / (prof["k2_ms"] * 1e-3) / 1e12
+        line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": pk8.value, "unit": "TOP/s (int8)", "frac": ach / pk8.value if pk8.value else None,
+                            "traffic": None, "kernel": "trigemm_i8_kernel (K2, int8 emulation)", "int8_ops_per_candidate": ops,
+                            "candidates_per_launch": cand_per_launch, "avg_launch_ms": 1e3 * k2_s,
+                            "fp64_equivalent_tflops": achieved, "fp64_dmma_peak_tflops": peak.value,
+                            "peak_source": "live tcgen05.mma kind::i8 issue-rate microbenchmark on this GPU (ibo_i8_peak)"}
     # ---- the "maximizeEI wall ms" half of the metric (this rank's GPU; DIRECT is latency bound and is not sharded) ----
     if rank == 0 and wl.id == 2:
         from ibo_b200.gaussianprocess.kernel import GaussianKernel_ard
