@@ -264,12 +264,15 @@ void divide(Driver& D, Store& R, const std::vector<unsigned>& order, bool seq, b
                         for (int j2 = 0; j2 < nu; j2++) own = own || (((mask >> j2) & 1) && p.udim[j2] == (int)i);
                         if (own) { W.specMap.push_back(-1); continue; }
                         W.specMap.push_back(nspec);
-                        size_t o = W.spec.size();
-                        W.spec.insert(W.spec.end(), cu.begin(), cu.end());
-                        for (int j2 = 0; j2 < nu; j2++) if ((mask >> j2) & 1) W.spec[o + p.udim[j2]] = cs[p.udim[j2]];
-                        W.spec.insert(W.spec.end(), W.spec.begin() + o, W.spec.begin() + o + N);
-                        W.spec[o + i] = lb[i] + (s1 - lb[i]) / 2.;
-                        W.spec[o + N + i] = s2 + (ub[i] - s2) / 2.;
+                        const size_t o = W.spec.size();
+                        W.spec.resize(o + 2 * (size_t)N);
+                        double* c1 = &W.spec[o];
+                        double* c3 = c1 + N;
+                        std::memcpy(c1, cu.data(), sizeof(double) * N);
+                        for (int j2 = 0; j2 < nu; j2++) if ((mask >> j2) & 1) c1[p.udim[j2]] = cs[p.udim[j2]];
+                        std::memcpy(c3, c1, sizeof(double) * N);
+                        c1[i] = lb[i] + (s1 - lb[i]) / 2.;
+                        c3[i] = s2 + (ub[i] - s2) / 2.;
                         nspec += 2;
                     }
                 }
