@@ -33,6 +33,7 @@ ACQ_EI, ACQ_PI, ACQ_UCB = 0, 1, 2
 FLAG_MODE_CPP, FLAG_MODE_PY, FLAG_KSTAR_EXPAND, FLAG_DIRECT_SEQ, FLAG_PROFILE, FLAG_GRAD_EXACT, FLAG_SHARD = 0x0, 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
 FLAG_DIRECT_SPECULATE = 0x40
 FLAG_INT8 = 0x80
+FLAG_INT8_G9 = 0x100
 E_BADARG, E_CUDA, E_NOTSPD, E_NOMEM, E_COMM = -1, -2, -3, -4, -5
 
 BATCH_OBJECTIVE = ctypes.CFUNCTYPE(None, c_void_p, c_long, c_int, POINTER(c_double), POINTER(c_double))

@@ -919,7 +919,7 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
             nlaunch++;
         }
         if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[2], st));
-        if (i8) launch_trigemm_i8(m, tiles, Mpad, i8Slab, chunkPart, st);
+        if (i8) launch_trigemm_i8(m, tiles, Mpad, i8Slab, chunkPart, st, (rq.flags & IBO_FLAG_INT8_G9) != 0);
         else if ((rc = launch_trigemm(m, narrow, pl, m->npb > 0, ctaTiles, Mpad, chunkM, st))) return rc;
         nlaunch++; nK2++;
         if (vm) {

@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(256) kstar_i8_kernel(const double* __restrict_
 // (work ~ i + 1), each one a full sweep over its 4 (i + 1) k-steps into the seven group accumulators, then the epilogue
 // warps assemble V in FP64 and reduce sum_r V_r^2 per candidate in a fixed order.
 // ---------------------------------------------------------------------------------------------
+template <int NG>     // accumulator groups: 7 (t + u <= 8, the validated default) or 8 (t + u <= 9: IBO_FLAG_INT8_G9, untested so far)
 __global__ void __launch_bounds__(I8_THREADS, 1) trigemm_i8_kernel(const uint8_t* __restrict__ Wi8, const uint8_t* __restrict__ Ki8,
                                                                     const double* __restrict__ rowScaleSf, double* __restrict__ part,
                                                                     int nb, long Mpad) {
@@ -264,13 +265,23 @@ __global__ void __launch_bounds__(I8_THREADS, 1) trigemm_i8_kernel(const uint8_t
                     // slice t of W against B slices u0 .. u0+n-1: columns 64 (t + u0 - 2), N = 64 n
 #define I8_MMA(t, u0, n, acc) umma_i8(tb + 64u * ((t) + (u0) - 2), umma_smem_desc(a0 + ((t) - 1) * I8_A_SLICE), \
                                       umma_smem_desc(b0 + ((u0) - 1) * I8_B_SLICE), umma_idesc_i8(128, 64 * (n)), acc)
-                    I8_MMA(1, 1, 4, first); I8_MMA(1, 5, 3, first);          // the two t = 1 instructions touch every group first
-                    I8_MMA(2, 1, 4, 1u);    I8_MMA(2, 5, 2, 1u);
-                    I8_MMA(3, 1, 4, 1u);    I8_MMA(3, 5, 1, 1u);
-                    I8_MMA(4, 1, 4, 1u);
-                    I8_MMA(5, 1, 3, 1u);
-                    I8_MMA(6, 1, 2, 1u);
-                    I8_MMA(7, 1, 1, 1u);
+                    I8_MMA(1, 1, 4, first); I8_MMA(1, 5, 3, first);          // the two t = 1 instructions touch groups 2..8 first
+                    if (NG == 7) {
+                        I8_MMA(2, 1, 4, 1u);    I8_MMA(2, 5, 2, 1u);
+                        I8_MMA(3, 1, 4, 1u);    I8_MMA(3, 5, 1, 1u);
+                        I8_MMA(4, 1, 4, 1u);
+                        I8_MMA(5, 1, 3, 1u);
+                        I8_MMA(6, 1, 2, 1u);
+                        I8_MMA(7, 1, 1, 1u);
+                    } else {
+                        // 34 pairs, t + u <= 9; group 9 (columns 448..511) is first touched by (t = 2, u = 7)
+                        I8_MMA(2, 1, 4, 1u);    I8_MMA(2, 5, 2, 1u);    I8_MMA(2, 7, 1, first);
+                        I8_MMA(3, 1, 4, 1u);    I8_MMA(3, 5, 2, 1u);
+                        I8_MMA(4, 1, 4, 1u);    I8_MMA(4, 5, 1, 1u);
+                        I8_MMA(5, 1, 4, 1u);
+                        I8_MMA(6, 1, 3, 1u);
+                        I8_MMA(7, 1, 2, 1u);
+                    }
 #undef I8_MMA
                     umma_commit(&empty[s]);                          // the stage is free once these MMAs have read it
                     if (++s == I8_STAGES) { s = 0; ph ^= 1; }
@@ -292,18 +303,20 @@ __global__ void __launch_bounds__(I8_THREADS, 1) trigemm_i8_kernel(const uint8_t
             tc_fence_after();
 #pragma unroll 1
             for (int c8 = 0; c8 < 8; c8++) {
-                uint32_t D[I8_S][8];
+                uint32_t D[NG][8];
 #pragma unroll
-                for (int gq = 0; gq < I8_S; gq++) tmem_ld8_nowait(tb + ((uint32_t)(qd * 32) << 16) + 64u * gq + 8u * c8, D[gq]);
+                for (int gq = 0; gq < NG; gq++) tmem_ld8_nowait(tb + ((uint32_t)(qd * 32) << 16) + 64u * gq + 8u * c8, D[gq]);
                 tmem_ld_wait();
 #pragma unroll
                 for (int e = 0; e < 8; e++) {
                     const long long hi = (long long)(int)D[0][e] * 16384 + (long long)(int)D[1][e] * 128 + (long long)(int)D[2][e];
                     const long long mid = (long long)(int)D[3][e] * 16384 + (long long)(int)D[4][e] * 128 + (long long)(int)D[5][e];
-                    const double lo = (double)(int)D[6][e];
+                    // group 8 at 2^-56 (and group 9 at 2^-63 when it is kept)
+                    const double lo = NG == 7 ? (double)(int)D[6][e] * 1.387778780781445675529539585113525390625e-17
+                                              : (double)((long long)(int)D[6][e] * 128 + (long long)(int)D[NG - 1][e]) * 1.084202172485504434007452800869941711425781e-19;
                     double v = fma((double)hi, 3.7252902984619140625e-09,                     // 2^-28
                                    fma((double)mid, 1.7763568394002504646778106689453125e-15, // 2^-49
-                                       lo * 1.387778780781445675529539585113525390625e-17));  // 2^-56
+                                       lo));
                     v *= rs;
                     double sq = v * v;
 #pragma unroll
@@ -344,10 +357,12 @@ static int ensure_i8(ibo_model* m) {
     g_launches += 2;
     launch_tri_matvec_t(m->dW, m->dBetaY, m->dAlphaY, Np, Np, st);       // alpha = W^T (W Y)
     launch_tri_matvec_t(m->dW, m->dBeta1, m->dAlpha1, Np, Np, st);
-    IBO_CUDA_TRY(cudaFuncSetAttribute(trigemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
+    IBO_CUDA_TRY(cudaFuncSetAttribute(trigemm_i8_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
+    IBO_CUDA_TRY(cudaFuncSetAttribute(trigemm_i8_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
+    IBO_CUDA_TRY(cudaFuncSetAttribute(trigemm_i8_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     // K1 CTAs of the next chunk are meant to run next to a resident K2 CTA (174 KiB): ask for the largest shared-memory
     // carve-out so that the 21 KiB a smaller configuration would leave do not limit them to one per SM
-    IBO_CUDA_TRY(cudaFuncSetAttribute(trigemm_i8_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    IBO_CUDA_TRY(cudaFuncSetAttribute(trigemm_i8_kernel<7>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     IBO_CUDA_TRY(cudaGetLastError());
     for (auto& e : m->evI8) if (!e) IBO_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     m->i8Valid = true;
@@ -358,7 +373,7 @@ static int ensure_i8(ibo_model* m) {
 static bool i8_requested(int flags) {
     static int env = -1;
     if (env < 0) { const char* e = getenv("IBO_INT8"); env = (e && e[0] == '1') ? 1 : 0; }
-    return env == 1 || (flags & IBO_FLAG_INT8) != 0;
+    return env == 1 || (flags & (IBO_FLAG_INT8 | IBO_FLAG_INT8_G9)) != 0;
 }
 
 template <int DMAX>
@@ -387,11 +402,15 @@ static void launch_kstar_i8(ibo_model* m, const double* dCand, long tiles, long 
 }
 
 // K2 of one chunk on the int8 path
-static void launch_trigemm_i8(ibo_model* m, long tiles, long Mpad, const uint8_t* Ki8, double* part, cudaStream_t st) {
+static void launch_trigemm_i8(ibo_model* m, long tiles, long Mpad, const uint8_t* Ki8, double* part, cudaStream_t st, bool g9 = false) {
     int G = std::max(1, m->nb / 4);
     if (tiles * 2 * G < g_num_sms) G = (int)std::min<long>(m->nb, (g_num_sms + tiles * 2 - 1) / (tiles * 2));
-    trigemm_i8_kernel<<<dim3(G, (unsigned)(tiles * 2)), I8_THREADS, I8_SMEM, st>>>(reinterpret_cast<const uint8_t*>(m->dWi8), Ki8,
-                                                                                  m->dRowScale + m->Np, part, m->nb, Mpad);
+    if (g9)
+        trigemm_i8_kernel<8><<<dim3(G, (unsigned)(tiles * 2)), I8_THREADS, I8_SMEM, st>>>(reinterpret_cast<const uint8_t*>(m->dWi8), Ki8,
+                                                                                         m->dRowScale + m->Np, part, m->nb, Mpad);
+    else
+        trigemm_i8_kernel<7><<<dim3(G, (unsigned)(tiles * 2)), I8_THREADS, I8_SMEM, st>>>(reinterpret_cast<const uint8_t*>(m->dWi8), Ki8,
+                                                                                         m->dRowScale + m->Np, part, m->nb, Mpad);
 }
 
 // ---- live INT8 tensor peak (bench.py): back-to-back 128 x 256 x 32 MMAs from resident operands, one CTA per SM ----

@@ -104,3 +104,15 @@ def test_int8_follows_append_and_ignores_small_batches():
     a = gp.model.score(Xs[:500], _lib.ACQ_EI, max(gp.Y), 0.01, flags=_lib.FLAG_MODE_PY, want_posterior=True)
     b = gp.model.score(Xs[:500], _lib.ACQ_EI, max(gp.Y), 0.01, flags=fl, want_posterior=True)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+
+
+@pytest.mark.skipif(__import__("os").environ.get("IBO_EXPERIMENTAL_TESTS") != "1",
+                    reason="IBO_FLAG_INT8_G9 (eighth accumulator group) has not been run on a device yet; set IBO_EXPERIMENTAL_TESTS=1")
+def test_int8_g9_variant_is_tighter():
+    from ibo_b200 import _lib
+    gp, o, Xs, Y = _case(2048, 6, 20000)
+    a = gp.model.score(Xs, _lib.ACQ_EI, Y.max(), 0.01, flags=_lib.FLAG_MODE_CPP, want_posterior=True)
+    b = gp.model.score(Xs, _lib.ACQ_EI, Y.max(), 0.01, flags=_lib.FLAG_MODE_CPP | _lib.FLAG_INT8, want_posterior=True)
+    c = gp.model.score(Xs, _lib.ACQ_EI, Y.max(), 0.01, flags=_lib.FLAG_MODE_CPP | _lib.FLAG_INT8_G9, want_posterior=True)
+    assert _rel(c[2], a[2], 1e-300) <= 0.1 * max(_rel(b[2], a[2], 1e-300), 1e-13)
+    assert _rel(c[0], a[0], 1e-5) <= 1e-11 and a[4] == c[4]
