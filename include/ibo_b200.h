@@ -64,8 +64,8 @@ extern "C" {
                                        slices, exact INT32 accumulation, FP64 assembly; ibo_b200/csrc/score_i8.cuh) and mu as
                                        k* . alpha.  Off by default; IBO_INT8=1 in the environment forces it. */
 #define IBO_FLAG_INT8_G9       0x100 /* IBO_FLAG_INT8 with an eighth accumulator group (slice pairs t + u <= 9: 34 instead of 28 products,
-                                        all 512 TMEM columns): 128x smaller truncation error for models whose sigma^2 gets close to its
-                                        floor.  Written for the next round; NOT yet run on a device. */
+                                        all 512 TMEM columns): ~10x smaller error (the 2^-49 operand rounding remains) for models whose
+                                        sigma^2 gets close to its floor.  Written for the next round; NOT yet run on a device. */
 #define IBO_FLAG_GRAD_EXACT    0x10 /* ibo_nlml / ibo_kernel_matrix: analytic Matern-3/2 length-scale derivative instead of
                                        the reference's expression with the unscaled distance (kernel.py:217-222) */
 
