@@ -141,12 +141,14 @@ class GaussianProcess(object):
             return m, np.ones(len(X))
         return self.model.posterior(X, _lib.FLAG_MODE_PY)
 
-    def score_batch(self, Xs, acq='ei', xi=0.01, parm=None, mode='py', want_posterior=False, out=None):
+    def score_batch(self, Xs, acq='ei', xi=0.01, parm=None, mode='py', want_posterior=False, out=None, int8=False):
         """Acquisition values for a candidate array (batched EI.negf / PI.negf / UCB.negf, negated).
 
-        Returns (scores, best_score, best_index[, mu, sigma2]).  `parm` overrides xi (UCB multiplier)."""
+        Returns (scores, best_score, best_index[, mu, sigma2]).  `parm` overrides xi (UCB multiplier).
+        `int8=True` (experimental, more than 2048 candidates): sigma^2 through the INT8 tensor-core emulation of the FP64
+        triangular GEMM (IBO_FLAG_INT8; about 3x faster, absolute error of sum v^2 ~1e-11)."""
         acq_id = {'ei': _lib.ACQ_EI, 'pi': _lib.ACQ_PI, 'ucb': _lib.ACQ_UCB}[acq]
-        flags = _lib.FLAG_MODE_PY if mode == 'py' else _lib.FLAG_MODE_CPP
+        flags = (_lib.FLAG_MODE_PY if mode == 'py' else _lib.FLAG_MODE_CPP) | (_lib.FLAG_INT8 if int8 else 0)
         sc, mu, s2, best, bidx = self.model.score(Xs, acq_id, np.max(self.Y), xi if parm is None else parm, flags,
                                                   want_posterior=want_posterior, out=out)
         if want_posterior:
