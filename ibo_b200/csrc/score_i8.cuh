@@ -62,23 +62,34 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ---------------------------------------------------------------------------------------------
 // model side: per-row power-of-two scale of W and the seven slices, packed per (row-block, k-step)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) i8_rowscale_kernel(const double* __restrict__ W, int Np, double sf2, double* __restrict__ rowScale) {
+__global__ void __launch_bounds__(256) i8_rowscale_kernel(const double* __restrict__ W, int Np, int N, double sf2, int headroom,
+                                                          double* __restrict__ rowScale) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= Np) return;
-    double mx = 0.0;
-    for (int k = lane; k <= row; k += 32) mx = fmax(mx, fabs(W[(size_t)row * Np + k]));
-    for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    // 2^e with |w| / 2^e < 1/2 for the whole row (balanced digits: the top one must stay within [-64, 64]); slot 0: the scale used for slicing, slot 1: the same times sf2 (K* is sliced
-    // as k / sf2 in [0, 1]) which the epilogue multiplies back
+    double mx = 0.0, sum = 0.0;
+    for (int k = lane; k <= row; k += 32) {
+        const double w = W[(size_t)row * Np + k];
+        mx = fmax(mx, fabs(w));
+        if (k < N) sum += w;
+    }
+    for (int o = 16; o; o >>= 1) { mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); sum += __shfl_xor_sync(0xffffffffu, sum, o); }
+    // 2^e with |w| / 2^e < 2^(1 - headroom) for the whole row (balanced digits: the top one must fit its int8).
+    //   7-bit digits: headroom 2 (|top| <= 64); slot 1 = scale * sf2 (K* is sliced as k / sf2 in [0, 1]), multiplied back by the epilogue
+    //   8-bit digits: headroom 3 (|top| <= 64); K* is sliced as (k / sf2 - 1/2) / 2 in [-1/4, 1/4]: slot 1 = 2 * scale * sf2 and
+    //                 slot 2 = sf2 / 2 * sum_{k < N} W[row][k], the constant the shift leaves behind
     if (lane == 0) {
-        const double sc = mx > 0.0 ? scalbn(1.0, ilogb(mx) + 2) : 1.0;
+        const double sc = mx > 0.0 ? scalbn(1.0, ilogb(mx) + headroom) : 1.0;
         rowScale[row] = sc;
-        rowScale[Np + row] = sc * sf2;
+        rowScale[Np + row] = headroom == 2 ? sc * sf2 : 2.0 * sc * sf2;
+        rowScale[2 * Np + row] = 0.5 * sf2 * sum;
     }
 }
 
+template <int BITS>     // digit width: 7 (validated) or 8 (IBO_FLAG_INT8_D8)
 __global__ void __launch_bounds__(256) i8_slice_w_kernel(const double* __restrict__ W, const double* __restrict__ rowScale, int Np,
                                                          uint8_t* __restrict__ Wi8) {
+    constexpr int FR = BITS * I8_S;                          // fixed-point bits: 49 or 56
+    constexpr long long HALF = 1ll << (BITS - 1), MASK = (1ll << BITS) - 1;
     const int j = blockIdx.x, i = blockIdx.y;                 // k-step, row-block
     if (j >= (i + 1) * 4) return;
     const int r = threadIdx.x & 127, c16 = threadIdx.x >> 7;  // row of the block, 16-byte k chunk of the step
@@ -88,10 +99,10 @@ __global__ void __launch_bounds__(256) i8_slice_w_kernel(const double* __restric
 #pragma unroll
     for (int kk = 0; kk < 16; kk++) {
         const double w = W[(size_t)row * Np + k0 + kk];        // exact zeros above the diagonal
-        q[kk] = __double2ll_rn(w * inv * 562949953421312.0);   // 2^49, round to nearest; |w| * inv < 1/2 -> |q| <= 2^48
+        q[kk] = __double2ll_rn(w * inv * (double)(1ll << FR));  // round to nearest; |w| * inv < 1/2 (7-bit) or 1/4 (8-bit digits)
     }
     uint8_t* dst = Wi8 + wi8_base(i) + (size_t)j * I8_A_STAGE + i8_canon(r, c16 * 16);
-    // balanced digits, least significant first: d_t in [-64, 63] for t = 7 .. 2, the rest (|d_1| <= 64) is the top digit.
+    // balanced digits, least significant first: d_t in [-2^(BITS-1), 2^(BITS-1) - 1] for t = 7 .. 2, the rest (|d_1| <= 64) is the top digit.
     // Zero-mean digits make the dropped slice pairs (t + u > 8) a zero-mean error that grows like sqrt(N), not N.
 #pragma unroll
     for (int t = I8_S; t >= 1; t--) {
@@ -103,7 +114,7 @@ __global__ void __launch_bounds__(256) i8_slice_w_kernel(const double* __restric
             for (int b = 0; b < 4; b++) {
                 const int kk = v * 4 + b;
                 long long dgt;
-                if (t > 1) { dgt = ((q[kk] + 64) & 127) - 64; q[kk] = (q[kk] - dgt) >> 7; }
+                if (t > 1) { dgt = ((q[kk] + HALF) & MASK) - HALF; q[kk] = (q[kk] - dgt) >> BITS; }
                 else dgt = q[kk];
                 word |= ((uint32_t)(int)dgt & 0xffu) << (8 * b);
             }
@@ -118,7 +129,7 @@ __global__ void __launch_bounds__(256) i8_slice_w_kernel(const double* __restric
 // direct differences, sliced from a 49-bit fixed-point image, 16 bytes (one core-matrix row) per store; the partial dot
 // products k* . alphaY / k* . alpha1 of the block go to planes 1 / 2 of `part` (what K2 writes as V . beta).
 // ---------------------------------------------------------------------------------------------
-template <int KC, int DMAX>
+template <int KC, int DMAX, int BITS>
 __global__ void __launch_bounds__(256) kstar_i8_kernel(const double* __restrict__ Xt, const double* __restrict__ cand,
                                                        const double* __restrict__ inv_theta, const double* __restrict__ center,
                                                        const double* __restrict__ alphaY, const double* __restrict__ alpha1,
@@ -163,21 +174,47 @@ __global__ void __launch_bounds__(256) kstar_i8_kernel(const double* __restrict_
             const double v = (i * 128 + k) < N ? cov_r2_t<KC>(1.0, r2a + r2b) : 0.0;   // in [0, 1]
             sy = fma(v, sAy[k], sy);
             s1 = fma(v, sA1[k], s1);
-            unsigned long long qq = (unsigned long long)__double2ll_rn(v * 562949953421312.0);      // 2^49, round to nearest
-            q[kk] = qq > 562949953421311ull ? 562949953421311ull : qq;                 // v == 1 (candidate on a training point)
+            if (BITS == 7) {
+                unsigned long long qq = (unsigned long long)__double2ll_rn(v * 562949953421312.0);      // 2^49, round to nearest
+                q[kk] = qq > 562949953421311ull ? 562949953421311ull : qq;                 // v == 1 (candidate on a training point)
+            } else {
+                // 8-bit digits: (v - 1/2) / 2 in [-1/4, 1/4] at 56 fractional bits, signed; rows beyond N contribute nothing
+                q[kk] = (i * 128 + k) < N ? (unsigned long long)__double2ll_rn((v - 0.5) * 36028797018963968.0) : 0ull;   // 2^55
+            }
         }
         uint8_t* dst = dst0 + i8_canon(c, c16 * 16);
+        if (BITS == 7) {
 #pragma unroll
-        for (int t = 1; t <= I8_S; t++) {
-            uint32_t w4[4];
+            for (int t = 1; t <= I8_S; t++) {
+                uint32_t w4[4];
 #pragma unroll
-            for (int v = 0; v < 4; v++) {
-                uint32_t word = 0;
+                for (int v = 0; v < 4; v++) {
+                    uint32_t word = 0;
 #pragma unroll
-                for (int b = 0; b < 4; b++) word |= (uint32_t)((q[v * 4 + b] >> (I8_FRAC - 7 * t)) & 127ull) << (8 * b);
-                w4[v] = word;
+                    for (int b = 0; b < 4; b++) word |= (uint32_t)((q[v * 4 + b] >> (I8_FRAC - 7 * t)) & 127ull) << (8 * b);
+                    w4[v] = word;
+                }
+                *reinterpret_cast<uint4*>(dst + (size_t)(t - 1) * I8_B_SLICE) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
             }
-            *reinterpret_cast<uint4*>(dst + (size_t)(t - 1) * I8_B_SLICE) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        } else {
+            // balanced base-256 digits, least significant first (as the W slices)
+#pragma unroll
+            for (int t = I8_S; t >= 1; t--) {
+                uint32_t w4[4];
+#pragma unroll
+                for (int v = 0; v < 4; v++) {
+                    uint32_t word = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        long long qs = (long long)q[v * 4 + b], dgt;
+                        if (t > 1) { dgt = ((qs + 128) & 255) - 128; q[v * 4 + b] = (unsigned long long)((qs - dgt) >> 8); }
+                        else dgt = qs;
+                        word |= ((uint32_t)(int)dgt & 0xffu) << (8 * b);
+                    }
+                    w4[v] = word;
+                }
+                *reinterpret_cast<uint4*>(dst + (size_t)(t - 1) * I8_B_SLICE) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            }
         }
     }
     red[kg * 64 + c] = sy;
@@ -196,10 +233,14 @@ __global__ void __launch_bounds__(256) kstar_i8_kernel(const double* __restrict_
 // (work ~ i + 1), each one a full sweep over its 4 (i + 1) k-steps into the seven group accumulators, then the epilogue
 // warps assemble V in FP64 and reduce sum_r V_r^2 per candidate in a fixed order.
 // ---------------------------------------------------------------------------------------------
-template <int NG>     // accumulator groups: 7 (t + u <= 8, the validated default) or 8 (t + u <= 9: IBO_FLAG_INT8_G9, untested so far)
+// NG accumulator groups: 7 (t + u <= 8, the validated default) or 8 (t + u <= 9: IBO_FLAG_INT8_G9); BITS: digit width 7 (validated) or 8
+// (IBO_FLAG_INT8_D8: same 28 products, operands rounded at 2^-56 instead of 2^-49; K* sliced as (k - 1/2) / 2 with signed digits, the
+// constant the shift leaves behind comes back as rowConst).  The non-default variants are written for the next round and untested.
+template <int NG, int BITS>
 __global__ void __launch_bounds__(I8_THREADS, 1) trigemm_i8_kernel(const uint8_t* __restrict__ Wi8, const uint8_t* __restrict__ Ki8,
                                                                     const double* __restrict__ rowScaleSf, double* __restrict__ part,
                                                                     int nb, long Mpad) {
+    // rowScaleSf[row]: the factor that turns the assembled integer sum into v; rowScaleSf[Np + row] (8-bit digits): the additive constant
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;                                          // [stage][7][128 x 32]
     uint8_t* sB = smem + I8_STAGES * I8_A_STAGE;                 // [stage][7][64 x 32]
@@ -299,6 +340,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) trigemm_i8_kernel(const uint8_t
             if (idx >= nb) continue;
             const int i = nb - 1 - idx;
             const double rs = rowScaleSf[i * 128 + qd * 32 + lane];
+            const double rc = BITS == 8 ? rowScaleSf[(size_t)nb * 128 + i * 128 + qd * 32 + lane] : 0.0;
             mbar_wait(tfull, (uint32_t)(rb & 1));
             tc_fence_after();
 #pragma unroll 1
@@ -309,15 +351,28 @@ __global__ void __launch_bounds__(I8_THREADS, 1) trigemm_i8_kernel(const uint8_t
                 tmem_ld_wait();
 #pragma unroll
                 for (int e = 0; e < 8; e++) {
-                    const long long hi = (long long)(int)D[0][e] * 16384 + (long long)(int)D[1][e] * 128 + (long long)(int)D[2][e];
-                    const long long mid = (long long)(int)D[3][e] * 16384 + (long long)(int)D[4][e] * 128 + (long long)(int)D[5][e];
-                    // group 8 at 2^-56 (and group 9 at 2^-63 when it is kept)
-                    const double lo = NG == 7 ? (double)(int)D[6][e] * 1.387778780781445675529539585113525390625e-17
-                                              : (double)((long long)(int)D[6][e] * 128 + (long long)(int)D[NG - 1][e]) * 1.084202172485504434007452800869941711425781e-19;
-                    double v = fma((double)hi, 3.7252902984619140625e-09,                     // 2^-28
-                                   fma((double)mid, 1.7763568394002504646778106689453125e-15, // 2^-49
-                                       lo));
-                    v *= rs;
+                    double v;
+                    if (BITS == 7) {
+                        const long long hi = (long long)(int)D[0][e] * 16384 + (long long)(int)D[1][e] * 128 + (long long)(int)D[2][e];
+                        const long long mid = (long long)(int)D[3][e] * 16384 + (long long)(int)D[4][e] * 128 + (long long)(int)D[5][e];
+                        // group 8 at 2^-56 (and group 9 at 2^-63 when it is kept)
+                        const double lo = NG == 7 ? (double)(int)D[6][e] * 1.387778780781445675529539585113525390625e-17
+                                                  : (double)((long long)(int)D[6][e] * 128 + (long long)(int)D[NG - 1][e]) * 1.084202172485504434007452800869941711425781e-19;
+                        v = fma((double)hi, 3.7252902984619140625e-09,                     // 2^-28
+                                fma((double)mid, 1.7763568394002504646778106689453125e-15, // 2^-49
+                                    lo));
+                        v *= rs;
+                    } else {
+                        // base-256 digits: groups 2..4 at 2^-32, 5..7 at 2^-56, 8 at 2^-64 (9 at 2^-72)
+                        const long long hi = (long long)(int)D[0][e] * 65536 + (long long)(int)D[1][e] * 256 + (long long)(int)D[2][e];
+                        const long long mid = (long long)(int)D[3][e] * 65536 + (long long)(int)D[4][e] * 256 + (long long)(int)D[5][e];
+                        const double lo = NG == 7 ? (double)(int)D[6][e] * 5.42101086242752217003726400434970855712890625e-20
+                                                  : (double)((long long)(int)D[6][e] * 256 + (long long)(int)D[NG - 1][e]) * 2.1175823681357508476708062516990986740112305e-22;
+                        v = fma((double)hi, 2.3283064365386962890625e-10,                  // 2^-32
+                                fma((double)mid, 1.387778780781445675529539585113525390625e-17,   // 2^-56
+                                    lo));
+                        v = fma(v, rs, rc);
+                    }
                     double sq = v * v;
 #pragma unroll
                     for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
@@ -343,29 +398,44 @@ __global__ void __launch_bounds__(I8_THREADS, 1) trigemm_i8_kernel(const uint8_t
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static int ensure_i8(ibo_model* m) {
-    if (m->i8Valid) return IBO_OK;
-    cudaStream_t st = m->stream;
-    const int Np = m->Np, nb = m->nb;
-    for (double** p : {&m->dWi8, &m->dRowScale, &m->dAlphaY, &m->dAlpha1}) if (*p) { pool_free(*p); *p = nullptr; }
-    IBO_CUDA_TRY(pool_malloc((void**)&m->dWi8, wi8_base(nb)));
-    IBO_CUDA_TRY(pool_malloc((void**)&m->dRowScale, sizeof(double) * 2 * Np));
-    IBO_CUDA_TRY(pool_malloc((void**)&m->dAlphaY, sizeof(double) * Np));
-    IBO_CUDA_TRY(pool_malloc((void**)&m->dAlpha1, sizeof(double) * Np));
-    i8_rowscale_kernel<<<(Np + 7) / 8, 256, 0, st>>>(m->dW, Np, m->sf2, m->dRowScale);
-    i8_slice_w_kernel<<<dim3(nb * 4, nb), 256, 0, st>>>(m->dW, m->dRowScale, Np, reinterpret_cast<uint8_t*>(m->dWi8));
-    g_launches += 2;
-    launch_tri_matvec_t(m->dW, m->dBetaY, m->dAlphaY, Np, Np, st);       // alpha = W^T (W Y)
-    launch_tri_matvec_t(m->dW, m->dBeta1, m->dAlpha1, Np, Np, st);
-    IBO_CUDA_TRY(cudaFuncSetAttribute(trigemm_i8_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
-    IBO_CUDA_TRY(cudaFuncSetAttribute(trigemm_i8_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
-    IBO_CUDA_TRY(cudaFuncSetAttribute(trigemm_i8_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+template <int NG, int BITS>
+static cudaError_t i8_set_k2_attrs() {
+    cudaError_t e = cudaFuncSetAttribute(trigemm_i8_kernel<NG, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM);
     // K1 CTAs of the next chunk are meant to run next to a resident K2 CTA (174 KiB): ask for the largest shared-memory
     // carve-out so that the 21 KiB a smaller configuration would leave do not limit them to one per SM
-    IBO_CUDA_TRY(cudaFuncSetAttribute(trigemm_i8_kernel<7>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(trigemm_i8_kernel<NG, BITS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    return e;
+}
+
+// builds (once per model state) the packed digit slices of W for `bits`-wide digits, the row scales / constants, alpha
+static int ensure_i8(ibo_model* m, int bits) {
+    const int Np = m->Np, nb = m->nb;
+    cudaStream_t st = m->stream;
+    if (!m->dAlphaY || !(m->i8Valid || m->i8Valid8)) {
+        for (double** p : {&m->dAlphaY, &m->dAlpha1}) if (*p) { pool_free(*p); *p = nullptr; }
+        IBO_CUDA_TRY(pool_malloc((void**)&m->dAlphaY, sizeof(double) * Np));
+        IBO_CUDA_TRY(pool_malloc((void**)&m->dAlpha1, sizeof(double) * Np));
+        launch_tri_matvec_t(m->dW, m->dBetaY, m->dAlphaY, Np, Np, st);       // alpha = W^T (W Y)
+        launch_tri_matvec_t(m->dW, m->dBeta1, m->dAlpha1, Np, Np, st);
+        IBO_CUDA_TRY((i8_set_k2_attrs<7, 7>()));
+        IBO_CUDA_TRY((i8_set_k2_attrs<8, 7>()));
+        IBO_CUDA_TRY((i8_set_k2_attrs<7, 8>()));
+        IBO_CUDA_TRY((i8_set_k2_attrs<8, 8>()));
+        for (auto& e : m->evI8) if (!e) IBO_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    bool& valid = bits == 8 ? m->i8Valid8 : m->i8Valid;
+    if (valid) return IBO_OK;
+    double*& slices = bits == 8 ? m->dWi8b : m->dWi8;
+    double*& scale = bits == 8 ? m->dRowScale8 : m->dRowScale;
+    for (double** p : {&slices, &scale}) if (*p) { pool_free(*p); *p = nullptr; }
+    IBO_CUDA_TRY(pool_malloc((void**)&slices, wi8_base(nb)));
+    IBO_CUDA_TRY(pool_malloc((void**)&scale, sizeof(double) * 3 * Np));
+    i8_rowscale_kernel<<<(Np + 7) / 8, 256, 0, st>>>(m->dW, Np, m->N, m->sf2, bits == 8 ? 3 : 2, scale);
+    if (bits == 8) i8_slice_w_kernel<8><<<dim3(nb * 4, nb), 256, 0, st>>>(m->dW, scale, Np, reinterpret_cast<uint8_t*>(slices));
+    else i8_slice_w_kernel<7><<<dim3(nb * 4, nb), 256, 0, st>>>(m->dW, scale, Np, reinterpret_cast<uint8_t*>(slices));
+    g_launches += 2;
     IBO_CUDA_TRY(cudaGetLastError());
-    for (auto& e : m->evI8) if (!e) IBO_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    m->i8Valid = true;
+    valid = true;
     return IBO_OK;
 }
 
@@ -373,44 +443,54 @@ static int ensure_i8(ibo_model* m) {
 static bool i8_requested(int flags) {
     static int env = -1;
     if (env < 0) { const char* e = getenv("IBO_INT8"); env = (e && e[0] == '1') ? 1 : 0; }
-    return env == 1 || (flags & (IBO_FLAG_INT8 | IBO_FLAG_INT8_G9)) != 0;
+    return env == 1 || (flags & (IBO_FLAG_INT8 | IBO_FLAG_INT8_G9 | IBO_FLAG_INT8_D8)) != 0;
 }
+// 8-bit digits: |D_g| <= 7 pairs x N x 128 x 128 must fit INT32
+static int i8_bits(const ibo_model* m, int flags) { return ((flags & IBO_FLAG_INT8_D8) && m->Np <= 16384) ? 8 : 7; }
 
-template <int DMAX>
+template <int DMAX, int BITS>
 static void launch_kstar_i8_d(ibo_model* m, const double* dCand, dim3 g1, long M, long m0, long Mpad, uint8_t* Ki8, double* part, cudaStream_t st) {
     const int p1 = m->npb > 0 ? 1 : 0;
     if (m->kind <= IBO_KERNEL_SE_ISO)
-        kstar_i8_kernel<0, DMAX><<<g1, 256, 0, st>>>(m->dXt, dCand, m->dInvTheta, m->dCenter, m->dAlphaY, m->dAlpha1, Ki8, part, m->N, m->d, m->nb, M, m0, Mpad, m->sf2, p1);
+        kstar_i8_kernel<0, DMAX, BITS><<<g1, 256, 0, st>>>(m->dXt, dCand, m->dInvTheta, m->dCenter, m->dAlphaY, m->dAlpha1, Ki8, part, m->N, m->d, m->nb, M, m0, Mpad, m->sf2, p1);
     else if (m->kind == IBO_KERNEL_MATERN3)
-        kstar_i8_kernel<1, DMAX><<<g1, 256, 0, st>>>(m->dXt, dCand, m->dInvTheta, m->dCenter, m->dAlphaY, m->dAlpha1, Ki8, part, m->N, m->d, m->nb, M, m0, Mpad, m->sf2, p1);
+        kstar_i8_kernel<1, DMAX, BITS><<<g1, 256, 0, st>>>(m->dXt, dCand, m->dInvTheta, m->dCenter, m->dAlphaY, m->dAlpha1, Ki8, part, m->N, m->d, m->nb, M, m0, Mpad, m->sf2, p1);
     else
-        kstar_i8_kernel<2, DMAX><<<g1, 256, 0, st>>>(m->dXt, dCand, m->dInvTheta, m->dCenter, m->dAlphaY, m->dAlpha1, Ki8, part, m->N, m->d, m->nb, M, m0, Mpad, m->sf2, p1);
+        kstar_i8_kernel<2, DMAX, BITS><<<g1, 256, 0, st>>>(m->dXt, dCand, m->dInvTheta, m->dCenter, m->dAlphaY, m->dAlpha1, Ki8, part, m->N, m->d, m->nb, M, m0, Mpad, m->sf2, p1);
+}
+
+template <int BITS>
+static void launch_kstar_i8_b(ibo_model* m, const double* dCand, long tiles, long M, long m0, long Mpad, uint8_t* Ki8, double* part, cudaStream_t st) {
+    dim3 g1((unsigned)(tiles * 2), m->nb);
+    const int d = m->d;
+    if (d <= 2) launch_kstar_i8_d<2, BITS>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
+    else if (d <= 4) launch_kstar_i8_d<4, BITS>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
+    else if (d <= 6) launch_kstar_i8_d<6, BITS>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
+    else if (d <= 8) launch_kstar_i8_d<8, BITS>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
+    else if (d <= 12) launch_kstar_i8_d<12, BITS>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
+    else if (d <= 16) launch_kstar_i8_d<16, BITS>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
+    else if (d <= 24) launch_kstar_i8_d<24, BITS>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
+    else launch_kstar_i8_d<32, BITS>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
 }
 
 // K1 of one chunk on the int8 path; tiles = 128-candidate tiles of the chunk (the slab holds 2 * tiles 64-candidate tiles)
-static void launch_kstar_i8(ibo_model* m, const double* dCand, long tiles, long M, long m0, long Mpad, uint8_t* Ki8, double* part, cudaStream_t st) {
-    dim3 g1((unsigned)(tiles * 2), m->nb);
-    const int d = m->d;
-    if (d <= 2) launch_kstar_i8_d<2>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
-    else if (d <= 4) launch_kstar_i8_d<4>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
-    else if (d <= 6) launch_kstar_i8_d<6>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
-    else if (d <= 8) launch_kstar_i8_d<8>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
-    else if (d <= 12) launch_kstar_i8_d<12>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
-    else if (d <= 16) launch_kstar_i8_d<16>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
-    else if (d <= 24) launch_kstar_i8_d<24>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
-    else launch_kstar_i8_d<32>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
+static void launch_kstar_i8(ibo_model* m, const double* dCand, long tiles, long M, long m0, long Mpad, uint8_t* Ki8, double* part, cudaStream_t st,
+                            int bits = 7) {
+    if (bits == 8) launch_kstar_i8_b<8>(m, dCand, tiles, M, m0, Mpad, Ki8, part, st);
+    else launch_kstar_i8_b<7>(m, dCand, tiles, M, m0, Mpad, Ki8, part, st);
 }
 
 // K2 of one chunk on the int8 path
-static void launch_trigemm_i8(ibo_model* m, long tiles, long Mpad, const uint8_t* Ki8, double* part, cudaStream_t st, bool g9 = false) {
+static void launch_trigemm_i8(ibo_model* m, long tiles, long Mpad, const uint8_t* Ki8, double* part, cudaStream_t st, bool g9 = false, int bits = 7) {
     int G = std::max(1, m->nb / 4);
     if (tiles * 2 * G < g_num_sms) G = (int)std::min<long>(m->nb, (g_num_sms + tiles * 2 - 1) / (tiles * 2));
-    if (g9)
-        trigemm_i8_kernel<8><<<dim3(G, (unsigned)(tiles * 2)), I8_THREADS, I8_SMEM, st>>>(reinterpret_cast<const uint8_t*>(m->dWi8), Ki8,
-                                                                                         m->dRowScale + m->Np, part, m->nb, Mpad);
-    else
-        trigemm_i8_kernel<7><<<dim3(G, (unsigned)(tiles * 2)), I8_THREADS, I8_SMEM, st>>>(reinterpret_cast<const uint8_t*>(m->dWi8), Ki8,
-                                                                                         m->dRowScale + m->Np, part, m->nb, Mpad);
+    const dim3 grid(G, (unsigned)(tiles * 2));
+    const uint8_t* Wsl = reinterpret_cast<const uint8_t*>(bits == 8 ? m->dWi8b : m->dWi8);
+    const double* rs = (bits == 8 ? m->dRowScale8 : m->dRowScale) + m->Np;
+    if (bits == 8 && g9) trigemm_i8_kernel<8, 8><<<grid, I8_THREADS, I8_SMEM, st>>>(Wsl, Ki8, rs, part, m->nb, Mpad);
+    else if (bits == 8) trigemm_i8_kernel<7, 8><<<grid, I8_THREADS, I8_SMEM, st>>>(Wsl, Ki8, rs, part, m->nb, Mpad);
+    else if (g9) trigemm_i8_kernel<8, 7><<<grid, I8_THREADS, I8_SMEM, st>>>(Wsl, Ki8, rs, part, m->nb, Mpad);
+    else trigemm_i8_kernel<7, 7><<<grid, I8_THREADS, I8_SMEM, st>>>(Wsl, Ki8, rs, part, m->nb, Mpad);
 }
 
 // ---- live INT8 tensor peak (bench.py): back-to-back 128 x 256 x 32 MMAs from resident operands, one CTA per SM ----

@@ -66,6 +66,9 @@ extern "C" {
 #define IBO_FLAG_INT8_G9       0x100 /* IBO_FLAG_INT8 with an eighth accumulator group (slice pairs t + u <= 9: 34 instead of 28 products,
                                         all 512 TMEM columns): ~10x smaller error (the 2^-49 operand rounding remains) for models whose
                                         sigma^2 gets close to its floor.  Written for the next round; NOT yet run on a device. */
+#define IBO_FLAG_INT8_D8       0x200 /* IBO_FLAG_INT8 with 8-bit instead of 7-bit digits (same 28 products; operands rounded at 2^-56 instead of
+                                        2^-49: ~100x smaller error in the CPU model of the scheme, tests/test_int8_model.py).  Written for the
+                                        next round; NOT yet run on a device.  Models beyond N = 16384 fall back to 7-bit digits. */
 #define IBO_FLAG_GRAD_EXACT    0x10 /* ibo_nlml / ibo_kernel_matrix: analytic Matern-3/2 length-scale derivative instead of
                                        the reference's expression with the unscaled distance (kernel.py:217-222) */
 
