@@ -860,7 +860,7 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
     if (i8 && (rc = ensure_i8(m, i8bits))) return rc;
     // int8 path: K1 of chunk c+1 (FP64 / integer pipes, stream2) runs under K2 of chunk c (tensor pipe, main stream); slab and
     // partial-sum planes are double buffered.  With IBO_FLAG_PROFILE the chunks run back to back so that K1 / K2 can be timed.
-    const bool i8pipe = i8 && !prof;
+    const bool i8pipe = i8 && !prof && i8_pipe_enabled();
     const size_t i8SlabBytes = (size_t)chunkTiles * 2 * nb * 4 * I8_B_STAGE, i8PartDbl = (size_t)3 * nb * Mpad;
     if (i8) {
         if ((rc = grow(&m->dSlab, &m->slabCap, 2 * ((i8SlabBytes + 7) / 8)))) return rc;
@@ -920,7 +920,7 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
             nlaunch++;
         }
         if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[2], st));
-        if (i8) launch_trigemm_i8(m, tiles, Mpad, i8Slab, chunkPart, st, (rq.flags & IBO_FLAG_INT8_G9) != 0, i8bits);
+        if (i8) launch_trigemm_i8(m, tiles, Mpad, i8Slab, chunkPart, st, i8_g9(rq.flags), i8bits);
         else if ((rc = launch_trigemm(m, narrow, pl, m->npb > 0, ctaTiles, Mpad, chunkM, st))) return rc;
         nlaunch++; nK2++;
         if (vm) {

@@ -439,14 +439,31 @@ static int ensure_i8(ibo_model* m, int bits) {
     return IBO_OK;
 }
 
-// d <= 32 (K1's register-resident candidate), no variance model
-static bool i8_requested(int flags) {
+// IBO_INT8 in the environment forces the path for every wide scoring call: 1 = the validated 7-bit digits, 8 = 8-bit digits
+// (IBO_FLAG_INT8_D8), 9 = eighth accumulator group (IBO_FLAG_INT8_G9), 89 = both.  IBO_I8_PIPE=0 runs K1 and K2 back to back
+// on one stream (A/B of the two-stream pipeline).
+static int i8_env() {
     static int env = -1;
-    if (env < 0) { const char* e = getenv("IBO_INT8"); env = (e && e[0] == '1') ? 1 : 0; }
-    return env == 1 || (flags & (IBO_FLAG_INT8 | IBO_FLAG_INT8_G9 | IBO_FLAG_INT8_D8)) != 0;
+    if (env < 0) { const char* e = getenv("IBO_INT8"); env = e ? atoi(e) : 0; }
+    return env;
 }
+static int i8_effective_flags(int flags) {
+    const int env = i8_env();
+    if (env == 1) flags |= IBO_FLAG_INT8;
+    if (env == 8 || env == 89) flags |= IBO_FLAG_INT8_D8;
+    if (env == 9 || env == 89) flags |= IBO_FLAG_INT8_G9;
+    return flags;
+}
+// d <= 32 (K1's register-resident candidate), no variance model
+static bool i8_requested(int flags) { return (i8_effective_flags(flags) & (IBO_FLAG_INT8 | IBO_FLAG_INT8_G9 | IBO_FLAG_INT8_D8)) != 0; }
 // 8-bit digits: |D_g| <= 7 pairs x N x 128 x 128 must fit INT32
-static int i8_bits(const ibo_model* m, int flags) { return ((flags & IBO_FLAG_INT8_D8) && m->Np <= 16384) ? 8 : 7; }
+static int i8_bits(const ibo_model* m, int flags) { return ((i8_effective_flags(flags) & IBO_FLAG_INT8_D8) && m->Np <= 16384) ? 8 : 7; }
+static bool i8_g9(int flags) { return (i8_effective_flags(flags) & IBO_FLAG_INT8_G9) != 0; }
+static bool i8_pipe_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("IBO_I8_PIPE"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
 
 template <int DMAX, int BITS>
 static void launch_kstar_i8_d(ibo_model* m, const double* dCand, dim3 g1, long M, long m0, long Mpad, uint8_t* Ki8, double* part, cudaStream_t st) {
