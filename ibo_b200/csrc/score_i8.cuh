@@ -407,6 +407,34 @@ static cudaError_t i8_set_k2_attrs() {
     return e;
 }
 
+// Every K1 variant asks for the same (largest) shared-memory carve-out as K2: an SM has one carve-out at a time, and a K1 CTA that
+// configured it smaller would keep the 174 KiB K2 CTA of the other stream off that SM until it drains (and the other way round).
+template <int KC, int DMAX, int BITS>
+static cudaError_t i8_set_k1_attr() {
+    return cudaFuncSetAttribute(kstar_i8_kernel<KC, DMAX, BITS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+template <int DMAX>
+static cudaError_t i8_set_k1_attrs_d() {
+    cudaError_t e = i8_set_k1_attr<0, DMAX, 7>();
+    if (e == cudaSuccess) e = i8_set_k1_attr<1, DMAX, 7>();
+    if (e == cudaSuccess) e = i8_set_k1_attr<2, DMAX, 7>();
+    if (e == cudaSuccess) e = i8_set_k1_attr<0, DMAX, 8>();
+    if (e == cudaSuccess) e = i8_set_k1_attr<1, DMAX, 8>();
+    if (e == cudaSuccess) e = i8_set_k1_attr<2, DMAX, 8>();
+    return e;
+}
+static cudaError_t i8_set_k1_attrs() {
+    cudaError_t e = i8_set_k1_attrs_d<2>();
+    if (e == cudaSuccess) e = i8_set_k1_attrs_d<4>();
+    if (e == cudaSuccess) e = i8_set_k1_attrs_d<6>();
+    if (e == cudaSuccess) e = i8_set_k1_attrs_d<8>();
+    if (e == cudaSuccess) e = i8_set_k1_attrs_d<12>();
+    if (e == cudaSuccess) e = i8_set_k1_attrs_d<16>();
+    if (e == cudaSuccess) e = i8_set_k1_attrs_d<24>();
+    if (e == cudaSuccess) e = i8_set_k1_attrs_d<32>();
+    return e;
+}
+
 // builds (once per model state) the packed digit slices of W for `bits`-wide digits, the row scales / constants, alpha
 static int ensure_i8(ibo_model* m, int bits) {
     const int Np = m->Np, nb = m->nb;
@@ -421,6 +449,7 @@ static int ensure_i8(ibo_model* m, int bits) {
         IBO_CUDA_TRY((i8_set_k2_attrs<8, 7>()));
         IBO_CUDA_TRY((i8_set_k2_attrs<7, 8>()));
         IBO_CUDA_TRY((i8_set_k2_attrs<8, 8>()));
+        { static cudaError_t k1e = i8_set_k1_attrs(); IBO_CUDA_TRY(k1e); }
         for (auto& e : m->evI8) if (!e) IBO_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     bool& valid = bits == 8 ? m->i8Valid8 : m->i8Valid;
