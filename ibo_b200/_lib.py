@@ -35,6 +35,7 @@ FLAG_DIRECT_SPECULATE = 0x40
 FLAG_INT8 = 0x80
 FLAG_INT8_G9 = 0x100
 FLAG_INT8_D8 = 0x200
+FLAG_INT8_S6 = 0x400
 E_BADARG, E_CUDA, E_NOTSPD, E_NOMEM, E_COMM = -1, -2, -3, -4, -5
 
 BATCH_OBJECTIVE = ctypes.CFUNCTYPE(None, c_void_p, c_long, c_int, POINTER(c_double), POINTER(c_double))

@@ -572,7 +572,7 @@ static int grow_model_rows(ibo_model* m, int NpNew) {
 }
 
 int append_rows(ibo_model* m, const double* X, const double* Y, int k, int* info) {
-    m->i8Valid = m->i8Valid8 = false;      // W changes: the int8 slices are rebuilt on the next use
+    m->i8Valid = m->i8Valid8 = m->i8Valid6 = false;      // W changes: the int8 slices are rebuilt on the next use
     const int d = m->d;
     IBO_CUDA_TRY(cudaSetDevice(m->device));
     cudaStream_t st = m->stream;
@@ -734,7 +734,7 @@ static void free_model(ibo_model* m) {
     if (m->stream) cudaStreamSynchronize(m->stream);   // blocks go back to the pool: nothing may still be using them
     double** ptrs[] = {&m->dXt, &m->dInvTheta, &m->dCenter, &m->dA, &m->dAorig, &m->dW, &m->dD, &m->dWpack, &m->dBetaY, &m->dBeta1, &m->dY,
                        &m->dPmeans, &m->dPbeta, &m->dPlb, &m->dPwidth, &m->dCand, &m->dSlab, &m->dPart, &m->dOut, &m->dBlkBest, &m->dBest, &m->dAppend,
-                       &m->dWi8, &m->dRowScale, &m->dAlphaY, &m->dAlpha1, &m->dWi8b, &m->dRowScale8};
+                       &m->dWi8, &m->dRowScale, &m->dAlphaY, &m->dAlpha1, &m->dWi8b, &m->dRowScale8, &m->dWi8c};
     for (auto p : ptrs) if (*p) { pool_free(*p); *p = nullptr; }
     if (m->dInfo) cudaFree(m->dInfo);
     if (m->dBlkIdx) cudaFree(m->dBlkIdx);

@@ -36,7 +36,8 @@ struct ibo_model {
     // ([Np] slicing scale, [Np] scale * sf2), alpha = W^T W Y and W^T W 1
     double* dWi8 = nullptr; double* dRowScale = nullptr; double* dAlphaY = nullptr; double* dAlpha1 = nullptr;
     double* dWi8b = nullptr; double* dRowScale8 = nullptr;      // the same for 8-bit digits (IBO_FLAG_INT8_D8)
-    bool i8Valid = false, i8Valid8 = false;
+    double* dWi8c = nullptr;                                     // six 8-bit digits (IBO_FLAG_INT8_S6; scales shared with dRowScale8)
+    bool i8Valid = false, i8Valid8 = false, i8Valid6 = false;
     cudaEvent_t evI8[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // K1 done [2], K2+K3 done [2], fork
     // prior (RBF network), device copies
     int npb = 0;

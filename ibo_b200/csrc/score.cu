@@ -856,8 +856,8 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
     const K2Plan plan = narrow ? plan_narrow_cached(m, ctaTilesAll) : K2Plan{8, pick_groups_wide(nb, chunkTiles)};
     const int subs = 8 / plan.MT;
     const bool i8 = !narrow && !vm && m->d <= 32 && i8_requested(rq.flags);      // experimental int8-emulated K2 (score_i8.cuh)
-    const int i8bits = i8 ? i8_bits(m, rq.flags) : 7;
-    if (i8 && (rc = ensure_i8(m, i8bits))) return rc;
+    const int i8mode = i8 ? i8_mode(m, rq.flags) : 0;
+    if (i8 && (rc = ensure_i8(m, i8mode))) return rc;
     // int8 path: K1 of chunk c+1 (FP64 / integer pipes, stream2) runs under K2 of chunk c (tensor pipe, main stream); slab and
     // partial-sum planes are double buffered.  With IBO_FLAG_PROFILE the chunks run back to back so that K1 / K2 can be timed.
     const bool i8pipe = i8 && !prof && i8_pipe_enabled();
@@ -908,11 +908,11 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
         double* const chunkPart = i8 ? m->dPart + (size_t)buf * i8PartDbl : m->dPart;
         if (i8pipe) {
             if (ci >= 2) IBO_CUDA_TRY(cudaStreamWaitEvent(m->stream2, m->evI8[2 + buf], 0));     // chunk ci-2 is done with this buffer
-            launch_kstar_i8(m, dCand, tiles, M, m0, Mpad, i8Slab, chunkPart, m->stream2, i8bits);
+            launch_kstar_i8(m, dCand, tiles, M, m0, Mpad, i8Slab, chunkPart, m->stream2, i8mode);
             IBO_CUDA_TRY(cudaEventRecord(m->evI8[buf], m->stream2));
             IBO_CUDA_TRY(cudaStreamWaitEvent(st, m->evI8[buf], 0));
         }
-        else if (i8) launch_kstar_i8(m, dCand, tiles, M, m0, Mpad, i8Slab, chunkPart, st, i8bits);
+        else if (i8) launch_kstar_i8(m, dCand, tiles, M, m0, Mpad, i8Slab, chunkPart, st, i8mode);
         else launch_kstar(m, dCand, m->dSlab, tiles, M, m0, st, inl);
         nlaunch++;
         if (vm) {
@@ -920,7 +920,7 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
             nlaunch++;
         }
         if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[2], st));
-        if (i8) launch_trigemm_i8(m, tiles, Mpad, i8Slab, chunkPart, st, i8_g9(rq.flags), i8bits);
+        if (i8) launch_trigemm_i8(m, tiles, Mpad, i8Slab, chunkPart, st, i8_g9(rq.flags), i8mode);
         else if ((rc = launch_trigemm(m, narrow, pl, m->npb > 0, ctaTiles, Mpad, chunkM, st))) return rc;
         nlaunch++; nK2++;
         if (vm) {

@@ -85,10 +85,12 @@ __global__ void __launch_bounds__(256) i8_rowscale_kernel(const double* __restri
     }
 }
 
-template <int BITS>     // digit width: 7 (validated) or 8 (IBO_FLAG_INT8_D8)
+// BITS: digit width, 7 (validated) or 8 (IBO_FLAG_INT8_D8); S: digits per operand, 7 or (8-bit digits only, IBO_FLAG_INT8_S6) 6.
+// The 6-digit variant keeps the 7-slice stage stride and simply leaves the last slice slot unused.
+template <int BITS, int S>
 __global__ void __launch_bounds__(256) i8_slice_w_kernel(const double* __restrict__ W, const double* __restrict__ rowScale, int Np,
                                                          uint8_t* __restrict__ Wi8) {
-    constexpr int FR = BITS * I8_S;                          // fixed-point bits: 49 or 56
+    constexpr int FR = BITS * S;                             // fixed-point bits: 49, 56 or 48
     constexpr long long HALF = 1ll << (BITS - 1), MASK = (1ll << BITS) - 1;
     const int j = blockIdx.x, i = blockIdx.y;                 // k-step, row-block
     if (j >= (i + 1) * 4) return;
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(256) i8_slice_w_kernel(const double* __restric
     // balanced digits, least significant first: d_t in [-2^(BITS-1), 2^(BITS-1) - 1] for t = 7 .. 2, the rest (|d_1| <= 64) is the top digit.
     // Zero-mean digits make the dropped slice pairs (t + u > 8) a zero-mean error that grows like sqrt(N), not N.
 #pragma unroll
-    for (int t = I8_S; t >= 1; t--) {
+    for (int t = S; t >= 1; t--) {
         uint32_t w4[4];
 #pragma unroll
         for (int v = 0; v < 4; v++) {
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(256) i8_slice_w_kernel(const double* __restric
 // direct differences, sliced from a 49-bit fixed-point image, 16 bytes (one core-matrix row) per store; the partial dot
 // products k* . alphaY / k* . alpha1 of the block go to planes 1 / 2 of `part` (what K2 writes as V . beta).
 // ---------------------------------------------------------------------------------------------
-template <int KC, int DMAX, int BITS>
+template <int KC, int DMAX, int BITS, int S>
 __global__ void __launch_bounds__(256) kstar_i8_kernel(const double* __restrict__ Xt, const double* __restrict__ cand,
                                                        const double* __restrict__ inv_theta, const double* __restrict__ center,
                                                        const double* __restrict__ alphaY, const double* __restrict__ alpha1,
@@ -179,7 +181,7 @@ __global__ void __launch_bounds__(256) kstar_i8_kernel(const double* __restrict_
                 q[kk] = qq > 562949953421311ull ? 562949953421311ull : qq;                 // v == 1 (candidate on a training point)
             } else {
                 // 8-bit digits: (v - 1/2) / 2 in [-1/4, 1/4] at 56 fractional bits, signed; rows beyond N contribute nothing
-                q[kk] = (i * 128 + k) < N ? (unsigned long long)__double2ll_rn((v - 0.5) * 36028797018963968.0) : 0ull;   // 2^55
+                q[kk] = (i * 128 + k) < N ? (unsigned long long)__double2ll_rn((v - 0.5) * (double)(1ll << (8 * S - 1))) : 0ull;   // 2^55 (2^47 with 6 digits)
             }
         }
         uint8_t* dst = dst0 + i8_canon(c, c16 * 16);
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(256) kstar_i8_kernel(const double* __restrict_
         } else {
             // balanced base-256 digits, least significant first (as the W slices)
 #pragma unroll
-            for (int t = I8_S; t >= 1; t--) {
+            for (int t = S; t >= 1; t--) {
                 uint32_t w4[4];
 #pragma unroll
                 for (int v = 0; v < 4; v++) {
@@ -236,7 +238,7 @@ __global__ void __launch_bounds__(256) kstar_i8_kernel(const double* __restrict_
 // NG accumulator groups: 7 (t + u <= 8, the validated default) or 8 (t + u <= 9: IBO_FLAG_INT8_G9); BITS: digit width 7 (validated) or 8
 // (IBO_FLAG_INT8_D8: same 28 products, operands rounded at 2^-56 instead of 2^-49; K* sliced as (k - 1/2) / 2 with signed digits, the
 // constant the shift leaves behind comes back as rowConst).  The non-default variants are written for the next round and untested.
-template <int NG, int BITS>
+template <int NG, int BITS, int S>
 __global__ void __launch_bounds__(I8_THREADS, 1) trigemm_i8_kernel(const uint8_t* __restrict__ Wi8, const uint8_t* __restrict__ Ki8,
                                                                     const double* __restrict__ rowScaleSf, double* __restrict__ part,
                                                                     int nb, long Mpad) {
@@ -281,9 +283,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) trigemm_i8_kernel(const uint8_t
                 const uint8_t* Ab = Wi8 + wi8_base(i);
                 for (int j = 0; j < (i + 1) * 4; j++) {
                     mbar_wait(&empty[s], ph ^ 1);
-                    mbar_arrive_expect_tx(&full[s], I8_A_STAGE + I8_B_STAGE);
-                    bulk_g2s(sA + s * I8_A_STAGE, Ab + (size_t)j * I8_A_STAGE, I8_A_STAGE, &full[s]);
-                    bulk_g2s(sB + s * I8_B_STAGE, Bb + (size_t)j * I8_B_STAGE, I8_B_STAGE, &full[s]);
+                    // S slices of each operand (the stage stride stays that of 7 slices)
+                    mbar_arrive_expect_tx(&full[s], S * (I8_A_SLICE + I8_B_SLICE));
+                    bulk_g2s(sA + s * I8_A_STAGE, Ab + (size_t)j * I8_A_STAGE, S * I8_A_SLICE, &full[s]);
+                    bulk_g2s(sB + s * I8_B_STAGE, Bb + (size_t)j * I8_B_STAGE, S * I8_B_SLICE, &full[s]);
                     if (++s == I8_STAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -306,6 +309,15 @@ __global__ void __launch_bounds__(I8_THREADS, 1) trigemm_i8_kernel(const uint8_t
                     // slice t of W against B slices u0 .. u0+n-1: columns 64 (t + u0 - 2), N = 64 n
 #define I8_MMA(t, u0, n, acc) umma_i8(tb + 64u * ((t) + (u0) - 2), umma_smem_desc(a0 + ((t) - 1) * I8_A_SLICE), \
                                       umma_smem_desc(b0 + ((u0) - 1) * I8_B_SLICE), umma_idesc_i8(128, 64 * (n)), acc)
+                    if (S == 6) {
+                        // six 8-bit digits, 21 pairs, t + u <= 7: groups 2..7 on columns 0..383
+                        I8_MMA(1, 1, 4, first); I8_MMA(1, 5, 2, first);
+                        I8_MMA(2, 1, 4, 1u);    I8_MMA(2, 5, 1, 1u);
+                        I8_MMA(3, 1, 4, 1u);
+                        I8_MMA(4, 1, 3, 1u);
+                        I8_MMA(5, 1, 2, 1u);
+                        I8_MMA(6, 1, 1, 1u);
+                    } else {
                     I8_MMA(1, 1, 4, first); I8_MMA(1, 5, 3, first);          // the two t = 1 instructions touch groups 2..8 first
                     if (NG == 7) {
                         I8_MMA(2, 1, 4, 1u);    I8_MMA(2, 5, 2, 1u);
@@ -322,6 +334,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) trigemm_i8_kernel(const uint8_t
                         I8_MMA(5, 1, 4, 1u);
                         I8_MMA(6, 1, 3, 1u);
                         I8_MMA(7, 1, 2, 1u);
+                    }
                     }
 #undef I8_MMA
                     umma_commit(&empty[s]);                          // the stage is free once these MMAs have read it
@@ -356,8 +369,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) trigemm_i8_kernel(const uint8_t
                         const long long hi = (long long)(int)D[0][e] * 16384 + (long long)(int)D[1][e] * 128 + (long long)(int)D[2][e];
                         const long long mid = (long long)(int)D[3][e] * 16384 + (long long)(int)D[4][e] * 128 + (long long)(int)D[5][e];
                         // group 8 at 2^-56 (and group 9 at 2^-63 when it is kept)
-                        const double lo = NG == 7 ? (double)(int)D[6][e] * 1.387778780781445675529539585113525390625e-17
-                                                  : (double)((long long)(int)D[6][e] * 128 + (long long)(int)D[NG - 1][e]) * 1.084202172485504434007452800869941711425781e-19;
+                        constexpr int G8 = NG >= 7 ? 6 : NG - 1;            // (NG == 6 exists only with 8-bit digits; keeps the indices in range)
+                        const double lo = NG == 7 ? (double)(int)D[G8][e] * 1.387778780781445675529539585113525390625e-17
+                                                  : (double)((long long)(int)D[G8][e] * 128 + (long long)(int)D[NG - 1][e]) * 1.084202172485504434007452800869941711425781e-19;
                         v = fma((double)hi, 3.7252902984619140625e-09,                     // 2^-28
                                 fma((double)mid, 1.7763568394002504646778106689453125e-15, // 2^-49
                                     lo));
@@ -366,8 +380,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) trigemm_i8_kernel(const uint8_t
                         // base-256 digits: groups 2..4 at 2^-32, 5..7 at 2^-56, 8 at 2^-64 (9 at 2^-72)
                         const long long hi = (long long)(int)D[0][e] * 65536 + (long long)(int)D[1][e] * 256 + (long long)(int)D[2][e];
                         const long long mid = (long long)(int)D[3][e] * 65536 + (long long)(int)D[4][e] * 256 + (long long)(int)D[5][e];
-                        const double lo = NG == 7 ? (double)(int)D[6][e] * 5.42101086242752217003726400434970855712890625e-20
-                                                  : (double)((long long)(int)D[6][e] * 256 + (long long)(int)D[NG - 1][e]) * 2.1175823681357508476708062516990986740112305e-22;
+                        const double lo = NG == 6 ? 0.0
+                                        : NG == 7 ? (double)(int)D[NG - 1][e] * 5.42101086242752217003726400434970855712890625e-20
+                                                  : (double)((long long)(int)D[NG - 2][e] * 256 + (long long)(int)D[NG - 1][e]) * 2.1175823681357508476708062516990986740112305e-22;
                         v = fma((double)hi, 2.3283064365386962890625e-10,                  // 2^-32
                                 fma((double)mid, 1.387778780781445675529539585113525390625e-17,   // 2^-56
                                     lo));
@@ -398,20 +413,20 @@ __global__ void __launch_bounds__(I8_THREADS, 1) trigemm_i8_kernel(const uint8_t
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-template <int NG, int BITS>
+template <int NG, int BITS, int S = 7>
 static cudaError_t i8_set_k2_attrs() {
-    cudaError_t e = cudaFuncSetAttribute(trigemm_i8_kernel<NG, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(trigemm_i8_kernel<NG, BITS, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM);
     // K1 CTAs of the next chunk are meant to run next to a resident K2 CTA (174 KiB): ask for the largest shared-memory
     // carve-out so that the 21 KiB a smaller configuration would leave do not limit them to one per SM
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(trigemm_i8_kernel<NG, BITS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(trigemm_i8_kernel<NG, BITS, S>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     return e;
 }
 
 // Every K1 variant asks for the same (largest) shared-memory carve-out as K2: an SM has one carve-out at a time, and a K1 CTA that
 // configured it smaller would keep the 174 KiB K2 CTA of the other stream off that SM until it drains (and the other way round).
-template <int KC, int DMAX, int BITS>
+template <int KC, int DMAX, int BITS, int S = 7>
 static cudaError_t i8_set_k1_attr() {
-    return cudaFuncSetAttribute(kstar_i8_kernel<KC, DMAX, BITS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    return cudaFuncSetAttribute(kstar_i8_kernel<KC, DMAX, BITS, S>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 template <int DMAX>
 static cudaError_t i8_set_k1_attrs_d() {
@@ -421,6 +436,9 @@ static cudaError_t i8_set_k1_attrs_d() {
     if (e == cudaSuccess) e = i8_set_k1_attr<0, DMAX, 8>();
     if (e == cudaSuccess) e = i8_set_k1_attr<1, DMAX, 8>();
     if (e == cudaSuccess) e = i8_set_k1_attr<2, DMAX, 8>();
+    if (e == cudaSuccess) e = i8_set_k1_attr<0, DMAX, 8, 6>();
+    if (e == cudaSuccess) e = i8_set_k1_attr<1, DMAX, 8, 6>();
+    if (e == cudaSuccess) e = i8_set_k1_attr<2, DMAX, 8, 6>();
     return e;
 }
 static cudaError_t i8_set_k1_attrs() {
@@ -435,11 +453,12 @@ static cudaError_t i8_set_k1_attrs() {
     return e;
 }
 
-// builds (once per model state) the packed digit slices of W for `bits`-wide digits, the row scales / constants, alpha
-static int ensure_i8(ibo_model* m, int bits) {
+// digit modes: 0 = 7 x 7-bit (validated), 1 = 7 x 8-bit (IBO_FLAG_INT8_D8), 2 = 6 x 8-bit, 21 slice pairs (IBO_FLAG_INT8_S6)
+// builds (once per model state) the packed digit slices of W for the mode, the row scales / constants, alpha
+static int ensure_i8(ibo_model* m, int mode) {
     const int Np = m->Np, nb = m->nb;
     cudaStream_t st = m->stream;
-    if (!m->dAlphaY || !(m->i8Valid || m->i8Valid8)) {
+    if (!m->dAlphaY || !(m->i8Valid || m->i8Valid8 || m->i8Valid6)) {
         for (double** p : {&m->dAlphaY, &m->dAlpha1}) if (*p) { pool_free(*p); *p = nullptr; }
         IBO_CUDA_TRY(pool_malloc((void**)&m->dAlphaY, sizeof(double) * Np));
         IBO_CUDA_TRY(pool_malloc((void**)&m->dAlpha1, sizeof(double) * Np));
@@ -449,28 +468,36 @@ static int ensure_i8(ibo_model* m, int bits) {
         IBO_CUDA_TRY((i8_set_k2_attrs<8, 7>()));
         IBO_CUDA_TRY((i8_set_k2_attrs<7, 8>()));
         IBO_CUDA_TRY((i8_set_k2_attrs<8, 8>()));
+        IBO_CUDA_TRY((i8_set_k2_attrs<6, 8, 6>()));
         { static cudaError_t k1e = i8_set_k1_attrs(); IBO_CUDA_TRY(k1e); }
         for (auto& e : m->evI8) if (!e) IBO_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
-    bool& valid = bits == 8 ? m->i8Valid8 : m->i8Valid;
+    bool& valid = mode == 2 ? m->i8Valid6 : (mode == 1 ? m->i8Valid8 : m->i8Valid);
     if (valid) return IBO_OK;
-    double*& slices = bits == 8 ? m->dWi8b : m->dWi8;
-    double*& scale = bits == 8 ? m->dRowScale8 : m->dRowScale;
-    for (double** p : {&slices, &scale}) if (*p) { pool_free(*p); *p = nullptr; }
+    double*& slices = mode == 2 ? m->dWi8c : (mode == 1 ? m->dWi8b : m->dWi8);
+    double*& scale = mode == 0 ? m->dRowScale : m->dRowScale8;       // the two 8-bit modes share scales and constants
+    if (slices) { pool_free(slices); slices = nullptr; }
     IBO_CUDA_TRY(pool_malloc((void**)&slices, wi8_base(nb)));
-    IBO_CUDA_TRY(pool_malloc((void**)&scale, sizeof(double) * 3 * Np));
-    i8_rowscale_kernel<<<(Np + 7) / 8, 256, 0, st>>>(m->dW, Np, m->N, m->sf2, bits == 8 ? 3 : 2, scale);
-    if (bits == 8) i8_slice_w_kernel<8><<<dim3(nb * 4, nb), 256, 0, st>>>(m->dW, scale, Np, reinterpret_cast<uint8_t*>(slices));
-    else i8_slice_w_kernel<7><<<dim3(nb * 4, nb), 256, 0, st>>>(m->dW, scale, Np, reinterpret_cast<uint8_t*>(slices));
-    g_launches += 2;
+    const bool haveScale = mode != 0 && (m->i8Valid8 || m->i8Valid6) && scale;
+    if (!haveScale) {
+        if (scale) { pool_free(scale); scale = nullptr; }
+        IBO_CUDA_TRY(pool_malloc((void**)&scale, sizeof(double) * 3 * Np));
+        i8_rowscale_kernel<<<(Np + 7) / 8, 256, 0, st>>>(m->dW, Np, m->N, m->sf2, mode == 0 ? 2 : 3, scale);
+        g_launches++;
+    }
+    const dim3 grid(nb * 4, nb);
+    if (mode == 2) i8_slice_w_kernel<8, 6><<<grid, 256, 0, st>>>(m->dW, scale, Np, reinterpret_cast<uint8_t*>(slices));
+    else if (mode == 1) i8_slice_w_kernel<8, 7><<<grid, 256, 0, st>>>(m->dW, scale, Np, reinterpret_cast<uint8_t*>(slices));
+    else i8_slice_w_kernel<7, 7><<<grid, 256, 0, st>>>(m->dW, scale, Np, reinterpret_cast<uint8_t*>(slices));
+    g_launches++;
     IBO_CUDA_TRY(cudaGetLastError());
     valid = true;
     return IBO_OK;
 }
 
-// IBO_INT8 in the environment forces the path for every wide scoring call: 1 = the validated 7-bit digits, 8 = 8-bit digits
-// (IBO_FLAG_INT8_D8), 9 = eighth accumulator group (IBO_FLAG_INT8_G9), 89 = both.  IBO_I8_PIPE=0 runs K1 and K2 back to back
-// on one stream (A/B of the two-stream pipeline).
+// IBO_INT8 in the environment forces the path for every wide scoring call: 1 = the validated 7 x 7-bit digits, 8 = 7 x 8-bit digits
+// (IBO_FLAG_INT8_D8), 6 = 6 x 8-bit digits (IBO_FLAG_INT8_S6), 9 = eighth accumulator group (IBO_FLAG_INT8_G9), 89 = 8 and 9.
+// IBO_I8_PIPE=0 runs K1 and K2 back to back on one stream (A/B of the two-stream pipeline).
 static int i8_env() {
     static int env = -1;
     if (env < 0) { const char* e = getenv("IBO_INT8"); env = e ? atoi(e) : 0; }
@@ -481,12 +508,19 @@ static int i8_effective_flags(int flags) {
     if (env == 1) flags |= IBO_FLAG_INT8;
     if (env == 8 || env == 89) flags |= IBO_FLAG_INT8_D8;
     if (env == 9 || env == 89) flags |= IBO_FLAG_INT8_G9;
+    if (env == 6) flags |= IBO_FLAG_INT8_S6;
     return flags;
 }
 // d <= 32 (K1's register-resident candidate), no variance model
-static bool i8_requested(int flags) { return (i8_effective_flags(flags) & (IBO_FLAG_INT8 | IBO_FLAG_INT8_G9 | IBO_FLAG_INT8_D8)) != 0; }
+static bool i8_requested(int flags) {
+    return (i8_effective_flags(flags) & (IBO_FLAG_INT8 | IBO_FLAG_INT8_G9 | IBO_FLAG_INT8_D8 | IBO_FLAG_INT8_S6)) != 0;
+}
 // 8-bit digits: |D_g| <= 7 pairs x N x 128 x 128 must fit INT32
-static int i8_bits(const ibo_model* m, int flags) { return ((i8_effective_flags(flags) & IBO_FLAG_INT8_D8) && m->Np <= 16384) ? 8 : 7; }
+static int i8_mode(const ibo_model* m, int flags) {
+    const int f = i8_effective_flags(flags);
+    if (m->Np > 16384) return 0;
+    return (f & IBO_FLAG_INT8_S6) ? 2 : ((f & IBO_FLAG_INT8_D8) ? 1 : 0);
+}
 static bool i8_g9(int flags) { return (i8_effective_flags(flags) & IBO_FLAG_INT8_G9) != 0; }
 static bool i8_pipe_enabled() {
     static int v = -1;
@@ -494,49 +528,51 @@ static bool i8_pipe_enabled() {
     return v == 1;
 }
 
-template <int DMAX, int BITS>
+template <int DMAX, int BITS, int S>
 static void launch_kstar_i8_d(ibo_model* m, const double* dCand, dim3 g1, long M, long m0, long Mpad, uint8_t* Ki8, double* part, cudaStream_t st) {
     const int p1 = m->npb > 0 ? 1 : 0;
     if (m->kind <= IBO_KERNEL_SE_ISO)
-        kstar_i8_kernel<0, DMAX, BITS><<<g1, 256, 0, st>>>(m->dXt, dCand, m->dInvTheta, m->dCenter, m->dAlphaY, m->dAlpha1, Ki8, part, m->N, m->d, m->nb, M, m0, Mpad, m->sf2, p1);
+        kstar_i8_kernel<0, DMAX, BITS, S><<<g1, 256, 0, st>>>(m->dXt, dCand, m->dInvTheta, m->dCenter, m->dAlphaY, m->dAlpha1, Ki8, part, m->N, m->d, m->nb, M, m0, Mpad, m->sf2, p1);
     else if (m->kind == IBO_KERNEL_MATERN3)
-        kstar_i8_kernel<1, DMAX, BITS><<<g1, 256, 0, st>>>(m->dXt, dCand, m->dInvTheta, m->dCenter, m->dAlphaY, m->dAlpha1, Ki8, part, m->N, m->d, m->nb, M, m0, Mpad, m->sf2, p1);
+        kstar_i8_kernel<1, DMAX, BITS, S><<<g1, 256, 0, st>>>(m->dXt, dCand, m->dInvTheta, m->dCenter, m->dAlphaY, m->dAlpha1, Ki8, part, m->N, m->d, m->nb, M, m0, Mpad, m->sf2, p1);
     else
-        kstar_i8_kernel<2, DMAX, BITS><<<g1, 256, 0, st>>>(m->dXt, dCand, m->dInvTheta, m->dCenter, m->dAlphaY, m->dAlpha1, Ki8, part, m->N, m->d, m->nb, M, m0, Mpad, m->sf2, p1);
+        kstar_i8_kernel<2, DMAX, BITS, S><<<g1, 256, 0, st>>>(m->dXt, dCand, m->dInvTheta, m->dCenter, m->dAlphaY, m->dAlpha1, Ki8, part, m->N, m->d, m->nb, M, m0, Mpad, m->sf2, p1);
 }
 
-template <int BITS>
+template <int BITS, int S>
 static void launch_kstar_i8_b(ibo_model* m, const double* dCand, long tiles, long M, long m0, long Mpad, uint8_t* Ki8, double* part, cudaStream_t st) {
     dim3 g1((unsigned)(tiles * 2), m->nb);
     const int d = m->d;
-    if (d <= 2) launch_kstar_i8_d<2, BITS>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
-    else if (d <= 4) launch_kstar_i8_d<4, BITS>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
-    else if (d <= 6) launch_kstar_i8_d<6, BITS>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
-    else if (d <= 8) launch_kstar_i8_d<8, BITS>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
-    else if (d <= 12) launch_kstar_i8_d<12, BITS>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
-    else if (d <= 16) launch_kstar_i8_d<16, BITS>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
-    else if (d <= 24) launch_kstar_i8_d<24, BITS>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
-    else launch_kstar_i8_d<32, BITS>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
+    if (d <= 2) launch_kstar_i8_d<2, BITS, S>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
+    else if (d <= 4) launch_kstar_i8_d<4, BITS, S>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
+    else if (d <= 6) launch_kstar_i8_d<6, BITS, S>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
+    else if (d <= 8) launch_kstar_i8_d<8, BITS, S>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
+    else if (d <= 12) launch_kstar_i8_d<12, BITS, S>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
+    else if (d <= 16) launch_kstar_i8_d<16, BITS, S>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
+    else if (d <= 24) launch_kstar_i8_d<24, BITS, S>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
+    else launch_kstar_i8_d<32, BITS, S>(m, dCand, g1, M, m0, Mpad, Ki8, part, st);
 }
 
 // K1 of one chunk on the int8 path; tiles = 128-candidate tiles of the chunk (the slab holds 2 * tiles 64-candidate tiles)
 static void launch_kstar_i8(ibo_model* m, const double* dCand, long tiles, long M, long m0, long Mpad, uint8_t* Ki8, double* part, cudaStream_t st,
-                            int bits = 7) {
-    if (bits == 8) launch_kstar_i8_b<8>(m, dCand, tiles, M, m0, Mpad, Ki8, part, st);
-    else launch_kstar_i8_b<7>(m, dCand, tiles, M, m0, Mpad, Ki8, part, st);
+                            int mode = 0) {
+    if (mode == 2) launch_kstar_i8_b<8, 6>(m, dCand, tiles, M, m0, Mpad, Ki8, part, st);
+    else if (mode == 1) launch_kstar_i8_b<8, 7>(m, dCand, tiles, M, m0, Mpad, Ki8, part, st);
+    else launch_kstar_i8_b<7, 7>(m, dCand, tiles, M, m0, Mpad, Ki8, part, st);
 }
 
 // K2 of one chunk on the int8 path
-static void launch_trigemm_i8(ibo_model* m, long tiles, long Mpad, const uint8_t* Ki8, double* part, cudaStream_t st, bool g9 = false, int bits = 7) {
+static void launch_trigemm_i8(ibo_model* m, long tiles, long Mpad, const uint8_t* Ki8, double* part, cudaStream_t st, bool g9 = false, int mode = 0) {
     int G = std::max(1, m->nb / 4);
     if (tiles * 2 * G < g_num_sms) G = (int)std::min<long>(m->nb, (g_num_sms + tiles * 2 - 1) / (tiles * 2));
     const dim3 grid(G, (unsigned)(tiles * 2));
-    const uint8_t* Wsl = reinterpret_cast<const uint8_t*>(bits == 8 ? m->dWi8b : m->dWi8);
-    const double* rs = (bits == 8 ? m->dRowScale8 : m->dRowScale) + m->Np;
-    if (bits == 8 && g9) trigemm_i8_kernel<8, 8><<<grid, I8_THREADS, I8_SMEM, st>>>(Wsl, Ki8, rs, part, m->nb, Mpad);
-    else if (bits == 8) trigemm_i8_kernel<7, 8><<<grid, I8_THREADS, I8_SMEM, st>>>(Wsl, Ki8, rs, part, m->nb, Mpad);
-    else if (g9) trigemm_i8_kernel<8, 7><<<grid, I8_THREADS, I8_SMEM, st>>>(Wsl, Ki8, rs, part, m->nb, Mpad);
-    else trigemm_i8_kernel<7, 7><<<grid, I8_THREADS, I8_SMEM, st>>>(Wsl, Ki8, rs, part, m->nb, Mpad);
+    const uint8_t* Wsl = reinterpret_cast<const uint8_t*>(mode == 2 ? m->dWi8c : (mode == 1 ? m->dWi8b : m->dWi8));
+    const double* rs = (mode == 0 ? m->dRowScale : m->dRowScale8) + m->Np;
+    if (mode == 2) trigemm_i8_kernel<6, 8, 6><<<grid, I8_THREADS, I8_SMEM, st>>>(Wsl, Ki8, rs, part, m->nb, Mpad);
+    else if (mode == 1 && g9) trigemm_i8_kernel<8, 8, 7><<<grid, I8_THREADS, I8_SMEM, st>>>(Wsl, Ki8, rs, part, m->nb, Mpad);
+    else if (mode == 1) trigemm_i8_kernel<7, 8, 7><<<grid, I8_THREADS, I8_SMEM, st>>>(Wsl, Ki8, rs, part, m->nb, Mpad);
+    else if (g9) trigemm_i8_kernel<8, 7, 7><<<grid, I8_THREADS, I8_SMEM, st>>>(Wsl, Ki8, rs, part, m->nb, Mpad);
+    else trigemm_i8_kernel<7, 7, 7><<<grid, I8_THREADS, I8_SMEM, st>>>(Wsl, Ki8, rs, part, m->nb, Mpad);
 }
 
 // ---- live INT8 tensor peak (bench.py): back-to-back 128 x 256 x 32 MMAs from resident operands, one CTA per SM ----

@@ -69,6 +69,8 @@ extern "C" {
 #define IBO_FLAG_INT8_D8       0x200 /* IBO_FLAG_INT8 with 8-bit instead of 7-bit digits (same 28 products; operands rounded at 2^-56 instead of
                                         2^-49: ~100x smaller error in the CPU model of the scheme, tests/test_int8_model.py).  Written for the
                                         next round; NOT yet run on a device.  Models beyond N = 16384 fall back to 7-bit digits. */
+#define IBO_FLAG_INT8_S6       0x400 /* IBO_FLAG_INT8 with six 8-bit digits per operand: 21 instead of 28 slice products at the accuracy of the
+                                        validated 7 x 7-bit scheme (CPU model).  Written for the next round; NOT yet run on a device. */
 #define IBO_FLAG_GRAD_EXACT    0x10 /* ibo_nlml / ibo_kernel_matrix: analytic Matern-3/2 length-scale derivative instead of
                                        the reference's expression with the unscaled distance (kernel.py:217-222) */
 

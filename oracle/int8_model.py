@@ -74,14 +74,14 @@ def emulated_product(W, K, groups=7):
 
 
 # ---------------------------------------------------------------------------------------------
-# 8-bit digits (IBO_FLAG_INT8_D8): same 28 products, operands rounded at 2^-56
+# 8-bit digits (IBO_FLAG_INT8_D8: 7 digits, same 28 products, operands rounded at 2^-56; IBO_FLAG_INT8_S6: 6 digits, 21 products)
 #   W  (row r) = 2^e_r sum_t 2^(-8t) A_t          A_t: balanced base-256 digits of rint(w 2^(56 - e_r)), |w| 2^-e_r < 1/4
 #   K*         = 1/2 + 2 sum_u 2^(-8u) B_u        B_u: balanced base-256 digits of rint((k - 1/2) 2^55)   (signed: (k - 1/2)/2 in [-1/4, 1/4])
 #   V          = 2 * 2^e_r [2^-32 (D_2 2^16 + D_3 2^8 + D_4) + 2^-56 (D_5 2^16 + D_6 2^8 + D_7) + 2^-64 D_8] + 1/2 sum_k W[r, k]
 # ---------------------------------------------------------------------------------------------
-def _balanced256(q):
-    out = [None] * S
-    for t in range(S, 1, -1):
+def _balanced256(q, ndig):
+    out = [None] * ndig
+    for t in range(ndig, 1, -1):
         dgt = ((q + 128) & 255) - 128
         q = (q - dgt) >> 8
         out[t - 1] = dgt
@@ -89,23 +89,25 @@ def _balanced256(q):
     return out
 
 
-def emulated_product_d8(W, K):
+def emulated_product_d8(W, K, ndig=7):
+    """ndig = 7: IBO_FLAG_INT8_D8 (28 pairs, t + u <= 8); ndig = 6: IBO_FLAG_INT8_S6 (21 pairs, t + u <= 7, operands at 2^-48)"""
     mx = np.max(np.abs(W), axis=1)
     e = np.zeros(len(mx))
     e[mx > 0] = np.floor(np.log2(mx[mx > 0])) + 3
-    A = _balanced256(np.rint(W / 2.0 ** e[:, None] * 2.0 ** 56).astype(np.int64))
-    B = _balanced256(np.rint((K - 0.5) * 2.0 ** 55).astype(np.int64))
+    A = _balanced256(np.rint(W / 2.0 ** e[:, None] * 2.0 ** (8 * ndig)).astype(np.int64), ndig)
+    B = _balanced256(np.rint((K - 0.5) * 2.0 ** (8 * ndig - 1)).astype(np.int64), ndig)
     assert np.max(np.abs(A[0])) <= 64 and np.max(np.abs(B[0])) <= 64
     D = []
-    for g in range(2, 9):
+    for g in range(2, ndig + 2):
         acc = np.zeros((W.shape[0], K.shape[1]), dtype=np.int64)
-        for t in range(1, S + 1):
+        for t in range(1, ndig + 1):
             u = g - t
-            if 1 <= u <= S:
+            if 1 <= u <= ndig:
                 acc += A[t - 1] @ B[u - 1]
         assert np.max(np.abs(acc)) < 2 ** 31
         D.append(acc)
     hi = D[0] * 65536 + D[1] * 256 + D[2]
     mid = D[3] * 65536 + D[4] * 256 + D[5]
-    v = hi.astype(float) * 2.0 ** -32 + (mid.astype(float) * 2.0 ** -56 + D[6].astype(float) * 2.0 ** -64)
+    lo = D[6].astype(float) * 2.0 ** -64 if ndig == 7 else 0.0
+    v = hi.astype(float) * 2.0 ** -32 + (mid.astype(float) * 2.0 ** -56 + lo)
     return v * (2.0 * 2.0 ** e[:, None]) + 0.5 * np.sum(W, axis=1)[:, None]

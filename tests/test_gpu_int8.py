@@ -130,3 +130,15 @@ def test_int8_d8_variant_is_two_digits_tighter(N, d, M, kind, prior):
     c = gp.model.score(Xs, _lib.ACQ_EI, Y.max(), 0.01, flags=_lib.FLAG_MODE_CPP | _lib.FLAG_INT8_D8, want_posterior=True)
     assert _rel(c[1], a[1], 1e-3) <= 1e-12 and _rel(c[2], a[2], 1e-300) <= 1e-12 and _rel(c[0], a[0], 1e-5) <= 1e-11
     assert a[4] == c[4]
+
+
+@pytest.mark.skipif(__import__("os").environ.get("IBO_EXPERIMENTAL_TESTS") != "1",
+                    reason="IBO_FLAG_INT8_S6 (six 8-bit digits, 21 products) has not been run on a device yet; set IBO_EXPERIMENTAL_TESTS=1")
+@pytest.mark.parametrize("N,d,M,kind,prior", [(300, 3, 5000, "se", False), (200, 2, 4100, "se", True), (2048, 6, 20000, "se", False)])
+def test_int8_s6_variant_keeps_the_parity_bound(N, d, M, kind, prior):
+    from ibo_b200 import _lib
+    gp, o, Xs, Y = _case(N, d, M, kind, prior)
+    a = gp.model.score(Xs, _lib.ACQ_EI, Y.max(), 0.01, flags=_lib.FLAG_MODE_CPP, want_posterior=True)
+    c = gp.model.score(Xs, _lib.ACQ_EI, Y.max(), 0.01, flags=_lib.FLAG_MODE_CPP | _lib.FLAG_INT8_S6, want_posterior=True)
+    assert _rel(c[1], a[1], 1e-3) <= TOL and _rel(c[2], a[2], 1e-300) <= TOL and _rel(c[0], a[0], 1e-5) <= TOL
+    assert a[4] == c[4]

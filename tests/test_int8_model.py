@@ -59,5 +59,8 @@ def test_emulated_sigma2_and_ei_stay_inside_the_parity_bound():
     V8 = i8.emulated_product_d8(W, Ks)                    # 8-bit digits (IBO_FLAG_INT8_D8): same 28 products
     s28 = np.clip(1.1 - np.sum(V8 * V8, axis=0), 1e-8, 10)
     assert np.max(np.abs(s28 - s20) / s20) <= 2e-13 and np.max(np.abs(s28 - s20) / s20) <= 0.05 * errs[7][0]
+    V6 = i8.emulated_product_d8(W, Ks, ndig=6)            # six 8-bit digits (IBO_FLAG_INT8_S6): 21 products, today's accuracy
+    s26 = np.clip(1.1 - np.sum(V6 * V6, axis=0), 1e-8, 10)
+    assert np.max(np.abs(s26 - s20) / s20) <= 1e-11
     assert errs[7][0] <= 1e-11 and errs[7][1] <= 1e-10
     assert errs[8][0] <= 0.2 * errs[7][0]                # the eighth group buys a decimal digit (then the 2^-49 rounding of the operands dominates)

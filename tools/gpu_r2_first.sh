@@ -3,8 +3,8 @@
 set -x
 mkdir -p gpurun_out
 ( time timeout 200 python -m pytest tests -x -q -m gpu ) > gpurun_out/r2a_pytest.log 2>&1; tail -4 gpurun_out/r2a_pytest.log
-IBO_EXPERIMENTAL_TESTS=1 timeout 200 python -m pytest tests/test_gpu_int8.py -q -k "d8 or g9" 2>&1 | tail -15
-for v in 1 8 9; do
+IBO_EXPERIMENTAL_TESTS=1 timeout 200 python -m pytest tests/test_gpu_int8.py -q -k "d8 or g9 or s6" 2>&1 | tail -15
+for v in 1 8 6 9; do
   IBO_INT8=$v timeout 100 python bench.py --int8 --steps 3 --warmup 2 --no-cpu-baseline 2>/dev/null | python -c "
 import sys, json
 j = json.loads(sys.stdin.read())
