@@ -194,7 +194,9 @@ int ibo_debug_exp(int device, const double* x, long n, double* out_fast, double*
 /* ---- DIRECT ----------------------------------------------------------------------------------
  * Batched DIRECT following the reference's rectangle rules (cpp/direct.cpp:146-235,372-498).
  * The callback receives n points (n x ndim row-major, original box coordinates) and fills y[n]
- * with the objective being MINIMISED.
+ * with the objective being MINIMISED.  One call per iteration carries every probe point and every child centre that does not
+ * depend on the division order; a second, small call follows only for rectangles whose child centres do (see
+ * IBO_FLAG_DIRECT_SPECULATE).  The set of points evaluated without that flag is exactly the reference's.
  */
 typedef void (*ibo_batch_objective_t)(void* user, long n, int ndim, const double* X, double* y);
 int ibo_direct_batched(ibo_batch_objective_t f, void* user, int ndim, const double* lb, const double* ub,
