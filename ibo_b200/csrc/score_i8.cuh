@@ -469,7 +469,8 @@ static int ensure_i8(ibo_model* m, int mode) {
         IBO_CUDA_TRY((i8_set_k2_attrs<7, 8>()));
         IBO_CUDA_TRY((i8_set_k2_attrs<8, 8>()));
         IBO_CUDA_TRY((i8_set_k2_attrs<6, 8, 6>()));
-        { static cudaError_t k1e = i8_set_k1_attrs(); IBO_CUDA_TRY(k1e); }
+        // (A/B switch for the next round: not part of the configuration that was run on a device)
+        if (getenv("IBO_I8_K1_CARVEOUT")) { static cudaError_t k1e = i8_set_k1_attrs(); IBO_CUDA_TRY(k1e); }
         for (auto& e : m->evI8) if (!e) IBO_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     bool& valid = mode == 2 ? m->i8Valid6 : (mode == 1 ? m->i8Valid8 : m->i8Valid);

@@ -14,4 +14,8 @@ IBO_INT8=1 IBO_I8_PIPE=0 timeout 100 python bench.py --int8 --steps 3 --warmup 2
 import sys, json
 j = json.loads(sys.stdin.read())
 print('no pipeline', 'value', round(j['value']), 'ms/step', round(j['ms_per_step'], 2))"
+IBO_INT8=1 IBO_I8_K1_CARVEOUT=1 timeout 100 python bench.py --int8 --steps 3 --warmup 2 --no-cpu-baseline 2>/dev/null | python -c "
+import sys, json
+j = json.loads(sys.stdin.read())
+print('K1 carve-out hint', 'value', round(j['value']), 'ms/step', round(j['ms_per_step'], 2))"
 timeout 80 python tools/research/i8_check_8192.py 2>&1 | tail -2
