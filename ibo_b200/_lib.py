@@ -21,21 +21,20 @@ EXPORTED = [
     "ibo_nlml", "ibo_kernel_matrix",
     "ibo_posterior_batch", "ibo_score_batch",
     "ibo_cands_create", "ibo_cands_destroy", "ibo_score_resident", "ibo_get_profile", "ibo_launch_count",
-    "ibo_fp64_peak", "ibo_i8_peak", "ibo_host_register", "ibo_host_unregister", "ibo_stream_mark", "ibo_stream_elapsed_ms",
+    "ibo_fp64_peak", "ibo_i8_peak", "ibo_i8_peak2", "ibo_host_register", "ibo_host_unregister", "ibo_stream_mark", "ibo_stream_elapsed_ms",
     "ibo_device_synchronize", "ibo_debug_exp",
     "ibo_direct_batched", "ibo_acqmax", "direct", "acqmaxGP",
     "ibo_comm_unique_id", "ibo_comm_init", "ibo_comm_destroy", "ibo_comm_argmax", "ibo_comm_bcast", "ibo_comm_barrier",
     "ibo_comm_rank", "ibo_comm_size", "ibo_comm_allgather",
+    "ibo_set_option", "ibo_get_option", "ibo_model_last_guarded",
 ]
 
 KERNEL_SE_ARD, KERNEL_SE_ISO, KERNEL_MATERN3, KERNEL_MATERN5, KERNEL_MATERN5_ARD = 0, 1, 2, 3, 4
 ACQ_EI, ACQ_PI, ACQ_UCB = 0, 1, 2
 FLAG_MODE_CPP, FLAG_MODE_PY, FLAG_KSTAR_EXPAND, FLAG_DIRECT_SEQ, FLAG_PROFILE, FLAG_GRAD_EXACT, FLAG_SHARD = 0x0, 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
 FLAG_DIRECT_SPECULATE = 0x40
-FLAG_INT8 = 0x80
-FLAG_INT8_G9 = 0x100
-FLAG_INT8_D8 = 0x200
-FLAG_INT8_S6 = 0x400
+FLAG_INT8 = 0x80      # take the INT8 tensor-core path of wide batches even when option "int8" is 0 (it is on by default)
+FLAG_FP64 = 0x100     # FP64 DMMA kernels for every candidate
 E_BADARG, E_CUDA, E_NOTSPD, E_NOMEM, E_COMM = -1, -2, -3, -4, -5
 
 BATCH_OBJECTIVE = ctypes.CFUNCTYPE(None, c_void_p, c_long, c_int, POINTER(c_double), POINTER(c_double))
@@ -104,6 +103,7 @@ def lib():
     L.ibo_get_profile.argtypes = [c_void_p, pd]
     L.ibo_fp64_peak.argtypes = [c_int, pd]
     L.ibo_i8_peak.argtypes = [c_int, pd]
+    L.ibo_i8_peak2.argtypes = [c_int, c_double, pd, pd]
     L.ibo_host_register.argtypes = [c_void_p, ctypes.c_ulong]
     L.ibo_host_unregister.argtypes = [c_void_p]
     L.ibo_stream_mark.argtypes = [c_void_p, c_int]
@@ -122,6 +122,9 @@ def lib():
     L.ibo_comm_argmax.argtypes = [pd, pl]
     L.ibo_comm_bcast.argtypes = [pd, c_long, c_int]
     L.ibo_comm_allgather.argtypes = [pd, c_long, pd]
+    L.ibo_set_option.argtypes = [c_char_p, c_long]
+    L.ibo_get_option.argtypes = [c_char_p, pl]
+    L.ibo_model_last_guarded.argtypes = [c_void_p]
     _lib = L
     return L
 
@@ -133,6 +136,17 @@ def check(rc, info=None):
     if rc == E_NOTSPD:
         raise NotPositiveDefinite(rc, msg, info)
     raise IBOError(rc, msg)
+
+
+def set_option(name, value):
+    """Process-wide tuning switch of the library (include/ibo_b200.h, "options")."""
+    check(lib().ibo_set_option(name.encode(), int(value)))
+
+
+def get_option(name):
+    v = c_long(0)
+    check(lib().ibo_get_option(name.encode(), ctypes.byref(v)))
+    return v.value
 
 
 def require_gpu():
@@ -283,6 +297,10 @@ class Model(object):
         check(lib().ibo_acqmax(self._h, dptr(lb), dptr(ub), acq, float(ymax), float(parm), flags, int(maxiter), int(maxtime),
                                int(maxsample), ctypes.byref(opt), dptr(optx), ctypes.byref(ns), ctypes.byref(it)))
         return opt.value, optx, ns.value, it.value
+
+    def last_guarded(self):
+        """candidates the last scoring call re-scored on the DMMA path (guard of the INT8 path)"""
+        return int(lib().ibo_model_last_guarded(self._h))
 
     def profile(self):
         out = np.zeros(6)

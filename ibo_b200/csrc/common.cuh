@@ -45,6 +45,20 @@ void set_error(const std::string& s);
 
 extern long g_launches;   // kernels launched by this library (bench.py's gpu_launches)
 
+// ---------------------------------------------------------------------------------------------
+// per-device state and tuning options (util.cu)
+// ---------------------------------------------------------------------------------------------
+// cudaFuncSetAttribute is per device: every kernel family records, per device ordinal, that its attributes are set.
+enum { ATTR_MODEL = 0, ATTR_SCORE, ATTR_TINY, ATTR_I8, ATTR_COUNT };
+struct DevInfo { int sms = 148; bool known = false; bool attrs[ATTR_COUNT] = {false, false, false, false}; };
+DevInfo& dev_info(int device);            // SM count filled on first use
+// Runs `setter` once per (device, family) with `device` current; returns the CUDA error of the first failing call.
+cudaError_t ensure_attrs(int device, int family, cudaError_t (*setter)());
+
+}  // namespace ibo
+#include "options.h"
+namespace ibo {
+
 // A small candidate batch can travel in a kernel's parameter buffer: the launch itself delivers it, no H2D DMA and no PCIe
 // read inside the kernel.  448 doubles keep the parameter block inside the classic 4 KiB limit.
 constexpr int CAND_INLINE = 448;
@@ -85,6 +99,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}"
         ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// Warp-level wait: one lane polls, the others park on the warp barrier.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+    if ((threadIdx.x & 31) == 0) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "WAITW_%=:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+            "@p bra DONEW_%=;\n\t"
+            "bra WAITW_%=;\n\t"
+            "DONEW_%=:\n\t}"
+            ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+    __syncwarp();
 }
 // 1-D bulk async copy global -> shared (TMA engine, SASS: UBLKCP), completion on an mbarrier.
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {

@@ -11,6 +11,7 @@
 // the reference's O(R^2) pair scan, on the same slope expressions, with bit-identical accept / reject
 // decisions (see select()).
 #include "../../include/ibo_b200.h"
+#include "options.h"
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -527,7 +528,7 @@ int run_direct(ibo_batch_objective_t f, void* user, int ndim, const double* lb, 
         if (time(NULL) - start > maxtime) break;
         if (D.nsamples > (long)(unsigned)maxsample) break;
     }
-    if (getenv("IBO_DIRECT_TIMING"))
+    if (ibo::get_option(ibo::OPT_DIRECT_TIMING))
         fprintf(stderr, "[run_direct] host phases: select %.3f ms, probe build %.3f ms, child build %.3f ms, replay+append %.3f ms; "
                         "%zu rectangles, %zu classes; select: class table %.3f ms, %ld slope scans, %ld scan steps\n", 1e3 * g_pt.select, 1e3 * g_pt.probes, 1e3 * g_pt.children, 1e3 * g_pt.replay,
                 R.d.size(), R.ncls, 1e3 * g_pt.sel_build, g_pt.scans, g_pt.scan_steps);
@@ -604,7 +605,7 @@ extern "C" int ibo_acqmax(ibo_model* m, const double* lb, const double* ub, int 
     auto t0 = std::chrono::steady_clock::now();
     // the GPU objective is a pure function of the point (DESIGN.md "Determinism"): the driver may speculate
     int rc = run_direct(gpu_batch, &g, ibo_model_dim(m), lb, ub, maxiter, maxtime, maxsample, flags | IBO_FLAG_DIRECT_SPECULATE, &fmin, optx, nsamples, iterations);
-    if (getenv("IBO_DIRECT_TIMING")) {
+    if (ibo::get_option(ibo::OPT_DIRECT_TIMING)) {
         double tt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         fprintf(stderr, "[ibo_acqmax] total %.3f ms, GPU batches %.3f ms (%ld batches, %ld sharded, %ld points, %.1f us/batch), host driver %.3f ms\n",
                 1e3 * tt, 1e3 * g.t_eval, g.batches, g.sharded_batches, g.points, g.batches ? 1e6 * g.t_eval / g.batches : 0.0, 1e3 * (tt - g.t_eval));

@@ -572,7 +572,7 @@ static int grow_model_rows(ibo_model* m, int NpNew) {
 }
 
 int append_rows(ibo_model* m, const double* X, const double* Y, int k, int* info) {
-    m->i8Valid = m->i8Valid8 = m->i8Valid6 = false;      // W changes: the int8 slices are rebuilt on the next use
+    m->i8Valid = false;      // W changes: the int8 slices are rebuilt on the next use
     const int d = m->d;
     IBO_CUDA_TRY(cudaSetDevice(m->device));
     cudaStream_t st = m->stream;
@@ -618,19 +618,21 @@ int append_rows(ibo_model* m, const double* X, const double* Y, int k, int* info
     return IBO_OK;
 }
 
-static bool g_attr_done = false;
-static std::mutex g_attr_mu;
-static int set_kernel_attrs() {
-    std::lock_guard<std::mutex> lk(g_attr_mu);
-    if (g_attr_done) return IBO_OK;
+// dynamic shared-memory opt-ins of the factorisation kernels (per device: ensure_attrs)
+static cudaError_t set_model_attrs() {
     const int tile_smem = TILE_SMEM_DOUBLES * 8;
-    IBO_CUDA_TRY(cudaFuncSetAttribute(block_step_kernel<MODE_CHOL_PANEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem));
-    IBO_CUDA_TRY(cudaFuncSetAttribute(block_step_kernel<MODE_CHOL_TRAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem));
-    IBO_CUDA_TRY(cudaFuncSetAttribute(block_step_kernel<MODE_TRTRI_SCALE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem));
-    IBO_CUDA_TRY(cudaFuncSetAttribute(block_step_kernel<MODE_TRTRI_UPDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem));
-    IBO_CUDA_TRY(cudaFuncSetAttribute(syrk_identity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem));
-    IBO_CUDA_TRY(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 * PS + 128 + 128 * 129 / 2) * 8));
-    g_attr_done = true;
+    cudaError_t e = cudaFuncSetAttribute(block_step_kernel<MODE_CHOL_PANEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(block_step_kernel<MODE_CHOL_TRAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(block_step_kernel<MODE_TRTRI_SCALE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(block_step_kernel<MODE_TRTRI_UPDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk_identity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 * PS + 128 + 128 * 129 / 2) * 8);
+    return e;
+}
+static int set_kernel_attrs() {
+    int dev = 0;
+    IBO_CUDA_TRY(cudaGetDevice(&dev));
+    IBO_CUDA_TRY(ensure_attrs(dev, ATTR_MODEL, set_model_attrs));
     return IBO_OK;
 }
 
@@ -734,7 +736,7 @@ static void free_model(ibo_model* m) {
     if (m->stream) cudaStreamSynchronize(m->stream);   // blocks go back to the pool: nothing may still be using them
     double** ptrs[] = {&m->dXt, &m->dInvTheta, &m->dCenter, &m->dA, &m->dAorig, &m->dW, &m->dD, &m->dWpack, &m->dBetaY, &m->dBeta1, &m->dY,
                        &m->dPmeans, &m->dPbeta, &m->dPlb, &m->dPwidth, &m->dCand, &m->dSlab, &m->dPart, &m->dOut, &m->dBlkBest, &m->dBest, &m->dAppend,
-                       &m->dWi8, &m->dRowScale, &m->dAlphaY, &m->dAlpha1, &m->dWi8b, &m->dRowScale8, &m->dWi8c};
+                       &m->dWi8s, &m->dWi8t, &m->dRowScale, &m->dAlphaY, &m->dAlpha1, &m->dGuard, &m->dGuardList};
     for (auto p : ptrs) if (*p) { pool_free(*p); *p = nullptr; }
     if (m->dInfo) cudaFree(m->dInfo);
     if (m->dBlkIdx) cudaFree(m->dBlkIdx);
@@ -795,8 +797,12 @@ static int create_common(int device, int kind, const double* hyper, int nhyper, 
     const int Np = m->Np, nb = m->nb;
     auto fail = [&](int code) { free_model(m); return code; };
 #define TRYM(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { set_error(std::string(#expr) + ": " + cudaGetErrorString(e__)); cudaGetLastError(); return fail(e__ == cudaErrorMemoryAllocation ? IBO_E_NOMEM : IBO_E_CUDA); } } while (0)
-    TRYM(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
-    TRYM(cudaStreamCreateWithFlags(&m->stream2, cudaStreamNonBlocking));
+    // main stream at the highest priority, the helper stream at the lowest: on the INT8 path K1 of the next chunk (stream2) fills
+    // the SM resources the resident K2 CTAs (main stream) leave free, and must never keep a K2 CTA waiting for a slot
+    int prLo = 0, prHi = 0;
+    TRYM(cudaDeviceGetStreamPriorityRange(&prLo, &prHi));
+    TRYM(cudaStreamCreateWithPriority(&m->stream, cudaStreamNonBlocking, prHi));
+    TRYM(cudaStreamCreateWithPriority(&m->stream2, cudaStreamNonBlocking, prLo));
     TRYM(cudaEventCreateWithFlags(&m->evStep, cudaEventDisableTiming));
     for (auto& e : m->ev) TRYM(cudaEventCreate(&e));
     TRYM(pool_malloc((void**)&m->dXt, sizeof(double) * (size_t)Np * d));
@@ -826,7 +832,7 @@ static int create_common(int device, int kind, const double* hyper, int nhyper, 
         for (int j = 0; j < d; j++) xt[(size_t)i * d + j] = X[(size_t)i * d + j] * it[j] - ctr[j];
         yp[i] = Y[i]; ones[i] = 1.0;
     }
-    m->hInvTheta = it; m->hCenter = ctr; m->has_cinv = (Cinv != nullptr);
+    m->hInvTheta = it; m->hCenter = ctr; m->has_cinv = (Cinv != nullptr); m->from_inverse = (invR != nullptr);
     TRYM(cudaMemcpyAsync(m->dXt, xt.data(), sizeof(double) * xt.size(), cudaMemcpyHostToDevice, st));
     TRYM(cudaMemcpyAsync(m->dInvTheta, it.data(), sizeof(double) * d, cudaMemcpyHostToDevice, st));
     TRYM(cudaMemcpyAsync(m->dCenter, ctr.data(), sizeof(double) * d, cudaMemcpyHostToDevice, st));
@@ -923,6 +929,7 @@ extern "C" int ibo_model_append(ibo_model* m, const double* X, const double* Y, 
 
 extern "C" int ibo_model_destroy(ibo_model* m) { free_model(m); return IBO_OK; }
 extern "C" int ibo_model_n(const ibo_model* m) { return m ? m->N : IBO_E_BADARG; }
+extern "C" int ibo_model_last_guarded(const ibo_model* m) { return m ? m->lastGuarded : IBO_E_BADARG; }
 extern "C" int ibo_model_dim(const ibo_model* m) { return m ? m->d : IBO_E_BADARG; }
 
 extern "C" int ibo_model_set_variance_model(ibo_model* m, ibo_model* aug) {

@@ -32,13 +32,17 @@ struct ibo_model {
     double* dBeta1 = nullptr;   // [Np]  W 1
     double* dY = nullptr;       // [Np]
     int* dInfo = nullptr;
-    // experimental int8-emulated K2 (score_i8.cuh), built on first use: packed 7-bit slices of W, per-row scales
-    // ([Np] slicing scale, [Np] scale * sf2), alpha = W^T W Y and W^T W 1
-    double* dWi8 = nullptr; double* dRowScale = nullptr; double* dAlphaY = nullptr; double* dAlpha1 = nullptr;
-    double* dWi8b = nullptr; double* dRowScale8 = nullptr;      // the same for 8-bit digits (IBO_FLAG_INT8_D8)
-    double* dWi8c = nullptr;                                     // six 8-bit digits (IBO_FLAG_INT8_S6; scales shared with dRowScale8)
-    bool i8Valid = false, i8Valid8 = false, i8Valid6 = false;
+    bool from_inverse = false;        // built from a caller-supplied inverse (legacy acqmaxGP): sigma^2 >= noise is not guaranteed
+    // INT8 path of wide batches (score_i8.cuh), built on first use: base-256 digits of W -- digits 5..7 packed for shared memory
+    // (dWi8s), digits 1..4 for the TMEM loaders (dWi8t) --, per-row scales ([Np] slicing scale, [Np] 2 scale sf2, [Np] shift
+    // constant), alpha = W^T W Y and W^T W 1
+    double* dWi8s = nullptr; double* dWi8t = nullptr; double* dRowScale = nullptr; double* dAlphaY = nullptr; double* dAlpha1 = nullptr;
+    bool i8Valid = false; int i8Ntm = -1;
     cudaEvent_t evI8[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // K1 done [2], K2+K3 done [2], fork
+    // guard pass of the INT8 path: per-candidate flags + block counts; index list, gathered candidates and their re-scored values
+    double* dGuard = nullptr; size_t guardCap = 0;
+    double* dGuardList = nullptr; size_t guardListCap = 0;
+    int lastGuarded = 0;              // candidates the last scoring call re-scored on the DMMA path
     // prior (RBF network), device copies
     int npb = 0;
     double ptheta = 0;

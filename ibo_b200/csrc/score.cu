@@ -434,6 +434,7 @@ struct EpiParams {
     int nbVarPart; long MpadVar;
     double *score, *mu, *s2;
     double* blkBest; long long* blkIdx; long blk0;
+    double guard_s2; unsigned char* flag;       // INT8 path: candidates with sigma^2 < guard_s2 are flagged for the DMMA re-score
 };
 
 __global__ void __launch_bounds__(256) epilogue_kernel(EpiParams P) {
@@ -490,6 +491,10 @@ __global__ void __launch_bounds__(256) epilogue_kernel(EpiParams P) {
         if (P.npb > 0) m0 = prior_mean(P.cand + (size_t)m * P.d, P.d, P.npb, P.pmeans, P.pbeta, P.ptheta, P.plb, P.pwidth);
         double mu = m0 + p - m0 * p1;
         double s2 = (1.0 + P.noise) - q;
+        // INT8 path only: too close to total cancellation for the integer scheme's absolute error -- the guard pass re-scores
+        // this candidate with the DMMA kernels and merges it into the argmax; here it takes no part in it
+        const bool guarded = P.flag != nullptr && s2 < P.guard_s2;
+        if (P.flag) P.flag[m] = guarded ? 1 : 0;
         const double floor_ = P.mode_py ? 10e-8 : 1e-8;   // gaussianprocess/__init__.py:224 vs cpp/optimizeGP.cpp:150
         s2 = s2 < floor_ ? floor_ : (s2 > 10.0 ? 10.0 : s2);
         if (P.mu) P.mu[m] = mu;
@@ -497,8 +502,10 @@ __global__ void __launch_bounds__(256) epilogue_kernel(EpiParams P) {
         if (P.acq >= 0) {
             double v = acq_value(P.acq, P.mode_py, mu, s2, P.ymax, P.parm);
             if (P.score) P.score[m] = v;
-            if (v == v) { sc = v; idx = m; }   // NaN never wins
-            else idx = m;
+            if (!guarded) {
+                if (v == v) { sc = v; idx = m; }   // NaN never wins
+                else idx = m;
+            }
         }
     }
     if (P.acq < 0 || !P.want_argmax) return;
@@ -546,12 +553,85 @@ __global__ void __launch_bounds__(256) argmax_final_kernel(const double* __restr
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Guard pass of the INT8 path: ordered compaction of the flagged candidates (ascending index, so that "lowest index wins" keeps
+// its meaning), their coordinates gathered for a DMMA re-score, the results scattered back and merged into the argmax.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) guard_count_kernel(const unsigned char* __restrict__ flag, long M, int* __restrict__ blkCount) {
+    const long base = (long)blockIdx.x * 1024 + threadIdx.x * 4;
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) if (base + j < M && flag[base + j]) c++;
+    c = __reduce_add_sync(0xffffffffu, c);
+    __shared__ int ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; w++) t += ws[w]; blkCount[blockIdx.x] = t; }
+}
+// exclusive scan of the block counts in place (one block; nblk <= a few ten thousand); total -> *count
+__global__ void __launch_bounds__(256) guard_scan_kernel(int* __restrict__ blkCount, int nblk, int* __restrict__ count) {
+    __shared__ int part[256];
+    const int per = (nblk + 255) / 256, b0 = threadIdx.x * per, b1 = min(nblk, b0 + per);
+    int s = 0;
+    for (int b = b0; b < b1; b++) s += blkCount[b];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { int run = 0; for (int t = 0; t < 256; t++) { int v = part[t]; part[t] = run; run += v; } *count = run; }
+    __syncthreads();
+    int run = part[threadIdx.x];
+    for (int b = b0; b < b1; b++) { int v = blkCount[b]; blkCount[b] = run; run += v; }
+}
+__global__ void __launch_bounds__(256) guard_gather_kernel(const unsigned char* __restrict__ flag, long M, const int* __restrict__ blkOff,
+                                                           const double* __restrict__ cand, int d, long long* __restrict__ list,
+                                                           double* __restrict__ gcand) {
+    const long base = (long)blockIdx.x * 1024 + threadIdx.x * 4;
+    int f[4], c = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) { f[j] = (base + j < M && flag[base + j]) ? 1 : 0; c += f[j]; }
+    // exclusive prefix of c over the block: warp scan, then the warps in order
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if ((threadIdx.x & 31) >= o) incl += v; }
+    __shared__ int ws[8];
+    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    int off = blkOff[blockIdx.x] + incl - c;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); w++) off += ws[w];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        if (f[j]) {
+            list[off] = base + j;
+            for (int t = 0; t < d; t++) gcand[(size_t)off * d + t] = cand[(size_t)(base + j) * d + t];
+            off++;
+        }
+}
+// out planes [score | mu | s2][M] <- the re-scored values; (best, index) merged with the re-scored set's own argmax
+__global__ void __launch_bounds__(256) guard_scatter_kernel(const long long* __restrict__ list, int count, const double* __restrict__ gout,
+                                                            double* __restrict__ out, long M, int wscore, int wmu, int ws2, int wargmax) {
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k < count) {
+        const long long m = list[k];
+        if (wscore) out[m] = gout[k];
+        if (wmu) out[M + m] = gout[(size_t)count + k];
+        if (ws2) out[2 * M + m] = gout[2 * (size_t)count + k];
+    }
+    if (wargmax && k == 0) {
+        const double gs = gout[3 * (size_t)count];
+        long long gi; memcpy(&gi, &gout[3 * (size_t)count + 1], 8);
+        if (gi >= 0 && gi < count) {
+            const long long gm = list[gi];
+            double bs = out[3 * M];
+            long long bi; memcpy(&bi, &out[3 * M + 1], 8);
+            // the main pass left (-inf, sentinel) when every candidate was guarded; NaN scores never win on either side
+            if (gs > bs || (gs == bs && gm < bi) || !(bs == bs)) { out[3 * M] = gs; memcpy(&out[3 * M + 1], &gm, 8); }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host-side orchestration
 // ---------------------------------------------------------------------------------------------
-static std::once_flag g_score_attr_once;
-static cudaError_t g_score_attr_err = cudaSuccess;
-static int g_num_sms = 148;
 template <int NT, int MT>
 static cudaError_t set_k2_attr() {
     cudaError_t e = cudaFuncSetAttribute(trigemm_kernel<NT, MT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2Cfg<NT, MT>::SMEM);
@@ -562,34 +642,23 @@ static cudaError_t set_k2_attr() {
     }
     return e;
 }
-static void set_score_attrs() {
-    g_score_attr_err = set_k2_attr<4, 8>();
-    if (g_score_attr_err == cudaSuccess) g_score_attr_err = set_k2_attr<1, 8>();
-    if (g_score_attr_err == cudaSuccess) g_score_attr_err = set_k2_attr<1, 4>();
-    if (g_score_attr_err == cudaSuccess) g_score_attr_err = set_k2_attr<1, 2>();
-    if (g_score_attr_err == cudaSuccess) g_score_attr_err = set_k2_attr<1, 1>();
-    if (g_score_attr_err == cudaSuccess)
-        g_score_attr_err = cudaFuncSetAttribute(kstar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 65 * 8);
-    int dev = 0; cudaGetDevice(&dev);
-    cudaDeviceProp pr;
-    if (cudaGetDeviceProperties(&pr, dev) == cudaSuccess) g_num_sms = pr.multiProcessorCount;
+// dynamic shared-memory opt-ins of the scoring kernels; cudaFuncSetAttribute is per device (ensure_attrs runs this once per device)
+static cudaError_t set_score_attrs() {
+    cudaError_t e = set_k2_attr<4, 8>();
+    if (e == cudaSuccess) e = set_k2_attr<1, 8>();
+    if (e == cudaSuccess) e = set_k2_attr<1, 4>();
+    if (e == cudaSuccess) e = set_k2_attr<1, 2>();
+    if (e == cudaSuccess) e = set_k2_attr<1, 1>();
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kstar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 65 * 8);
+    return e;
 }
 
-static long chunk_tiles_default() {
-    static long v = -1;
-    if (v < 0) {
-        const char* e = getenv("IBO_CHUNK_TILES");     // tuning knob (tools/perf_sweep.sh)
-        v = e ? atol(e) : 0;
-        if (v <= 0) v = 2L * g_num_sms;
-    }
-    return v;
+static long chunk_tiles_default(int sms) {
+    const long v = get_option(OPT_CHUNK_TILES);     // tuning knob (tools/perf_sweep.sh)
+    return v > 0 ? v : 2L * sms;
 }
 
-static long narrow_threshold() {
-    static long v = -1;
-    if (v < 0) { const char* e = getenv("IBO_NARROW_MAX"); v = e ? atol(e) : 2048; }
-    return v;
-}
+static long narrow_threshold() { return get_option(OPT_NARROW_MAX); }
 
 // ---------------------------------------------------------------------------------------------
 // K2 launch plans.  A plan fixes the CTA shape (MT), the number G of CTAs that share one candidate tile, and the table
@@ -646,9 +715,8 @@ static void snake_deal(int nb, int G, std::vector<int>* units, std::vector<int>*
 
 struct K2Plan { int MT; int G; };
 
-static K2Plan plan_narrow(int nb, long ctaTiles) {
-    static int forceMT = -1;
-    if (forceMT < 0) { const char* e = getenv("IBO_NARROW_MT"); forceMT = e ? atoi(e) : 0; }
+static K2Plan plan_narrow(int nb, long ctaTiles, int g_num_sms) {
+    const int forceMT = (int)get_option(OPT_NARROW_MT);
     const int mts[4] = {8, 4, 2, 1};
     const int resident[4] = {1, 2, 2, 3};
     const double eff[4] = {1.0, 0.95, 0.75, 0.5};        // achievable share of the DMMA rate (operand traffic per DMMA grows as MT shrinks)
@@ -679,14 +747,14 @@ static K2Plan plan_narrow(int nb, long ctaTiles) {
 static K2Plan plan_narrow_cached(ibo_model* m, long ctaTiles) {
     auto it = m->planCache.find(ctaTiles);
     if (it == m->planCache.end()) {
-        K2Plan pl = plan_narrow(m->nb, ctaTiles);
-        if (getenv("IBO_DEBUG_PLAN")) fprintf(stderr, "[plan_narrow] nb=%d ctaTiles=%ld -> MT=%d G=%d (%ld CTAs)\n", m->nb, ctaTiles, pl.MT, pl.G, ctaTiles * pl.G);
+        K2Plan pl = plan_narrow(m->nb, ctaTiles, dev_info(m->device).sms);
+        if (get_option(OPT_DEBUG_PLAN)) fprintf(stderr, "[plan_narrow] nb=%d ctaTiles=%ld -> MT=%d G=%d (%ld CTAs)\n", m->nb, ctaTiles, pl.MT, pl.G, ctaTiles * pl.G);
         it = m->planCache.emplace(ctaTiles, std::make_pair(pl.MT, pl.G)).first;
     }
     return K2Plan{it->second.first, it->second.second};
 }
 
-static int pick_groups_wide(int nb, long tiles) {
+static int pick_groups_wide(int nb, long tiles, int g_num_sms) {
     long G = std::max(1, nb / 4);
     if (tiles * G < g_num_sms) G = (g_num_sms + tiles - 1) / tiles;
     return (int)std::min<long>(G, nb);
@@ -723,22 +791,17 @@ static cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size
     return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
-static bool pdl_enabled() {
-    const char* e = getenv("IBO_PDL");
-    return !(e && e[0] == '0');
-}
+static bool pdl_enabled() { return get_option(OPT_PDL) != 0; }
 
-static int deep_mode() {       // IBO_K2_DEEP: 0 = never, 1 = whenever the shape is a small one, unset = when the grid fits the SMs
-    const char* e = getenv("IBO_K2_DEEP");
-    return e ? atoi(e) : -1;
-}
+// option k2_deep: 0 = never, 1 = whenever the shape is a small one, -1 (default) = when the grid fits the SMs
+static int deep_mode() { return (int)get_option(OPT_K2_DEEP); }
 
 template <int NT, int MT>
 static void launch_k2_shape(const ibo_model* m, bool p1, dim3 grid, const int* dUnits, const int* dStart, long Mpad, long Mvalid, cudaStream_t st) {
     const bool pdl = (NT == 1) && pdl_enabled();     // small batches only: the throughput shape must not sit on SMs K1 is using
     if constexpr (NT == 1) {
         const int dm = deep_mode();
-        if (dm == 1 || (dm < 0 && (long)grid.x * grid.y <= g_num_sms)) {
+        if (dm == 1 || (dm < 0 && (long)grid.x * grid.y <= dev_info(m->device).sms)) {
             if (p1) launch_ex(trigemm_kernel<NT, MT, true, NT == 1>, grid, dim3(K2_THREADS), K2Cfg<NT, MT, NT == 1>::SMEM, st, pdl,
                               m->dWpack, m->dSlab, m->dBetaY, m->dBeta1, m->dPart, dUnits, dStart, m->nb, Mpad, Mvalid);
             else launch_ex(trigemm_kernel<NT, MT, false, NT == 1>, grid, dim3(K2_THREADS), K2Cfg<NT, MT, NT == 1>::SMEM, st, pdl,
@@ -780,11 +843,7 @@ static void launch_kstar_mma(dim3 grid, cudaStream_t st, const ibo_model* m, con
         kstar_mma_kernel<DP4, 2><<<grid, 256, smem, st>>>(m->dXt, dCand, m->dInvTheta, m->dCenter, slab, m->N, m->d, m->nb, M, m0, m->kind, m->sf2, inl);
 }
 
-static bool kstar_uses_mma(const ibo_model* m) {
-    static int mode = -1;
-    if (mode < 0) { const char* e = getenv("IBO_KSTAR"); mode = (e && !strcmp(e, "direct")) ? 0 : 1; }
-    return mode == 1 && (m->d + 3) / 4 <= 8;
-}
+static bool kstar_uses_mma(const ibo_model* m) { return get_option(OPT_KSTAR_DIRECT) == 0 && (m->d + 3) / 4 <= 8; }
 
 // cross-covariance of one chunk; expansion on the tensor pipe for d <= 32 unless IBO_KSTAR=direct
 // inl != nullptr: the candidates are in *inl (host copy for the parameter buffer) and dCand is not valid
@@ -802,7 +861,7 @@ static void launch_kstar(const ibo_model* m, const double* dCand, double* slab, 
     }
     // few CTAs (DIRECT / gallery batches): split each candidate tile's n-tiles over grid.z until the grid covers the SMs
     unsigned z = 1;
-    while (z < 16 && (long)tiles * m->nb * z < g_num_sms) z *= 2;
+    while (z < 16 && (long)tiles * m->nb * z < dev_info(m->device).sms) z *= 2;
     grid.z = z;
     switch (dp4) {
         case 1: launch_kstar_mma<1>(grid, st, m, dCand, slab, M, m0, I); break;
@@ -821,19 +880,38 @@ static void launch_kstar(const ibo_model* m, const double* dCand, double* slab, 
 #include "score_i8.cuh"
 namespace ibo {
 
+constexpr int FLAG_FORCE_WIDE = 0x40000000;     // internal: K2's throughput shape (and no fused small-model kernel) whatever the batch size
+
+static cudaError_t set_i8_attrs() {
+    cudaError_t e = cudaFuncSetAttribute(trigemm_i8_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Cfg<4>::SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(trigemm_i8_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Cfg<0>::SMEM);
+    return e;
+}
+
+// Which arithmetic scores this batch.  Wide batches (more than `narrow_max` candidates) of a plain model go through the INT8
+// tensor-core path unless the caller forces FP64 (IBO_FLAG_FP64, option int8 = 0); small batches, models with a variance model
+// (PrefGP aug), d > 32 and N > 16384 (INT32 head-room of the 8-bit digits) always take the DMMA kernels.
+static bool use_i8(const ibo_model* m, bool narrow, int flags) {
+    if (narrow || m->var_model || m->d > 32 || m->Np > 16384 || (flags & IBO_FLAG_FP64)) return false;
+    return (flags & IBO_FLAG_INT8) || get_option(OPT_INT8) != 0;
+}
+
 // Runs K1..K4 for M candidates resident at dCand; results land in m->dOut ([score|mu|s2][M]) and
-// the (best score, best index) pair at m->dOut[3M], [3M+1].  Everything is enqueued on m->stream; no host sync here.
+// the (best score, best index) pair at m->dOut[3M], [3M+1].  Everything is enqueued on m->stream; the only host
+// synchronisation is the 4-byte read of the guard count on the INT8 path of a small-noise model.
 static int score_device(ibo_model* m, const double* dCand, long M, const ScoreReq& rq, double* outBase = nullptr,
                         const double* hostCand = nullptr) {
-    std::call_once(g_score_attr_once, set_score_attrs);
-    if (g_score_attr_err != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(g_score_attr_err)); return IBO_E_CUDA; }
+    cudaError_t ae = ensure_attrs(m->device, ATTR_SCORE, set_score_attrs);
+    if (ae != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ae)); return IBO_E_CUDA; }
     if (m->d > 64) { set_error("d > 64 not supported"); return IBO_E_BADARG; }
-    if (tiny_eligible(m, M)) {       // N <= 128, small batch: one fused launch (tiny.cu)
+    const bool forceWide = (rq.flags & FLAG_FORCE_WIDE) != 0;
+    if (!forceWide && tiny_eligible(m, M)) {       // N <= 128, small batch: one fused launch (tiny.cu)
         int rc0;
         if (!outBase && (rc0 = grow(&m->dOut, &m->outCap, (size_t)3 * M + 2))) return rc0;
         return score_tiny(m, dCand, M, rq, outBase ? outBase : m->dOut, hostCand);
     }
     cudaStream_t st = m->stream;
+    const int sms = dev_info(m->device).sms;
     const bool prof = (rq.flags & IBO_FLAG_PROFILE) != 0;
     ibo_model* vm = m->var_model;
     const int nb = m->nb;
@@ -845,31 +923,39 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
         inl = &inlBuf;
     }
     const long tilesTotal = (M + TN - 1) / TN;
-    long chunkTiles = std::min<long>(tilesTotal, chunk_tiles_default());
-    // keep the slab below ~6 GiB
-    while (chunkTiles > 1 && (double)chunkTiles * nb * KB_PER_BLOCK * BLOB * 8.0 > 6.0e9) chunkTiles = (chunkTiles + 1) / 2;
+    long chunkTiles = std::min<long>(tilesTotal, chunk_tiles_default(sms));
+    const bool narrow = !forceWide && M <= narrow_threshold();
+    const bool i8 = use_i8(m, narrow, rq.flags);
+    // keep the slab below ~6 GiB (FP64: 8 N bytes per candidate; INT8: 7 N bytes, double buffered)
+    while (chunkTiles > 1 && (double)chunkTiles * nb * KB_PER_BLOCK * BLOB * (i8 ? 14.0 : 8.0) > 6.0e9) chunkTiles = (chunkTiles + 1) / 2;
     const long Mpad = chunkTiles * TN;
     int rc;
-    if ((rc = grow(&m->dSlab, &m->slabCap, (size_t)chunkTiles * nb * KB_PER_BLOCK * BLOB))) return rc;
-    const bool narrow = M <= narrow_threshold();
     const long ctaTilesAll = narrow ? (std::min<long>(M, Mpad) + 31) / 32 : chunkTiles;      // K2 CTAs along the candidate axis
-    const K2Plan plan = narrow ? plan_narrow_cached(m, ctaTilesAll) : K2Plan{8, pick_groups_wide(nb, chunkTiles)};
+    const K2Plan plan = narrow ? plan_narrow_cached(m, ctaTilesAll) : K2Plan{8, pick_groups_wide(nb, chunkTiles, sms)};
     const int subs = 8 / plan.MT;
-    const bool i8 = !narrow && !vm && m->d <= 32 && i8_requested(rq.flags);      // experimental int8-emulated K2 (score_i8.cuh)
-    const int i8mode = i8 ? i8_mode(m, rq.flags) : 0;
-    if (i8 && (rc = ensure_i8(m, i8mode))) return rc;
-    // int8 path: K1 of chunk c+1 (FP64 / integer pipes, stream2) runs under K2 of chunk c (tensor pipe, main stream); slab and
-    // partial-sum planes are double buffered.  With IBO_FLAG_PROFILE the chunks run back to back so that K1 / K2 can be timed.
-    const bool i8pipe = i8 && !prof && i8_pipe_enabled();
+    if (i8) {
+        ae = ensure_attrs(m->device, ATTR_I8, set_i8_attrs);
+        if (ae != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ae)); return IBO_E_CUDA; }
+        if ((rc = ensure_i8(m))) return rc;
+    }
+    // int8 path: K1 of chunk c+1 (FP64 / integer pipes, low-priority stream2) runs under K2 of chunk c (tensor pipe, main stream);
+    // slab and partial-sum planes are double buffered.  With IBO_FLAG_PROFILE the chunks run back to back so that K1 / K2 can be timed.
+    const bool i8pipe = i8 && !prof && get_option(OPT_I8_PIPE) != 0;
     const size_t i8SlabBytes = (size_t)chunkTiles * 2 * nb * 4 * I8_B_STAGE, i8PartDbl = (size_t)3 * nb * Mpad;
+    // guard pass: only a model whose sigma^2 can get below the threshold needs it (sigma^2 >= noise for a model built from R)
+    const bool guard = i8 && get_option(OPT_I8_GUARD) != 0 && (m->noise < I8_GUARD_S2 || m->from_inverse);
     if (i8) {
         if ((rc = grow(&m->dSlab, &m->slabCap, 2 * ((i8SlabBytes + 7) / 8)))) return rc;
         if ((rc = grow(&m->dPart, &m->partCap, 2 * i8PartDbl))) return rc;
+        if (guard && (rc = grow(&m->dGuard, &m->guardCap, (size_t)(M + 7) / 8 + (size_t)(M + 1023) / 1024 / 2 + 4))) return rc;
         if (i8pipe) {
             IBO_CUDA_TRY(cudaEventRecord(m->evI8[4], st));
             IBO_CUDA_TRY(cudaStreamWaitEvent(m->stream2, m->evI8[4], 0));
         }
+    } else {
+        if ((rc = grow(&m->dSlab, &m->slabCap, (size_t)chunkTiles * nb * KB_PER_BLOCK * BLOB))) return rc;
     }
+    unsigned char* const dFlag = guard ? reinterpret_cast<unsigned char*>(m->dGuard) : nullptr;
     long ci = 0;
     if ((rc = grow(&m->dPart, &m->partCap, (size_t)3 * nb * subs * Mpad))) return rc;
     if ((rc = grow(&m->dOut, &m->outCap, (size_t)3 * M + 2))) return rc;
@@ -879,7 +965,7 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
     }
     K2Plan planV{8, 1};
     if (vm) {
-        planV = narrow ? plan_narrow_cached(vm, ctaTilesAll) : K2Plan{8, pick_groups_wide(vm->nb, chunkTiles)};
+        planV = narrow ? plan_narrow_cached(vm, ctaTilesAll) : K2Plan{8, pick_groups_wide(vm->nb, chunkTiles, sms)};
         if ((rc = grow(&vm->dPart, &vm->partCap, (size_t)3 * vm->nb * (8 / planV.MT) * Mpad))) return rc;
     }
     const long nblkTotal = (M + 7) / 8 + tilesTotal;       // generous upper bound (chunk boundaries, 8-candidate blocks of small batches)
@@ -901,18 +987,18 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
         const long chunkM = std::min<long>(tiles * TN, M - m0);
         const long ctaTiles = narrow ? (chunkM + 31) / 32 : tiles;      // K2 CTAs along the candidate axis
         K2Plan pl = plan;
-        if (!narrow && tiles != chunkTiles) pl.G = pick_groups_wide(nb, tiles);      // last, shorter chunk
+        if (!narrow && tiles != chunkTiles) pl.G = pick_groups_wide(nb, tiles, sms);      // last, shorter chunk
         if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[1], st));
         const int buf = (int)(ci & 1);
         uint8_t* const i8Slab = reinterpret_cast<uint8_t*>(m->dSlab) + (size_t)buf * (((i8SlabBytes + 7) / 8) * 8);
         double* const chunkPart = i8 ? m->dPart + (size_t)buf * i8PartDbl : m->dPart;
         if (i8pipe) {
             if (ci >= 2) IBO_CUDA_TRY(cudaStreamWaitEvent(m->stream2, m->evI8[2 + buf], 0));     // chunk ci-2 is done with this buffer
-            launch_kstar_i8(m, dCand, tiles, M, m0, Mpad, i8Slab, chunkPart, m->stream2, i8mode);
+            launch_kstar_i8(m, dCand, tiles, M, m0, Mpad, i8Slab, chunkPart, m->stream2);
             IBO_CUDA_TRY(cudaEventRecord(m->evI8[buf], m->stream2));
             IBO_CUDA_TRY(cudaStreamWaitEvent(st, m->evI8[buf], 0));
         }
-        else if (i8) launch_kstar_i8(m, dCand, tiles, M, m0, Mpad, i8Slab, chunkPart, st, i8mode);
+        else if (i8) launch_kstar_i8(m, dCand, tiles, M, m0, Mpad, i8Slab, chunkPart, st);
         else launch_kstar(m, dCand, m->dSlab, tiles, M, m0, st, inl);
         nlaunch++;
         if (vm) {
@@ -920,12 +1006,12 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
             nlaunch++;
         }
         if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[2], st));
-        if (i8) launch_trigemm_i8(m, tiles, Mpad, i8Slab, chunkPart, st, i8_g9(rq.flags), i8mode);
+        if (i8) launch_trigemm_i8(m, tiles, Mpad, i8Slab, chunkPart, st);
         else if ((rc = launch_trigemm(m, narrow, pl, m->npb > 0, ctaTiles, Mpad, chunkM, st))) return rc;
         nlaunch++; nK2++;
         if (vm) {
             K2Plan plv = planV;
-            if (!narrow && tiles != chunkTiles) plv.G = pick_groups_wide(vm->nb, tiles);
+            if (!narrow && tiles != chunkTiles) plv.G = pick_groups_wide(vm->nb, tiles, sms);
             if ((rc = launch_trigemm(vm, narrow, plv, false, ctaTiles, Mpad, chunkM, st))) return rc;
             nlaunch++; nK2++;
         }
@@ -942,6 +1028,7 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
         P.s2 = rq.want_s2 ? out + 2 * M : nullptr;
         P.want_argmax = rq.want_argmax ? 1 : 0;
         P.blkBest = m->dBlkBest; P.blkIdx = m->dBlkIdx; P.blk0 = blk0;
+        P.guard_s2 = I8_GUARD_S2; P.flag = dFlag;
         P.rowLanes = !narrow ? 1 : (std::max(P.nbPart, P.nbVarPart) >= 64 ? 32 : (P.nbPart > 16 ? 8 : 1));
         const int cpb = 256 / P.rowLanes;
         const unsigned nblk = (unsigned)((chunkM + cpb - 1) / cpb);
@@ -965,6 +1052,36 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
         nlaunch++;
     }
     g_launches += nlaunch;
+    int guarded = 0;
+    if (guard) {
+        // ---- guard pass: the flagged candidates (ascending index) are re-scored by the DMMA kernels and merged ----
+        const int nblkG = (int)((M + 1023) / 1024);
+        int* blkCnt = reinterpret_cast<int*>(dFlag + (((size_t)M + 7) / 8) * 8);
+        int* dCount = blkCnt + nblkG;
+        guard_count_kernel<<<nblkG, 256, 0, st>>>(dFlag, M, blkCnt);
+        guard_scan_kernel<<<1, 256, 0, st>>>(blkCnt, nblkG, dCount);
+        int count = 0;
+        IBO_CUDA_TRY(cudaMemcpyAsync(&count, dCount, sizeof(int), cudaMemcpyDeviceToHost, st));
+        IBO_CUDA_TRY(cudaStreamSynchronize(st));
+        g_launches += 2;
+        guarded = count;
+        if (count > 0) {
+            if ((rc = grow(&m->dGuardList, &m->guardListCap, (size_t)count * (1 + m->d) + 3 * (size_t)count + 2))) return rc;
+            long long* list = reinterpret_cast<long long*>(m->dGuardList);
+            double* gcand = m->dGuardList + count;
+            double* gout = gcand + (size_t)count * m->d;
+            guard_gather_kernel<<<nblkG, 256, 0, st>>>(dFlag, M, blkCnt, dCand, m->d, list, gcand);
+            ScoreReq r2 = rq;
+            // the throughput shape whatever the count: a guarded candidate then gets exactly the value the FP64 path gives it in any
+            // wide batch -- its score stays a function of (model, x) only
+            r2.flags = (rq.flags | IBO_FLAG_FP64 | FLAG_FORCE_WIDE) & ~(IBO_FLAG_INT8 | IBO_FLAG_PROFILE);
+            if ((rc = score_device(m, gcand, count, r2, gout))) return rc;
+            guard_scatter_kernel<<<(count + 255) / 256, 256, 0, st>>>(list, count, gout, out, M, rq.want_score ? 1 : 0, rq.want_mu ? 1 : 0,
+                                                                       rq.want_s2 ? 1 : 0, (rq.acq >= 0 && rq.want_argmax) ? 1 : 0);
+            g_launches += 2;
+        }
+    }
+    m->lastGuarded = guarded;
     if (prof) {
         IBO_CUDA_TRY(cudaEventRecord(m->ev[5], st));
         IBO_CUDA_TRY(cudaEventSynchronize(m->ev[5]));
@@ -1108,37 +1225,73 @@ extern "C" int ibo_get_profile(ibo_model* m, double* out6) {
     return IBO_OK;
 }
 
-// live INT8 tensor-pipe peak of `device` in TOP/s (int8 multiply-adds x 2), tcgen05.mma kind::i8 issue rate
-extern "C" int ibo_i8_peak(int device, double* tops) {
-    if (!tops) { set_error("bad argument"); return IBO_E_BADARG; }
+// live INT8 tensor-pipe peaks of `device` in TOP/s (int8 multiply-adds x 2), tcgen05.mma kind::i8 issue rate:
+//   burst      best of a few ~2 ms launches with near-constant operand bytes -- the pipe's ceiling at the full SM clock
+//   sustained  pseudo-random operand bytes, launches back to back for `seconds`; the rate over the second half of that time --
+//              what the power cap lets a dense INT8 kernel with real data sustain (the denominator for a kernel timed inside a long step)
+extern "C" int ibo_i8_peak2(int device, double seconds, double* burst_tops, double* sustained_tops) {
     if (ibo_device_count() <= 0) { set_error("no CUDA device available (libibo_b200 has no CPU fallback)"); return IBO_E_CUDA; }
     IBO_CUDA_TRY(cudaSetDevice(device));
-    cudaDeviceProp pr;
-    IBO_CUDA_TRY(cudaGetDeviceProperties(&pr, device));
-    const int sms = pr.multiProcessorCount, iters = 4000, smem = (128 + 256) * 128;
+    const int sms = dev_info(device).sms, iters = 4000, smem = (128 + 256) * 128;
     IBO_CUDA_TRY(cudaFuncSetAttribute(i8_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int* sink = nullptr;
     IBO_CUDA_TRY(cudaMalloc(&sink, sizeof(int) * 128 * sms));
     cudaEvent_t e0, e1;
     IBO_CUDA_TRY(cudaEventCreate(&e0));
     IBO_CUDA_TRY(cudaEventCreate(&e1));
-    double best = 0;
-    for (int r = 0; r < 5; r++) {
+    const double ops = 2.0 * 128 * 256 * 128 * (double)iters * sms;
+    if (burst_tops) {
+        double best = 0;
+        for (int r = 0; r < 5; r++) {
+            IBO_CUDA_TRY(cudaEventRecord(e0));
+            i8_peak_kernel<<<sms, 128, smem>>>(iters, 0, sink);
+            IBO_CUDA_TRY(cudaEventRecord(e1));
+            IBO_CUDA_TRY(cudaEventSynchronize(e1));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (r >= 1) best = std::max(best, ops / (ms * 1e-3) / 1e12);
+            g_launches++;
+        }
+        *burst_tops = best;
+    }
+    if (sustained_tops) {
+        // launches of 10 x iters (~20 ms) back to back; timed over the second half of the run
+        const int big = 10 * iters;
+        int nl = 0, nhalf = 0;
+        float elapsed = 0;
         IBO_CUDA_TRY(cudaEventRecord(e0));
-        i8_peak_kernel<<<sms, 128, smem>>>(iters, sink);
+        while (elapsed < 500.0f * seconds) {             // first half: reach the steady clock
+            i8_peak_kernel<<<sms, 128, smem>>>(big, 1, sink);
+            IBO_CUDA_TRY(cudaEventRecord(e1));
+            IBO_CUDA_TRY(cudaEventSynchronize(e1));
+            cudaEventElapsedTime(&elapsed, e0, e1);
+            nl++;
+        }
+        nhalf = std::max(nl, 1);
+        IBO_CUDA_TRY(cudaEventRecord(e0));
+        for (int r = 0; r < nhalf; r++) i8_peak_kernel<<<sms, 128, smem>>>(big, 1, sink);
         IBO_CUDA_TRY(cudaEventRecord(e1));
         IBO_CUDA_TRY(cudaEventSynchronize(e1));
-        float ms = 0;
-        cudaEventElapsedTime(&ms, e0, e1);
-        const double t = 2.0 * 128 * 256 * 128 * (double)iters * sms / (ms * 1e-3) / 1e12;
-        if (r >= 1 && t > best) best = t;
-        g_launches++;
+        cudaEventElapsedTime(&elapsed, e0, e1);
+        *sustained_tops = 10.0 * ops * nhalf / (elapsed * 1e-3) / 1e12;
+        g_launches += nl + nhalf;
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
     IBO_CUDA_TRY(cudaGetLastError());
-    *tops = best;
     return IBO_OK;
 }
+extern "C" int ibo_i8_peak(int device, double* tops) {
+    if (!tops) { set_error("bad argument"); return IBO_E_BADARG; }
+    return ibo_i8_peak2(device, 0.0, tops, nullptr);
+}
+
+#ifdef IBO_I8_TRACE
+extern "C" int ibo_debug_i8_trace(long long* out, int n) {
+    IBO_CUDA_TRY(cudaDeviceSynchronize());
+    IBO_CUDA_TRY(cudaMemcpyFromSymbol(out, ibo::g_i8_trace, sizeof(long long) * (n < 4096 ? n : 4096)));
+    return IBO_OK;
+}
+#endif
 
 // test hook: K1's exp_nonpos next to libdevice exp for n arguments <= 0 (host arrays)
 extern "C" int ibo_debug_exp(int device, const double* x, long n, double* out_fast, double* out_ref) {

@@ -208,9 +208,13 @@ __global__ void __launch_bounds__(256) tiny_argmax_kernel(const double* __restri
     if (threadIdx.x == 0) { *best = ws[0]; *bestIdx = wi[0]; }
 }
 
-std::once_flag g_tiny_once;
-cudaError_t g_tiny_err = cudaSuccess;
-int g_tiny_sms = 148;
+cudaError_t set_tiny_attrs() {
+    const int maxsm = 200 * 1024;
+    cudaError_t e = cudaFuncSetAttribute(tiny_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tiny_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tiny_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
+    return e;
+}
 
 size_t tiny_smem(int N, int Nvar, int d) {
     return sizeof(double) * ((size_t)(N + Nvar) * (WS + (d | 1)) + TC * 128 + (size_t)TC * d + 3 * d + 3 * 4 * TC);
@@ -231,24 +235,16 @@ bool tiny_eligible(const ibo_model* m, long M) {
     const ibo_model* vm = m->var_model;
     if (vm && (vm->nb != 1 || vm->kind != m->kind || vm->sf2 != m->sf2)) return false;
     if (tiny_smem(m->N, vm ? vm->N : 0, m->d) > TINY_SMEM_MAX) return false;
-    const char* e = getenv("IBO_TINY");          // read per call: the tests compare both paths in one process
-    return !(e && e[0] == '0');
+    return get_option(OPT_TINY) != 0;            // option tiny = 0 disables (the tests compare both paths in one process)
 }
 
 // Scores M candidates at `cand` (device memory, or mapped pinned host memory) into out = [score | mu | s2][M] (+ the argmax
 // pair at out[3M], out[3M+1]); everything is enqueued on m->stream.
 // `host_cand`: the same candidates in host memory when the caller has them there (small batches ride in the parameter buffer)
 int score_tiny(ibo_model* m, const double* cand, long M, const ScoreReq& rq, double* out, const double* host_cand) {
-    std::call_once(g_tiny_once, [] {
-        const int maxsm = (int)TINY_SMEM_MAX;
-        g_tiny_err = cudaFuncSetAttribute(tiny_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
-        if (g_tiny_err == cudaSuccess) g_tiny_err = cudaFuncSetAttribute(tiny_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
-        if (g_tiny_err == cudaSuccess) g_tiny_err = cudaFuncSetAttribute(tiny_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
-        int dev = 0; cudaGetDevice(&dev);
-        cudaDeviceProp pr;
-        if (cudaGetDeviceProperties(&pr, dev) == cudaSuccess) g_tiny_sms = pr.multiProcessorCount;
-    });
-    if (g_tiny_err != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(g_tiny_err)); return IBO_E_CUDA; }
+    const cudaError_t ae = ensure_attrs(m->device, ATTR_TINY, set_tiny_attrs);
+    if (ae != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ae)); return IBO_E_CUDA; }
+    const int g_tiny_sms = dev_info(m->device).sms;
     cudaStream_t st = m->stream;
     const bool prof = (rq.flags & IBO_FLAG_PROFILE) != 0;
     const long ntile = (M + TC - 1) / TC;

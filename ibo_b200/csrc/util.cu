@@ -3,6 +3,88 @@
 //                      denominator on the GPU the bench runs on (MEASURED_PEAKS.json has no FP64 entry)
 //   ibo_host_register  pin a caller-owned NumPy buffer so H2D/D2H copies of the e2e leg are DMA'd directly
 #include "model.cuh"
+#include <cctype>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+
+namespace ibo {
+
+static std::mutex g_dev_mu;
+static DevInfo g_dev[64];
+
+DevInfo& dev_info(int device) {
+    if (device < 0 || device >= 64) device = 0;
+    DevInfo& D = g_dev[device];
+    if (!D.known) {
+        std::lock_guard<std::mutex> lk(g_dev_mu);
+        if (!D.known) {
+            cudaDeviceProp pr;
+            if (cudaGetDeviceProperties(&pr, device) == cudaSuccess) D.sms = pr.multiProcessorCount;
+            else cudaGetLastError();
+            D.known = true;
+        }
+    }
+    return D;
+}
+
+cudaError_t ensure_attrs(int device, int family, cudaError_t (*setter)()) {
+    DevInfo& D = dev_info(device);
+    if (D.attrs[family]) return cudaSuccess;
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    if (D.attrs[family]) return cudaSuccess;
+    int cur = 0;
+    cudaError_t e = cudaGetDevice(&cur);
+    if (e == cudaSuccess && cur != device) e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = setter();
+    if (cur != device) cudaSetDevice(cur);
+    if (e == cudaSuccess) D.attrs[family] = true;
+    return e;
+}
+
+struct OptDef { const char* name; long def; };
+static const OptDef g_optdef[OPT_COUNT] = {
+    {"int8", 1}, {"i8_pipe", 1}, {"chunk_tiles", 0}, {"narrow_max", 2048}, {"narrow_mt", 0}, {"k2_deep", -1}, {"pdl", 1},
+    {"kstar_direct", 0}, {"debug_plan", 0}, {"tiny", -1}, {"direct_timing", 0}, {"shard_min", 0}, {"i8_guard", 1}, {"i8_ntm", 0}, {"i8_dbg", 0}};
+static long g_opt[OPT_COUNT];
+static std::once_flag g_opt_once;
+static void init_options() {
+    for (int i = 0; i < OPT_COUNT; i++) {
+        g_opt[i] = g_optdef[i].def;
+        std::string env = "IBO_";
+        for (const char* c = g_optdef[i].name; *c; c++) env += (char)toupper(*c);
+        const char* e = getenv(env.c_str());
+        if (e && *e) g_opt[i] = atol(e);
+    }
+    // spelling of round 1: IBO_KSTAR=direct
+    const char* e = getenv("IBO_KSTAR");
+    if (e && !strcmp(e, "direct")) g_opt[OPT_KSTAR_DIRECT] = 1;
+}
+long get_option(int id) {
+    std::call_once(g_opt_once, init_options);
+    return (id >= 0 && id < OPT_COUNT) ? g_opt[id] : 0;
+}
+static int find_option(const char* name) {
+    if (!name) return -1;
+    for (int i = 0; i < OPT_COUNT; i++) if (!strcmp(name, g_optdef[i].name)) return i;
+    return -1;
+}
+
+}  // namespace ibo
+
+extern "C" int ibo_set_option(const char* name, long value) {
+    const int id = ibo::find_option(name);
+    if (id < 0) { ibo::set_error(std::string("unknown option: ") + (name ? name : "(null)")); return IBO_E_BADARG; }
+    ibo::get_option(id);          // make sure the defaults / environment presets are in place
+    ibo::g_opt[id] = value;
+    return IBO_OK;
+}
+extern "C" int ibo_get_option(const char* name, long* value) {
+    const int id = ibo::find_option(name);
+    if (id < 0 || !value) { ibo::set_error(std::string("unknown option: ") + (name ? name : "(null)")); return IBO_E_BADARG; }
+    *value = ibo::get_option(id);
+    return IBO_OK;
+}
 
 namespace {
 __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters, double a0, double b0) {

@@ -59,18 +59,13 @@ extern "C" {
                                        instead of in a second batch.  The callback then sees a few points the reference never
                                        samples; their values are discarded, so FMIN/XMIN/nsamples and the trajectory are unchanged.
                                        ibo_acqmax sets it (the GPU objective is pure). */
-#define IBO_FLAG_INT8          0x80 /* EXPERIMENTAL, scoring calls with more than 2048 candidates on models without a variance model:
-                                       sigma^2 through an INT8 tensor-core emulation of the FP64 triangular GEMM (7 x 7-bit Ozaki
-                                       slices, exact INT32 accumulation, FP64 assembly; ibo_b200/csrc/score_i8.cuh) and mu as
-                                       k* . alpha.  Off by default; IBO_INT8=1 in the environment forces it. */
-#define IBO_FLAG_INT8_G9       0x100 /* IBO_FLAG_INT8 with an eighth accumulator group (slice pairs t + u <= 9: 34 instead of 28 products,
-                                        all 512 TMEM columns): ~10x smaller error (the 2^-49 operand rounding remains) for models whose
-                                        sigma^2 gets close to its floor.  Written for the next round; NOT yet run on a device. */
-#define IBO_FLAG_INT8_D8       0x200 /* IBO_FLAG_INT8 with 8-bit instead of 7-bit digits (same 28 products; operands rounded at 2^-56 instead of
-                                        2^-49: ~100x smaller error in the CPU model of the scheme, tests/test_int8_model.py).  Written for the
-                                        next round; NOT yet run on a device.  Models beyond N = 16384 fall back to 7-bit digits. */
-#define IBO_FLAG_INT8_S6       0x400 /* IBO_FLAG_INT8 with six 8-bit digits per operand: 21 instead of 28 slice products at the accuracy of the
-                                        validated 7 x 7-bit scheme (CPU model).  Written for the next round; NOT yet run on a device. */
+#define IBO_FLAG_INT8          0x80 /* scoring calls: take the INT8 tensor-core path even when the option "int8" is 0.  It is the DEFAULT for
+                                       batches of more than 2048 candidates on models without a variance model, d <= 32, N <= 16384:
+                                       sigma^2 through an exact-integer emulation of the FP64 triangular GEMM (7 x 7 base-256 digits,
+                                       28 digit products in INT32 on tcgen05.mma kind::i8, FP64 assembly; ibo_b200/csrc/score_i8.cuh) and
+                                       mu as k* . alpha.  Its error on sum v^2 is that of the FP64 GEMM (~4e-15 vs ~2e-15); candidates
+                                       whose sigma^2 comes out below 2^-10 are re-scored by the FP64 DMMA kernels in the same call. */
+#define IBO_FLAG_FP64          0x100 /* scoring calls: FP64 DMMA kernels for every candidate (no INT8 path) */
 #define IBO_FLAG_GRAD_EXACT    0x10 /* ibo_nlml / ibo_kernel_matrix: analytic Matern-3/2 length-scale derivative instead of
                                        the reference's expression with the unscaled distance (kernel.py:217-222) */
 
@@ -180,8 +175,12 @@ long ibo_launch_count(void);
 /* measurement helpers (bench.py): live FP64 tensor-pipe peak of `device` in TFLOP/s (DMMA.8x8x4 issue rate);
  * page-lock / unlock a caller-owned host buffer so the copies of the end-to-end leg run from pinned memory */
 int ibo_fp64_peak(int device, double* tflops);
-/* live INT8 tensor-pipe peak in TOP/s (tcgen05.mma kind::i8 issue rate): the roofline of the experimental IBO_FLAG_INT8 path */
+/* live INT8 tensor-pipe peak in TOP/s (tcgen05.mma kind::i8 issue rate): the roofline of the INT8 path of wide batches */
 int ibo_i8_peak(int device, double* tops);
+/* the same pipe measured two ways: burst (a few ~2 ms launches, near-constant operand bytes: full SM clock) and sustained
+ * (pseudo-random operand bytes, back to back for `seconds`, rate over the second half: what the power cap lets a dense INT8 kernel
+ * with real data hold).  Either pointer may be NULL. */
+int ibo_i8_peak2(int device, double seconds, double* burst_tops, double* sustained_tops);
 int ibo_host_register(void* p, unsigned long bytes);
 int ibo_host_unregister(void* p);
 /* CUDA events on the model's stream (slot 0 = start, 1 = stop) and their elapsed device time */
@@ -190,6 +189,23 @@ int ibo_stream_elapsed_ms(ibo_model* m, float* ms);
 int ibo_device_synchronize(int device);
 /* test hook: the cross-covariance kernel's own exp (x <= 0) next to libdevice exp, host arrays of n values */
 int ibo_debug_exp(int device, const double* x, long n, double* out_fast, double* out_ref);
+
+/* ---- options -----------------------------------------------------------------------------------
+ * Process-wide tuning / debugging switches, visible at the boundary (no hidden environment reads in the launch paths; an
+ * environment variable IBO_<NAME IN CAPITALS> presets the option when the library is loaded).  Names:
+ *   int8 (1)          wide batches take the INT8 tensor-core path (0: FP64 DMMA everywhere; per call: IBO_FLAG_INT8 / IBO_FLAG_FP64)
+ *   i8_guard (1)      INT8 path: re-score candidates with sigma^2 < 2^-10 on the DMMA path
+ *   i8_pipe (1)       INT8 path: cross-covariance of chunk c+1 on a low-priority stream under the GEMM of chunk c
+ *   chunk_tiles (0)   128-candidate tiles per chunk (0: 2 x number of SMs)
+ *   narrow_max (2048) batches up to this size use the latency shapes of the FP64 GEMM
+ *   narrow_mt (0), k2_deep (-1), pdl (1), kstar_direct (0), tiny (-1)   shape / launch switches of the small-batch path
+ *   debug_plan (0), direct_timing (0)   diagnostics on stderr
+ *   shard_min (0)     sharded DIRECT: batches below this many points are not sharded (0: 64 x ranks)
+ * Unknown names return IBO_E_BADARG. */
+int ibo_set_option(const char* name, long value);
+int ibo_get_option(const char* name, long* value);
+/* candidates the last scoring call on `m` re-scored on the DMMA path (guard of the INT8 path); 0 when the path was not taken */
+int ibo_model_last_guarded(const ibo_model* m);
 
 /* ---- DIRECT ----------------------------------------------------------------------------------
  * Batched DIRECT following the reference's rectangle rules (cpp/direct.cpp:146-235,372-498).

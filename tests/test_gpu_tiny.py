@@ -1,5 +1,5 @@
 """GPU tests of the fused small-model kernel (ibo_b200/csrc/tiny.cu, N <= 128): against the oracle, against the general
-K1 -> K2 -> K3 path (IBO_TINY=0), argmax rules, batch-shape independence, big candidate sets."""
+K1 -> K2 -> K3 path (option tiny = 0), argmax rules, batch-shape independence, big candidate sets."""
 import os
 
 import numpy as np
@@ -11,11 +11,12 @@ pytestmark = pytest.mark.gpu
 
 
 def _general(fn):
-    os.environ["IBO_TINY"] = "0"
+    from ibo_b200 import _lib
+    _lib.set_option("tiny", 0)
     try:
         return fn()
     finally:
-        del os.environ["IBO_TINY"]
+        _lib.set_option("tiny", -1)
 
 
 CASES = [
