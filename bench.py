@@ -6,8 +6,11 @@ Workload (config #2 of BASELINE.json): GaussianProcess, SE-ARD ker
 observations (X ~ U[0,1]^6 seed 0, Y = -Hartman6(X), theta = [.53,.57,2.5,.34,.27,.35], noise 0.1,
 xi 0.01), EI over 2^20 uniform random candidates per GPU (seed 1 + rank).  A "step" is one pass of the
 hot path (K1 cross-covariance -> K2 triangular DMMA GEMM + reduction -> K3 EI epilogue -> argmax) over
-the whole candidate set.  With N>1 every rank scores its own 2^20-candidate shard (weak scaling) and the
-ranks all-reduce the (EI, global index) argmax over NCCL each step.
+the whole candidate set.  Wide batches take the library's default arithmetic: sigma^2 through the INT8 tensor-core emulation of
+the FP64 triangular GEMM (tcgen05.mma kind::i8, exact integer digit products, error of the FP64 GEMM); `--fp64` makes the FP64
+DMMA kernels the main arm, and whichever is not the main arm is timed beside it.  With N>1 every rank scores its own
+2^20-candidate shard (weak scaling) and the ranks all-reduce the (EI, global index) argmax over NCCL each step; a second,
+strong-scaling leg splits rank 0's candidate set over the ranks and checks the NCCL argmax against the single-GPU one.
 
     python bench.py --gpus 1 --steps 5 --warmup 3
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
@@ -118,6 +121,40 @@ class Workload(object):
                       % (self.N * self.M * 8 / 1e9)}
 
 
+def kernel_sass_sha16(kernel):
+    """sha256 (first 16 hex digits) of the SASS instruction text of every instantiation of `kernel` in the shipped library"""
+    import hashlib
+    import re
+    from ibo_b200 import _lib
+    txt = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=120).stdout
+    h, on = hashlib.sha256(), False
+    for ln in txt.splitlines():
+        if "Function :" in ln:
+            on = kernel in ln
+        elif on:
+            m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(.*?);", ln)
+            if m:
+                h.update(m.group(1).strip().encode())
+    return h.hexdigest()[:16]
+
+
+def fp64_peak_crosscheck(clocks):
+    """two independent figures beside the live DMMA peak: the datasheet arithmetic at the clock sampled during the run, and the
+    cuBLAS DGEMM rate measured on this pool in round 1 (profiles/r01_cublas_dgemm.json)"""
+    out = {}
+    try:
+        mhz = clocks.get("sm_mhz") or 1965.0
+        out["datasheet_tflops"] = 148 * 64 * 2 * mhz * 1e6 / 1e12          # 64 FP64 FMA per SM per clock
+        out["datasheet_at_mhz"] = mhz
+    except Exception:
+        pass
+    try:
+        out["cublas_dgemm_tflops_round1"] = json.load(open(os.path.join(ROOT, "profiles", "r01_cublas_dgemm.json")))["cublas_dgemm_tflops"]
+    except Exception:
+        pass
+    return out
+
+
 def flops_per_candidate_k2(N):
     """algorithmic FP64 flops of the dominant kernel per candidate: TRSM N^2 + the two fused N-long
     reductions 4N (F(N,d) = N^2 + N(2d+8); the remaining N(2d+4) belong to K1)."""
@@ -226,18 +263,61 @@ def reference_inputs(wl):
 
 
 def cpu_baseline(wl, seconds=12.0):
+    """(i) the reference's C++ evaluator on all host threads (the headline baseline) and on ONE core; (ii) the reference's
+    NumPy path restated scalar-faithfully (two general LU solves against L per candidate, gaussianprocess/__init__.py:209-210) and the
+    vectorised triangular-solve variant for context.  Every leg is a bounded sample of the workload's candidates."""
+    from oracle import ibo_oracle as orc          # allowed here: cpu_baseline / --impl reference legs only
     kind, cores, run = reference_evaluator()
     invR, X, Y, hyper = reference_inputs(wl)
-    probe = wl.candidates(0)[:4 * cores] if wl.id != 4 else sobol_block(wl.d, 0, 4 * cores)
+    gen = (lambda n: sobol_block(wl.d, 0, n)) if wl.id == 4 else (lambda n: synthetic_candidates(n, wl.d, 0))
+    probe = gen(4 * cores)
     t, _ = run(invR, X, Y, hyper, probe)
     n = int(min(max(len(probe) * seconds / max(t, 1e-6), 4 * cores), 200000))
-    Xs = synthetic_candidates(n, wl.d, 0) if wl.id != 4 else sobol_block(wl.d, 0, n)
+    Xs = gen(n)
     t, _ = run(invR, X, Y, hyper, Xs)
     what = "reference cpp/optimizeGP.cpp GP_Maximizer::negei via oracle/_ref" if kind == "reference" else "oracle/oracle_port.c"
     if wl.id == 4:
         what += "; SE-ARD kernel, the reference has no Matern-5/2 ARD"
-    return {"value": n / t, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": "%d of the workload's candidates, %.1f s on %d host threads (%s)" % (n, t, cores, what)}
+    out = {"value": n / t, "unit": UNIT, "cores": cores, "kind": kind,
+           "sample": "%d of the workload's candidates, %.1f s on %d host threads (%s)" % (n, t, cores, what)}
+    try:    # one core (the reference is single-threaded; the harness fans candidates out over threads)
+        n1 = max(8, int(n / max(cores, 1) * 3.0 / max(t, 1e-6)))
+        n1 = min(n1, 20000)
+        if kind == "reference":
+            pd = POINTER(c_double)
+            H = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libego_harness.so"))
+            H.ref_eval.argtypes = [c_int, c_long, pd, pd, pd, pd, c_int]
+            X1 = gen(n1); o1 = np.empty(n1)
+            t0 = time.perf_counter()
+            H.ref_eval(0, n1, X1.ctypes.data_as(pd), o1.ctypes.data_as(pd), None, None, 1)
+            t1 = time.perf_counter() - t0
+            out["single_core"] = {"value": n1 / t1, "unit": UNIT, "cores": 1, "sample": "%d candidates, %.1f s, same evaluator on one thread" % (n1, t1)}
+    except Exception as e:
+        out["single_core"] = {"error": str(e)}
+    try:    # NumPy path of the reference, scalar-faithful: posterior() per candidate with two general solves against L
+        kspec = orc.KernelSpec(orc.K_MATERN5_ARD if wl.id == 4 else orc.K_SE_ARD, list(wl.theta) + ([1.0] if wl.id == 4 else []), wl.d)
+        gpo = orc.GPOracle(kspec, X, Y, NOISE)
+        ns = 6 if wl.N > 4096 else 16
+        Xn = gen(ns)
+        t0 = time.perf_counter()
+        for x in Xn:
+            mu_, s2_ = gpo.posterior_scalar(x)
+            orc.ei_py(mu_, s2_, float(np.max(Y)), XI)
+        tn = time.perf_counter() - t0
+        nv = 2048
+        Xv = gen(nv)
+        t0 = time.perf_counter()
+        mu_, s2_ = gpo.posterior_batch(Xv)
+        orc.score(orc.ACQ_EI, "py", mu_, s2_, float(np.max(Y)), XI)
+        tv = time.perf_counter() - t0
+        out["numpy_path"] = {"value": ns / tn, "unit": UNIT, "cores": os.cpu_count() or 1,
+                             "sample": "%d candidates, %.1f s: oracle restatement of GaussianProcess.posterior + EI.negf, two numpy.linalg.solve "
+                                       "(general LU) against L per candidate as the reference does (LAPACK threads as configured)" % (ns, tn),
+                             "vectorised_triangular_solve": {"value": nv / tv, "unit": UNIT,
+                                                             "sample": "%d candidates in one scipy solve_triangular call, %.2f s (not what the reference does)" % (nv, tv)}}
+    except Exception as e:
+        out["numpy_path"] = {"error": str(e)}
+    return out
 
 
 def run_reference_arm(args, rank, world):
@@ -507,8 +587,8 @@ def main():
                     help="2: BASELINE configs[1] (default, the metric's config); 4: configs[3], N=8192 Matern-5/2 ARD, 16M Sobol, strong scaling; "
                          "5: configs[4], batched-DIRECT maximizeEI d=20, N=4096, 200 iterations, batches sharded over the GPUs (wall ms)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--int8", action="store_true",
-                    help="time the experimental INT8-tensor-core emulation of K2 (IBO_FLAG_INT8) as the main arm instead of the FP64 DMMA path")
+    ap.add_argument("--fp64", action="store_true",
+                    help="make the FP64 DMMA kernels (IBO_FLAG_FP64) the main arm instead of the library default (INT8 tensor-core path for wide batches)")
     ap.add_argument("--suite", action="store_true", help="extra measurements (maximizeEI wall ms, model build, configs #1/#4/#5)")
     args = ap.parse_args()
     if args.suite:
@@ -551,7 +631,9 @@ def main():
     ymax = float(np.max(Y))
     Xs = wl.candidates(rank)
     cands = _lib.ResidentCandidates(model, Xs)
-    flags = _lib.FLAG_MODE_CPP | (_lib.FLAG_INT8 if args.int8 else 0)
+    use_i8 = (not args.fp64) and N > 128 and N <= 16384 and d <= 32 and _lib.get_option("int8") == 1
+    flags = _lib.FLAG_MODE_CPP | (0 if use_i8 else _lib.FLAG_FP64)
+    other_flags = _lib.FLAG_MODE_CPP | (_lib.FLAG_FP64 if use_i8 else _lib.FLAG_INT8)
 
     def step_resident():
         best, bidx, ms = cands.score(_lib.ACQ_EI, ymax, XI, flags)
@@ -587,53 +669,119 @@ def main():
     t_wall = tw1 - tw0
 
     # ---- dominant kernel (K2) timing from CUDA events on the launching stream, same workload ----
-    k2 = []
-    for _ in range(max(2, min(args.steps, 3)) if wl.id == 2 else 1):
-        cands.score(_lib.ACQ_EI, ymax, XI, flags | _lib.FLAG_PROFILE)
-        k2.append(model.profile())
-    prof = min(k2, key=lambda p: p["k2_ms"])
+    def profile_arm(fl, reps):
+        k2 = []
+        for _ in range(reps):
+            cands.score(_lib.ACQ_EI, ymax, XI, fl | _lib.FLAG_PROFILE)
+            k2.append(model.profile())
+        return min(k2, key=lambda p: p["k2_ms"])
+    prof = profile_arm(flags, max(2, min(args.steps, 3)) if wl.id == 2 else 1)
     peak = c_double(0)
     _lib.check(L.ibo_fp64_peak(device, ctypes.byref(peak)))
+    pk8b, pk8s = c_double(0), c_double(0)
+    if N > 128:
+        _lib.check(L.ibo_i8_peak2(device, 1.5, ctypes.byref(pk8b), ctypes.byref(pk8s)))
+    nbk = (N + 127) // 128
+    i8_ops = 2.0 * 28 * 128 * 32 * 4 * (nbk * (nbk + 1) // 2)           # int8 ops per candidate: 28 digit products per 32-deep k-step
 
-    # ---- experimental INT8-emulated K2 on the same resident candidates (untimed region of the main arm): rate + agreement ----
-    int8_leg = None
+    def k2_traffic(kernel, cpl):
+        """dram__bytes_read.sum + dram__bytes_write.sum of K2 per launch from the committed ncu --set full capture -- used only when
+        the capture was taken from THIS build of the kernel (SASS hash) at this model size"""
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_k2_traffic.json")))[kernel]
+            if tj["n_obs"] != N or tj["sass_sha16"] != kernel_sass_sha16(kernel):
+                return None
+            return (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * cpl / tj["candidates_per_launch"]
+        except Exception:
+            return None
+
+    def k2_roofline(p, int8):
+        """roofline of the dominant kernel of one arm: algorithmic work per launch / average launch time / live peak"""
+        k2_s = p["k2_ms"] * 1e-3 / max(p["k2_launches"], 1)
+        cpl = M / max(p["k2_launches"], 1)
+        fp64_equiv = cpl * flops_per_candidate_k2(N) / k2_s / 1e12
+        if int8:
+            ach = cpl * i8_ops / k2_s / 1e12
+            return {"bound": "tensor", "achieved": ach, "peak": pk8s.value, "unit": "TOP/s (int8)",
+                    "frac": ach / pk8s.value if pk8s.value else None, "traffic": k2_traffic("trigemm_i8_kernel", cpl),
+                    "kernel": "trigemm_i8_kernel (K2 on tcgen05.mma kind::i8)", "int8_ops_per_candidate": i8_ops,
+                    "candidates_per_launch": cpl, "avg_launch_ms": 1e3 * k2_s,
+                    "peak_burst": pk8b.value, "frac_of_burst_peak": ach / pk8b.value if pk8b.value else None,
+                    "fp64_equivalent_tflops": fp64_equiv, "fp64_dmma_peak_tflops": peak.value,
+                    "peak_source": "ibo_i8_peak2 on this GPU: `peak` = tcgen05.mma kind::i8 from resident pseudo-random operands, back to back for "
+                                   "1.5 s, rate over the second half (the kernel runs inside a long, power-capped step: SM clock ~1650 of 1965 MHz); "
+                                   "`peak_burst` = best 2 ms launch with near-constant operand bytes at the full clock"}
+        return {"bound": "tensor", "achieved": fp64_equiv, "peak": peak.value, "unit": "TFLOP/s", "frac": fp64_equiv / peak.value if peak.value else None,
+                "traffic": k2_traffic("trigemm_kernel", cpl), "kernel": "trigemm_kernel (K2 on DMMA.8x8x4)", "flops_per_candidate": flops_per_candidate_k2(N),
+                "candidates_per_launch": cpl, "avg_launch_ms": 1e3 * k2_s,
+                "peak_source": "live DMMA.8x8x4 issue-rate microbenchmark on this GPU (ibo_fp64_peak); MEASURED_PEAKS.json and the profiling "
+                               "guide carry no FP64 figure",
+                "peak_crosscheck": fp64_peak_crosscheck(clocks)}
+
+    # ---- the other arithmetic on the same resident candidates (untimed region of the main arm): rate + agreement ----
+    other_arm = None
     if wl.id == 2 and N > 128:
         try:
-            f8 = _lib.FLAG_MODE_CPP | _lib.FLAG_INT8
-            s_ref, s_i8 = np.empty(M), np.empty(M)
-            b_ref = cands.score(_lib.ACQ_EI, ymax, XI, _lib.FLAG_MODE_CPP, scores_out=s_ref)
-            b_i8 = cands.score(_lib.ACQ_EI, ymax, XI, f8, scores_out=s_i8)
-            ts8 = []
-            for _ in range(3):
-                ts8.append(cands.score(_lib.ACQ_EI, ymax, XI, f8)[2])
-            cands.score(_lib.ACQ_EI, ymax, XI, f8 | _lib.FLAG_PROFILE)
-            p8 = model.profile()
-            pk8 = c_double(0)
-            _lib.check(L.ibo_i8_peak(device, ctypes.byref(pk8)))
-            nbk = (N + 127) // 128
-            ops = 2.0 * 28 * 128 * 32 * 4 * (nbk * (nbk + 1) // 2)           # int8 ops per candidate: 28 slice pairs per k-step
-            int8_leg = {"value": M / (min(ts8) * 1e-3), "unit": UNIT, "ms_per_step": min(ts8),
-                        "k1_ms": p8["k1_ms"], "k2_ms": p8["k2_ms"], "k3_ms": p8["k3_ms"],
-                        "k2_int8_tops": M * ops / (p8["k2_ms"] * 1e-3) / 1e12, "int8_peak_tops": pk8.value,
-                        "k2_frac_of_int8_peak": (M * ops / (p8["k2_ms"] * 1e-3) / 1e12 / pk8.value) if pk8.value else None,
-                        "max_rel_dEI_vs_fp64_path": float(np.max(np.abs(s_i8 - s_ref) / np.maximum(np.abs(s_ref), 1e-5))),
-                        "same_argmax": bool(b_ref[1] == b_i8[1]),
-                        "note": "IBO_FLAG_INT8: sigma^2 through 7 x 7-bit Ozaki slices on tcgen05.mma kind::i8 (28 exact INT32 slice products "
-                                "per FP64 product, FP64 assembly), mu as k*.alpha; K1 of chunk c+1 overlaps K2 of chunk c; off by default"}
-        except Exception as e:       # the experimental leg must never take the main arm down
-            int8_leg = {"error": str(e)}
+            s_main, s_oth = np.empty(M), np.empty(M)
+            b_main = cands.score(_lib.ACQ_EI, ymax, XI, flags, scores_out=s_main)
+            b_oth = cands.score(_lib.ACQ_EI, ymax, XI, other_flags, scores_out=s_oth)
+            tso = [cands.score(_lib.ACQ_EI, ymax, XI, other_flags)[2] for _ in range(3)]
+            po = profile_arm(other_flags, 1)
+            other_arm = {"arithmetic": "FP64 DMMA kernels (IBO_FLAG_FP64)" if use_i8 else "INT8 tensor-core path (IBO_FLAG_INT8)",
+                         "value": M / (min(tso) * 1e-3), "unit": UNIT, "ms_per_step": min(tso),
+                         "kernel_ms_per_step": {"k1_kstar": po["k1_ms"], "k2_trigemm": po["k2_ms"], "k3_epilogue": po["k3_ms"]},
+                         "roofline": k2_roofline(po, not use_i8),
+                         "max_rel_dEI_between_arms": float(np.max(np.abs(s_main - s_oth) / np.maximum(np.abs(s_oth), 1e-5))),
+                         "same_argmax": bool(b_main[1] == b_oth[1])}
+        except Exception as e:       # the side leg must never take the main arm down
+            other_arm = {"error": str(e)}
+
+    # ---- strong-scaling leg (N > 1): rank 0's candidate set cut into one contiguous slice per rank, NCCL argmax checked ----
+    strong = None
+    if world > 1 and wl.id == 2:
+        from ibo_b200.utils.sharding import shard_range
+        X0 = synthetic_candidates(M, d, 0)                       # every rank regenerates rank 0's set (seed 1)
+        lo, hi = shard_range(M, world, rank)
+        csl = _lib.ResidentCandidates(model, np.ascontiguousarray(X0[lo:hi]))
+
+        def step_strong():
+            bs, bi, _ = csl.score(_lib.ACQ_EI, ymax, XI, flags)
+            gi = ctypes.c_long(lo + bi); sv = c_double(bs)
+            _lib.check(L.ibo_comm_argmax(ctypes.byref(sv), ctypes.byref(gi)))
+            return sv.value, gi.value
+        for _ in range(2):
+            step_strong()
+        sync_all()
+        nst = max(3, args.steps)
+        _lib.check(L.ibo_stream_mark(model.handle, 0))
+        for _ in range(nst):
+            sbest = step_strong()
+        _lib.check(L.ibo_stream_mark(model.handle, 1))
+        sync_all()
+        ms_s = c_float(0)
+        _lib.check(L.ibo_stream_elapsed_ms(model.handle, ctypes.byref(ms_s)))
+        single = [0.0, -1.0, 0.0]
+        if rank == 0:                                            # the whole set on one GPU: the N = 1 answer and its time
+            c0 = _lib.ResidentCandidates(model, X0)
+            c0.score(_lib.ACQ_EI, ymax, XI, flags)
+            r1 = [c0.score(_lib.ACQ_EI, ymax, XI, flags) for _ in range(2)]
+            single = [r1[0][0], float(r1[0][1]), min(r[2] for r in r1)]
+            c0.close()
+        strong = (ms_s.value / nst, sbest, single)
+        csl.close()
 
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region ----
+    int8_arg = None if use_i8 else False
     out = np.empty(M)
     L.ibo_host_register(Xs.ctypes.data_as(ctypes.c_void_p), Xs.nbytes)
     L.ibo_host_register(out.ctypes.data_as(ctypes.c_void_p), out.nbytes)
     for _ in range(2 if wl.id == 2 else 1):
-        gp.score_batch(Xs, 'ei', xi=XI, mode='cpp', out=out)
+        gp.score_batch(Xs, 'ei', xi=XI, mode='cpp', out=out, int8=int8_arg)
     sync_all()
     te0 = time.perf_counter()
     n_e2e = max(2, min(args.steps, 5)) if wl.id == 2 else max(1, min(args.steps, 2))
     for _ in range(n_e2e):
-        sc, b, bi = gp.score_batch(Xs, 'ei', xi=XI, mode='cpp', out=out)
+        sc, b, bi = gp.score_batch(Xs, 'ei', xi=XI, mode='cpp', out=out, int8=int8_arg)
         gidx = ctypes.c_long(rank * M + bi); scv = c_double(b)
         if world > 1:
             _lib.check(L.ibo_comm_argmax(ctypes.byref(scv), ctypes.byref(gidx)))
@@ -654,16 +802,16 @@ def main():
     t_dev, t_wall, t_e2e = rmax(t_dev), rmax(t_wall), rmax(t_e2e)
     t_step = max(t_dev, 0.0) / args.steps
     value = world * M / t_step
-    k2_s = prof["k2_ms"] * 1e-3 / max(prof["k2_launches"], 1)
-    cand_per_launch = M / max(prof["k2_launches"], 1)
-    achieved = cand_per_launch * flops_per_candidate_k2(N) / k2_s / 1e12
-    traffic = None
-    try:   # dram__bytes_read.sum + dram__bytes_write.sum of K2 from the committed ncu --set full capture, scaled per launch
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k2_traffic.json")))
-        if tj["n_obs"] == N:
-            traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * cand_per_launch / tj["candidates_per_launch"]
-    except Exception:
-        pass
+    # the step's own argmax, checked on every multi-GPU run: every rank must hold the same (score, global index) after
+    # ibo_comm_argmax, and it must be the maximum over the ranks' local winners (lowest index on ties)
+    argmax_ok = None
+    if dist is not None:
+        loc = cands.score(_lib.ACQ_EI, ymax, XI, flags)
+        allw = [None] * world
+        dist.all_gather_object(allw, (loc[0], rank * M + loc[1], best[0], best[1]))
+        want = max(((w[0], -w[1]) for w in allw))
+        argmax_ok = bool(all((w[2], w[3]) == (want[0], -want[1]) for w in allw))
+    F_step = float(N) * N + N * (2.0 * d + 8.0)
     line = {
         "metric": wl.metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_step, "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None, "dtype": "f64",
@@ -672,34 +820,31 @@ def main():
         "e2e": {"value": world * M / t_e2e, "unit": UNIT, "h2d_bytes_per_step": int(Xs.nbytes), "d2h_bytes_per_step": int(out.nbytes + 16),
                 "api": "GaussianProcess.score_batch -> ibo_score_batch (host buffers, pinned)"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value if peak.value else None,
-                     "traffic": traffic, "kernel": "trigemm_kernel (K2)", "flops_per_candidate": flops_per_candidate_k2(N),
-                     "candidates_per_launch": cand_per_launch, "avg_launch_ms": 1e3 * k2_s,
-                     # the whole step (K1 + K2 + K3 + argmax) against the same peak: F(N,d) = N^2 + N(2d+8) flops per candidate
-                     "step": {"flops_per_candidate": float(N) * N + N * (2.0 * d + 8.0),
-                              "achieved": M * (float(N) * N + N * (2.0 * d + 8.0)) / t_step / 1e12,
-                              "frac": (M * (float(N) * N + N * (2.0 * d + 8.0)) / t_step / 1e12 / peak.value) if peak.value else None},
-                     "peak_source": "live DMMA.8x8x4 issue-rate microbenchmark on this GPU (ibo_fp64_peak); MEASURED_PEAKS.json "
-                                    "and the profiling guide carry no FP64 figure"},
-        "kernel_ms_per_step": {"k1_kstar": prof["k1_ms"], "k2_trigemm": prof["k2_ms"], "k3_epilogue": prof["k3_ms"], "total": prof["total_ms"]},
+        "roofline": k2_roofline(prof, use_i8),
+        "kernel_ms_per_step": {"k1_kstar": prof["k1_ms"], "k2_trigemm": prof["k2_ms"], "k3_epilogue": prof["k3_ms"], "total": prof["total_ms"],
+                               "note": "CUDA events around each kernel with the chunks run back to back (IBO_FLAG_PROFILE); the timed steps "
+                                       "overlap K1 of chunk c+1 with K2 of chunk c on the INT8 path"},
         "wall_ms_per_step": 1e3 * t_wall / args.steps,
         "model_build_s": t_factor, "best": {"ei": best[0], "index": best[1]},
     }
-    if int8_leg is not None:
-        line["int8_emulation"] = int8_leg
-    if args.int8:
-        # main arm on the INT8 path: the dominant kernel is trigemm_i8_kernel, bounded by the INT8 tensor pipe
-        line["config"]["arithmetic"] += " + IBO_FLAG_INT8 (sigma^2 via INT8 tensor-core emulation of the FP64 GEMM)"
-        pk8 = c_double(0)
-        _lib.check(L.ibo_i8_peak(device, ctypes.byref(pk8)))
-        nbk = (N + 127) // 128
-        ops = 2.0 * 28 * 128 * 32 * 4 * (nbk * (nbk + 1) // 2)
-        ach = M * ops / (prof["k2_ms"] * 1e-3) / 1e12
-        line["roofline"] = {"bound": "tensor", "achieved": ach, "peak": pk8.value, "unit": "TOP/s (int8)", "frac": ach / pk8.value if pk8.value else None,
-                            "traffic": None, "kernel": "trigemm_i8_kernel (K2, int8 emulation)", "int8_ops_per_candidate": ops,
-                            "candidates_per_launch": cand_per_launch, "avg_launch_ms": 1e3 * k2_s,
-                            "fp64_equivalent_tflops": achieved, "fp64_dmma_peak_tflops": peak.value,
-                            "peak_source": "live tcgen05.mma kind::i8 issue-rate microbenchmark on this GPU (ibo_i8_peak)"}
+    # the whole step (K1 + K2 + K3 + argmax) as FP64-equivalent work against the DMMA peak: F(N,d) = N^2 + N(2d+8) flops per candidate
+    line["roofline"]["step"] = {"flops_per_candidate": F_step, "fp64_equivalent_tflops": M * F_step / t_step / 1e12,
+                                "frac_of_fp64_dmma_peak": (M * F_step / t_step / 1e12 / peak.value) if peak.value else None}
+    line["config"]["arithmetic"] += ("; sigma^2 through the INT8 tensor-core emulation of the FP64 GEMM (library default for wide batches), "
+                                     "mu as k*.alpha in FP64" if use_i8 else "; FP64 DMMA kernels (IBO_FLAG_FP64)")
+    if other_arm is not None:
+        line["fp64_dmma_arm" if use_i8 else "int8_arm"] = other_arm
+    if argmax_ok is not None:
+        line["argmax_is_max_over_ranks"] = argmax_ok
+    if strong is not None:
+        ms_strong = rmax(strong[0])
+        import torch
+        sg = torch.tensor(strong[2], dtype=torch.float64)
+        dist.broadcast(sg, src=0)
+        line["strong"] = {"workload": "rank 0's %d candidates cut into %d contiguous slices (shard_range), NCCL argmax every step" % (M, world),
+                          "value": M / (ms_strong * 1e-3), "unit": UNIT, "ms_per_step": ms_strong,
+                          "single_gpu_ms_per_step": float(sg[2]), "efficiency_vs_single_gpu": float(sg[2]) / (world * ms_strong),
+                          "argmax_matches_single_gpu": bool(strong[1][0] == float(sg[0]) and strong[1][1] == int(sg[1]))}
     # ---- the "maximizeEI wall ms" half of the metric (this rank's GPU; DIRECT is latency bound and is not sharded) ----
     if rank == 0 and wl.id == 2:
         from ibo_b200.gaussianprocess.kernel import GaussianKernel_ard

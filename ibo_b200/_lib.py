@@ -35,7 +35,7 @@ FLAG_MODE_CPP, FLAG_MODE_PY, FLAG_KSTAR_EXPAND, FLAG_DIRECT_SEQ, FLAG_PROFILE, F
 FLAG_DIRECT_SPECULATE = 0x40
 FLAG_INT8 = 0x80      # take the INT8 tensor-core path of wide batches even when option "int8" is 0 (it is on by default)
 FLAG_FP64 = 0x100     # FP64 DMMA kernels for every candidate
-E_BADARG, E_CUDA, E_NOTSPD, E_NOMEM, E_COMM = -1, -2, -3, -4, -5
+E_BADARG, E_CUDA, E_NOTSPD, E_NOMEM, E_COMM, E_OBJECTIVE = -1, -2, -3, -4, -5, -6
 
 BATCH_OBJECTIVE = ctypes.CFUNCTYPE(None, c_void_p, c_long, c_int, POINTER(c_double), POINTER(c_double))
 OBJECTIVE = ctypes.CFUNCTYPE(c_double, c_int, POINTER(c_double))

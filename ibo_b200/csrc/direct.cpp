@@ -118,6 +118,7 @@ struct Driver {
     double FMIN = MAX_DOUBLE;
     std::vector<double> XMIN;
     long nsamples = 0;
+    bool failed = false;        // the objective reported a failed evaluation (NaN): the run stops, nothing else is evaluated
     std::vector<double> xbuf;   // batch staging (box coordinates)
 
     // unit cube -> box (cpp/direct.cpp:113-120)
@@ -137,7 +138,14 @@ struct Driver {
         xbuf.resize((size_t)n * N);
         y.resize(n);
         for (long p = 0; p < n; p++) to_box(&unit_pts[(size_t)p * N], &xbuf[(size_t)p * N]);
+        // NaN is how a batch objective says "this evaluation failed" (a CUDA error, a failed peer rank, a Python exception in the
+        // callback): DIRECT on NaN values is meaningless, so the first one ends the run with IBO_E_OBJECTIVE instead of iterating
+        // on garbage until maxiter.  Under IBO_FLAG_SHARD every rank sees the same values, hence stops at the same batch.
+        if (failed) { for (long p = 0; p < n; p++) y[p] = 0.0; return; }
         if (n > 0) f(user, n, N, xbuf.data(), y.data());
+        for (long p = 0; p < n; p++)
+            if (y[p] != y[p]) { failed = true; break; }
+        if (failed) for (long p = 0; p < n; p++) y[p] = 0.0;
     }
 };
 
@@ -525,6 +533,7 @@ int run_direct(ibo_batch_objective_t f, void* user, int ndim, const double* lb, 
             if (ns > (long)(unsigned)maxsample) { done = true; break; }
         }
         divide(D, R, order, seq, speculate, W);
+        if (D.failed) break;
         if (time(NULL) - start > maxtime) break;
         if (D.nsamples > (long)(unsigned)maxsample) break;
     }
@@ -533,6 +542,7 @@ int run_direct(ibo_batch_objective_t f, void* user, int ndim, const double* lb, 
                         "%zu rectangles, %zu classes; select: class table %.3f ms, %ld slope scans, %ld scan steps\n", 1e3 * g_pt.select, 1e3 * g_pt.probes, 1e3 * g_pt.children, 1e3 * g_pt.replay,
                 R.d.size(), R.ncls, 1e3 * g_pt.sel_build, g_pt.scans, g_pt.scan_steps);
     g_pt = PhaseTimes();
+    if (D.failed) { set_error("DIRECT: the objective reported a failed evaluation (NaN)"); return IBO_E_OBJECTIVE; }
     if (fmin) *fmin = D.FMIN;
     if (xmin) for (int i = 0; i < ndim; i++) xmin[i] = D.XMIN.empty() ? lb[i] : D.XMIN[i];
     if (nsamples) *nsamples = D.nsamples;
@@ -556,31 +566,43 @@ struct GpuObjective {
 };
 void gpu_batch(void* user, long n, int ndim, const double* X, double* y) {
     GpuObjective* g = static_cast<GpuObjective*>(user);
-    if (g->rc != IBO_OK) { for (long i = 0; i < n; i++) y[i] = 0.0; return; }
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    // (the driver stops calling after the first NaN; under IBO_FLAG_SHARD all ranks are then in the same state)
+    if (g->rc != IBO_OK) { for (long i = 0; i < n; i++) y[i] = nan; return; }
     auto t0 = std::chrono::steady_clock::now();
     const int world = (g->flags & IBO_FLAG_SHARD) ? ibo_comm_size() : 1;
     if (world > 1 && n >= g->shard_min) {
         // Every rank runs the same deterministic driver on the same model; a batch is cut into `world` contiguous slices
         // of `per` points, rank r evaluates slice r, and the values are all-gathered (NCCL over NVLink).  A candidate's
         // value does not depend on the batch it is evaluated in (DESIGN.md "Determinism"), so the trajectory is the
-        // single-GPU one bit for bit.
+        // single-GPU one bit for bit.  Slot `per` of every rank's block carries its status: a local failure reaches
+        // every rank in the same collective, and all of them end the query (nobody is left waiting in the next all-gather).
         const long per = (n + world - 1) / world;
         const int rank = ibo_comm_rank();
         const long lo = std::min((long)rank * per, n), hi = std::min(lo + per, n);
-        g->mine.assign((size_t)per, 0.0);
-        g->all.resize((size_t)per * world);
-        if (hi > lo) g->rc = eval_neg_acq(g->m, X + (size_t)lo * ndim, hi - lo, g->acq, g->ymax, g->parm, g->flags, g->mine.data());
-        // the collective is entered even after a local failure so that the other ranks are not left waiting
-        int rc2 = ibo_comm_allgather(g->mine.data(), per, g->all.data());
-        if (g->rc == IBO_OK) g->rc = rc2;
-        if (g->rc == IBO_OK) std::memcpy(y, g->all.data(), sizeof(double) * (size_t)n);
+        g->mine.assign((size_t)per + 1, 0.0);
+        g->all.resize((size_t)(per + 1) * world);
+        int rcLocal = IBO_OK;
+        if (hi > lo) rcLocal = eval_neg_acq(g->m, X + (size_t)lo * ndim, hi - lo, g->acq, g->ymax, g->parm, g->flags, g->mine.data());
+        g->mine[(size_t)per] = rcLocal == IBO_OK ? 0.0 : 1.0;
+        int rc2 = ibo_comm_allgather(g->mine.data(), per + 1, g->all.data());
+        g->rc = rcLocal != IBO_OK ? rcLocal : rc2;
+        if (g->rc == IBO_OK) {
+            for (int r = 0; r < world; r++)
+                if (g->all[(size_t)r * (per + 1) + per] != 0.0) { g->rc = IBO_E_COMM; set_error("sharded DIRECT: rank " + std::to_string(r) + " failed to evaluate its slice"); break; }
+        }
+        if (g->rc == IBO_OK)
+            for (int r = 0; r < world; r++) {
+                const long a = std::min((long)r * per, n), b = std::min(a + per, n);
+                if (b > a) std::memcpy(y + a, g->all.data() + (size_t)r * (per + 1), sizeof(double) * (size_t)(b - a));
+            }
         g->sharded_batches++;
     } else {
         g->rc = eval_neg_acq(g->m, X, n, g->acq, g->ymax, g->parm, g->flags, y);
     }
     g->t_eval += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     g->batches++; g->points += n;
-    if (g->rc != IBO_OK) for (long i = 0; i < n; i++) y[i] = 0.0;
+    if (g->rc != IBO_OK) for (long i = 0; i < n; i++) y[i] = nan;
 }
 
 }  // namespace

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <mutex>
 #include <map>
+#include <set>
 
 namespace ibo {
 
@@ -729,8 +730,19 @@ extern "C" int ibo_device_count(void) {
     return n;
 }
 
+// live models: destroying one that is still attached as another model's variance model detaches it there first
+static std::mutex g_live_mu;
+static std::set<ibo_model*> g_live;
+
+static void register_model(ibo_model* m) { std::lock_guard<std::mutex> lk(g_live_mu); g_live.insert(m); }
+
 static void free_model(ibo_model* m) {
     if (!m) return;
+    {
+        std::lock_guard<std::mutex> lk(g_live_mu);
+        g_live.erase(m);
+        for (ibo_model* o : g_live) if (o->var_model == m) o->var_model = nullptr;
+    }
     cudaSetDevice(m->device);
     if (m->stream2) cudaStreamSynchronize(m->stream2);
     if (m->stream) cudaStreamSynchronize(m->stream);   // blocks go back to the pool: nothing may still be using them
@@ -888,6 +900,7 @@ static int create_common(int device, int kind, const double* hyper, int nhyper, 
         return fail(IBO_E_NOTSPD);
     }
 #undef TRYM
+    register_model(m);
     *out = m;
     return IBO_OK;
 }

@@ -218,10 +218,21 @@ class GaussianProcess(object):
         if self._Cinv is not None:
             Cinv[:n, :n] = self._Cinv
         self._augCinv = Cinv
-        if self._augmodel is not None:
-            self._augmodel.close()
-        self._augmodel = self._build(self.augX, np.zeros(na), Cinv)
-        self._model.set_variance_model(self._augmodel)
+        # build the new factor first and swap it in before the old one goes away: if the build fails (not positive definite,
+        # out of memory) the main model must not keep pointing at a destroyed variance model
+        old = self._augmodel
+        try:
+            new = self._build(self.augX, np.zeros(na), Cinv)
+        except Exception:
+            self._model.set_variance_model(None)
+            self._augmodel = None
+            if old is not None:
+                old.close()
+            raise
+        self._model.set_variance_model(new)
+        self._augmodel = new
+        if old is not None:
+            old.close()
 
     def __del__(self):
         try:

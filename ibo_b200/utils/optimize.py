@@ -30,20 +30,19 @@ def _run(batch_cb, bounds, maxiter, maxtime, maxsample, flags):
     err = []
 
     def cb(user, n, ndim, X, y):
+        out = np.ctypeslib.as_array(y, shape=(n,))
         try:
             P = np.ctypeslib.as_array(X, shape=(n, ndim))
-            vals = np.asarray(batch_cb(P), dtype=float).reshape(-1)
-            for i in range(n):
-                y[i] = vals[i]
-        except BaseException as e:     # never unwind through C
+            out[:] = np.asarray(batch_cb(P), dtype=float).reshape(-1)
+        except BaseException as e:     # never unwind through C: NaN tells the driver to stop (IBO_E_OBJECTIVE)
             err.append(e)
-            for i in range(n):
-                y[i] = 0.0
-    _lib.check(_lib.lib().ibo_direct_batched(_lib.BATCH_OBJECTIVE(cb), None, len(lower), _lib.dptr(lower), _lib.dptr(upper),
-                                             int(maxiter), int(maxtime), int(maxsample), flags, ctypes.byref(fmin), _lib.dptr(xmin),
-                                             ctypes.byref(ns), ctypes.byref(it)))
+            out[:] = np.nan
+    rc = _lib.lib().ibo_direct_batched(_lib.BATCH_OBJECTIVE(cb), None, len(lower), _lib.dptr(lower), _lib.dptr(upper),
+                                       int(maxiter), int(maxtime), int(maxsample), flags, ctypes.byref(fmin), _lib.dptr(xmin),
+                                       ctypes.byref(ns), ctypes.byref(it))
     if err:
         raise err[0]
+    _lib.check(rc)
     return fmin.value, xmin, ns.value
 
 

@@ -2,8 +2,8 @@
 rank r scores the contiguous index range shard_range(M, world, r) with no data-path collective; the only
 exchange is the (score, global index) argmax, merged with the lowest-global-index-wins rule so that the result
 equals first-occurrence argmax over the whole set.  On GPUs the exchange is ibo_comm_argmax (NCCL all-gather of
-16-byte pairs, ibo_b200/csrc/comm.cu); `allreduce_argmax` can also run over any torch.distributed group (gloo in
-the CPU tests) so the host logic is testable without NCCL."""
+16-byte pairs, ibo_b200/csrc/comm.cu).  The gloo twins used by the CPU tests (the same merge rule and the same batch
+slicing over torch.distributed) live in tests/dist_helpers.py: nothing in this package imports torch."""
 import numpy as np
 
 
@@ -27,42 +27,18 @@ def merge_argmax(scores, indices):
     return float(best_s), int(best_i)
 
 
-def allreduce_argmax(score, index, group_dist=None):
-    """all ranks receive the global (score, index)"""
-    if group_dist is None:
-        import ctypes
-        from .. import _lib
-        s, i = ctypes.c_double(score), ctypes.c_long(index)
-        _lib.check(_lib.lib().ibo_comm_argmax(ctypes.byref(s), ctypes.byref(i)))
-        return s.value, i.value
-    import torch
-    world = group_dist.get_world_size()
-    mine = torch.tensor([score, float(index)], dtype=torch.float64)   # indices < 2^53 are exact in f64
-    allp = [torch.zeros(2, dtype=torch.float64) for _ in range(world)]
-    group_dist.all_gather(allp, mine)
-    return merge_argmax([float(p[0]) for p in allp], [int(p[1]) for p in allp])
+def allreduce_argmax(score, index):
+    """all ranks receive the global (score, index): ibo_comm_argmax over the communicator set up with ibo_comm_init"""
+    import ctypes
+    from .. import _lib
+    s, i = ctypes.c_double(score), ctypes.c_long(index)
+    _lib.check(_lib.lib().ibo_comm_argmax(ctypes.byref(s), ctypes.byref(i)))
+    return s.value, i.value
 
 
-def sharded_batch_objective(batch_fn, group_dist, min_points=0):
-    """Wrap a batch objective P (n, d) -> values (n,) so that each rank of `group_dist` (a torch.distributed-like module:
-    get_rank / get_world_size / all_gather) evaluates one contiguous slice of ceil(n / world) points and the values are
-    all-gathered -- the host-side twin of IBO_FLAG_SHARD in ibo_acqmax (ibo_b200/csrc/direct.cpp: gpu_batch), usable with
-    utils.optimize.direct(batch_objective=...).  Every rank must drive the same deterministic DIRECT."""
-    import torch
-    world, rank = group_dist.get_world_size(), group_dist.get_rank()
-
-    def f(P):
-        P = np.asarray(P, dtype=float)
-        n = len(P)
-        if world == 1 or n < min_points:
-            return np.asarray(batch_fn(P), dtype=float).reshape(-1)
-        per = (n + world - 1) // world
-        lo = min(rank * per, n)
-        hi = min(lo + per, n)
-        mine = torch.zeros(per, dtype=torch.float64)
-        if hi > lo:
-            mine[:hi - lo] = torch.from_numpy(np.ascontiguousarray(np.asarray(batch_fn(P[lo:hi]), dtype=float).reshape(-1)))
-        parts = [torch.zeros(per, dtype=torch.float64) for _ in range(world)]
-        group_dist.all_gather(parts, mine)
-        return torch.cat(parts).numpy()[:n].copy()
-    return f
+def batch_slice(n, world, rank):
+    """[lo, hi) of the slice of an n-point DIRECT batch that `rank` evaluates under IBO_FLAG_SHARD (ibo_b200/csrc/direct.cpp:
+    gpu_batch): ceil(n / world) points per rank, the last ranks may get fewer or none"""
+    per = (int(n) + int(world) - 1) // int(world)
+    lo = min(rank * per, n)
+    return lo, min(lo + per, n)

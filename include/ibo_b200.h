@@ -76,6 +76,7 @@ extern "C" {
 #define IBO_E_NOTSPD     -3   /* Cholesky failed; *info = 1-based index of the first bad pivot */
 #define IBO_E_NOMEM      -4
 #define IBO_E_COMM       -5
+#define IBO_E_OBJECTIVE  -6   /* DIRECT: the batch objective reported a failed evaluation (a NaN value); the run was stopped */
 
 typedef struct ibo_model ibo_model;   /* opaque: owns device memory + one CUDA stream */
 typedef struct ibo_cands ibo_cands;   /* opaque: a candidate set resident in HBM */
@@ -213,6 +214,8 @@ int ibo_model_last_guarded(const ibo_model* m);
  * with the objective being MINIMISED.  One call per iteration carries every probe point and every child centre that does not
  * depend on the division order; a second, small call follows only for rectangles whose child centres do (see
  * IBO_FLAG_DIRECT_SPECULATE).  The set of points evaluated without that flag is exactly the reference's.
+ * A NaN value means "this evaluation failed": the driver stops at once and returns IBO_E_OBJECTIVE (the reference has no error
+ * channel -- an exception in its Python callback aborts the C call through ctypes).
  */
 typedef void (*ibo_batch_objective_t)(void* user, long n, int ndim, const double* X, double* y);
 int ibo_direct_batched(ibo_batch_objective_t f, void* user, int ndim, const double* lb, const double* ub,

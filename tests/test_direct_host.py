@@ -269,3 +269,24 @@ def test_one_batch_per_iteration():
     # interior optimum: already one batch per iteration without speculation (within a few late batches)
     interior = count(4, 0, maxiter=30)
     assert len(interior[4]) <= interior[3] + 2 + 3
+
+
+def test_objective_failure_stops_the_driver_at_once():
+    """a Python objective that raises must not keep DIRECT iterating on made-up values until maxiter (the callback reports NaN,
+    the driver returns IBO_E_OBJECTIVE, the exception is re-raised); a NaN returned by the objective itself is an error too"""
+    from ibo_b200 import _lib
+    from ibo_b200.utils.optimize import direct
+    calls = []
+
+    def boom(P):
+        calls.append(len(P))
+        if len(calls) == 3:
+            raise RuntimeError("objective failed")
+        return np.sum((np.asarray(P) - 0.3) ** 2, axis=1)
+
+    with pytest.raises(RuntimeError, match="objective failed"):
+        direct(None, [(0., 1.)] * 3, maxiter=10 ** 6, batch_objective=boom)
+    assert len(calls) == 3
+    with pytest.raises(_lib.IBOError) as ei:
+        direct(lambda x: float("nan") if x[0] > 0.6 else float(np.sum(x ** 2)), [(0., 1.)] * 2, maxiter=50)
+    assert ei.value.code == _lib.E_OBJECTIVE

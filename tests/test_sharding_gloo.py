@@ -16,7 +16,9 @@ import os, sys, json
 import numpy as np
 sys.path.insert(0, %(root)r)
 import torch.distributed as dist
-from ibo_b200.utils.sharding import shard_range, allreduce_argmax
+from ibo_b200.utils.sharding import shard_range
+sys.path.insert(0, os.path.join(%(root)r, 'tests'))
+from dist_helpers import allreduce_argmax
 dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
 rank, world = dist.get_rank(), dist.get_world_size()
 out = []
@@ -94,7 +96,8 @@ import numpy as np
 sys.path.insert(0, %(root)r)
 import torch.distributed as dist
 from ibo_b200.utils.optimize import direct
-from ibo_b200.utils.sharding import sharded_batch_objective
+sys.path.insert(0, os.path.join(%(root)r, 'tests'))
+from dist_helpers import sharded_batch_objective
 from oracle import ibo_oracle as orc
 dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
 rs = np.random.RandomState(7)
