@@ -510,9 +510,12 @@ def run_suite(args):
 
 # ------------------------------------------------------------------------------------------------
 def run_direct_workload(args, rank, world, device, dist):
-    """BASELINE configs[4]: end-to-end batched-DIRECT maximizeEI, d=20, N=4096, 200 iterations.  One process per GPU, every rank
-    drives the same deterministic DIRECT; with N>1 each batch is cut into one slice per rank and the values are all-gathered
-    over NCCL (IBO_FLAG_SHARD).  A step is one whole maximizeEI query; the value is its wall time (max over ranks)."""
+    """BASELINE configs[4]: end-to-end batched-DIRECT maximizeEI, d=20, N=4096, 200 iterations per query.  One process per GPU.
+    A query is latency bound (batches of 10^2-10^3 points, ~200 dependent round trips), so the GPUs of a box are used for
+    THROUGHPUT: every rank answers its own queries (same model replicated, different incumbents / xi so that the trajectories
+    differ), no collective on the data path -- `value` = queries per second over all ranks (weak scaling).  Beside it: the latency
+    of ONE query, unsharded on one GPU and with every batch cut into one slice per GPU (IBO_FLAG_SHARD + NCCL all-gather), which
+    must give the same point bit for bit."""
     from ibo_b200 import _lib
     from ibo_b200.acquisition import cdirectGP, maximizeEI
     from ibo_b200.gaussianprocess import GaussianProcess
@@ -530,45 +533,65 @@ def run_direct_workload(args, rank, world, device, dist):
             dist.barrier()
         _lib.check(L.ibo_device_synchronize(device))
 
-    def query(shard):
-        return maximizeEI(gp, bounds, xi=0.01, maxiter=iters, maxtime=10 ** 6, maxsample=10 ** 9, shard=shard)
+    def query(shard, xi=0.01):
+        return maximizeEI(gp, bounds, xi=xi, maxiter=iters, maxtime=10 ** 6, maxsample=10 ** 9, shard=shard)
 
+    nq = max(args.steps, 1)
+    my_xi = [0.01 + 0.003 * ((rank * nq + q) % 7) for q in range(nq)]      # this rank's queries
     for _ in range(max(args.warmup, 1)):
-        opt, optx = query(world > 1)
+        query(False, my_xi[0])
     sampler = ClockSampler(device)
     sync_all()
     sampler.start()
     launches0 = L.ibo_launch_count()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        opt, optx = query(world > 1)
+    samples = 0
+    for q in range(nq):
+        query(False, my_xi[q])
+        samples += cdirectGP.last["nsamples"]
     sync_all()
-    t_wall = (time.perf_counter() - t0) / args.steps
+    t_tp = time.perf_counter() - t0
     launches = L.ibo_launch_count() - launches0
     clocks = sampler.stop()
-    nsamples, its = cdirectGP.last["nsamples"], cdirectGP.last["iterations"]
-    # the unsharded query on this rank's GPU alone (what N=1 gives), for the same-trajectory check and the comparison
+    # ---- latency of one query: unsharded on this GPU, and sharded over all GPUs ----
     t0 = time.perf_counter()
     opt1, optx1 = query(False)
     t_single = time.perf_counter() - t0
-    same = bool(opt == opt1 and np.array_equal(optx, optx1) and cdirectGP.last["nsamples"] == nsamples)
+    n1, its = cdirectGP.last["nsamples"], cdirectGP.last["iterations"]
+    t_shard, same = None, None
+    if world > 1:
+        query(True)
+        sync_all()
+        t0 = time.perf_counter()
+        opt, optx = query(True)
+        sync_all()
+        t_shard = time.perf_counter() - t0
+        same = bool(opt == opt1 and np.array_equal(optx, optx1) and cdirectGP.last["nsamples"] == n1)
     if dist is not None:
         import torch
-        t = torch.tensor([t_wall, t_single, 0.0 if same else 1.0], dtype=torch.float64)
+        t = torch.tensor([t_tp, t_single, t_shard, 0.0 if same else 1.0], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_wall, t_single, same = float(t[0]), float(t[1]), bool(t[2] == 0.0)
+        t_tp, t_single, t_shard, same = float(t[0]), float(t[1]), float(t[2]), bool(t[3] == 0.0)
+        tot = torch.tensor([float(samples)], dtype=torch.float64)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        samples = int(tot[0])
     if rank == 0:
-        print(json.dumps({
-            "metric": "maximizeEI wall ms (batched DIRECT, N=4096, d=20, 200 iterations)", "value": 1e3 * t_wall, "unit": "ms",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * t_wall, "higher_is_better": False,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "config #5: GaussianProcess SE-ARD d=20, N=4096, maximizeEI xi=0.01 through batched DIRECT, 200 iterations, "
-                                   "batches of >= %d points cut into one slice per GPU + NCCL all-gather of the values" % (64 * world),
-                       "n_obs": N, "dim": d, "iterations": its, "nsamples": nsamples, "l2": "latency-bound small batches (10^2-10^3 points)"},
-            "clocks": clocks, "gpu_launches": int(launches), "evals_per_s": nsamples / t_wall,
-            "single_gpu_unsharded_wall_ms": 1e3 * t_single, "same_result_as_unsharded": same, "opt": opt,
-            "e2e": {"value": 1e3 * t_wall, "unit": "ms", "h2d_bytes_per_step": int(nsamples * d * 8), "d2h_bytes_per_step": int(nsamples * 8),
-                    "api": "maximizeEI -> cdirectGP -> ibo_acqmax (host candidates in, values out, every batch)"}}))
+        qps = world * nq / t_tp
+        line = {
+            "metric": "maximizeEI queries/sec (batched DIRECT, N=4096, d=20, 200 iterations per query)", "value": qps, "unit": "queries/s",
+            "n_gpus": world, "steps": nq, "warmup": max(args.warmup, 1), "ms_per_step": 1e3 * t_tp / nq, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "config #5: GaussianProcess SE-ARD d=20, N=4096, maximizeEI through batched DIRECT, 200 iterations per query; "
+                                   "every GPU answers its own queries (step = one query per GPU), model replicated, no data-path collective",
+                       "n_obs": N, "dim": d, "iterations": its, "nsamples_per_query": n1, "l2": "latency-bound small batches (10^2-10^3 points)"},
+            "clocks": clocks, "gpu_launches": int(launches), "evals_per_s": samples / t_tp,
+            "single_query": {"unsharded_one_gpu_wall_ms": 1e3 * t_single,
+                             "sharded_over_all_gpus_wall_ms": None if t_shard is None else 1e3 * t_shard,
+                             "same_result_as_unsharded": same, "opt": opt1,
+                             "note": "IBO_FLAG_SHARD cuts every batch of >= 64 x ranks points into one slice per GPU and all-gathers the values over NCCL"},
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": int(n1 * d * 8), "d2h_bytes_per_step": int(n1 * 8),
+                    "api": "maximizeEI -> cdirectGP -> ibo_acqmax (host candidates in, values out, every batch)"}}
+        print(json.dumps(line))
     if dist is not None:
         L.ibo_comm_destroy()
         dist.destroy_process_group()
@@ -629,6 +652,9 @@ def main():
     model = gp.model                                   # builds R, Cholesky, W = inv(L), packing on the device
     t_factor = time.perf_counter() - t0
     ymax = float(np.max(Y))
+    # FP64 tensor-pipe peak first, on a GPU that is not yet power-limited by the INT8 steps (the DMMA path never reaches the cap)
+    peak = c_double(0)
+    _lib.check(L.ibo_fp64_peak(device, ctypes.byref(peak)))
     Xs = wl.candidates(rank)
     cands = _lib.ResidentCandidates(model, Xs)
     use_i8 = (not args.fp64) and N > 128 and N <= 16384 and d <= 32 and _lib.get_option("int8") == 1
@@ -676,8 +702,6 @@ def main():
             k2.append(model.profile())
         return min(k2, key=lambda p: p["k2_ms"])
     prof = profile_arm(flags, max(2, min(args.steps, 3)) if wl.id == 2 else 1)
-    peak = c_double(0)
-    _lib.check(L.ibo_fp64_peak(device, ctypes.byref(peak)))
     pk8b, pk8s = c_double(0), c_double(0)
     if N > 128:
         _lib.check(L.ibo_i8_peak2(device, 1.5, ctypes.byref(pk8b), ctypes.byref(pk8s)))

@@ -23,7 +23,7 @@ EXPORTED = [
     "ibo_cands_create", "ibo_cands_destroy", "ibo_score_resident", "ibo_get_profile", "ibo_launch_count",
     "ibo_fp64_peak", "ibo_i8_peak", "ibo_i8_peak2", "ibo_host_register", "ibo_host_unregister", "ibo_stream_mark", "ibo_stream_elapsed_ms",
     "ibo_device_synchronize", "ibo_debug_exp",
-    "ibo_direct_batched", "ibo_acqmax", "direct", "acqmaxGP",
+    "ibo_direct_batched", "ibo_acqmax", "ibo_acqmax_many", "direct", "acqmaxGP",
     "ibo_comm_unique_id", "ibo_comm_init", "ibo_comm_destroy", "ibo_comm_argmax", "ibo_comm_bcast", "ibo_comm_barrier",
     "ibo_comm_rank", "ibo_comm_size", "ibo_comm_allgather",
     "ibo_set_option", "ibo_get_option", "ibo_model_last_guarded",
@@ -112,6 +112,7 @@ def lib():
     L.ibo_debug_exp.argtypes = [c_int, pd, c_long, pd, pd]
     L.ibo_direct_batched.argtypes = [BATCH_OBJECTIVE, c_void_p, c_int, pd, pd, c_int, c_int, c_int, c_int, pd, pd, pl, pi]
     L.ibo_acqmax.argtypes = [c_void_p, pd, pd, c_int, c_double, c_double, c_int, c_int, c_int, c_int, pd, pd, pl, pi]
+    L.ibo_acqmax_many.argtypes = [c_int, POINTER(c_void_p), pd, pd, c_int, pd, pd, c_int, c_int, c_int, c_int, pd, pd, pl, pi, pi]
     L.direct.restype = POINTER(c_double)
     L.direct.argtypes = [OBJECTIVE, c_int, pd, pd, c_int, c_int, c_int]
     L.acqmaxGP.restype = POINTER(c_double)
@@ -306,6 +307,22 @@ class Model(object):
         out = np.zeros(6)
         check(lib().ibo_get_profile(self._h, dptr(out)))
         return dict(k1_ms=out[0], k2_ms=out[1], k3_ms=out[2], total_ms=out[3], launches=int(out[4]), k2_launches=int(out[5]))
+
+
+def acqmax_many(models, lb, ub, acq, ymax, parm, flags=FLAG_MODE_CPP, maxiter=50, maxtime=30, maxsample=10000):
+    """independent queries side by side (ibo_acqmax_many): models[q] with incumbent ymax[q] and parameter parm[q];
+    returns (opt[nq], optx[nq, d], nsamples[nq], iterations[nq])"""
+    nq = len(models)
+    lb, ub = as_f64(lb), as_f64(ub)
+    ymax = as_f64(np.broadcast_to(np.asarray(ymax, dtype=float), (nq,)))
+    parm = as_f64(np.broadcast_to(np.asarray(parm, dtype=float), (nq,)))
+    handles = (c_void_p * nq)(*[m.handle for m in models])
+    d = models[0].d
+    opt, optx = np.empty(nq), np.empty((nq, d))
+    ns, it, st = (c_long * nq)(), (c_int * nq)(), (c_int * nq)()
+    check(lib().ibo_acqmax_many(nq, handles, dptr(lb), dptr(ub), acq, dptr(ymax), dptr(parm), flags, int(maxiter), int(maxtime),
+                                int(maxsample), dptr(opt), dptr(optx), ns, it, st))
+    return opt, optx, np.array(ns[:]), np.array(it[:])
 
 
 class ResidentCandidates(object):

@@ -27,6 +27,7 @@
 #include <vector>
 #include <chrono>
 #include <cstdio>
+#include <thread>
 
 namespace ibo {
 void set_error(const std::string& s);
@@ -639,6 +640,41 @@ extern "C" int ibo_acqmax(ibo_model* m, const double* lb, const double* ub, int 
 }
 
 // ---- legacy symbols ---------------------------------------------------------------------------
+// Independent queries side by side: one host thread per query, each driving its own model handle (own stream, own device
+// workspace; the rectangle store of the driver is per thread).  Queries on different devices use the GPUs of a box for
+// throughput -- a single DIRECT query is a chain of ~200 dependent small batches and does not get faster with more GPUs --;
+// queries on the same device overlap each other's launch and round-trip latencies.
+extern "C" int ibo_acqmax_many(int nq, ibo_model* const* models, const double* lb, const double* ub, int acq, const double* ymax,
+                               const double* parm, int flags, int maxiter, int maxtime, int maxsample,
+                               double* opt, double* optx, long* nsamples, int* iterations, int* status) {
+    if (nq < 1 || !models || !lb || !ub || !ymax || !parm || !opt || !optx) { set_error("bad argument"); return IBO_E_BADARG; }
+    const int ndim = ibo_model_dim(models[0]);
+    for (int q = 0; q < nq; q++) {
+        if (!models[q] || ibo_model_dim(models[q]) != ndim) { set_error("ibo_acqmax_many: models must share the dimension"); return IBO_E_BADARG; }
+        for (int p = 0; p < q; p++)
+            if (models[p] == models[q]) { set_error("ibo_acqmax_many: every query needs its own model handle"); return IBO_E_BADARG; }
+    }
+    if (flags & IBO_FLAG_SHARD) { set_error("ibo_acqmax_many: queries are independent, IBO_FLAG_SHARD does not apply"); return IBO_E_BADARG; }
+    std::vector<int> rc(nq, IBO_OK);
+    std::vector<std::string> err(nq);
+    std::vector<std::thread> th;
+    for (int q = 0; q < nq; q++)
+        th.emplace_back([&, q]() {
+            long ns = 0; int it = 0;
+            rc[q] = ibo_acqmax(models[q], lb, ub, acq, ymax[q], parm[q], flags, maxiter, maxtime, maxsample, &opt[q], optx + (size_t)q * ndim, &ns, &it);
+            if (rc[q]) err[q] = ibo_last_error();
+            if (nsamples) nsamples[q] = ns;
+            if (iterations) iterations[q] = it;
+        });
+    for (auto& t : th) t.join();
+    int first = IBO_OK;
+    for (int q = 0; q < nq; q++) {
+        if (status) status[q] = rc[q];
+        if (rc[q] && !first) { first = rc[q]; set_error("query " + std::to_string(q) + ": " + err[q]); }
+    }
+    return first;
+}
+
 extern "C" const double* direct(objective_t objective, int ndim, double* lb, double* ub, int maxiter, int maxtime, int maxsample) {
     if (!objective || ndim < 1) return NULL;
     ScalarAdapter a{objective};
@@ -659,10 +695,13 @@ extern "C" const double* acqmaxGP(int ndim, double* lb, double* ub, double* invR
     }
     if (kerneltype < 0 || kerneltype > 3 || nx < 1 || ndim < 1) return NULL;
     // hyper-parameter layout as GP_Maximizer::posterior reads it (cpp/optimizeGP.cpp:70-112);
-    // sf2 = 1 for kernels 0-2 (:303-310), exp(2 log(hyper[1])) for Matern-5/2 (the magnitude slot).
+    // sf2 = 1 for kernels 0-2 (:303-310); for Matern-5/2 the reference takes exp(2 log(hyperparams[ndim])) (:313) -- the
+    // magnitude slot of the kernel's [theta, magnitude] array only when ndim == 1.  The drop-in reads the same element: a caller
+    // with ndim > 1 gets defined behaviour from the reference only by passing ndim + 1 values with the magnitude last, and gets
+    // the same answer here (tests/golden: matern5_2d / 4d / 10d).
     double sf2 = 1.0;
     int nh = (kerneltype == 0) ? ndim : 1;
-    if (kerneltype == 3) sf2 = std::exp(2.0 * std::log(hyperparams[1]));
+    if (kerneltype == 3) sf2 = std::exp(2.0 * std::log(hyperparams[ndim]));
     ibo_model* m = NULL;
     int info = 0;
     int rc = ibo_model_create_from_inverse(0, kerneltype, hyperparams, nh, X, Y, nx, ndim, noise, invR, sf2, npbases, pbasismeans,

@@ -227,6 +227,14 @@ int ibo_acqmax(ibo_model* m, const double* lb, const double* ub, int acq, double
                int maxiter, int maxtime, int maxsample,
                double* opt, double* optx, long* nsamples, int* iterations);
 
+/* nq independent queries at once, one host thread each: query q maximises over the same box on models[q] (distinct handles, any
+ * devices) with incumbent ymax[q] and parameter parm[q].  opt[nq], optx[nq x ndim]; nsamples / iterations / status (per-query
+ * return codes) may be NULL.  Returns the first non-zero status.  This is how several GPUs serve DIRECT: throughput across
+ * queries -- one query is a chain of dependent small batches. */
+int ibo_acqmax_many(int nq, ibo_model* const* models, const double* lb, const double* ub, int acq, const double* ymax,
+                    const double* parm, int flags, int maxiter, int maxtime, int maxsample,
+                    double* opt, double* optx, long* nsamples, int* iterations, int* status);
+
 /* ---- legacy drop-in symbols (same names, same ABI as libego) ---------------------------------- */
 typedef double (*objective_t)(int, double*);                                    /* cpp/direct.h:14 */
 const double* direct(objective_t objective, int ndim, double* lb, double* ub,

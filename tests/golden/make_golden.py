@@ -79,7 +79,35 @@ def scenario(name):
         X = rs.rand(15, 1) * 4
         Y = np.sin(2 * X[:, 0])
         return dict(kind=3, hyper=[0.8, 0.9], X=X, Y=Y, noise=0.1, bounds=[[0., 4.]], prior=None)
+    if name in ("matern5_2d", "matern5_4d", "matern5_10d"):
+        # Matern-5/2 beyond one dimension.  GP_Maximizer::posterior evaluates the isotropic formula at any d
+        # (cpp/optimizeGP.cpp:99-110) and acqmaxGP reads the magnitude from hyperparams[ndim] (:313), so the reference is well
+        # defined when it is handed an array of length ndim + 1: [theta, (unused) ..., magnitude] -- `ref_hyper`.
+        d = int(name.split("_")[1][:-1])
+        rs = np.random.RandomState(20 + d)
+        n = {2: 30, 4: 60, 10: 120}[d]
+        X = rs.rand(n, d) * 2.0
+        Y = np.sin(2 * X).sum(axis=1) / d
+        theta, mag = {2: (0.9, 1.0), 4: (1.3, 0.8), 10: (2.1, 0.9)}[d]     # (R keeps 1 + noise on its diagonal whatever the magnitude: mag <= 1)
+        ref_hyper = np.zeros(d + 1)
+        ref_hyper[0] = theta; ref_hyper[d] = mag
+        return dict(kind=3, hyper=[theta, mag], ref_hyper=ref_hyper, X=X, Y=Y, noise=0.1, bounds=[[0., 2.]] * d, prior=None)
     raise KeyError(name)
+
+
+class quiet_stdout(object):
+    """kerneltype 3 streams every kernel value to std::cout (cpp/optimizeGP.cpp:109): silence fd 1 around the reference's acqmaxGP"""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+
+    def __exit__(self, *a):
+        os.dup2(self.saved, 1)
+        os.close(self.null)
+        os.close(self.saved)
 
 
 def model_arrays(sc):
@@ -108,23 +136,24 @@ def main():
     rs = np.random.RandomState(123)
     # ---- per-candidate values from GP_Maximizer::negei/negpi/negucb/posterior ----
     for name in ["shekel_iso2", "shekel_iso3", "branin_matern3a", "branin_matern3b", "branin_matern3c", "branin_ard50",
-                 "hartman_ard200", "prior_iso", "matern5_1d"]:
+                 "hartman_ard200", "prior_iso", "matern5_1d", "matern5_2d", "matern5_4d", "matern5_10d"]:
         sc = scenario(name)
         X = np.ascontiguousarray(sc["X"]); Y = np.ascontiguousarray(sc["Y"])
         N, d = X.shape
         gp, invR = model_arrays(sc)
         hyper = np.ascontiguousarray(np.array(sc["hyper"], dtype=float))
+        ref_hyper = np.ascontiguousarray(np.array(sc.get("ref_hyper", sc["hyper"]), dtype=float))
         npb, pm, pb, pt, plb, pw = prior_args(sc, d)
         b = np.array(sc["bounds"])
         M = 64
         Xs = np.ascontiguousarray(b[:, 0] + (b[:, 1] - b[:, 0]) * rs.rand(M, d))
         Xs[:3] = X[:3]
-        rec = dict(kind=sc["kind"], hyper=hyper, X=X, Y=Y, noise=sc["noise"], invR=invR, Xs=Xs, bounds=b)
+        rec = dict(kind=sc["kind"], hyper=hyper, ref_hyper=ref_hyper, X=X, Y=Y, noise=sc["noise"], invR=invR, Xs=Xs, bounds=b)
         if sc["prior"] is not None:
             rec.update(p_means=sc["prior"]["means"], p_beta=sc["prior"]["beta"], p_theta=sc["prior"]["theta"],
                        p_lowerb=sc["prior"]["lowerb"], p_width=sc["prior"]["width"])
         for acq, parm, tag in [(0, 0.01, "negei"), (0, 0.1, "negei_xi1"), (1, 0.01, "negpi"), (2, 1.3, "negucb")]:
-            har.ref_set_model(d, dp(invR), dp(X), dp(Y), N, sc["kind"], dp(hyper), npb, dp(pm), dp(pb), pt, dp(plb), dp(pw), parm, sc["noise"])
+            har.ref_set_model(d, dp(invR), dp(X), dp(Y), N, sc["kind"], dp(ref_hyper), npb, dp(pm), dp(pb), pt, dp(plb), dp(pw), parm, sc["noise"])
             v = np.empty(M); mu = np.empty(M); sg = np.empty(M)
             har.ref_eval(acq, M, dp(Xs), dp(v), dp(mu), dp(sg), 1)
             rec[tag] = v
@@ -140,17 +169,19 @@ def main():
             ("shekel_iso3", 0, 0.0, 20, 10000), ("shekel_iso3", 0, 0.01, 20, 10000), ("shekel_iso3", 0, 0.1, 20, 10000),
             ("shekel_iso2", 1, 0.01, 20, 10000), ("branin_matern3a", 0, 0.01, 20, 10000), ("branin_matern3b", 0, 0.01, 20, 10000),
             ("branin_matern3c", 0, 0.01, 20, 10000), ("branin_ard50", 0, 0.01, 50, 10000), ("branin_ard50", 2, 1.5, 30, 10000),
-            ("hartman_ard200", 0, 0.01, 30, 3000), ("prior_iso", 0, 0.01, 20, 10000)]:
+            ("hartman_ard200", 0, 0.01, 30, 3000), ("prior_iso", 0, 0.01, 20, 10000),
+            ("matern5_2d", 0, 0.01, 20, 10000), ("matern5_4d", 0, 0.01, 12, 3000), ("matern5_10d", 2, 1.5, 6, 1500)]:
         sc = scenario(name)
         X = np.ascontiguousarray(sc["X"]); Y = np.ascontiguousarray(sc["Y"])
         N, d = X.shape
         gp, invR = model_arrays(sc)
-        hyper = np.ascontiguousarray(np.array(sc["hyper"], dtype=float))
+        hyper = np.ascontiguousarray(np.array(sc.get("ref_hyper", sc["hyper"]), dtype=float))
         npb, pm, pb, pt, plb, pw = prior_args(sc, d)
         b = np.array(sc["bounds"])
         lb = np.ascontiguousarray(b[:, 0]); ub = np.ascontiguousarray(b[:, 1])
-        res = ego.acqmaxGP(d, dp(lb), dp(ub), dp(invR), dp(X), dp(Y), N, acq, sc["kind"], dp(hyper), npb, dp(pm), dp(pb), pt,
-                           dp(plb), dp(pw), parm, sc["noise"], maxiter, 100000, maxsample)
+        with quiet_stdout():
+            res = ego.acqmaxGP(d, dp(lb), dp(ub), dp(invR), dp(X), dp(Y), N, acq, sc["kind"], dp(hyper), npb, dp(pm), dp(pb), pt,
+                               dp(plb), dp(pw), parm, sc["noise"], maxiter, 100000, maxsample)
         key = "%s|acq%d|parm%g|it%d|ms%d" % (name, acq, parm, maxiter, maxsample)
         acq_out[key] = dict(fmin=res[0], xmin=[res[i + 1] for i in range(d)])
     # ---- the reference's C DIRECT on analytic functions, full sample trace ----

@@ -320,3 +320,27 @@ def test_fast_ucb_gallery_matches_oracle_restatement(with_prior, monkeypatch):
     assert len(gal) == len(ref) == 4
     for a, b in zip(gal, ref):
         assert np.allclose(a, b, rtol=0, atol=1e-9), (gal, ref)
+
+
+def test_acqmax_many_equals_one_query_at_a_time():
+    """independent queries on their own model handles, one host thread each: same points, sample counts and values as running
+    them one after the other"""
+    from ibo_b200 import _lib
+    rs = np.random.RandomState(3)
+    d = 5
+    models, ymax = [], []
+    for q in range(4):
+        N = 150 + 130 * q
+        X = rs.rand(N, d); Y = np.sin(3 * X).sum(axis=1)
+        models.append(_lib.Model(_lib.KERNEL_SE_ARD, [0.4 + 0.05 * q] * d, X, Y, 0.1))
+        ymax.append(float(Y.max()))
+    lb, ub = np.zeros(d), np.ones(d)
+    parm = [0.01, 0.02, 0.0, 0.05]
+    seq = [m.acqmax(lb, ub, _lib.ACQ_EI, ymax[q], parm[q], _lib.FLAG_MODE_CPP, 40, 10 ** 6, 10 ** 6) for q, m in enumerate(models)]
+    opt, optx, ns, it = _lib.acqmax_many(models, lb, ub, _lib.ACQ_EI, ymax, parm, _lib.FLAG_MODE_CPP, 40, 10 ** 6, 10 ** 6)
+    for q in range(4):
+        assert opt[q] == seq[q][0] and np.array_equal(optx[q], seq[q][1]) and ns[q] == seq[q][2] and it[q] == seq[q][3]
+    with pytest.raises(_lib.IBOError):
+        _lib.acqmax_many([models[0], models[0]], lb, ub, _lib.ACQ_EI, ymax[:2], parm[:2])
+    for m in models:
+        m.close()

@@ -48,7 +48,7 @@ gp = GaussianProcess(GaussianKernel_ard([0.8] * d), X, Y, noise=0.1, device=rank
 b = [[0., 1.]] * d
 o1 = maximizeEI(gp, b, xi=0.01, maxiter=60, maxtime=10 ** 6, maxsample=10 ** 9)
 n1 = cdirectGP.last["nsamples"]
-os.environ["IBO_SHARD_MIN"] = "2"
+_lib.set_option("shard_min", 2)          # shard every batch of >= 2 points (default: 64 x ranks)
 o2 = maximizeEI(gp, b, xi=0.01, maxiter=60, maxtime=10 ** 6, maxsample=10 ** 9, shard=True)
 n2 = cdirectGP.last["nsamples"]
 print("RESULT" + json.dumps([o1[0], list(o1[1]), n1, o2[0], list(o2[1]), n2]))
