@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libibo_b200.so")
 # every symbol include/ibo_b200.h declares (checked by tests/test_abi.py)
 EXPORTED = [
     "ibo_last_error", "ibo_version", "ibo_device_count",
-    "ibo_model_create", "ibo_model_create_from_inverse", "ibo_model_append", "ibo_model_destroy", "ibo_model_n", "ibo_model_dim",
+    "ibo_model_create", "ibo_model_create_pref", "ibo_model_create_laplace", "ibo_model_create_from_inverse", "ibo_model_append", "ibo_model_destroy", "ibo_model_n", "ibo_model_dim",
     "ibo_model_get_matrix", "ibo_model_set_variance_model", "ibo_pref_fit",
     "ibo_nlml", "ibo_kernel_matrix",
     "ibo_posterior_batch", "ibo_score_batch",
@@ -83,6 +83,9 @@ def lib():
     L.ibo_model_create.restype = c_int
     L.ibo_model_create.argtypes = [c_int, c_int, pd, c_int, pd, pd, c_int, c_int, c_double, pd,
                                    c_int, pd, pd, c_double, pd, pd, POINTER(c_void_p), pi]
+    L.ibo_model_create_pref.argtypes = [c_int, c_int, pd, c_int, pd, pd, c_int, c_int, c_double, c_int, pi, pi, pd, c_double,
+                                        POINTER(c_void_p), pi]
+    L.ibo_model_create_laplace.argtypes = [c_int, c_int, pd, c_int, pd, pd, c_int, c_int, c_double, pd, POINTER(c_void_p), pi]
     L.ibo_model_create_from_inverse.restype = c_int
     L.ibo_model_create_from_inverse.argtypes = [c_int, c_int, pd, c_int, pd, pd, c_int, c_int, c_double, pd, c_double,
                                                 c_int, pd, pd, c_double, pd, pd, POINTER(c_void_p), pi]
@@ -187,7 +190,9 @@ def kernel_matrix(kind, hyper, X, which=-1, flags=0, device=0):
 class Model(object):
     """Owner of an `ibo_model*` handle (device-resident L, W = inv(L), beta)."""
 
-    def __init__(self, kind, hyper, X, Y, noise, Cinv=None, prior=None, device=0, invR=None, sf2=1.0):
+    def __init__(self, kind, hyper, X, Y, noise, Cinv=None, prior=None, device=0, invR=None, sf2=1.0, pref=None, C=None):
+        """pref = (a, b, w, cdiag): Laplace term as preference pairs, C = dense Laplace matrix -- inv(C) is then formed on the
+        device (ibo_model_create_pref / ibo_model_create_laplace); Cinv = explicit inverse (ibo_model_create)"""
         L = lib()
         self.X = as_f64(X, 2)
         self.Y = as_f64(Y, 1).reshape(-1)
@@ -205,7 +210,17 @@ class Model(object):
             npb = pm.shape[0]
             pb, pt = as_f64(prior.beta), float(prior.theta)
             plb, pw = as_f64(prior.lowerb), as_f64(prior.width)
-        if invR is not None:
+        if pref is not None:
+            a = np.ascontiguousarray(pref[0], dtype=np.int32); b = np.ascontiguousarray(pref[1], dtype=np.int32)
+            w = as_f64(pref[2], 1)
+            ip = lambda z: z.ctypes.data_as(POINTER(c_int))
+            rc = L.ibo_model_create_pref(device, kind, dptr(hyper), len(hyper), dptr(self.X), dptr(self.Y), self.N, self.d, float(noise),
+                                         len(a), ip(a), ip(b), dptr(w), float(pref[3]), ctypes.byref(self._h), ctypes.byref(info))
+        elif C is not None:
+            C = as_f64(C, 2)
+            rc = L.ibo_model_create_laplace(device, kind, dptr(hyper), len(hyper), dptr(self.X), dptr(self.Y), self.N, self.d, float(noise),
+                                            dptr(C), ctypes.byref(self._h), ctypes.byref(info))
+        elif invR is not None:
             invR = as_f64(invR, 2)
             rc = L.ibo_model_create_from_inverse(device, kind, dptr(hyper), len(hyper), dptr(self.X), dptr(self.Y), self.N, self.d,
                                                  float(noise), dptr(invR), float(sf2), npb, dptr(pm), dptr(pb), pt, dptr(plb), dptr(pw),

@@ -204,8 +204,6 @@ __global__ void __launch_bounds__(256) nlml_value_kernel(const double* __restric
     if (threadIdx.x == 0) out[0] = sh[0] + 0.5 * N * 1.8378770664093453;   // log(2 pi)
 }
 
-std::once_flag g_gram_attr;
-cudaError_t g_gram_attr_err = cudaSuccess;
 
 int describe(int kind, const double* hyper, int nhyper, int d, int flags, KDesc* kd, int* nh_total) {
     if (kind < 0 || kind > IBO_KERNEL_MATERN5_ARD || !hyper || nhyper < 1) { set_error("bad kernel description"); return IBO_E_BADARG; }
@@ -222,6 +220,19 @@ int describe(int kind, const double* hyper, int nhyper, int d, int flags, KDesc*
 }
 
 }  // namespace
+
+static cudaError_t set_gram_attrs() {
+    return cudaFuncSetAttribute(gram_wtw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_DOUBLES * 8);
+}
+// C (lower 128 x 128 tiles, incl. full diagonal tiles) = W^T W for the lower-triangular W of a factorised model: inv(A) of its matrix
+int launch_gram_wtw(double* C, const ibo_model* m, cudaStream_t st) {
+    cudaError_t e = ensure_attrs(m->device, ATTR_GRAM, set_gram_attrs);
+    if (e != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); return IBO_E_CUDA; }
+    gram_wtw_kernel<<<dim3(m->nb, m->nb), 256, TILE_SMEM_DOUBLES * 8, st>>>(C, m->dW, m->Np);
+    g_launches++;
+    return IBO_OK;
+}
+
 }  // namespace ibo
 
 using namespace ibo;
@@ -260,10 +271,7 @@ extern "C" int ibo_nlml(int device, int kerneltype, const double* hyper, int nhy
     g_launches++;
     std::vector<double> hout(1 + nh, 0.0);
     if (dnlml) {
-        std::call_once(g_gram_attr, [] {
-            g_gram_attr_err = cudaFuncSetAttribute(gram_wtw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_DOUBLES * 8);
-        });
-        TRYH(g_gram_attr_err);
+        TRYH(ensure_attrs(m->device, ATTR_GRAM, set_gram_attrs));
         TRYH(pool_malloc((void**)&dKinv, sizeof(double) * (size_t)Np * Np));
         const int ntile = (N + GT - 1) / GT;
         TRYH(pool_malloc((void**)&dPart, sizeof(double) * (size_t)ntile * ntile * GH));

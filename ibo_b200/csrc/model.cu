@@ -137,6 +137,40 @@ __global__ void build_A_kernel(double* __restrict__ A, const double* __restrict_
     A[(size_t)i * Np + j] = v;
 }
 
+// C = cdiag I + sum_p w_p (e_a - e_b)(e_a - e_b)^T over the preference pairs (a_p, b_p): the Laplace term of PrefGaussianProcess
+// (ego/gaussianprocess/__init__.py:461-486).  One thread per row walks the pairs in their given order, so every entry is summed
+// in a fixed order (no atomics); identity in the padding.
+__global__ void pref_build_C_kernel(double* __restrict__ C, int N, int Np, int P, const int* __restrict__ pa, const int* __restrict__ pb,
+                                    const double* __restrict__ w, double cdiag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Np) return;
+    double* row = C + (size_t)i * Np;
+    for (int j = 0; j < Np; j++) row[j] = 0.0;
+    if (i >= N) { row[i] = 1.0; return; }
+    double dg = cdiag;
+    for (int p = 0; p < P; p++) {
+        const int a = pa[p], b = pb[p];
+        if (a == b) continue;
+        if (a == i) { dg += w[p]; row[b] -= w[p]; }
+        else if (b == i) { dg += w[p]; row[a] -= w[p]; }
+    }
+    row[i] = dg;
+}
+// A[i][j] += S[max(i,j)][min(i,j)] for i, j < N: S holds the lower 128 x 128 tiles of a symmetric matrix (gram_wtw_kernel)
+// A = [C 0; 0 I]: a dense N x N matrix padded to Np x Np
+__global__ void pad_copy_kernel(double* __restrict__ A, const double* __restrict__ src, int N, int Np) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (j >= Np) return;
+    A[(size_t)i * Np + j] = (i < N && j < N) ? src[(size_t)i * N + j] : (i == j ? 1.0 : 0.0);
+}
+__global__ void add_symmetric_lower_kernel(double* __restrict__ A, const double* __restrict__ S, int N, int Np) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+    if (i >= N || j >= N) return;
+    const int hi = i > j ? i : j, lo = i > j ? j : i;
+    // inside a diagonal tile both triangles were computed; take the lower one so that the sum is exactly symmetric
+    A[(size_t)i * Np + j] += S[(size_t)hi * Np + lo];
+}
+
 // A_rev = J invR J (reversal of the leading N x N part), identity padding -- legacy acqmaxGP path.
 __global__ void build_reversed_kernel(double* __restrict__ A, const double* __restrict__ invR, int N, int Np) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -748,7 +782,7 @@ static void free_model(ibo_model* m) {
     if (m->stream) cudaStreamSynchronize(m->stream);   // blocks go back to the pool: nothing may still be using them
     double** ptrs[] = {&m->dXt, &m->dInvTheta, &m->dCenter, &m->dA, &m->dAorig, &m->dW, &m->dD, &m->dWpack, &m->dBetaY, &m->dBeta1, &m->dY,
                        &m->dPmeans, &m->dPbeta, &m->dPlb, &m->dPwidth, &m->dCand, &m->dSlab, &m->dPart, &m->dOut, &m->dBlkBest, &m->dBest, &m->dAppend,
-                       &m->dWi8s, &m->dWi8t, &m->dRowScale, &m->dAlphaY, &m->dAlpha1, &m->dGuard, &m->dGuardList};
+                       &m->dWi8s, &m->dWi8t, &m->dRowScale, &m->dAlphaY, &m->dAlpha1, &m->dGuard, &m->dGuardList, &m->dCinv};
     for (auto p : ptrs) if (*p) { pool_free(*p); *p = nullptr; }
     if (m->dInfo) cudaFree(m->dInfo);
     if (m->dBlkIdx) cudaFree(m->dBlkIdx);
@@ -786,10 +820,13 @@ static int theta_and_sf2(int kind, const double* hyper, int nhyper, int d, bool 
 
 // diag < 0: the GP's own diagonal 1 + noise; otherwise the value to put on the diagonal of A (marginal likelihood:
 // covMatrix(X) + noise I has sf2 + noise there).
+// the Laplace term given as preference pairs: inv(C) is formed on the device (Cholesky of C, triangular inverse, Gram product)
+struct PrefPairs { int P; const int* a; const int* b; const double* w; double cdiag; const double* denseC; };   // denseC: C itself, N x N (host)
+
 static int create_common(int device, int kind, const double* hyper, int nhyper, const double* X, const double* Y, int N, int d,
                          double noise, double diag, const double* Cinv, const double* invR, double sf2_override, bool legacy,
                          int npb, const double* pmeans, const double* pbeta, double ptheta, const double* plb, const double* pwidth,
-                         ibo_model** out, int* info) {
+                         ibo_model** out, int* info, const PrefPairs* pref = nullptr) {
     if (info) *info = 0;
     if (!out || !X || !Y || !hyper || N < 1 || d < 1 || kind < 0 || kind > IBO_KERNEL_MATERN5_ARD) { set_error("bad argument"); return IBO_E_BADARG; }
     if (npb > 0 && (!pmeans || !pbeta || !plb || !pwidth)) { set_error("prior arrays missing"); return IBO_E_BADARG; }
@@ -844,7 +881,7 @@ static int create_common(int device, int kind, const double* hyper, int nhyper, 
         for (int j = 0; j < d; j++) xt[(size_t)i * d + j] = X[(size_t)i * d + j] * it[j] - ctr[j];
         yp[i] = Y[i]; ones[i] = 1.0;
     }
-    m->hInvTheta = it; m->hCenter = ctr; m->has_cinv = (Cinv != nullptr); m->from_inverse = (invR != nullptr);
+    m->hInvTheta = it; m->hCenter = ctr; m->has_cinv = (Cinv != nullptr || pref != nullptr); m->from_inverse = (invR != nullptr);
     TRYM(cudaMemcpyAsync(m->dXt, xt.data(), sizeof(double) * xt.size(), cudaMemcpyHostToDevice, st));
     TRYM(cudaMemcpyAsync(m->dInvTheta, it.data(), sizeof(double) * d, cudaMemcpyHostToDevice, st));
     TRYM(cudaMemcpyAsync(m->dCenter, ctr.data(), sizeof(double) * d, cudaMemcpyHostToDevice, st));
@@ -870,7 +907,46 @@ static int create_common(int device, int kind, const double* hyper, int nhyper, 
             TRYM(pool_malloc((void**)&dTmp, sizeof(double) * (size_t)N * N));
             TRYM(cudaMemcpyAsync(dTmp, Cinv, sizeof(double) * (size_t)N * N, cudaMemcpyHostToDevice, st));
         }
+        if (pref) {
+            // inv(C) without leaving the device: C -> dA, C = Lc Lc^T, Wc = inv(Lc) (the model's own factorisation kernels),
+            // inv(C) = Wc^T Wc (DMMA Gram product, lower tiles); then A = R + inv(C) is built in place and factorised as usual
+            int* dPairs = nullptr; double* dWts = nullptr;
+            if (pref->denseC) {
+                TRYM(pool_malloc((void**)&dWts, sizeof(double) * (size_t)N * N));
+                TRYM(cudaMemcpyAsync(dWts, pref->denseC, sizeof(double) * (size_t)N * N, cudaMemcpyHostToDevice, st));
+                pad_copy_kernel<<<dim3((Np + 255) / 256, Np), 256, 0, st>>>(m->dA, dWts, N, Np);
+            } else {
+                TRYM(pool_malloc((void**)&dPairs, sizeof(int) * 2 * (size_t)std::max(pref->P, 1)));
+                TRYM(pool_malloc((void**)&dWts, sizeof(double) * (size_t)std::max(pref->P, 1)));
+                if (pref->P > 0) {
+                    TRYM(cudaMemcpyAsync(dPairs, pref->a, sizeof(int) * pref->P, cudaMemcpyHostToDevice, st));
+                    TRYM(cudaMemcpyAsync(dPairs + pref->P, pref->b, sizeof(int) * pref->P, cudaMemcpyHostToDevice, st));
+                    TRYM(cudaMemcpyAsync(dWts, pref->w, sizeof(double) * pref->P, cudaMemcpyHostToDevice, st));
+                }
+                pref_build_C_kernel<<<(Np + 127) / 128, 128, 0, st>>>(m->dA, N, Np, pref->P, dPairs, dPairs + pref->P, dWts, pref->cdiag);
+            }
+            g_launches++;
+            rc = launch_factorize(m, false, false);
+            int cinfo = 0;
+            if (!rc) {
+                TRYM(cudaMemcpyAsync(&cinfo, m->dInfo, sizeof(int), cudaMemcpyDeviceToHost, st));
+                TRYM(cudaStreamSynchronize(st));
+            }
+            if (dPairs) pool_free(dPairs);
+            pool_free(dWts);
+            if (rc) return fail(rc);
+            if (cinfo != 0) {
+                if (info) *info = cinfo;
+                set_error("the Laplace matrix C is not positive definite (pivot " + std::to_string(cinfo) + ")");
+                return fail(IBO_E_NOTSPD);
+            }
+            TRYM(pool_malloc((void**)&m->dCinv, sizeof(double) * (size_t)Np * Np));
+            TRYM(cudaMemsetAsync(m->dCinv, 0, sizeof(double) * (size_t)Np * Np, st));
+            if ((rc = launch_gram_wtw(m->dCinv, m, st))) return fail(rc);
+            TRYM(cudaMemsetAsync(m->dInfo, 0, sizeof(int), st));
+        }
         build_A_kernel<<<g2, 256, 0, st>>>(m->dA, m->dXt, dTmp, N, Np, d, kind, sf2, diag < 0 ? 1.0 + noise : diag);
+        if (pref) { add_symmetric_lower_kernel<<<dim3((N + 255) / 256, N), 256, 0, st>>>(m->dA, m->dCinv, N, Np); g_launches++; }
     }
     g_launches++;
     if (Np <= 4096 && !invR) {   // keep A for get_matrix(0)
@@ -913,6 +989,25 @@ extern "C" int ibo_model_create(int device, int kerneltype, const double* hyper,
                          npbases, pmeans, pbeta, ptheta, plowerb, pwidth, out, info);
 }
 
+extern "C" int ibo_model_create_pref(int device, int kerneltype, const double* hyper, int nhyper, const double* X, const double* Y,
+                                     int N, int d, double noise, int P, const int* pa, const int* pb, const double* w, double cdiag,
+                                     ibo_model** out, int* info) {
+    if (P < 0 || (P > 0 && (!pa || !pb || !w)) || !(cdiag > 0)) { set_error("bad argument"); return IBO_E_BADARG; }
+    for (int p = 0; p < P; p++)
+        if (pa[p] < 0 || pa[p] >= N || pb[p] < 0 || pb[p] >= N) { set_error("preference index out of range"); return IBO_E_BADARG; }
+    PrefPairs pr{P, pa, pb, w, cdiag, nullptr};
+    return create_common(device, kerneltype, hyper, nhyper, X, Y, N, d, noise, -1.0, nullptr, nullptr, 1.0, false,
+                         0, nullptr, nullptr, 0.0, nullptr, nullptr, out, info, &pr);
+}
+
+extern "C" int ibo_model_create_laplace(int device, int kerneltype, const double* hyper, int nhyper, const double* X, const double* Y,
+                                        int N, int d, double noise, const double* C, ibo_model** out, int* info) {
+    if (!C) { set_error("C is NULL"); return IBO_E_BADARG; }
+    PrefPairs pr{0, nullptr, nullptr, nullptr, 1.0, C};
+    return create_common(device, kerneltype, hyper, nhyper, X, Y, N, d, noise, -1.0, nullptr, nullptr, 1.0, false,
+                         0, nullptr, nullptr, 0.0, nullptr, nullptr, out, info, &pr);
+}
+
 extern "C" int ibo_model_create_from_inverse(int device, int kerneltype, const double* hyper, int nhyper, const double* X,
                                              const double* Y, int N, int d, double noise, const double* invR, double sf2,
                                              int npbases, const double* pmeans, const double* pbeta, double ptheta,
@@ -953,14 +1048,17 @@ extern "C" int ibo_model_set_variance_model(ibo_model* m, ibo_model* aug) {
 }
 
 extern "C" int ibo_model_get_matrix(ibo_model* m, int which, double* out) {
-    if (!m || !out || which < 0 || which > 2) { set_error("bad argument"); return IBO_E_BADARG; }
+    if (!m || !out || which < 0 || which > 3) { set_error("bad argument"); return IBO_E_BADARG; }
     IBO_CUDA_TRY(cudaSetDevice(m->device));
-    const double* src = which == 0 ? m->dAorig : (which == 1 ? m->dA : m->dW);
+    const double* src = which == 0 ? m->dAorig : (which == 1 ? m->dA : (which == 2 ? m->dW : m->dCinv));
     if (!src) { set_error("matrix not retained for this model"); return IBO_E_BADARG; }
     IBO_CUDA_TRY(cudaStreamSynchronize(m->stream));
     IBO_CUDA_TRY(cudaMemcpy2D(out, sizeof(double) * m->N, src, sizeof(double) * m->Np, sizeof(double) * m->N, m->N, cudaMemcpyDeviceToHost));
     if (which == 1)
         for (int i = 0; i < m->N; i++)
             for (int j = i + 1; j < m->N; j++) out[(size_t)i * m->N + j] = 0.0;
+    if (which == 3)          // the device keeps the lower tiles of the symmetric inv(C)
+        for (int i = 0; i < m->N; i++)
+            for (int j = i + 1; j < m->N; j++) out[(size_t)i * m->N + j] = out[(size_t)j * m->N + i];
     return IBO_OK;
 }

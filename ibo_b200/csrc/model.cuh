@@ -17,6 +17,7 @@ struct ibo_model {
     double noise = 0, sf2 = 1;
     bool cpp_prior = false;
     bool has_cinv = false;            // A = R + inv(C): no rank-1 append
+    double* dCinv = nullptr;          // [Np][Np] lower tiles of inv(C) when it was formed on the device (ibo_model_create_pref)
     std::vector<double> hInvTheta, hCenter;   // host copies (append scales new points the same way)
     double* dAppend = nullptr; size_t appendCap = 0;   // append workspace: [x_new (d) | kvec (Np) | l (Np) | u (Np) | lambda]
     // device arrays
@@ -91,5 +92,6 @@ int launch_syrk_identity(double* C, const double* G, int Np, int K, cudaStream_t
 // model whose A carries `diag` on the diagonal instead of 1 + noise (hyper.cu: K = covMatrix(X) + noise I)
 int create_model_with_diag(int device, int kind, const double* hyper, int nhyper, const double* X, const double* Y, int N, int d,
                            double noise, double diag, ibo_model** out, int* info);
+int launch_gram_wtw(double* C, const ibo_model* m, cudaStream_t st);      // hyper.cu: C (lower tiles) = W^T W = inv(A)
 const char* get_error();
 }  // namespace ibo

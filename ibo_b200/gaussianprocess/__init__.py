@@ -74,8 +74,9 @@ class GaussianProcess(object):
         self.G = None
         self.name = 'GP'
         self.starttime = time()
-        self._model = None          # _lib.Model for (X, Y, Cinv)
-        self._Cinv = None
+        self._model = None          # _lib.Model for (X, Y [, Laplace term])
+        self._laplace = None        # PrefGaussianProcess: ("pairs", a, b, w, cdiag) or ("dense", C); inv(C) is formed on the device
+        self._Cinv_host = None
         self._augmodel = None
         self.augX = None
         self.selected = None
@@ -91,9 +92,24 @@ class GaussianProcess(object):
                 m.close()
             setattr(self, attr, None)
 
-    def _build(self, X, Y, Cinv=None):
+    def _build(self, X, Y, Cinv=None, laplace=None):
         kind, hyper = self.kernel.spec(X.shape[1])
+        if laplace is not None:
+            if self.prior is not None:
+                raise NotImplementedError("a preference GP has no mean prior")
+            if laplace[0] == "pairs":
+                return _lib.Model(kind, hyper, X, Y, self.noise, pref=laplace[1:], device=self.device)
+            return _lib.Model(kind, hyper, X, Y, self.noise, C=laplace[1], device=self.device)
         return _lib.Model(kind, hyper, X, Y, self.noise, Cinv=Cinv, prior=self.prior, device=self.device)
+
+    @property
+    def _Cinv(self):
+        """inv(C) of a fitted preference model, read back from the device on demand (None for a plain GP)"""
+        if self._laplace is None:
+            return None
+        if self._Cinv_host is None:
+            self._Cinv_host = self.model.matrix(3)
+        return self._Cinv_host
 
     @property
     def model(self):
@@ -101,7 +117,7 @@ class GaussianProcess(object):
         if self._model is None:
             if len(self.X) == 0:
                 raise ValueError("GP has no data")
-            self._model = self._build(self.X, self.Y, self._Cinv)
+            self._model = self._build(self.X, self.Y, laplace=self._laplace)
             if self.augX is not None:
                 self._attach_aug()
         return self._model
@@ -183,7 +199,7 @@ class GaussianProcess(object):
         # models get the new rows appended on the device (O(N^2) per point, ibo_model_append); small ones are simply
         # rebuilt (sub-millisecond, and a rebuilt model is a pure function of (X, Y), which keeps the reference's
         # sequential == batch training property, ego/unittest_GP.py:109-156, exact).
-        if (self._model is not None and self._Cinv is None and self._augmodel is None and self.augX is None
+        if (self._model is not None and self._laplace is None and self._augmodel is None and self.augX is None
                 and nold >= self.append_above and len(X) <= self.append_max_rows):
             try:
                 self._model.append(X, Y)
@@ -246,18 +262,22 @@ class PrefGaussianProcess(GaussianProcess):
     GP trained on pairwise preferences with a Laplace approximation (:331-527).  Triples are
     (xv, xu, d): xv preferred to xu, d = degree (0 standard, 1 greatly preferred).
 
-    The MAP fit of the latents runs on the device (ibo_pref_fit, Newton in whitened coordinates) for all but
-    tiny problems; the O(P) assembly of C is host bookkeeping, and everything downstream of (X, Y, C) --
-    L = chol(R + inv(C)), posteriors, acquisition -- runs on the GPU.  `fromLaplace` builds the process directly
-    from a fitted (X, Y, C).
+    Everything numerical runs on the device: the MAP fit of the latents (ibo_pref_fit, Newton in whitened coordinates), the
+    assembly of the Laplace matrix C from the preference pairs, inv(C) (Cholesky + triangular inverse + Gram product -- no
+    explicit inverse on the host), L = chol(R + inv(C)), posteriors and acquisition.  The host indexes the distinct points and
+    evaluates the P pair weights.  `reference_exact = True` restores the reference's optimiser for the latents (SciPy BFGS on
+    numerical gradients, :441-442; ibo_b200/gaussianprocess/reference_fit.py) for problems small enough to afford it.
+    `fromLaplace` builds the process directly from a fitted (X, Y, C).
     """
 
-    device_fit_above = 40
+    reference_exact = False
 
     def __init__(self, kernel, prefs=None, **kwargs):
         super(PrefGaussianProcess, self).__init__(kernel, **kwargs)
         self.preferences = []
-        self.C = None
+        self._pairs = None          # (a, b, w): C = cdiag I + sum w (e_a - e_b)(e_a - e_b)^T
+        self._denseC = None
+        self._cdiag = 5.0
         if prefs is not None:
             self.addPreferences(prefs)
 
@@ -266,26 +286,46 @@ class PrefGaussianProcess(GaussianProcess):
         gp = cls(kernel, **kwargs)
         gp.X = np.array(X, dtype=float, ndmin=2)
         gp.Y = np.array(Y, dtype=float).reshape(-1)
-        gp._set_C(np.array(C, dtype=float))
+        gp._denseC = np.array(C, dtype=float)
+        gp._factor_with_C()
         return gp
 
-    def _set_C(self, C):
-        """L = chol(R + inv(C)), retrying with C += I up to 10 times when not SPD (:487-498)."""
-        self.C = C
+    @property
+    def C(self):
+        """the Laplace matrix (:461-486), assembled on the host only when somebody asks for it"""
+        if self._denseC is not None:
+            return self._denseC
+        if self._pairs is None:
+            return None
+        a, b, w = self._pairs
+        n = len(self.X)
+        C = np.eye(n) * self._cdiag
+        keep = a != b
+        np.add.at(C, (a[keep], a[keep]), w[keep]); np.add.at(C, (b[keep], b[keep]), w[keep])
+        np.subtract.at(C, (a[keep], b[keep]), w[keep]); np.subtract.at(C, (b[keep], a[keep]), w[keep])
+        return C
+
+    def _factor_with_C(self):
+        """L = chol(R + inv(C)) on the device, retrying with C += I up to 10 times when not SPD (:487-498)."""
         for attempt in range(11):
             self._invalidate()
-            self._Cinv = np.linalg.inv(self.C)
+            self._Cinv_host = None
+            if self._denseC is not None:
+                self._laplace = ("dense", self._denseC)
+            else:
+                self._laplace = ("pairs",) + tuple(self._pairs) + (self._cdiag,)
             try:
                 self.model   # builds and factorises on the device; raises NotPositiveDefinite
                 return
             except np.linalg.LinAlgError:
                 print('[addPreferences] GP.C matrix is ill-conditioned, adding regularizer delta = %d' % (attempt + 1))
-                self.C = self.C + np.eye(len(self.X))
+                if self._denseC is not None:
+                    self._denseC = self._denseC + np.eye(len(self.X))
+                else:
+                    self._cdiag += 1.0
         raise np.linalg.LinAlgError("R + inv(C) is not positive definite after 10 regularisation steps")
 
     def addPreferences(self, prefs, useC=True, showPrefLikelihood=False):
-        from scipy.linalg import solve_triangular
-        from scipy.optimize import fmin_bfgs
         self.preferences.extend(prefs)
         # index the distinct points in order of first appearance (:391-408)
         x2ind, prefinds, winners = {}, [], set()
@@ -303,30 +343,21 @@ class PrefGaussianProcess(GaussianProcess):
         start = np.array([lastY.get(tuple(x), ymax if tuple(x) in winners else ymin) for x in newX], dtype=float)
         # R and its factor come from the device (:433-438)
         self._invalidate()
-        self._Cinv, self.C, self.augX = None, None, None
+        self._laplace, self._pairs, self._denseC, self._Cinv_host, self.augX = None, None, None, None, None
+        self._cdiag = 5.0
         self.X, self.Y = newX, start.copy()
-        Lmat = self.L
         vi = np.array([p[0] for p in prefinds]); ui = np.array([p[1] for p in prefinds])
         dg = np.array([p[2] for p in prefinds], dtype=float)
-        verf = np.vectorize(erf, otypes=[float])
-
-        def S(x):
-            # -sum (d+1) log(CDF((x_v - x_u)/sqrt2) + 1e-10) + |L^-1 x|^2 / 2   (:373-386)
-            z = (x[vi] - x[ui]) / np.sqrt(2)
-            cdf = 0.5 * (1 + verf(z * 0.707106))
-            Lx = solve_triangular(Lmat, x, lower=True)
-            return -np.sum((dg + 1) * np.log(cdf + 1e-10)) + np.dot(Lx, Lx) / 2
-
-        # The reference minimises S with BFGS on *numerical* gradients (:442), i.e. N+1 evaluations of an O(N^2)
-        # functional per step -- hopeless at BASELINE config #3's ~1000 points.  Small problems keep that behaviour
-        # (same iterates as the reference); beyond `device_fit_above` points S is minimised on the device by Newton's
+        # The reference minimises S (:373-386) with BFGS on *numerical* gradients (:442), i.e. N+1 evaluations of an O(N^2)
+        # functional per step -- hopeless at BASELINE config #3's ~1000 points.  Here S is minimised on the device by Newton's
         # method (ibo_pref_fit: same functional, same minimiser, reached to 1e-9 instead of BFGS's 1e-5 tolerance).
         self.fit_info = None
-        if len(start) > self.device_fit_above:
+        if self.reference_exact:
+            from .reference_fit import bfgs_latents
+            self.Y = bfgs_latents(self.L, vi, ui, dg, start)
+        else:
             self.Y, Sval, gnorm, iters = self.model.pref_fit(vi, ui, dg, start)
             self.fit_info = dict(S=Sval, gnorm=gnorm, newton_iterations=iters)
-        else:
-            self.Y = np.asarray(fmin_bfgs(S, start, disp=0), dtype=float)
         # ordering fix-up (:445-458)
         losers = set(tuple(c1) for _, c1, _ in self.preferences)
         for r, c, _ in self.preferences:
@@ -337,14 +368,12 @@ class PrefGaussianProcess(GaussianProcess):
         # Laplace C matrix (:461-486): each preference (a,b) adds w to C[a,a], C[b,b] and -w to C[a,b], C[b,a]
         self._invalidate()
         mu_all = self.posteriors(self.X)[0]
-        C = np.eye(len(self.X), dtype=float) * 5
-        for a, b, _ in prefinds:
-            d = (mu_all[a] - mu_all[b]) / (np.sqrt(2) * np.sqrt(self.noise))
-            cdf, pdf = max(CDF(d), 1e-10), max(PDF(d), 1e-10)
-            w = 1.0 / (2 * self.noise) * (pdf ** 2 / cdf ** 2 + d * pdf / cdf)
-            C[a, a] += w; C[b, b] += w
-            C[a, b] -= w; C[b, a] -= w
-        self._set_C(C)
+        dd = (mu_all[vi] - mu_all[ui]) / (np.sqrt(2) * np.sqrt(self.noise))
+        cdf = np.maximum(np.array([CDF(z) for z in dd]), 1e-10)
+        pdf = np.maximum(np.array([PDF(z) for z in dd]), 1e-10)
+        w = 1.0 / (2 * self.noise) * (pdf ** 2 / cdf ** 2 + dd * pdf / cdf)
+        self._pairs = (vi.astype(np.int32), ui.astype(np.int32), w)
+        self._factor_with_C()
 
     def addObservationPoint(self, X):
         """Add a point at which we will observe but have no observation yet (:502-519): the variance is

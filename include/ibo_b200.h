@@ -100,6 +100,22 @@ int ibo_model_create(int device, int kerneltype, const double* hyper, int nhyper
                      const double* plowerb, const double* pwidth,
                      ibo_model** out, int* info);
 
+/* PrefGaussianProcess after the Laplace fit (ego/gaussianprocess/__init__.py:461-498) without any explicit inverse on the host:
+ *   C = cdiag I + sum_p w[p] (e_a - e_b)(e_a - e_b)^T  over the P preference pairs (a[p], b[p]) (indices into X; the reference's
+ *   triple loop adds +w to C[a,a], C[b,b] and -w to C[a,b], C[b,a], starting from 5 I),
+ *   A = K_offdiag(X) + (1+noise) I + inv(C),  L = chol(A), ...  -- C is assembled, factorised and inverted (Cholesky, triangular
+ * inverse, Gram product) on the device.  IBO_E_NOTSPD with *info = pivot when C or A is not positive definite (the caller retries
+ * with cdiag + 1 as the reference does with C += I, :487-498).  ibo_model_get_matrix(m, 3, out) returns inv(C). */
+int ibo_model_create_pref(int device, int kerneltype, const double* hyper, int nhyper,
+                          const double* X, const double* Y, int N, int d, double noise,
+                          int P, const int* a, const int* b, const double* w, double cdiag,
+                          ibo_model** out, int* info);
+
+/* the same with C given as a dense symmetric N x N matrix (a Laplace fit made elsewhere): inv(C) is still formed on the device */
+int ibo_model_create_laplace(int device, int kerneltype, const double* hyper, int nhyper,
+                             const double* X, const double* Y, int N, int d, double noise, const double* C,
+                             ibo_model** out, int* info);
+
 /* Same model from an explicit inverse (legacy acqmaxGP layout, N x N row-major): factors invR = W'W. */
 int ibo_model_create_from_inverse(int device, int kerneltype, const double* hyper, int nhyper,
                                   const double* X, const double* Y, int N, int d, double noise,
@@ -117,7 +133,8 @@ int ibo_model_append(ibo_model* m, const double* X, const double* Y, int k, int*
 int ibo_model_destroy(ibo_model* m);
 int ibo_model_n(const ibo_model* m);
 int ibo_model_dim(const ibo_model* m);
-/* copy back N x N row-major matrices: which = 0 -> A (=R [+Cinv]), 1 -> L (lower, zeros above), 2 -> W = inv(L) */
+/* copy back N x N row-major matrices: which = 0 -> A (=R [+Cinv]), 1 -> L (lower, zeros above), 2 -> W = inv(L),
+ * 3 -> inv(C) of a model made by ibo_model_create_pref */
 int ibo_model_get_matrix(ibo_model* m, int which, double* out);
 /* secondary ("aug") factor used for the variance only (PrefGaussianProcess.addObservationPoint,
  * ego/gaussianprocess/__init__.py:214-223,502-519): sigma^2 comes from `aug`, mu from `m`. */

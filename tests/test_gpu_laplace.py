@@ -73,3 +73,37 @@ def test_pref_gp_uses_device_fit_and_respects_preferences():
     assert gp.fit_info is not None and gp.fit_info["gnorm"] <= 1e-9
     idx = dict((tuple(x), i) for i, x in enumerate(gp.X))
     assert all(gp.Y[idx[tuple(v)]] > gp.Y[idx[tuple(u)]] for v, u, _ in prefs)      # MAP latents order every pair
+
+
+def test_laplace_matrix_is_assembled_and_inverted_on_the_device():
+    """ibo_model_create_pref: C from the preference pairs, inv(C) and chol(R + inv(C)) without any host inverse -- against NumPy
+    (ego/gaussianprocess/__init__.py:461-498); the dense-C entry (fromLaplace) must give the same factor; repeated pairs and a
+    self-pair are handled; a non-SPD C is reported like the reference's LinAlgError."""
+    from ibo_b200 import _lib
+    rs = np.random.RandomState(12)
+    N, d, P = 300, 4, 700
+    X = rs.rand(N, d) * 10; Y = rs.randn(N)
+    a = rs.randint(0, N, P).astype(np.int32); b = rs.randint(0, N, P).astype(np.int32)
+    a[5], b[5] = a[4], b[4]                     # a repeated pair
+    b[6] = a[6]                                 # a pair of a point with itself contributes nothing
+    w = rs.rand(P) * 3
+    theta = [5.146, 4.189, 4.622, 5.843]
+    m = _lib.Model(_lib.KERNEL_SE_ARD, theta, X, Y, 0.1, pref=(a, b, w, 5.0))
+    C = np.eye(N) * 5.0
+    for p in range(P):
+        if a[p] != b[p]:
+            C[a[p], a[p]] += w[p]; C[b[p], b[p]] += w[p]; C[a[p], b[p]] -= w[p]; C[b[p], a[p]] -= w[p]
+    Cinv = np.linalg.inv(C)
+    o = orc.GPOracle(orc.KernelSpec(orc.K_SE_ARD, theta, d), X, Y, 0.1, Cinv=Cinv)
+    got = m.matrix(3)
+    assert np.array_equal(got, got.T) and np.max(np.abs(got - Cinv)) <= 1e-13
+    assert np.max(np.abs(m.matrix(1) - o.L)) <= 1e-11
+    Xs = rs.rand(500, d) * 10
+    sc, mu, s2, best, bidx = m.score(Xs, _lib.ACQ_UCB, Y.max(), 1.3, _lib.FLAG_MODE_PY, want_posterior=True)
+    mu_o, s2_o = o.posterior_batch(Xs)
+    assert np.max(np.abs(mu - mu_o) / np.maximum(np.abs(mu_o), 1e-3)) <= 1e-10 and np.max(np.abs(s2 - s2_o) / s2_o) <= 1e-10
+    m2 = _lib.Model(_lib.KERNEL_SE_ARD, theta, X, Y, 0.1, C=C)
+    assert np.max(np.abs(m2.matrix(1) - m.matrix(1))) <= 1e-12
+    with pytest.raises(np.linalg.LinAlgError):
+        _lib.Model(_lib.KERNEL_SE_ARD, theta, X, Y, 0.1, pref=(a, b, -w, 0.5))
+    m.close(); m2.close()
