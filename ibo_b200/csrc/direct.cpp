@@ -32,6 +32,7 @@
 namespace ibo {
 void set_error(const std::string& s);
 int eval_neg_acq(ibo_model* m, const double* Xs, long n, int acq, double ymax, double parm, int flags, double* y);
+int batch_uses_i8(ibo_model* m, long n, int flags);
 
 namespace {
 
@@ -584,7 +585,10 @@ void gpu_batch(void* user, long n, int ndim, const double* X, double* y) {
         g->mine.assign((size_t)per + 1, 0.0);
         g->all.resize((size_t)(per + 1) * world);
         int rcLocal = IBO_OK;
-        if (hi > lo) rcLocal = eval_neg_acq(g->m, X + (size_t)lo * ndim, hi - lo, g->acq, g->ymax, g->parm, g->flags, g->mine.data());
+        // INT8 or FP64 kernels: decided from the size of the whole batch, exactly as the unsharded query decides it, so that every
+        // candidate gets the same bits on whatever rank and in whatever slice it is evaluated
+        const int sliceFlags = g->flags | (batch_uses_i8(g->m, n, g->flags) ? 0x20000000 : IBO_FLAG_FP64);
+        if (hi > lo) rcLocal = eval_neg_acq(g->m, X + (size_t)lo * ndim, hi - lo, g->acq, g->ymax, g->parm, sliceFlags, g->mine.data());
         g->mine[(size_t)per] = rcLocal == IBO_OK ? 0.0 : 1.0;
         int rc2 = ibo_comm_allgather(g->mine.data(), per + 1, g->all.data());
         g->rc = rcLocal != IBO_OK ? rcLocal : rc2;

@@ -128,7 +128,9 @@ struct Scratch {
             for (auto p : ptrs) if (*p) pool_free(*p);
             if (B->dInfo) cudaFree(B->dInfo);
             if (B->evStep) cudaEventDestroy(B->evStep);
+            if (B->evRest) cudaEventDestroy(B->evRest);
             if (B->stream2) cudaStreamDestroy(B->stream2);
+            if (B->stream3) cudaStreamDestroy(B->stream3);
             delete B;
         }
         if (dV) cudaFree(dV);
@@ -163,7 +165,9 @@ extern "C" int ibo_pref_fit(ibo_model* m, int P, const int* v, const int* u, con
     ibo_model* B = sc.B;
     B->device = m->device; B->N = N; B->Np = Np; B->nb = nb; B->stream = st;
     TRYS(cudaStreamCreateWithFlags(&B->stream2, cudaStreamNonBlocking));
+    TRYS(cudaStreamCreateWithFlags(&B->stream3, cudaStreamNonBlocking));
     TRYS(cudaEventCreateWithFlags(&B->evStep, cudaEventDisableTiming));
+    TRYS(cudaEventCreateWithFlags(&B->evRest, cudaEventDisableTiming));
     TRYS(pool_malloc((void**)&B->dA, sizeof(double) * (size_t)Np * Np));
     TRYS(pool_malloc((void**)&B->dW, sizeof(double) * (size_t)Np * Np));
     TRYS(pool_malloc((void**)&B->dD, sizeof(double) * (size_t)nb * 128 * 128));

@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(256, 1) syrk_identity_kernel(double* __restric
 
 template <int MODE>
 __global__ void __launch_bounds__(256, 1) block_step_kernel(double* __restrict__ A, double* __restrict__ W,
-                                                            const double* __restrict__ D, int Np, int k) {
+                                                            const double* __restrict__ D, int Np, int k, int jofs = 0) {
     extern __shared__ double sm[];
     double acc[8][4][2];
 #pragma unroll
@@ -393,8 +393,8 @@ __global__ void __launch_bounds__(256, 1) block_step_kernel(double* __restrict__
         tile_gemm_core<true>(C, Np, D + (size_t)k * 128 * 128, 128, 128, acc, sm);
         subtract = false;
     } else if (MODE == MODE_CHOL_TRAIL) {
-        // A_ij -= L_ik L_jk^T for k < j <= i
-        int i = k + 1 + blockIdx.y, j = k + 1 + blockIdx.x;
+        // A_ij -= L_ik L_jk^T for k < j <= i   (jofs: first block column of this launch -- the look-ahead splits column k+1 off)
+        int i = k + 1 + blockIdx.y, j = k + 1 + jofs + blockIdx.x;
         if (j > i) return;
         C = A + (size_t)i * 128 * Np + (size_t)j * 128;
         tile_gemm_core<true>(A + (size_t)i * 128 * Np + (size_t)k * 128, Np, A + (size_t)j * 128 * Np + (size_t)k * 128, Np, 128, acc, sm);
@@ -692,6 +692,13 @@ int launch_factorize(ibo_model* m, bool from_inverse_reversed, bool pack) {
         set_identity_kernel<<<g2, 256, 0, s2>>>(m->dW, Np);
         g_launches++;
     }
+    // Look-ahead of depth one.  The trailing update of step k is split: block column k+1 stays on the critical stream (it is all
+    // potrf(k+1) and panel(k+1) wait for), the rest goes to a low-priority bulk stream.  The one-CTA diagonal factorisation and the
+    // thin panel of step k+1 then run while the bulk update of step k still fills the GPU.  Dependencies: rest(k) reads the panel
+    // of step k (evStep) and follows rest(k-1) in stream order; first(k+1) updates column k+2, which rest(k) wrote (evRest).
+    cudaStream_t sb = m->stream3;
+    IBO_CUDA_TRY(cudaEventRecord(m->evRest, st));
+    IBO_CUDA_TRY(cudaStreamWaitEvent(sb, m->evRest, 0));
     for (int k = 0; k < nb; k++) {
         potrf_diag_kernel<<<1, 512, potrf_smem, st>>>(m->dA, Np, k, m->dD, m->dInfo);
         g_launches++;
@@ -700,8 +707,8 @@ int launch_factorize(ibo_model* m, bool from_inverse_reversed, bool pack) {
             block_step_kernel<MODE_CHOL_PANEL><<<nrem, 256, tile_smem, st>>>(m->dA, nullptr, m->dD, Np, k);
             g_launches++;
         }
+        IBO_CUDA_TRY(cudaEventRecord(m->evStep, st));
         if (!from_inverse_reversed) {
-            IBO_CUDA_TRY(cudaEventRecord(m->evStep, st));
             IBO_CUDA_TRY(cudaStreamWaitEvent(s2, m->evStep, 0));
             block_step_kernel<MODE_TRTRI_SCALE><<<k + 1, 256, tile_smem, s2>>>(m->dA, m->dW, m->dD, Np, k);
             g_launches++;
@@ -711,10 +718,19 @@ int launch_factorize(ibo_model* m, bool from_inverse_reversed, bool pack) {
             }
         }
         if (nrem > 0) {
-            block_step_kernel<MODE_CHOL_TRAIL><<<dim3(nrem, nrem), 256, tile_smem, st>>>(m->dA, nullptr, m->dD, Np, k);
+            if (k > 0) IBO_CUDA_TRY(cudaStreamWaitEvent(st, m->evRest, 0));      // column k+1 carries the update of step k-1
+            block_step_kernel<MODE_CHOL_TRAIL><<<dim3(1, nrem), 256, tile_smem, st>>>(m->dA, nullptr, m->dD, Np, k, 0);
             g_launches++;
+            if (nrem > 1) {
+                IBO_CUDA_TRY(cudaStreamWaitEvent(sb, m->evStep, 0));
+                block_step_kernel<MODE_CHOL_TRAIL><<<dim3(nrem - 1, nrem), 256, tile_smem, sb>>>(m->dA, nullptr, m->dD, Np, k, 1);
+                g_launches++;
+                IBO_CUDA_TRY(cudaEventRecord(m->evRest, sb));
+            }
         }
     }
+    IBO_CUDA_TRY(cudaEventRecord(m->evRest, sb));
+    IBO_CUDA_TRY(cudaStreamWaitEvent(st, m->evRest, 0));
     if (from_inverse_reversed) {
         reverse_transpose_kernel<<<g2, 256, 0, st>>>(m->dW, m->dA, m->N, Np);
         g_launches++;
@@ -779,6 +795,7 @@ static void free_model(ibo_model* m) {
     }
     cudaSetDevice(m->device);
     if (m->stream2) cudaStreamSynchronize(m->stream2);
+    if (m->stream3) cudaStreamSynchronize(m->stream3);
     if (m->stream) cudaStreamSynchronize(m->stream);   // blocks go back to the pool: nothing may still be using them
     double** ptrs[] = {&m->dXt, &m->dInvTheta, &m->dCenter, &m->dA, &m->dAorig, &m->dW, &m->dD, &m->dWpack, &m->dBetaY, &m->dBeta1, &m->dY,
                        &m->dPmeans, &m->dPbeta, &m->dPlb, &m->dPwidth, &m->dCand, &m->dSlab, &m->dPart, &m->dOut, &m->dBlkBest, &m->dBest, &m->dAppend,
@@ -792,6 +809,8 @@ static void free_model(ibo_model* m) {
     if (m->hPinned) pinned_put(m->hPinned);
     for (auto& e : m->ev) if (e) cudaEventDestroy(e);
     if (m->evStep) cudaEventDestroy(m->evStep);
+    if (m->evRest) cudaEventDestroy(m->evRest);
+    if (m->stream3) cudaStreamDestroy(m->stream3);
     for (auto& e : m->evI8) if (e) cudaEventDestroy(e);
     if (m->stream2) cudaStreamDestroy(m->stream2);
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -852,6 +871,8 @@ static int create_common(int device, int kind, const double* hyper, int nhyper, 
     TRYM(cudaDeviceGetStreamPriorityRange(&prLo, &prHi));
     TRYM(cudaStreamCreateWithPriority(&m->stream, cudaStreamNonBlocking, prHi));
     TRYM(cudaStreamCreateWithPriority(&m->stream2, cudaStreamNonBlocking, prLo));
+    TRYM(cudaStreamCreateWithPriority(&m->stream3, cudaStreamNonBlocking, prLo));
+    TRYM(cudaEventCreateWithFlags(&m->evRest, cudaEventDisableTiming));
     TRYM(cudaEventCreateWithFlags(&m->evStep, cudaEventDisableTiming));
     for (auto& e : m->ev) TRYM(cudaEventCreate(&e));
     TRYM(pool_malloc((void**)&m->dXt, sizeof(double) * (size_t)Np * d));

@@ -9,8 +9,9 @@
 struct ibo_model {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t stream2 = nullptr;   // inversion pipeline of the model build
-    cudaEvent_t evStep = nullptr;
+    cudaStream_t stream2 = nullptr;   // inversion pipeline of the model build; K1 of the next chunk on the INT8 path
+    cudaStream_t stream3 = nullptr;   // bulk trailing updates of the look-ahead Cholesky
+    cudaEvent_t evStep = nullptr, evRest = nullptr;
     int N = 0, d = 0, kind = 0;
     int nb = 0;          // 128-row blocks
     int Np = 0;          // nb * 128 (identity padded)

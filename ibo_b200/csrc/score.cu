@@ -881,6 +881,8 @@ static void launch_kstar(const ibo_model* m, const double* dCand, double* slab, 
 namespace ibo {
 
 constexpr int FLAG_FORCE_WIDE = 0x40000000;     // internal: K2's throughput shape (and no fused small-model kernel) whatever the batch size
+constexpr int FLAG_I8_ANY_SIZE = 0x20000000;    // internal (sharded DIRECT): the INT8 path whatever the size of this slice -- the
+                                                // arithmetic of a candidate is chosen from the size of the FULL batch on every rank
 
 static cudaError_t set_i8_attrs() {
     cudaError_t e = cudaFuncSetAttribute(trigemm_i8_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8Cfg<4>::SMEM);
@@ -891,9 +893,17 @@ static cudaError_t set_i8_attrs() {
 // Which arithmetic scores this batch.  Wide batches (more than `narrow_max` candidates) of a plain model go through the INT8
 // tensor-core path unless the caller forces FP64 (IBO_FLAG_FP64, option int8 = 0); small batches, models with a variance model
 // (PrefGP aug), d > 32 and N > 16384 (INT32 head-room of the 8-bit digits) always take the DMMA kernels.
-static bool use_i8(const ibo_model* m, bool narrow, int flags) {
-    if (narrow || m->var_model || m->d > 32 || m->Np > 16384 || (flags & IBO_FLAG_FP64)) return false;
+static bool i8_eligible(const ibo_model* m, int flags) {
+    if (m->var_model || m->d > 32 || m->Np > 16384 || (flags & IBO_FLAG_FP64)) return false;
     return (flags & IBO_FLAG_INT8) || get_option(OPT_INT8) != 0;
+}
+// Batches of i8_min_batch .. narrow_max candidates (DIRECT's mid-size batches) on a model of more than one row-block: the FP64
+// latency shapes need N^2 flops per candidate at 37 TF/s, the INT8 kernels finish the same batch several times sooner.
+static bool i8_for_small_batch(const ibo_model* m, long M, int flags) {
+    if (!i8_eligible(m, flags) || m->nb < 2) return false;
+    if (flags & FLAG_I8_ANY_SIZE) return true;
+    const long lo = get_option(OPT_I8_MIN_BATCH);
+    return lo > 0 && M >= lo;
 }
 
 // Runs K1..K4 for M candidates resident at dCand; results land in m->dOut ([score|mu|s2][M]) and
@@ -924,8 +934,9 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
     }
     const long tilesTotal = (M + TN - 1) / TN;
     long chunkTiles = std::min<long>(tilesTotal, chunk_tiles_default(sms));
-    const bool narrow = !forceWide && M <= narrow_threshold();
-    const bool i8 = use_i8(m, narrow, rq.flags);
+    const bool i8small = !forceWide && M <= narrow_threshold() && i8_for_small_batch(m, M, rq.flags);
+    const bool narrow = !forceWide && !i8small && M <= narrow_threshold();
+    const bool i8 = !narrow && i8_eligible(m, rq.flags);
     // keep the slab below ~6 GiB (FP64: 8 N bytes per candidate; INT8: 7 N bytes, double buffered)
     while (chunkTiles > 1 && (double)chunkTiles * nb * KB_PER_BLOCK * BLOB * (i8 ? 14.0 : 8.0) > 6.0e9) chunkTiles = (chunkTiles + 1) / 2;
     const long Mpad = chunkTiles * TN;
@@ -940,7 +951,7 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
     }
     // int8 path: K1 of chunk c+1 (FP64 / integer pipes, low-priority stream2) runs under K2 of chunk c (tensor pipe, main stream);
     // slab and partial-sum planes are double buffered.  With IBO_FLAG_PROFILE the chunks run back to back so that K1 / K2 can be timed.
-    const bool i8pipe = i8 && !prof && get_option(OPT_I8_PIPE) != 0;
+    const bool i8pipe = i8 && !prof && get_option(OPT_I8_PIPE) != 0 && tilesTotal > chunkTiles;     // a single chunk has nothing to overlap
     const size_t i8SlabBytes = (size_t)chunkTiles * 2 * nb * 4 * I8_B_STAGE, i8PartDbl = (size_t)3 * nb * Mpad;
     // guard pass: only a model whose sigma^2 can get below the threshold needs it (sigma^2 >= noise for a model built from R)
     const bool guard = i8 && get_option(OPT_I8_GUARD) != 0 && (m->noise < I8_GUARD_S2 || m->from_inverse);
@@ -1152,6 +1163,12 @@ __global__ void debug_exp_kernel(const double* __restrict__ x, long n, double* _
 }
 
 // used by the DIRECT objective (direct.cpp): negated acquisition for n points
+// the arithmetic a DIRECT batch of n points gets (sharded DIRECT asks with the size of the full batch and forces the answer on
+// every rank's slice): 1 = INT8 path, 0 = FP64 kernels
+int batch_uses_i8(ibo_model* m, long n, int flags) {
+    if (n > narrow_threshold()) return i8_eligible(m, flags) ? 1 : 0;
+    return i8_for_small_batch(m, n, flags) ? 1 : 0;
+}
 int eval_neg_acq(ibo_model* m, const double* Xs, long n, int acq, double ymax, double parm, int flags, double* y) {
     ScoreReq rq{acq, ymax, parm, flags, true, false, false};
     rq.want_argmax = false;      // DIRECT consumes every value; the argmax kernels would be wasted launches

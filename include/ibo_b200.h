@@ -212,6 +212,7 @@ int ibo_debug_exp(int device, const double* x, long n, double* out_fast, double*
  * Process-wide tuning / debugging switches, visible at the boundary (no hidden environment reads in the launch paths; an
  * environment variable IBO_<NAME IN CAPITALS> presets the option when the library is loaded).  Names:
  *   int8 (1)          wide batches take the INT8 tensor-core path (0: FP64 DMMA everywhere; per call: IBO_FLAG_INT8 / IBO_FLAG_FP64)
+ *   i8_min_batch (192) batches of this many .. narrow_max candidates take the INT8 path too (DIRECT's mid-size batches; 0: wide only)
  *   i8_guard (1)      INT8 path: re-score candidates with sigma^2 < 2^-10 on the DMMA path
  *   i8_pipe (1)       INT8 path: cross-covariance of chunk c+1 on a low-priority stream under the GEMM of chunk c
  *   chunk_tiles (0)   128-candidate tiles per chunk (0: 2 x number of SMs)
