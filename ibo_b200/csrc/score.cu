@@ -1130,8 +1130,9 @@ static int score_host(ibo_model* m, const double* Xs, long M, const ScoreReq& rq
         const double* cand = m->dCand;
         const ibo_model* vmh = m->var_model;
         if (tiny_eligible(m, M)) cand = m->hPinned;
-        else if (nin <= (size_t)CAND_INLINE && m->npb == 0 && kstar_uses_mma(m) && (!vmh || kstar_uses_mma(vmh)))
-            cand = nullptr;          // K1 takes the batch from its parameter buffer (K3 reads candidates only for a prior mean)
+        else if (nin <= (size_t)CAND_INLINE && m->npb == 0 && kstar_uses_mma(m) && (!vmh || kstar_uses_mma(vmh)) &&
+                 !i8_for_small_batch(m, M, rq.flags))
+            cand = nullptr;          // the FP64 K1 takes the batch from its parameter buffer (K3 reads candidates only for a prior mean)
         else IBO_CUDA_TRY(cudaMemcpyAsync(m->dCand, m->hPinned, sizeof(double) * nin, cudaMemcpyHostToDevice, st));
         double* ho = m->hPinned + nin;
         if ((rc = score_device(m, cand, M, rq, ho, m->hPinned))) return rc;

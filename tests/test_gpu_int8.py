@@ -97,7 +97,7 @@ def test_int8_values_do_not_depend_on_the_batch():
     assert r[4] == int(np.argmax(full[0][:3000]))
 
 
-def test_int8_follows_append_and_small_batches_stay_fp64():
+def test_int8_follows_append_and_batch_size_classes():
     from ibo_b200 import _lib
     gp, o, Xs, Y = _case(250, 3, 3000)
     fl = _lib.FLAG_MODE_PY
@@ -109,10 +109,21 @@ def test_int8_follows_append_and_small_batches_stay_fp64():
     sc, mu, s2, best, bidx = gp.model.score(Xs, _lib.ACQ_EI, max(gp.Y), 0.01, flags=fl, want_posterior=True)
     mu_o, s2_o = o.posterior_batch(Xs)
     assert _rel(mu, mu_o, 1e-3) <= TOL and _rel(s2, s2_o, 1e-300) <= TOL
-    # batches of <= 2048 candidates take the FP64 latency shapes whatever the flag says
-    a = gp.model.score(Xs[:500], _lib.ACQ_EI, max(gp.Y), 0.01, flags=fl | _lib.FLAG_FP64, want_posterior=True)
-    b = gp.model.score(Xs[:500], _lib.ACQ_EI, max(gp.Y), 0.01, flags=fl | _lib.FLAG_INT8, want_posterior=True)
+    # batches below option i8_min_batch (192) take the FP64 latency shapes whatever the flag says ...
+    a = gp.model.score(Xs[:100], _lib.ACQ_EI, max(gp.Y), 0.01, flags=fl | _lib.FLAG_FP64, want_posterior=True)
+    b = gp.model.score(Xs[:100], _lib.ACQ_EI, max(gp.Y), 0.01, flags=fl | _lib.FLAG_INT8, want_posterior=True)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+    # ... DIRECT's mid-size batches (192 .. 2048 points) take the INT8 kernels, and a candidate gets the bits it gets in a wide batch
+    c = gp.model.score(Xs[:500], _lib.ACQ_EI, max(gp.Y), 0.01, flags=fl, want_posterior=True)
+    assert np.array_equal(c[0], sc[:500]) and np.array_equal(c[1], mu[:500]) and np.array_equal(c[2], s2[:500])
+    f = gp.model.score(Xs[:500], _lib.ACQ_EI, max(gp.Y), 0.01, flags=fl | _lib.FLAG_FP64, want_posterior=True)
+    assert not np.array_equal(f[2], c[2]) and _rel(c[2], f[2], 1e-300) <= 1e-12
+    _lib.set_option("i8_min_batch", 0)
+    try:
+        g = gp.model.score(Xs[:500], _lib.ACQ_EI, max(gp.Y), 0.01, flags=fl, want_posterior=True)
+    finally:
+        _lib.set_option("i8_min_batch", 192)
+    assert np.array_equal(g[2], f[2])
 
 
 def test_option_int8_off_means_dmma_everywhere():
