@@ -607,7 +607,7 @@ __global__ void __launch_bounds__(128) i8_peak_kernel(int iters, int rnd, int* _
     __syncthreads();
     tc_fence_after();
     const uint32_t td = tbase;
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
         // 128-byte-deep tiles: the k chunks of a row group are 128 B apart, row groups 8 * 128 B apart
         auto desc = [](uint32_t addr) {
             return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46);

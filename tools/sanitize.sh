@@ -17,3 +17,8 @@ compute-sanitizer --tool racecheck --error-exitcode 3 python -m pytest tests/tes
 echo "racecheck tiny rc=$?"
 compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest tests/test_gpu_append.py tests/test_gpu_laplace.py -x -q -m gpu -k "127 or small" 2>&1 | tail -6
 echo "memcheck append/laplace rc=$?"
+# round 2: INT8 wide-batch path (K1 / K2 / guard pass), device-side Laplace matrix, look-ahead factorisation (every model build above)
+compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest tests/test_gpu_int8.py -x -q -m gpu -k "(default_wide and (300-3 or 129-1 or 200-2)) or guard or batch_size_classes" 2>&1 | tail -6
+echo "memcheck int8 rc=$?"
+compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest tests/test_gpu_laplace.py -x -q -m gpu -k "assembled" 2>&1 | tail -6
+echo "memcheck pref-C rc=$?"
