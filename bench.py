@@ -112,13 +112,13 @@ class Workload(object):
             return {"workload": "config #4: GaussianProcess Matern-5/2 ARD d=10, N=8192 observations, EI xi=0.01 over %d unscrambled Sobol "
                                 "candidates sharded by index range (%d per GPU), NCCL argmax" % (self.total, self.M),
                     "n_obs": self.N, "dim": self.d, "candidates_per_gpu": self.M, "arithmetic": "libm-erf / floor 1e-8 (libego) mode",
-                    "l2": "inputs larger than L2: each step streams the packed K* slab (N x M x 8 B = %.1f GB per GPU) besides W and "
-                          "the candidates" % (self.N * self.M * 8 / 1e9)}
+                    "l2": "inputs larger than L2: each step streams the K* slab (N x M x 7 B of INT8 digits = %.1f GB per GPU; 8 B per "
+                          "element on the FP64 arm) besides W and the candidates" % (self.N * self.M * 7 / 1e9)}
         return {"workload": "config #2: GaussianProcess SE-ARD d=%d, N=%d observations (Hartman6), EI xi=%.2f over %d uniform random "
                             "candidates per GPU" % (self.d, self.N, XI, self.M),
                 "n_obs": self.N, "dim": self.d, "candidates_per_gpu": self.M, "arithmetic": "libm-erf / floor 1e-8 (libego) mode",
-                "l2": "inputs larger than L2: each step streams the packed K* slab (N x M x 8 B = %.1f GB) besides W and the candidates"
-                      % (self.N * self.M * 8 / 1e9)}
+                "l2": "inputs larger than L2: each step streams the K* slab (N x M x 7 B of INT8 digits = %.1f GB; 8 B per element on the "
+                      "FP64 arm) besides W and the candidates" % (self.N * self.M * 7 / 1e9)}
 
 
 def kernel_sass_sha16(kernel):
@@ -167,12 +167,17 @@ class ClockSampler(object):
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.idx, self.proc, self.lines = gpu_index, None, []
+    def __init__(self, gpu_index, rank=0, world=1):
+        """one sampler per node: rank 0 watches every GPU of the job (eight polling nvidia-smi processes would themselves disturb
+        the latency-bound workloads); the other ranks report nothing"""
+        self.idx = ",".join(str(i) for i in range(world)) if world > 1 else str(gpu_index)
+        self.proc, self.lines, self.active = None, [], rank == 0
 
     def start(self):
+        if not self.active:
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.idx, "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
                                           "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -184,6 +189,8 @@ class ClockSampler(object):
             self.lines.append(line.strip())
 
     def stop(self):
+        if not self.active:
+            return None
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
@@ -207,8 +214,8 @@ class ClockSampler(object):
                     reasons.add(nm)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(min(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "gpus": self.idx, "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -540,7 +547,7 @@ def run_direct_workload(args, rank, world, device, dist):
     my_xi = [0.01 + 0.003 * ((rank * nq + q) % 7) for q in range(nq)]      # this rank's queries
     for _ in range(max(args.warmup, 1)):
         query(False, my_xi[0])
-    sampler = ClockSampler(device)
+    sampler = ClockSampler(device, rank, world)
     sync_all()
     sampler.start()
     launches0 = L.ibo_launch_count()
@@ -676,7 +683,7 @@ def main():
 
     for _ in range(args.warmup):
         step_resident()
-    sampler = ClockSampler(device)
+    sampler = ClockSampler(device, rank, world)
     sync_all()
     sampler.start()
     launches0 = L.ibo_launch_count()

@@ -120,6 +120,7 @@ struct Driver {
     double FMIN = MAX_DOUBLE;
     std::vector<double> XMIN;
     long nsamples = 0;
+    bool timed_out = false;     // maxtime ran out in the middle of an iteration (rectangle-by-rectangle mode)
     bool failed = false;        // the objective reported a failed evaluation (NaN): the run stops, nothing else is evaluated
     std::vector<double> xbuf;   // batch staging (box coordinates)
 
@@ -194,7 +195,8 @@ static inline double now_s() { return std::chrono::duration<double>(std::chrono:
 
 // Divides the given rectangles (already in processing order): appends the new rectangles in the reference's
 // order and retires the sources.  seq: one rectangle per batch pair (the reference's exact call order).
-void divide(Driver& D, Store& R, const std::vector<unsigned>& order, bool seq, bool speculate, Scratch& W) {
+void divide(Driver& D, Store& R, const std::vector<unsigned>& order, bool seq, bool speculate, Scratch& W,
+            time_t start = 0, int maxtime = -1) {
     const int N = D.N;
     size_t g0 = 0;
     while (g0 < order.size()) {
@@ -379,6 +381,9 @@ void divide(Driver& D, Store& R, const std::vector<unsigned>& order, bool seq, b
         }
         g_pt.replay += now_s() - tC;
         g0 = g1;
+        // rectangle-by-rectangle mode (a scalar callback, possibly slow): the wall-clock budget is checked after every rectangle,
+        // as the reference does (cpp/direct.cpp:493-497); the batched modes check once per iteration
+        if (seq && maxtime >= 0 && time(NULL) - start > maxtime) { D.timed_out = true; break; }
     }
 }
 
@@ -534,8 +539,8 @@ int run_direct(ibo_batch_objective_t f, void* user, int ndim, const double* lb, 
             ns += 4L * k;
             if (ns > (long)(unsigned)maxsample) { done = true; break; }
         }
-        divide(D, R, order, seq, speculate, W);
-        if (D.failed) break;
+        divide(D, R, order, seq, speculate, W, start, maxtime);
+        if (D.failed || D.timed_out) break;
         if (time(NULL) - start > maxtime) break;
         if (D.nsamples > (long)(unsigned)maxsample) break;
     }

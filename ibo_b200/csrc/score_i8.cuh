@@ -577,7 +577,10 @@ static void launch_kstar_i8(ibo_model* m, const double* dCand, long tiles, long 
 // K2 of one chunk on the int8 path
 static void launch_trigemm_i8(ibo_model* m, long tiles, long Mpad, const uint8_t* Ki8, double* part, cudaStream_t st) {
     const int sms = dev_info(m->device).sms;
-    int G = std::max(1, m->nb / 4);
+    // row-blocks per CTA: nb / G.  More row-blocks per CTA = fewer CTA prologues (TMEM allocation, pipeline fill) per unit of
+    // work, fewer CTAs sharing a candidate tile's K* digits in L2 (option i8_rb_per_cta, default 4)
+    const int per = (int)std::max<long>(1, get_option(OPT_I8_RB_PER_CTA));
+    int G = std::max(1, m->nb / per);
     if (tiles * 2 * G < sms) G = (int)std::min<long>(m->nb, (sms + tiles * 2 - 1) / (tiles * 2));
     const dim3 grid(G, (unsigned)(tiles * 2));
     if (m->i8Ntm) trigemm_i8_kernel<4><<<grid, I8Cfg<4>::THREADS, I8Cfg<4>::SMEM, st>>>(reinterpret_cast<const uint8_t*>(m->dWi8s), reinterpret_cast<const uint8_t*>(m->dWi8t),

@@ -290,3 +290,27 @@ def test_objective_failure_stops_the_driver_at_once():
     with pytest.raises(_lib.IBOError) as ei:
         direct(lambda x: float("nan") if x[0] > 0.6 else float(np.sum(x ** 2)), [(0., 1.)] * 2, maxiter=50)
     assert ei.value.code == _lib.E_OBJECTIVE
+
+
+def test_maxtime_is_checked_after_every_rectangle_for_scalar_callbacks():
+    """the legacy `direct` symbol drives a scalar callback rectangle by rectangle and, like the reference
+    (cpp/direct.cpp:493-497), looks at the clock after each rectangle: a slow objective overshoots a 1 s budget by at most
+    one rectangle's evaluations, not by a whole iteration"""
+    import time
+    calls = [0]
+
+    def slow(n, x):
+        calls[0] += 1
+        time.sleep(0.02)
+        return float(sum((x[i] - 0.3) ** 2 for i in range(n)))
+
+    d = 6
+    lb = np.zeros(d); ub = np.ones(d)
+    t0 = time.time()
+    res = _lib.lib().direct(_lib.OBJECTIVE(slow), d, _lib.dptr(lb), _lib.dptr(ub), 10 ** 6, 1, 10 ** 6)
+    wall = time.time() - t0
+    assert res
+    libc = ctypes.CDLL(None); libc.free.argtypes = [ctypes.c_void_p]; libc.free(res)
+    # time() has one-second resolution: the budget of 1 s ends between 1 and 2 s after the start, plus at most one rectangle
+    # (4 d evaluations of 20 ms) -- an iteration of this problem would be several seconds
+    assert 1.0 <= wall <= 2.0 + 4 * d * 0.02 + 0.5, wall
