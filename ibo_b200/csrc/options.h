@@ -23,7 +23,7 @@ enum {
     OPT_I8_RB_PER_CTA,   // row-blocks a CTA of the INT8 K2 sweeps (G = nb / this many CTAs share a candidate tile)
     OPT_I8_NTM,          // 0 (default): every operand of the INT8 K2 in shared memory; 1: W digits 1..4 reach the tensor core through TMEM
                          // (measured 6-13 % slower under the power cap: profiles/r02_int8_k2.md)
-    OPT_I8_DBG,          // timing experiments on the INT8 K2 (results are wrong when != 0)
+    OPT_I8_DBG,          // timing experiments on the INT8 K2: honoured only by the debug build (EXTRA=-DIBO_I8_TRACE), ignored otherwise
     OPT_COUNT
 };
 long get_option(int id);

@@ -293,9 +293,16 @@ __global__ void __launch_bounds__(256, (DMAX <= 8 ? 4 : (DMAX <= 16 ? 3 : 2))) k
 template <int NTM>
 __global__ void __launch_bounds__(I8Cfg<NTM>::THREADS, (NTM ? 1 : 2)) trigemm_i8_kernel(const uint8_t* __restrict__ Ws, const uint8_t* __restrict__ Wt,
                                                                     const uint8_t* __restrict__ Ki8, const double* __restrict__ rowScaleSf,
-                                                                    double* __restrict__ part, int nb, long Mpad, int dbg) {
-    // dbg: timing experiments only (results are wrong when != 0): 1 loaders skip the L2 loads, 2 no TMEM feed at all, 4 no SS MMAs,
-    // 8 no TS MMAs, 16 no K* copy, 32 no W copy
+                                                                    double* __restrict__ part, int nb, long Mpad, int dbg_in) {
+    // dbg: timing experiments of the debug build only (make EXTRA=-DIBO_I8_TRACE; results are wrong when != 0): 1 loaders skip the
+    // L2 loads, 4 no MMAs from shared-memory A digits, 8 no MMAs from TMEM A digits, 16 no K* copy, 32 no W copy.  The shipped
+    // build compiles every switch out.
+#ifdef IBO_I8_TRACE
+    const int dbg = dbg_in;
+#else
+    constexpr int dbg = 0;
+    (void)dbg_in;
+#endif
     // rowScaleSf[row]: the factor that turns the assembled integer sum into v; rowScaleSf[Np + row]: the additive constant
     constexpr int STAGES = I8Cfg<NTM>::STAGES, AS_STAGE = I8Cfg<NTM>::AS_STAGE, AT_STEP = I8Cfg<NTM>::AT_STEP;
     extern __shared__ __align__(1024) uint8_t smem[];

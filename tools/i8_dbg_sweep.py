@@ -1,3 +1,5 @@
+"""Debug build only (make -C ibo_b200/csrc EXTRA=-DIBO_I8_TRACE): K2 of the INT8 path with one component removed at a time (option
+i8_dbg; results are wrong, only the time matters) -- how profiles/r02_int8_k2.md separated issue, feed and tensor time."""
 import sys, numpy as np
 sys.path.insert(0, '/root/repo')
 from ibo_b200 import _lib
