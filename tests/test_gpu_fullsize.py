@@ -91,3 +91,29 @@ def test_config5_batched_direct_equals_rectangle_by_rectangle():
     from ibo_b200 import _lib
     sc = gp.model.score(np.array([x1]), _lib.ACQ_EI, Y.max(), 0.01, _lib.FLAG_MODE_CPP)[0]
     assert abs(sc[0] - o1) <= 1e-11 * abs(o1)
+
+
+def test_int8_path_at_its_size_limit_and_fallback_above_it():
+    """N = 16384 is the largest model the INT8 path accepts (INT32 head-room of the 8-bit digit sums: 98304 N < 2^31,
+    tests/test_int8_model.py): there it must still agree with the FP64 DMMA kernels to rounding; one row-block more and a wide
+    batch silently stays on the DMMA kernels (bit-identical to IBO_FLAG_FP64)."""
+    from ibo_b200 import _lib
+    rs = np.random.RandomState(16)
+    d, M = 4, 2600
+    Xs = rs.rand(M, d)
+    for N, expect_i8 in ((16384, True), (16384 + 128, False)):
+        X = rs.rand(N, d)
+        Y = np.sin(3 * X).sum(axis=1)
+        m = _lib.Model(_lib.KERNEL_SE_ARD, [0.12, 0.15, 0.1, 0.2], X, Y, 0.1)
+        a = m.score(Xs, _lib.ACQ_EI, Y.max(), 0.01, _lib.FLAG_MODE_CPP | _lib.FLAG_FP64, want_posterior=True)
+        b = m.score(Xs, _lib.ACQ_EI, Y.max(), 0.01, _lib.FLAG_MODE_CPP, want_posterior=True)
+        if expect_i8:
+            assert not np.array_equal(a[2], b[2])
+            assert np.max(np.abs(a[2] - b[2]) / a[2]) <= 1e-11 and np.max(np.abs(a[1] - b[1]) / np.maximum(np.abs(a[1]), 1e-3)) <= 1e-11
+            assert np.max(np.abs(a[0] - b[0]) / np.maximum(np.abs(a[0]), 1e-5)) <= 1e-10 and a[4] == b[4]
+            # a training point: sigma^2 in [noise, 2 noise], mu pulled towards its observation
+            mu, s2 = m.posterior(X[:2600], _lib.FLAG_MODE_CPP)
+            assert np.all(s2 >= 0.1 - 1e-9) and np.all(s2 <= 0.2 + 1e-9)
+        else:
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+        m.close()
