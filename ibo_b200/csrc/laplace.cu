@@ -129,6 +129,9 @@ struct Scratch {
             if (B->dInfo) cudaFree(B->dInfo);
             if (B->evStep) cudaEventDestroy(B->evStep);
             if (B->evRest) cudaEventDestroy(B->evRest);
+            if (B->evScale) cudaEventDestroy(B->evScale);
+            if (B->evFar) cudaEventDestroy(B->evFar);
+            if (B->stream4) cudaStreamDestroy(B->stream4);
             if (B->stream2) cudaStreamDestroy(B->stream2);
             if (B->stream3) cudaStreamDestroy(B->stream3);
             delete B;
@@ -168,6 +171,9 @@ extern "C" int ibo_pref_fit(ibo_model* m, int P, const int* v, const int* u, con
     TRYS(cudaStreamCreateWithFlags(&B->stream3, cudaStreamNonBlocking));
     TRYS(cudaEventCreateWithFlags(&B->evStep, cudaEventDisableTiming));
     TRYS(cudaEventCreateWithFlags(&B->evRest, cudaEventDisableTiming));
+    TRYS(cudaStreamCreateWithFlags(&B->stream4, cudaStreamNonBlocking));
+    TRYS(cudaEventCreateWithFlags(&B->evScale, cudaEventDisableTiming));
+    TRYS(cudaEventCreateWithFlags(&B->evFar, cudaEventDisableTiming));
     TRYS(pool_malloc((void**)&B->dA, sizeof(double) * (size_t)Np * Np));
     TRYS(pool_malloc((void**)&B->dW, sizeof(double) * (size_t)Np * Np));
     TRYS(pool_malloc((void**)&B->dD, sizeof(double) * (size_t)nb * 128 * 128));

@@ -201,148 +201,209 @@ __global__ void set_identity_kernel(double* __restrict__ W, int Np) {
 
 // ---------------------------------------------------------------------------------------------
 // Diagonal block: L_kk = chol(A_kk) in place (lower), D_k = inv(L_kk) (dense 128x128, zeros above).
-// One CTA, 512 threads, the block lives in shared memory.
-//   * Cholesky: right-looking with 16-column panels -- inside a panel one column at a time (scale, then update the
-//     rest of the panel), then one rank-16 update of the trailing part (264 barriers instead of 384, and the O(n^2)
-//     work per column of the unblocked form becomes O(16 n)).
-//   * Inverse: recursive doubling from 16x16 diagonal blocks (see below).
+// One CTA, 512 threads, the block lives in shared memory.  The kernel sits on the critical path of every block step of the
+// factorisation (one launch per 128 columns, nothing else can run before it), so everything with more than 8 x 8 work in it
+// goes through the FP64 tensor-core instruction (mma.sync m8n8k4), 16 warps at a time:
+//   * Cholesky, right-looking over 16 panels of 8 columns: the threads of warps 0-3 factor the 8 x 8 diagonal block in
+//     registers (all the same values, no broadcast through shared memory; rsqrt instead of sqrt + divide) and thread t solves
+//     row t of the panel below it; the rank-8 update of the trailing triangle is one 8 x 8 tile = two MMAs per warp and turn.
+//   * Inverse in place by doubling: the sixteen 8 x 8 diagonal blocks first (one thread per column), then for b = 8, 16, 32, 64
+//     every pair of adjacent b x b inverses is merged, X21 = -X22 (L21 X11): two tile GEMMs that skip the zero blocks of the
+//     triangular factors, with the b x b product parked in a side buffer.
+// clock64 timeline of the debug build (tools/potrf_trace.py), before -> after this organisation: see DESIGN.md section 4.
 // info gets the first failing global pivot (1-based) if A is not SPD.
 // ---------------------------------------------------------------------------------------------
-constexpr int PS = 129;   // smem row stride of the 128x128 block
+#ifdef IBO_I8_TRACE
+__device__ long long g_potrf_stamp[72];
+#define PSTAMP(i) do { if (threadIdx.x == 0) g_potrf_stamp[i] = clock64(); } while (0)
+#else
+#define PSTAMP(i) do { } while (0)
+#endif
+constexpr int PS = 132;    // smem row stride of the 128 x 128 block: 4 mod 16 keeps the MMA fragment loads conflict-free
+constexpr int POTRF_SMEM = (128 * PS + 64 * 68 + 128) * 8;
 __global__ void __launch_bounds__(512) potrf_diag_kernel(double* __restrict__ A, int ld, int kblk,
                                                          double* __restrict__ Dall, int* __restrict__ info) {
-    extern __shared__ double sm[];
-    double* S = sm;                    // [128][PS]
-    double* dinv = sm + 128 * PS;      // [128] 1 / L[i][i]
-    const int tid = threadIdx.x;
+    extern __shared__ __align__(16) double sm[];
+    double* S = sm;                            // [128][PS] the block: L, then X = inv(L) in place; zeros above the diagonal
+    double* Tb = sm + 128 * PS;                // products L21 X11 of the merge step, one b x (b + 4) slab per pair
+    double* Dinv = Tb + 64 * 68;               // 1 / L_jj
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lr = lane >> 2, lc = lane & 3;   // MMA fragment coordinates of this lane
     double* Ablk = A + (size_t)kblk * 128 * ld + (size_t)kblk * 128;
-    for (int idx = tid; idx < 128 * 128; idx += 512) {
-        int r = idx >> 7, c = idx & 127;
-        S[r * PS + c] = (c <= r) ? Ablk[(size_t)r * ld + c] : 0.0;
+    for (int idx = tid; idx < 128 * 64; idx += 512) {
+        const int r = idx >> 6, c = (idx & 63) * 2;
+        double2 v = make_double2(0.0, 0.0);
+        if (c <= r) {
+            v = *reinterpret_cast<const double2*>(Ablk + (size_t)r * ld + c);
+            if (c + 1 > r) v.y = 0.0;
+        }
+        *reinterpret_cast<double2*>(S + r * PS + c) = v;
+    }
+    PSTAMP(0);
+    __syncthreads();
+    PSTAMP(1);
+    // ---------------- Cholesky ----------------
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 8) {
+        const int nbelow = 120 - c0;
+        double a[8][8], invd[8];
+        if (tid < 128) {
+            // (1) 8 x 8 diagonal block in registers, every thread the same (broadcast reads)
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+#pragma unroll
+                for (int c = 0; c <= r; c++) a[r][c] = S[(c0 + r) * PS + c0 + c];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                double piv = a[j][j];
+                if (!(piv > 0.0)) {   // also catches NaN
+                    if (tid == 0) atomicCAS(info, 0, kblk * 128 + c0 + j + 1);
+                    piv = 1.0;        // keep going with garbage; the host checks info
+                }
+                const double ij = rsqrt(piv);
+                a[j][j] = piv * ij; invd[j] = ij;
+#pragma unroll
+                for (int i = j + 1; i < 8; i++) a[i][j] *= ij;
+#pragma unroll
+                for (int i = j + 1; i < 8; i++)
+#pragma unroll
+                    for (int c = j + 1; c <= i; c++) a[i][c] = fma(-a[i][j], a[c][j], a[i][c]);
+            }
+            PSTAMP(2 + 3 * (c0 >> 3));
+            // (2) rows below: thread t solves row c0 + 8 + t of the panel, x L11^T = b
+            if (tid < nbelow) {
+                double2* row = reinterpret_cast<double2*>(S + (c0 + 8 + tid) * PS + c0);
+                double x[8];
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) { double2 v = row[j >> 1]; x[j] = v.x; x[j + 1] = v.y; }
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    double v = x[j];
+#pragma unroll
+                    for (int q = 0; q < j; q++) v = fma(-x[q], a[j][q], v);
+                    x[j] = v * invd[j];
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) row[j >> 1] = make_double2(x[j], x[j + 1]);
+            }
+        }
+        __syncthreads();
+        PSTAMP(3 + 3 * (c0 >> 3));
+        // L11 and its reciprocal diagonal go back to shared memory only now (before the barrier another warp may still be reading
+        // the unfactored block), split over two threads with static register indices; the trailing update never touches these rows
+        if (tid == 126) {
+#pragma unroll
+            for (int r = 0; r < 6; r++)
+#pragma unroll
+                for (int c = 0; c <= r; c++) S[(c0 + r) * PS + c0 + c] = a[r][c];
+        } else if (tid == 127) {
+#pragma unroll
+            for (int r = 6; r < 8; r++)
+#pragma unroll
+                for (int c = 0; c <= r; c++) S[(c0 + r) * PS + c0 + c] = a[r][c];
+#pragma unroll
+            for (int r = 0; r < 8; r++) Dinv[c0 + r] = invd[r];
+        }
+        // (3) trailing triangle (rows / cols >= c0 + 8) -= P P^T, P = the panel just solved: 8 x 8 tiles, two MMAs each.
+        // Tile rows i and n-1-i are folded into one run of n + 1 tiles, which enumerates the triangle without a square root.
+        {
+            const int n = nbelow >> 3, nfold = (n + 1) >> 1;
+            for (int q = warp; q < nfold * (n + 1); q += 16) {
+                const int pr = q / (n + 1), off = q - pr * (n + 1);
+                int ti, tj;
+                if (off <= pr) { ti = pr; tj = off; }
+                else { ti = n - 1 - pr; tj = off - pr - 1; if (ti == pr) continue; }
+                const int r0 = c0 + 8 + 8 * ti, q0 = c0 + 8 + 8 * tj;
+                const double* ap = S + (r0 + lr) * PS + c0 + lc;
+                const double* bp = S + (q0 + lr) * PS + c0 + lc;
+                double2* cp = reinterpret_cast<double2*>(S + (r0 + lr) * PS + q0 + 2 * lc);
+                const double a0 = -ap[0], a1 = -ap[4], b0 = bp[0], b1 = bp[4];
+                double2 c = *cp;
+                dmma884(c.x, c.y, a0, b0);
+                dmma884(c.x, c.y, a1, b1);
+                if (ti != tj) *cp = c;
+                else {   // diagonal tile: the upper triangle stays zero
+                    if (2 * lc <= lr) S[(r0 + lr) * PS + q0 + 2 * lc] = c.x;
+                    if (2 * lc + 1 <= lr) S[(r0 + lr) * PS + q0 + 2 * lc + 1] = c.y;
+                }
+            }
+        }
+        __syncthreads();
+        PSTAMP(4 + 3 * (c0 >> 3));
+    }
+    for (int idx = tid; idx < 128 * 64; idx += 512) {
+        const int r = idx >> 6, c = (idx & 63) * 2;
+        if (c + 1 <= r) *reinterpret_cast<double2*>(Ablk + (size_t)r * ld + c) = *reinterpret_cast<const double2*>(S + r * PS + c);
+        else if (c == r) Ablk[(size_t)r * ld + c] = S[r * PS + c];
+    }
+    __syncthreads();   // the inverse overwrites S
+    PSTAMP(50);
+    // ---------------- X = inv(L), in place ----------------
+    if (tid < 128) {
+        // X_jj = inv(L_jj): thread = (block j, column c); forward substitution down the column.  The eight threads of a block
+        // share a warp: everyone reads L_jj before anyone overwrites it.
+        const int j = tid >> 3, c = tid & 7, b0 = 8 * j;
+        double l[8][8], x[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int q = 0; q < r; q++) l[r][q] = S[(b0 + r) * PS + b0 + q];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            double v = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+            for (int q = 0; q < r; q++)
+                if (q >= c) v = fma(-l[r][q], x[q], v);
+            x[r] = (r >= c) ? v * Dinv[b0 + r] : 0.0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+            if (r >= c) S[(b0 + r) * PS + b0 + c] = x[r];
     }
     __syncthreads();
-    for (int c0 = 0; c0 < 128; c0 += 16) {
-        // Panel: eliminate one column at a time on the *unscaled* columns -- S[i][c] -= S[i][j] S[c][j] / piv_j needs only
-        // a reciprocal (one barrier per column); the 1/sqrt(piv) scaling of the 16 columns is deferred to the panel end.
-#pragma unroll
-        for (int jj = 0; jj < 16; jj++) {     // unrolled: nc below is a compile-time constant (no integer division)
-            const int j = c0 + jj;
-            double piv = S[j * PS + j];
-            if (!(piv > 0.0)) {   // also catches NaN
-                if (tid == 0) atomicCAS(info, 0, kblk * 128 + j + 1);
-                piv = 1.0;        // keep going with garbage; the host checks info
+    PSTAMP(51);
+    // merge pairs of b x b inverses: [X11 0; X21 X22] with X21 = -X22 (L21 X11); tiles are 8 x 8, `b` tiles per level in all
+    int level = 0;
+#pragma unroll 1
+    for (int b = 8; b <= 64; b <<= 1, level++) {
+        const int tb = b >> 3, ts = b + 4;
+        // T = L21 X11: X11 is lower triangular, so column tile nt needs k >= 8 nt only
+        for (int t = warp; t < b; t += 16) {
+            const int p = t / (tb * tb), tt = t - p * tb * tb, nt = tt / tb, mt = tt - nt * tb, base = 2 * p * b;
+            const double* ap = S + (base + b + 8 * mt + lr) * PS + base + lc;
+            const double* bp = S + (base + lc) * PS + base + 8 * nt + lr;
+            double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+            for (int k = 8 * nt; k < b; k += 8) {
+                dmma884(c0, c1, ap[k], bp[k * PS]);
+                dmma884(d0, d1, ap[k + 4], bp[(k + 4) * PS]);
             }
-            const int nc = 15 - jj, nr = 127 - j;
-            if (nc > 0) {
-                const double rp = 1.0 / piv;
-                for (int idx = tid; idx < nr * nc; idx += 512) {
-                    int ri = idx / nc, ci = idx - ri * nc;
-                    int i = j + 1 + ri, c = j + 1 + ci;
-                    if (i >= c) S[i * PS + c] -= S[i * PS + j] * S[c * PS + j] * rp;
-                }
-                __syncthreads();
-            }
-        }
-        // scale the panel: L[i][j] = S[i][j] / sqrt(piv_j), L[j][j] = sqrt(piv_j)
-        {
-            const int nrow = 128 - c0;
-            double myinv = 0.0; int mycol = -1;
-            for (int idx = tid; idx < nrow * 16; idx += 512) {
-                int ri = idx >> 4, jj = idx & 15;
-                int i = c0 + ri, j = c0 + jj;
-                if (i >= j) {
-                    if (jj != mycol) { double pv = S[j * PS + j]; if (!(pv > 0.0)) pv = 1.0; myinv = rsqrt(pv); mycol = jj; }
-                    if (i > j) S[i * PS + j] *= myinv;
-                }
-            }
-            __syncthreads();     // all reads of the unscaled pivots are done
-            if (tid < 16) {
-                int j = c0 + tid;
-                double pv = S[j * PS + j]; if (!(pv > 0.0)) pv = 1.0;
-                double iv = rsqrt(pv);
-                S[j * PS + j] = pv * iv; dinv[j] = iv;
-            }
-            __syncthreads();
-        }
-        // rank-16 update of the trailing block: rows / cols >= c0 + 16
-        const int t0 = c0 + 16, n = 128 - t0;
-        if (n > 0) {
-            // 32 x 16 thread tile walks the n x n square; tiles wholly above the diagonal are skipped
-            const int ty = tid >> 4, tx = tid & 15;
-            for (int rb = 0; rb < n; rb += 32) {
-                for (int cb = 0; cb <= rb + 31 && cb < n; cb += 16) {
-                    int i = t0 + rb + ty, c = t0 + cb + tx;
-                    if (i < 128 && c <= i) {
-                        double acc = 0;
-#pragma unroll
-                        for (int k = 0; k < 16; k++) acc = fma(S[i * PS + c0 + k], S[c * PS + c0 + k], acc);
-                        S[i * PS + c] -= acc;
-                    }
-                }
-            }
+            *reinterpret_cast<double2*>(Tb + p * b * ts + (8 * mt + lr) * ts + 8 * nt + 2 * lc) = make_double2(c0 + d0, c1 + d1);
         }
         __syncthreads();
-    }
-    for (int idx = tid; idx < 128 * 128; idx += 512) {
-        int r = idx >> 7, c = idx & 127;
-        if (c <= r) Ablk[(size_t)r * ld + c] = S[r * PS + c];
-    }
-    // ---- X = inv(L) by recursive doubling: inv([[A,0],[B,C]]) = [[inv A, 0], [-inv(C) B inv(A), inv C]].
-    //      Level 0 inverts the eight 16x16 diagonal blocks by forward substitution (4 threads per column); levels
-    //      1..3 (n = 16, 32, 64) are two small triangular matrix products per off-diagonal block, all 512 threads.
-    //      X is kept packed (lower triangle) in shared memory; T = B inv(A) goes to the free upper triangle of S.
-    double* Xp = dinv + 128;                       // packed lower triangle, X[i][c] at i(i+1)/2 + c
-#define XP(i, c) Xp[(((i) * ((i) + 1)) >> 1) + (c)]
-    {
-        const int col = tid >> 2, part = tid & 3;  // global column 0..127, its 16-block and offset
-        const int b0 = col & ~15;
-        for (int i = b0; i < b0 + 16; i++) {       // uniform trip count for all threads
-            double acc = 0;
-            if (i > col)
-                for (int t = col + part; t < i; t += 4) acc = fma(S[i * PS + t], XP(t, col), acc);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-            if (part == 0 && i >= col) XP(i, col) = (i == col) ? dinv[i] : -acc * dinv[i];
-            __syncthreads();
-        }
-    }
-    for (int n = 16; n < 128; n <<= 1) {
-        const int npairs = 128 / (2 * n);
-        // T = B * inv(A): T[r][c] = sum_{t=c}^{n-1} L[r0+n+r][r0+t] * X[r0+t][r0+c]  -> S[r0+r][r0+n+c] (upper triangle).
-        // Each thread owns four rows of one column (four independent FMA chains share the X load).
-        const int rg = n / 4, work = npairs * n * rg;
-        for (int idx = tid; idx < work; idx += 512) {
-            int pr = idx / (n * rg), e = idx - pr * (n * rg), c = e / rg, r = (e - c * rg) * 4, r0 = pr * 2 * n;
-            double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-            const double* Lr = S + (r0 + n + r) * PS + r0;
-            for (int t = c; t < n; t++) {
-                double x = XP(r0 + t, r0 + c);
-                a0 = fma(Lr[t], x, a0); a1 = fma(Lr[PS + t], x, a1); a2 = fma(Lr[2 * PS + t], x, a2); a3 = fma(Lr[3 * PS + t], x, a3);
+        // X21 = -X22 T: X22 is lower triangular, so row tile mt needs k < 8 (mt + 1) only; X21 replaces L21
+        for (int t = warp; t < b; t += 16) {
+            const int p = t / (tb * tb), tt = t - p * tb * tb, mt = tt / tb, nt = tt - mt * tb, base = 2 * p * b;
+            const double* ap = S + (base + b + 8 * mt + lr) * PS + base + b + lc;
+            const double* bp = Tb + p * b * ts + lc * ts + 8 * nt + lr;
+            double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+            for (int k = 0; k < 8 * (mt + 1); k += 8) {
+                dmma884(c0, c1, ap[k], bp[k * ts]);
+                dmma884(d0, d1, ap[k + 4], bp[(k + 4) * ts]);
             }
-            double* Tp = S + (r0 + r) * PS + r0 + n + c;
-            Tp[0] = a0; Tp[PS] = a1; Tp[2 * PS] = a2; Tp[3 * PS] = a3;
+            *reinterpret_cast<double2*>(S + (base + b + 8 * mt + lr) * PS + base + 8 * nt + 2 * lc) = make_double2(-(c0 + d0), -(c1 + d1));
         }
         __syncthreads();
-        // X21 = -inv(C) * T: X[r0+n+r][r0+c] = -sum_{t=0}^{r} X[r0+n+r][r0+n+t] * T[t][c]; four columns per thread
-        for (int idx = tid; idx < work; idx += 512) {
-            int pr = idx / (n * rg), e = idx - pr * (n * rg), r = e / rg, c = (e - r * rg) * 4, r0 = pr * 2 * n;
-            double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-            const double* Tp = S + r0 * PS + r0 + n + c;
-            for (int t = 0; t <= r; t++) {
-                double x = XP(r0 + n + r, r0 + n + t);
-                a0 = fma(x, Tp[t * PS], a0); a1 = fma(x, Tp[t * PS + 1], a1); a2 = fma(x, Tp[t * PS + 2], a2); a3 = fma(x, Tp[t * PS + 3], a3);
-            }
-            double* Xo = &XP(r0 + n + r, r0 + c);
-            Xo[0] = -a0; Xo[1] = -a1; Xo[2] = -a2; Xo[3] = -a3;
-        }
-        __syncthreads();
+        PSTAMP(52 + level);
     }
     double* D = Dall + (size_t)kblk * 128 * 128;
-    for (int idx = tid; idx < 128 * 128; idx += 512) {
-        int r = idx >> 7, c = idx & 127;
-        D[r * 128 + c] = (c <= r) ? XP(r, c) : 0.0;
+    for (int idx = tid; idx < 128 * 64; idx += 512) {
+        const int r = idx >> 6, c = (idx & 63) * 2;
+        double2 v = make_double2(0.0, 0.0);
+        if (c <= r) { v = *reinterpret_cast<const double2*>(S + r * PS + c); if (c + 1 > r) v.y = 0.0; }
+        *reinterpret_cast<double2*>(D + r * 128 + c) = v;
     }
-#undef XP
+    PSTAMP(67);
 }
 
 enum { MODE_CHOL_PANEL = 0, MODE_CHOL_TRAIL = 1, MODE_TRTRI_SCALE = 2, MODE_TRTRI_UPDATE = 3 };
@@ -374,30 +435,36 @@ __global__ void __launch_bounds__(256, 1) syrk_identity_kernel(double* __restric
 }
 
 
-template <int MODE>
-__global__ void __launch_bounds__(256, 1) block_step_kernel(double* __restrict__ A, double* __restrict__ W,
-                                                            const double* __restrict__ D, int Np, int k, int jofs = 0) {
+// MROWS = 64: the tile is split into an upper and a lower half (blockIdx.z), one 4-warp CTA each, two CTAs per SM
+template <int MODE, int MROWS = 128>
+__global__ void __launch_bounds__(2 * MROWS, MROWS == 128 ? 1 : 2) block_step_kernel(double* __restrict__ A, double* __restrict__ W,
+                                                            const double* __restrict__ D, int Np, int k, int jofs = 0,
+                                                            int c0 = -1, int kspan = 128) {
+    static_assert(MROWS == 128 || MODE != MODE_TRTRI_SCALE, "the in-place scaling reads all 128 rows of the block it overwrites");
     extern __shared__ double sm[];
     double acc[8][4][2];
 #pragma unroll
     for (int a = 0; a < 8; a++)
 #pragma unroll
         for (int b = 0; b < 4; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+    const size_t half = MROWS == 128 ? 0 : (size_t)blockIdx.z * 64 * Np;      // offset of this CTA's rows inside the block row
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wm = warp >> 2, wn = warp & 3;
     double* C;
     bool subtract;
     if (MODE == MODE_CHOL_PANEL) {
         // A_ik <- A_ik * D_k^T, i = k+1+blockIdx.x
         int i = k + 1 + blockIdx.x;
-        C = A + (size_t)i * 128 * Np + (size_t)k * 128;
-        tile_gemm_core<true>(C, Np, D + (size_t)k * 128 * 128, 128, 128, acc, sm);
+        C = A + (size_t)i * 128 * Np + half + (size_t)k * 128;
+        tile_gemm_core<true, false, MROWS>(C, Np, D + (size_t)k * 128 * 128, 128, 128, acc, sm);
         subtract = false;
     } else if (MODE == MODE_CHOL_TRAIL) {
-        // A_ij -= L_ik L_jk^T for k < j <= i   (jofs: first block column of this launch -- the look-ahead splits column k+1 off)
-        int i = k + 1 + blockIdx.y, j = k + 1 + jofs + blockIdx.x;
+        // A_ij -= sum over the block columns k .. k + kspan/128 - 1 of L_i. L_j.^T, for c0 <= j <= i: rows from block c0, columns from
+        // block c0 + jofs (the look-ahead launches the nearest columns separately)
+        if (c0 < 0) c0 = k + 1;
+        int i = c0 + blockIdx.y, j = c0 + jofs + blockIdx.x;
         if (j > i) return;
-        C = A + (size_t)i * 128 * Np + (size_t)j * 128;
-        tile_gemm_core<true>(A + (size_t)i * 128 * Np + (size_t)k * 128, Np, A + (size_t)j * 128 * Np + (size_t)k * 128, Np, 128, acc, sm);
+        C = A + (size_t)i * 128 * Np + half + (size_t)j * 128;
+        tile_gemm_core<true, false, MROWS>(A + (size_t)i * 128 * Np + half + (size_t)k * 128, Np, A + (size_t)j * 128 * Np + (size_t)k * 128, Np, kspan, acc, sm);
         subtract = true;
     } else if (MODE == MODE_TRTRI_SCALE) {
         // W_kj <- D_k * B_kj, j = blockIdx.x <= k   (B lives in W)
@@ -406,10 +473,11 @@ __global__ void __launch_bounds__(256, 1) block_step_kernel(double* __restrict__
         tile_gemm_core<false>(D + (size_t)k * 128 * 128, 128, C, Np, 128, acc, sm);
         subtract = false;
     } else {
-        // B_ij -= L_ik * W_kj for i > k, j <= k
-        int i = k + 1 + blockIdx.y, j = blockIdx.x;
-        C = W + (size_t)i * 128 * Np + (size_t)j * 128;
-        tile_gemm_core<false>(A + (size_t)i * 128 * Np + (size_t)k * 128, Np, W + (size_t)k * 128 * Np + (size_t)j * 128, Np, 128, acc, sm);
+        // B_ij -= sum over the block rows k .. k + kspan/128 - 1 of L_i. W_.j, for i >= c0 (default k + 1) and j = blockIdx.x
+        if (c0 < 0) c0 = k + 1;
+        int i = c0 + blockIdx.y, j = blockIdx.x;
+        C = W + (size_t)i * 128 * Np + half + (size_t)j * 128;
+        tile_gemm_core<false, false, MROWS>(A + (size_t)i * 128 * Np + half + (size_t)k * 128, Np, W + (size_t)k * 128 * Np + (size_t)j * 128, Np, kspan, acc, sm);
         subtract = true;
     }
     // all operand reads are complete (tile_gemm_core ends with __syncthreads) -> in-place write is safe
@@ -660,8 +728,12 @@ static cudaError_t set_model_attrs() {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(block_step_kernel<MODE_CHOL_TRAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(block_step_kernel<MODE_TRTRI_SCALE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(block_step_kernel<MODE_TRTRI_UPDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem);
+    const int half_smem = TileCfg<64>::SMEM_DOUBLES * 8;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(block_step_kernel<MODE_CHOL_PANEL, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, half_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(block_step_kernel<MODE_CHOL_TRAIL, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, half_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(block_step_kernel<MODE_TRTRI_UPDATE, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, half_smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(syrk_identity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 * PS + 128 + 128 * 129 / 2) * 8);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, POTRF_SMEM);
     return e;
 }
 static int set_kernel_attrs() {
@@ -678,57 +750,133 @@ int launch_factorize(ibo_model* m, bool from_inverse_reversed, bool pack) {
     if (rc) return rc;
     cudaStream_t st = m->stream;
     const int Np = m->Np, nb = m->nb;
-    const int tile_smem = TILE_SMEM_DOUBLES * 8;
-    const int potrf_smem = (128 * PS + 128 + 128 * 129 / 2) * 8;
+    const int tile_smem = TILE_SMEM_DOUBLES * 8, half_smem = TileCfg<64>::SMEM_DOUBLES * 8;
+    const int potrf_smem = POTRF_SMEM;
     IBO_CUDA_TRY(cudaMemsetAsync(m->dInfo, 0, sizeof(int), st));
     dim3 g2((Np + 255) / 256, Np);
-    // The inversion W = inv(L) runs on a second stream, one block step behind the factorisation: step k of the
-    // substitution needs only D_k and the finished block column k of L (potrf + panel of step k), so it overlaps the
-    // trailing update of step k and everything after it.
+    // Block columns go in groups of w = 1 or 2.  With w = 2 everything behind the pair (k, k+1) is updated with both columns at
+    // once: one pass with a 256-deep product instead of two 128-deep ones halves the read-modify-write traffic of the trailing
+    // matrix and the number of launches; it pays from ~48 block columns on (option chol_pair), below that the longer chain of
+    // one-tile kernels between two diagonal factorisations costs more than the bulk saves.
+    // Look-ahead: the update behind the group is split -- the w nearest block columns stay on the critical stream (they are all
+    // the next group's diagonal factorisations and panels wait for), the rest goes to a low-priority bulk stream, so the one-CTA
+    // diagonal kernels and thin panels of the next group run while the bulk update still fills the GPU.  Dependencies: bulk(k)
+    // reads the panels of the group (evStep) and follows bulk(k-w) in stream order; ahead(k) updates columns bulk(k-w) wrote (evRest).
+    // The inversion W = inv(L) is a forward substitution on B = I that follows the factorisation group by group on its own pair
+    // of streams, split the same way: rows k..k+w-1 are scaled by D (W_kj = D_k B_kj), the next group's rows are updated on the
+    // near stream, all later rows on the far stream (after evScale; near(k) waits for far(k-w) through evFar).
     cudaStream_t s2 = from_inverse_reversed ? st : m->stream2;
-    if (!from_inverse_reversed) {
-        IBO_CUDA_TRY(cudaEventRecord(m->evStep, st));            // orders s2 after whatever produced dA / dD users
+    cudaStream_t s4 = m->stream4;
+    const bool trtri = !from_inverse_reversed;
+    if (trtri) {
+        IBO_CUDA_TRY(cudaEventRecord(m->evStep, st));            // orders s2 / s4 after whatever produced dA / dD users
         IBO_CUDA_TRY(cudaStreamWaitEvent(s2, m->evStep, 0));
+        IBO_CUDA_TRY(cudaStreamWaitEvent(s4, m->evStep, 0));
         set_identity_kernel<<<g2, 256, 0, s2>>>(m->dW, Np);
         g_launches++;
+        IBO_CUDA_TRY(cudaEventRecord(m->evFar, s2));
+        IBO_CUDA_TRY(cudaStreamWaitEvent(s4, m->evFar, 0));
     }
-    // Look-ahead of depth one.  The trailing update of step k is split: block column k+1 stays on the critical stream (it is all
-    // potrf(k+1) and panel(k+1) wait for), the rest goes to a low-priority bulk stream.  The one-CTA diagonal factorisation and the
-    // thin panel of step k+1 then run while the bulk update of step k still fills the GPU.  Dependencies: rest(k) reads the panel
-    // of step k (evStep) and follows rest(k-1) in stream order; first(k+1) updates column k+2, which rest(k) wrote (evRest).
     cudaStream_t sb = m->stream3;
+    const long pair_opt = get_option(OPT_CHOL_PAIR);
+    const int w = (pair_opt < 0 ? nb >= 48 : pair_opt != 0) ? 2 : 1;
+#ifdef IBO_I8_TRACE
+    struct TlEv { cudaEvent_t e; int k; const char* tag; };
+    std::vector<TlEv> tl;
+    const bool tl_on = get_option(OPT_DEBUG_PLAN) == 7;
+    auto TL = [&](cudaStream_t s, int k, const char* tag) {
+        if (!tl_on) return;
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); tl.push_back({e, k, tag});
+    };
+    TL(st, -1, "start");
+#else
+#define TL(s, k, tag) do { } while (0)
+#endif
     IBO_CUDA_TRY(cudaEventRecord(m->evRest, st));
     IBO_CUDA_TRY(cudaStreamWaitEvent(sb, m->evRest, 0));
-    for (int k = 0; k < nb; k++) {
+    for (int k = 0; k < nb; k += w) {
+        // ---- block column k
         potrf_diag_kernel<<<1, 512, potrf_smem, st>>>(m->dA, Np, k, m->dD, m->dInfo);
         g_launches++;
-        int nrem = nb - 1 - k;
-        if (nrem > 0) {
-            block_step_kernel<MODE_CHOL_PANEL><<<nrem, 256, tile_smem, st>>>(m->dA, nullptr, m->dD, Np, k);
+        TL(st, k, "potrf");
+        int kl = k;                            // last block column of the group
+        if (k + 1 < nb) {
+            block_step_kernel<MODE_CHOL_PANEL, 64><<<dim3(nb - 1 - k, 1, 2), 128, half_smem, st>>>(m->dA, nullptr, m->dD, Np, k);
             g_launches++;
+            TL(st, k, "panel");
+            if (w == 2) {
+                // ---- block column k+1: its update by column k, then the same two kernels
+                kl = k + 1;
+                block_step_kernel<MODE_CHOL_TRAIL, 64><<<dim3(1, nb - 1 - k, 2), 128, half_smem, st>>>(m->dA, nullptr, m->dD, Np, k, 0, k + 1, 128);
+                TL(st, k, "first");
+                potrf_diag_kernel<<<1, 512, potrf_smem, st>>>(m->dA, Np, kl, m->dD, m->dInfo);
+                g_launches += 2;
+                TL(st, kl, "potrf");
+                if (kl + 1 < nb) {
+                    block_step_kernel<MODE_CHOL_PANEL, 64><<<dim3(nb - 1 - kl, 1, 2), 128, half_smem, st>>>(m->dA, nullptr, m->dD, Np, kl);
+                    g_launches++;
+                    TL(st, kl, "panel");
+                }
+            }
         }
+        const int gw = kl - k + 1;             // columns in this group (1 at the end of an odd count)
+        const int nbehind = nb - 1 - kl;       // block rows / columns behind the group
+        const int c0 = kl + 1, kspan = 128 * gw;
         IBO_CUDA_TRY(cudaEventRecord(m->evStep, st));
-        if (!from_inverse_reversed) {
+        if (trtri) {
             IBO_CUDA_TRY(cudaStreamWaitEvent(s2, m->evStep, 0));
             block_step_kernel<MODE_TRTRI_SCALE><<<k + 1, 256, tile_smem, s2>>>(m->dA, m->dW, m->dD, Np, k);
             g_launches++;
-            if (nrem > 0) {
-                block_step_kernel<MODE_TRTRI_UPDATE><<<dim3(k + 1, nrem), 256, tile_smem, s2>>>(m->dA, m->dW, m->dD, Np, k);
-                g_launches++;
+            if (gw == 2) {
+                block_step_kernel<MODE_TRTRI_UPDATE, 64><<<dim3(k + 1, 1, 2), 128, half_smem, s2>>>(m->dA, m->dW, m->dD, Np, k, 0, k + 1, 128);
+                block_step_kernel<MODE_TRTRI_SCALE><<<kl + 1, 256, tile_smem, s2>>>(m->dA, m->dW, m->dD, Np, kl);
+                g_launches += 2;
             }
+            if (nbehind > 0) {
+                // rows behind the group take all its block rows in one pass (the block W_(k),(k+1) above the diagonal is zero)
+                const int nnear = nbehind < w ? nbehind : w;
+                if (nbehind > nnear) {
+                    IBO_CUDA_TRY(cudaEventRecord(m->evScale, s2));
+                    IBO_CUDA_TRY(cudaStreamWaitEvent(s4, m->evScale, 0));
+                    block_step_kernel<MODE_TRTRI_UPDATE, 64><<<dim3(kl + 1, nbehind - nnear, 2), 128, half_smem, s4>>>(m->dA, m->dW, m->dD, Np, k, 0, c0 + nnear, kspan);
+                    g_launches++;
+                    TL(s4, k, "far");
+                }
+                IBO_CUDA_TRY(cudaStreamWaitEvent(s2, m->evFar, 0));        // far(k-w) wrote the near rows of this group
+                block_step_kernel<MODE_TRTRI_UPDATE, 64><<<dim3(kl + 1, nnear, 2), 128, half_smem, s2>>>(m->dA, m->dW, m->dD, Np, k, 0, c0, kspan);
+                g_launches++;
+                if (nbehind > nnear) IBO_CUDA_TRY(cudaEventRecord(m->evFar, s4));
+            }
+            TL(s2, k, "near");
         }
-        if (nrem > 0) {
-            if (k > 0) IBO_CUDA_TRY(cudaStreamWaitEvent(st, m->evRest, 0));      // column k+1 carries the update of step k-1
-            block_step_kernel<MODE_CHOL_TRAIL><<<dim3(1, nrem), 256, tile_smem, st>>>(m->dA, nullptr, m->dD, Np, k, 0);
+        if (nbehind > 0) {
+            // look-ahead columns (they carry the bulk update of the previous group), then the rest in the background
+            if (k > 0) IBO_CUDA_TRY(cudaStreamWaitEvent(st, m->evRest, 0));
+            const int nla = nbehind < w ? nbehind : w;
+            block_step_kernel<MODE_CHOL_TRAIL, 64><<<dim3(nla, nbehind, 2), 128, half_smem, st>>>(m->dA, nullptr, m->dD, Np, k, 0, c0, kspan);
             g_launches++;
-            if (nrem > 1) {
+            TL(st, k, "ahead");
+            if (nbehind > nla) {
                 IBO_CUDA_TRY(cudaStreamWaitEvent(sb, m->evStep, 0));
-                block_step_kernel<MODE_CHOL_TRAIL><<<dim3(nrem - 1, nrem), 256, tile_smem, sb>>>(m->dA, nullptr, m->dD, Np, k, 1);
+                block_step_kernel<MODE_CHOL_TRAIL, 64><<<dim3(nbehind - nla, nbehind, 2), 128, half_smem, sb>>>(m->dA, nullptr, m->dD, Np, k, nla, c0, kspan);
                 g_launches++;
                 IBO_CUDA_TRY(cudaEventRecord(m->evRest, sb));
+                TL(sb, k, "bulk");
             }
         }
     }
+#ifdef IBO_I8_TRACE
+    if (tl_on) {
+        cudaStreamSynchronize(st); cudaStreamSynchronize(sb); cudaStreamSynchronize(s2); cudaStreamSynchronize(s4);
+        for (auto& x : tl) {
+            float ms = 0; cudaEventElapsedTime(&ms, tl[0].e, x.e);
+            fprintf(stderr, "tl k=%d %s %.1f\n", x.k, x.tag, 1e3 * ms);
+        }
+        for (auto& x : tl) cudaEventDestroy(x.e);
+    }
+#else
+#undef TL
+#endif
     IBO_CUDA_TRY(cudaEventRecord(m->evRest, sb));
     IBO_CUDA_TRY(cudaStreamWaitEvent(st, m->evRest, 0));
     if (from_inverse_reversed) {
@@ -737,6 +885,8 @@ int launch_factorize(ibo_model* m, bool from_inverse_reversed, bool pack) {
     } else {
         IBO_CUDA_TRY(cudaEventRecord(m->evStep, s2));
         IBO_CUDA_TRY(cudaStreamWaitEvent(st, m->evStep, 0));
+        IBO_CUDA_TRY(cudaEventRecord(m->evFar, s4));
+        IBO_CUDA_TRY(cudaStreamWaitEvent(st, m->evFar, 0));
     }
     if (pack) { pack_w_kernel<<<dim3(nb * KB_PER_BLOCK, nb), 256, 0, st>>>(m->dW, m->dWpack, Np, nb); g_launches++; }
     tri_matvec_kernel<<<(Np + 7) / 8, 256, 0, st>>>(m->dW, m->dY, m->dBetaY, Np);
@@ -796,6 +946,7 @@ static void free_model(ibo_model* m) {
     cudaSetDevice(m->device);
     if (m->stream2) cudaStreamSynchronize(m->stream2);
     if (m->stream3) cudaStreamSynchronize(m->stream3);
+    if (m->stream4) cudaStreamSynchronize(m->stream4);
     if (m->stream) cudaStreamSynchronize(m->stream);   // blocks go back to the pool: nothing may still be using them
     double** ptrs[] = {&m->dXt, &m->dInvTheta, &m->dCenter, &m->dA, &m->dAorig, &m->dW, &m->dD, &m->dWpack, &m->dBetaY, &m->dBeta1, &m->dY,
                        &m->dPmeans, &m->dPbeta, &m->dPlb, &m->dPwidth, &m->dCand, &m->dSlab, &m->dPart, &m->dOut, &m->dBlkBest, &m->dBest, &m->dAppend,
@@ -811,6 +962,9 @@ static void free_model(ibo_model* m) {
     if (m->evStep) cudaEventDestroy(m->evStep);
     if (m->evRest) cudaEventDestroy(m->evRest);
     if (m->stream3) cudaStreamDestroy(m->stream3);
+    if (m->evScale) cudaEventDestroy(m->evScale);
+    if (m->evFar) cudaEventDestroy(m->evFar);
+    if (m->stream4) cudaStreamDestroy(m->stream4);
     for (auto& e : m->evI8) if (e) cudaEventDestroy(e);
     if (m->stream2) cudaStreamDestroy(m->stream2);
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -872,8 +1026,11 @@ static int create_common(int device, int kind, const double* hyper, int nhyper, 
     TRYM(cudaStreamCreateWithPriority(&m->stream, cudaStreamNonBlocking, prHi));
     TRYM(cudaStreamCreateWithPriority(&m->stream2, cudaStreamNonBlocking, prLo));
     TRYM(cudaStreamCreateWithPriority(&m->stream3, cudaStreamNonBlocking, prLo));
+    TRYM(cudaStreamCreateWithPriority(&m->stream4, cudaStreamNonBlocking, prLo));
     TRYM(cudaEventCreateWithFlags(&m->evRest, cudaEventDisableTiming));
     TRYM(cudaEventCreateWithFlags(&m->evStep, cudaEventDisableTiming));
+    TRYM(cudaEventCreateWithFlags(&m->evScale, cudaEventDisableTiming));
+    TRYM(cudaEventCreateWithFlags(&m->evFar, cudaEventDisableTiming));
     for (auto& e : m->ev) TRYM(cudaEventCreate(&e));
     TRYM(pool_malloc((void**)&m->dXt, sizeof(double) * (size_t)Np * d));
     TRYM(pool_malloc((void**)&m->dInvTheta, sizeof(double) * d));
@@ -1083,3 +1240,45 @@ extern "C" int ibo_model_get_matrix(ibo_model* m, int which, double* out) {
             for (int j = i + 1; j < m->N; j++) out[(size_t)i * m->N + j] = out[(size_t)j * m->N + i];
     return IBO_OK;
 }
+
+#ifdef IBO_I8_TRACE
+// debug build only: the diagonal-block kernel alone on a 128 x 128 SPD block; us = min over 20 launches, stamps = clock64 timeline
+extern "C" int ibo_debug_potrf(int device, long long* stamps72, double* us) {
+    using namespace ibo;
+    IBO_CUDA_TRY(cudaSetDevice(device));
+    int rc = set_kernel_attrs();
+    if (rc) return rc;
+    std::vector<double> h(128 * 128);
+    unsigned s = 12345u;
+    for (int r = 0; r < 128; r++)
+        for (int c = 0; c <= r; c++) {
+            s = s * 1664525u + 1013904223u;
+            double v = (double)(s >> 8) / (double)(1u << 24) - 0.5;
+            h[r * 128 + c] = h[c * 128 + r] = (r == c) ? 40.0 + v : v;
+        }
+    double *dA0, *dA, *dD; int* dInfo;
+    IBO_CUDA_TRY(cudaMalloc(&dA0, sizeof(double) * 128 * 128));
+    IBO_CUDA_TRY(cudaMalloc(&dA, sizeof(double) * 128 * 128));
+    IBO_CUDA_TRY(cudaMalloc(&dD, sizeof(double) * 128 * 128));
+    IBO_CUDA_TRY(cudaMalloc(&dInfo, sizeof(int)));
+    IBO_CUDA_TRY(cudaMemset(dInfo, 0, sizeof(int)));
+    IBO_CUDA_TRY(cudaMemcpy(dA0, h.data(), sizeof(double) * 128 * 128, cudaMemcpyHostToDevice));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int it = 0; it < 20; it++) {
+        IBO_CUDA_TRY(cudaMemcpy(dA, dA0, sizeof(double) * 128 * 128, cudaMemcpyDeviceToDevice));
+        cudaEventRecord(e0);
+        potrf_diag_kernel<<<1, 512, POTRF_SMEM>>>(dA, 128, 0, dD, dInfo);
+        cudaEventRecord(e1);
+        IBO_CUDA_TRY(cudaEventSynchronize(e1));
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    *us = 1e3 * best;
+    IBO_CUDA_TRY(cudaMemcpyFromSymbol(stamps72, g_potrf_stamp, sizeof(long long) * 72));
+    cudaFree(dA0); cudaFree(dA); cudaFree(dD); cudaFree(dInfo);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return IBO_OK;
+}
+#endif

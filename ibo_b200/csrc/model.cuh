@@ -11,7 +11,8 @@ struct ibo_model {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;   // inversion pipeline of the model build; K1 of the next chunk on the INT8 path
     cudaStream_t stream3 = nullptr;   // bulk trailing updates of the look-ahead Cholesky
-    cudaEvent_t evStep = nullptr, evRest = nullptr;
+    cudaStream_t stream4 = nullptr;   // bulk row updates of the inversion that follows it
+    cudaEvent_t evStep = nullptr, evRest = nullptr, evScale = nullptr, evFar = nullptr;
     int N = 0, d = 0, kind = 0;
     int nb = 0;          // 128-row blocks
     int Np = 0;          // nb * 128 (identity padded)

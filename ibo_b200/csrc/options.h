@@ -23,6 +23,7 @@ enum {
     OPT_I8_RB_PER_CTA,   // row-blocks a CTA of the INT8 K2 sweeps (G = nb / this many CTAs share a candidate tile)
     OPT_I8_NTM,          // 0 (default): every operand of the INT8 K2 in shared memory; 1: W digits 1..4 reach the tensor core through TMEM
                          // (measured 6-13 % slower under the power cap: profiles/r02_int8_k2.md)
+    OPT_CHOL_PAIR,       // model build: block columns in pairs (256-deep trailing updates); -1 = from 48 block columns on, 0 / 1 forced
     OPT_I8_DBG,          // timing experiments on the INT8 K2: honoured only by the debug build (EXTRA=-DIBO_I8_TRACE), ignored otherwise
     OPT_COUNT
 };
