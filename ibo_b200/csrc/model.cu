@@ -213,6 +213,41 @@ __global__ void set_identity_kernel(double* __restrict__ W, int Np) {
 // clock64 timeline of the debug build (tools/potrf_trace.py), before -> after this organisation: see DESIGN.md section 4.
 // info gets the first failing global pivot (1-based) if A is not SPD.
 // ---------------------------------------------------------------------------------------------
+// One level of the in-place inversion of potrf_diag_kernel: every pair of adjacent B x B inverses on the diagonal of S becomes one
+// 2B x 2B inverse, X21 = -X22 (L21 X11).  8 x 8 tiles, B tiles per level in all, dealt to the 16 warps; T = L21 X11 is parked in Tb.
+template <int B>
+__device__ __forceinline__ void potrf_merge_level(double* S, double* Tb, int warp, int lr, int lc) {
+    constexpr int PS_ = 132, tb = B >> 3, ts = B + 4;      // PS_: row stride of S (= PS below)
+    // T = L21 X11: X11 is lower triangular, so column tile nt needs k >= 8 nt only
+    for (int t = warp; t < B; t += 16) {
+        const int p = t / (tb * tb), tt = t % (tb * tb), nt = tt / tb, mt = tt % tb, base = 2 * p * B;
+        const double* ap = S + (base + B + 8 * mt + lr) * PS_ + base + lc;
+        const double* bp = S + (base + lc) * PS_ + base + 8 * nt + lr;
+        double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+#pragma unroll 2
+        for (int k = 8 * nt; k < B; k += 8) {
+            dmma884(c0, c1, ap[k], bp[k * PS_]);
+            dmma884(d0, d1, ap[k + 4], bp[(k + 4) * PS_]);
+        }
+        *reinterpret_cast<double2*>(Tb + p * B * ts + (8 * mt + lr) * ts + 8 * nt + 2 * lc) = make_double2(c0 + d0, c1 + d1);
+    }
+    __syncthreads();
+    // X21 = -X22 T: X22 is lower triangular, so row tile mt needs k < 8 (mt + 1) only; X21 replaces L21
+    for (int t = warp; t < B; t += 16) {
+        const int p = t / (tb * tb), tt = t % (tb * tb), mt = tt / tb, nt = tt % tb, base = 2 * p * B;
+        const double* ap = S + (base + B + 8 * mt + lr) * PS_ + base + B + lc;
+        const double* bp = Tb + p * B * ts + lc * ts + 8 * nt + lr;
+        double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+#pragma unroll 2
+        for (int k = 0; k < 8 * (mt + 1); k += 8) {
+            dmma884(c0, c1, ap[k], bp[k * ts]);
+            dmma884(d0, d1, ap[k + 4], bp[(k + 4) * ts]);
+        }
+        *reinterpret_cast<double2*>(S + (base + B + 8 * mt + lr) * PS_ + base + 8 * nt + 2 * lc) = make_double2(-(c0 + d0), -(c1 + d1));
+    }
+    __syncthreads();
+}
+
 #ifdef IBO_I8_TRACE
 __device__ long long g_potrf_stamp[72];
 #define PSTAMP(i) do { if (threadIdx.x == 0) g_potrf_stamp[i] = clock64(); } while (0)
@@ -221,6 +256,7 @@ __device__ long long g_potrf_stamp[72];
 #endif
 constexpr int PS = 132;    // smem row stride of the 128 x 128 block: 4 mod 16 keeps the MMA fragment loads conflict-free
 constexpr int POTRF_SMEM = (128 * PS + 64 * 68 + 128) * 8;
+static_assert(PS == 132, "potrf_merge_level carries the same stride");
 __global__ void __launch_bounds__(512) potrf_diag_kernel(double* __restrict__ A, int ld, int kblk,
                                                          double* __restrict__ Dall, int* __restrict__ info) {
     extern __shared__ __align__(16) double sm[];
@@ -306,6 +342,8 @@ __global__ void __launch_bounds__(512) potrf_diag_kernel(double* __restrict__ A,
         }
         // (3) trailing triangle (rows / cols >= c0 + 8) -= P P^T, P = the panel just solved: 8 x 8 tiles, two MMAs each.
         // Tile rows i and n-1-i are folded into one run of n + 1 tiles, which enumerates the triangle without a square root.
+        // (one tile and two chained MMAs per warp and turn measured fastest: batches of 2 or 4 tiles with independent accumulators
+        // cost ~220 clk per MMA and warp however they were arranged)
         {
             const int n = nbelow >> 3, nfold = (n + 1) >> 1;
             for (int q = warp; q < nfold * (n + 1); q += 16) {
@@ -363,39 +401,11 @@ __global__ void __launch_bounds__(512) potrf_diag_kernel(double* __restrict__ A,
     }
     __syncthreads();
     PSTAMP(51);
-    // merge pairs of b x b inverses: [X11 0; X21 X22] with X21 = -X22 (L21 X11); tiles are 8 x 8, `b` tiles per level in all
-    int level = 0;
-#pragma unroll 1
-    for (int b = 8; b <= 64; b <<= 1, level++) {
-        const int tb = b >> 3, ts = b + 4;
-        // T = L21 X11: X11 is lower triangular, so column tile nt needs k >= 8 nt only
-        for (int t = warp; t < b; t += 16) {
-            const int p = t / (tb * tb), tt = t - p * tb * tb, nt = tt / tb, mt = tt - nt * tb, base = 2 * p * b;
-            const double* ap = S + (base + b + 8 * mt + lr) * PS + base + lc;
-            const double* bp = S + (base + lc) * PS + base + 8 * nt + lr;
-            double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
-            for (int k = 8 * nt; k < b; k += 8) {
-                dmma884(c0, c1, ap[k], bp[k * PS]);
-                dmma884(d0, d1, ap[k + 4], bp[(k + 4) * PS]);
-            }
-            *reinterpret_cast<double2*>(Tb + p * b * ts + (8 * mt + lr) * ts + 8 * nt + 2 * lc) = make_double2(c0 + d0, c1 + d1);
-        }
-        __syncthreads();
-        // X21 = -X22 T: X22 is lower triangular, so row tile mt needs k < 8 (mt + 1) only; X21 replaces L21
-        for (int t = warp; t < b; t += 16) {
-            const int p = t / (tb * tb), tt = t - p * tb * tb, mt = tt / tb, nt = tt - mt * tb, base = 2 * p * b;
-            const double* ap = S + (base + b + 8 * mt + lr) * PS + base + b + lc;
-            const double* bp = Tb + p * b * ts + lc * ts + 8 * nt + lr;
-            double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
-            for (int k = 0; k < 8 * (mt + 1); k += 8) {
-                dmma884(c0, c1, ap[k], bp[k * ts]);
-                dmma884(d0, d1, ap[k + 4], bp[(k + 4) * ts]);
-            }
-            *reinterpret_cast<double2*>(S + (base + b + 8 * mt + lr) * PS + base + 8 * nt + 2 * lc) = make_double2(-(c0 + d0), -(c1 + d1));
-        }
-        __syncthreads();
-        PSTAMP(52 + level);
-    }
+    // merge pairs of b x b inverses: [X11 0; X21 X22] with X21 = -X22 (L21 X11)
+    potrf_merge_level<8>(S, Tb, warp, lr, lc);   PSTAMP(52);
+    potrf_merge_level<16>(S, Tb, warp, lr, lc);  PSTAMP(53);
+    potrf_merge_level<32>(S, Tb, warp, lr, lc);  PSTAMP(54);
+    potrf_merge_level<64>(S, Tb, warp, lr, lc);  PSTAMP(55);
     double* D = Dall + (size_t)kblk * 128 * 128;
     for (int idx = tid; idx < 128 * 64; idx += 512) {
         const int r = idx >> 6, c = (idx & 63) * 2;
@@ -435,6 +445,14 @@ __global__ void __launch_bounds__(256, 1) syrk_identity_kernel(double* __restric
 }
 
 
+// the tile a CTA will read-modify-write at its end, requested into L2 at its start (the trailing matrix does not stay in L2 between
+// two passes once N > ~3000)
+template <int MROWS>
+__device__ __forceinline__ void prefetch_tile_l2(const double* C, int Np) {
+    for (int idx = threadIdx.x; idx < MROWS * 8; idx += 2 * MROWS)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(C + (size_t)(idx >> 3) * Np + (idx & 7) * 16));
+}
+
 // MROWS = 64: the tile is split into an upper and a lower half (blockIdx.z), one 4-warp CTA each, two CTAs per SM
 template <int MODE, int MROWS = 128>
 __global__ void __launch_bounds__(2 * MROWS, MROWS == 128 ? 1 : 2) block_step_kernel(double* __restrict__ A, double* __restrict__ W,
@@ -464,6 +482,7 @@ __global__ void __launch_bounds__(2 * MROWS, MROWS == 128 ? 1 : 2) block_step_ke
         int i = c0 + blockIdx.y, j = c0 + jofs + blockIdx.x;
         if (j > i) return;
         C = A + (size_t)i * 128 * Np + half + (size_t)j * 128;
+        prefetch_tile_l2<MROWS>(C, Np);
         tile_gemm_core<true, false, MROWS>(A + (size_t)i * 128 * Np + half + (size_t)k * 128, Np, A + (size_t)j * 128 * Np + (size_t)k * 128, Np, kspan, acc, sm);
         subtract = true;
     } else if (MODE == MODE_TRTRI_SCALE) {
@@ -477,6 +496,7 @@ __global__ void __launch_bounds__(2 * MROWS, MROWS == 128 ? 1 : 2) block_step_ke
         if (c0 < 0) c0 = k + 1;
         int i = c0 + blockIdx.y, j = blockIdx.x;
         C = W + (size_t)i * 128 * Np + half + (size_t)j * 128;
+        prefetch_tile_l2<MROWS>(C, Np);
         tile_gemm_core<false, false, MROWS>(A + (size_t)i * 128 * Np + half + (size_t)k * 128, Np, W + (size_t)k * 128 * Np + (size_t)j * 128, Np, kspan, acc, sm);
         subtract = true;
     }
