@@ -897,13 +897,18 @@ static bool i8_eligible(const ibo_model* m, int flags) {
     if (m->var_model || m->d > 32 || m->Np > 16384 || (flags & IBO_FLAG_FP64)) return false;
     return (flags & IBO_FLAG_INT8) || get_option(OPT_INT8) != 0;
 }
-// Batches of i8_min_batch .. narrow_max candidates (DIRECT's mid-size batches) on a model of more than one row-block: the FP64
-// latency shapes need N^2 flops per candidate at 37 TF/s, the INT8 kernels finish the same batch several times sooner.
+// Mid-size batches (DIRECT's, up to narrow_max candidates) on a model of more than one row-block: the FP64 latency shapes need
+// N^2 flops per candidate at 37 TF/s, the INT8 kernels finish a large enough batch several times sooner.  Where "large enough"
+// starts was measured (tools/i8_crossover.py, host candidates in, scores out, d = 6 and 20): the INT8 call costs ~50 us + N / 60 us
+// up to ~256 candidates, the FP64 call ~40 us + 3.5e-8 us x M N^2; they cross at M = 735 / 300 / 133 / 62 for N = 1024 / 2048 /
+// 4096 / 8192.  Option i8_min_batch: -1 this rule, 0 never, > 0 a fixed batch size.
 static bool i8_for_small_batch(const ibo_model* m, long M, int flags) {
     if (!i8_eligible(m, flags) || m->nb < 2) return false;
     if (flags & FLAG_I8_ANY_SIZE) return true;
     const long lo = get_option(OPT_I8_MIN_BATCH);
-    return lo > 0 && M >= lo;
+    if (lo >= 0) return lo > 0 && M >= lo;
+    const double n = (double)m->Np;
+    return (double)M * 3.5e-8 * n * n >= 10.0 + n / 60.0;
 }
 
 // Runs K1..K4 for M candidates resident at dCand; results land in m->dOut ([score|mu|s2][M]) and

@@ -212,7 +212,9 @@ int ibo_debug_exp(int device, const double* x, long n, double* out_fast, double*
  * Process-wide tuning / debugging switches, visible at the boundary (no hidden environment reads in the launch paths; an
  * environment variable IBO_<NAME IN CAPITALS> presets the option when the library is loaded).  Names:
  *   int8 (1)          wide batches take the INT8 tensor-core path (0: FP64 DMMA everywhere; per call: IBO_FLAG_INT8 / IBO_FLAG_FP64)
- *   i8_min_batch (192) batches of this many .. narrow_max candidates take the INT8 path too (DIRECT's mid-size batches; 0: wide only)
+ *   i8_min_batch (-1) batches of this many .. narrow_max candidates take the INT8 path too (DIRECT's mid-size batches); -1: from the
+ *                     measured break-even with the FP64 latency shapes on (735 / 300 / 133 / 62 candidates at N = 1024 / 2048 /
+ *                     4096 / 8192), 0: wide batches only
  *   i8_guard (1)      INT8 path: re-score candidates with sigma^2 < 2^-10 on the DMMA path
  *   i8_pipe (1)       INT8 path: cross-covariance of chunk c+1 on a low-priority stream under the GEMM of chunk c
  *   chunk_tiles (0)   128-candidate tiles per chunk (0: 2 x number of SMs)
@@ -220,6 +222,7 @@ int ibo_debug_exp(int device, const double* x, long n, double* out_fast, double*
  *   narrow_mt (0), k2_deep (-1), pdl (1), kstar_direct (0), tiny (-1)   shape / launch switches of the small-batch path
  *   debug_plan (0), direct_timing (0)   diagnostics on stderr
  *   shard_min (0)     sharded DIRECT: batches below this many points are not sharded (0: 64 x ranks)
+ *   chol_pair (-1)    model build: block columns in pairs (256-deep trailing updates); -1: from 48 block columns on, 0 / 1 forced
  * Unknown names return IBO_E_BADARG. */
 int ibo_set_option(const char* name, long value);
 int ibo_get_option(const char* name, long* value);

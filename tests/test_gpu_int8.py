@@ -109,21 +109,42 @@ def test_int8_follows_append_and_batch_size_classes():
     sc, mu, s2, best, bidx = gp.model.score(Xs, _lib.ACQ_EI, max(gp.Y), 0.01, flags=fl, want_posterior=True)
     mu_o, s2_o = o.posterior_batch(Xs)
     assert _rel(mu, mu_o, 1e-3) <= TOL and _rel(s2, s2_o, 1e-300) <= TOL
-    # batches below option i8_min_batch (192) take the FP64 latency shapes whatever the flag says ...
-    a = gp.model.score(Xs[:100], _lib.ACQ_EI, max(gp.Y), 0.01, flags=fl | _lib.FLAG_FP64, want_posterior=True)
-    b = gp.model.score(Xs[:100], _lib.ACQ_EI, max(gp.Y), 0.01, flags=fl | _lib.FLAG_INT8, want_posterior=True)
-    assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
-    # ... DIRECT's mid-size batches (192 .. 2048 points) take the INT8 kernels, and a candidate gets the bits it gets in a wide batch
-    c = gp.model.score(Xs[:500], _lib.ACQ_EI, max(gp.Y), 0.01, flags=fl, want_posterior=True)
-    assert np.array_equal(c[0], sc[:500]) and np.array_equal(c[1], mu[:500]) and np.array_equal(c[2], s2[:500])
+    assert _lib.get_option("i8_min_batch") == -1
     f = gp.model.score(Xs[:500], _lib.ACQ_EI, max(gp.Y), 0.01, flags=fl | _lib.FLAG_FP64, want_posterior=True)
-    assert not np.array_equal(f[2], c[2]) and _rel(c[2], f[2], 1e-300) <= 1e-12
-    _lib.set_option("i8_min_batch", 0)
-    try:
-        g = gp.model.score(Xs[:500], _lib.ACQ_EI, max(gp.Y), 0.01, flags=fl, want_posterior=True)
-    finally:
-        _lib.set_option("i8_min_batch", 192)
+    # default rule: on a model this small (N = 260) a 500-point batch is below the break-even and stays on the FP64 latency shapes
+    g = gp.model.score(Xs[:500], _lib.ACQ_EI, max(gp.Y), 0.01, flags=fl, want_posterior=True)
     assert np.array_equal(g[2], f[2])
+    _lib.set_option("i8_min_batch", 192)
+    try:
+        # batches below a fixed i8_min_batch take the FP64 latency shapes whatever the flag says ...
+        a = gp.model.score(Xs[:100], _lib.ACQ_EI, max(gp.Y), 0.01, flags=fl | _lib.FLAG_FP64, want_posterior=True)
+        b = gp.model.score(Xs[:100], _lib.ACQ_EI, max(gp.Y), 0.01, flags=fl | _lib.FLAG_INT8, want_posterior=True)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+        # ... mid-size batches (192 .. 2048 points) take the INT8 kernels, and a candidate gets the bits it gets in a wide batch
+        c = gp.model.score(Xs[:500], _lib.ACQ_EI, max(gp.Y), 0.01, flags=fl, want_posterior=True)
+        assert np.array_equal(c[0], sc[:500]) and np.array_equal(c[1], mu[:500]) and np.array_equal(c[2], s2[:500])
+        assert not np.array_equal(f[2], c[2]) and _rel(c[2], f[2], 1e-300) <= 1e-12
+        _lib.set_option("i8_min_batch", 0)
+        g = gp.model.score(Xs[:500], _lib.ACQ_EI, max(gp.Y), 0.01, flags=fl, want_posterior=True)
+        assert np.array_equal(g[2], f[2])
+    finally:
+        _lib.set_option("i8_min_batch", -1)
+
+
+def test_mid_size_batches_cross_over_to_int8_by_model_size():
+    """default i8_min_batch rule: at N = 4096 a 256-point batch is past the break-even (133) and gets the bits of a wide batch,
+    a 64-point batch is not and gets the FP64 bits"""
+    from ibo_b200 import _lib
+    gp, o, Xs, Y = _case(4096, 5, 3000)
+    fl = _lib.FLAG_MODE_CPP
+    wide = gp.model.score(Xs, _lib.ACQ_EI, Y.max(), 0.01, flags=fl, want_posterior=True)
+    mid = gp.model.score(Xs[:256], _lib.ACQ_EI, Y.max(), 0.01, flags=fl, want_posterior=True)
+    assert np.array_equal(mid[0], wide[0][:256]) and np.array_equal(mid[2], wide[2][:256])
+    small = gp.model.score(Xs[:64], _lib.ACQ_EI, Y.max(), 0.01, flags=fl, want_posterior=True)
+    small64 = gp.model.score(Xs[:64], _lib.ACQ_EI, Y.max(), 0.01, flags=fl | _lib.FLAG_FP64, want_posterior=True)
+    assert np.array_equal(small[2], small64[2]) and not np.array_equal(small[2], wide[2][:64])
+    mu_o, s2_o = o.posterior_batch(Xs[:256])
+    assert _rel(mid[1], mu_o, 1e-3) <= TOL and _rel(mid[2], s2_o, 1e-300) <= TOL
 
 
 def test_option_int8_off_means_dmma_everywhere():
