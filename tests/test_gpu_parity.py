@@ -89,6 +89,30 @@ def test_factor_matches_numpy_cholesky():
     m.close()
 
 
+@pytest.mark.parametrize("N", [300, 640, 1100])
+@pytest.mark.parametrize("pair", [0, 1])
+def test_factor_schedules_match_numpy_cholesky(N, pair):
+    """both schedules of the build (block columns one at a time / in pairs with 256-deep updates; option chol_pair) on even and odd
+    block counts (3, 5, 9 row-blocks)"""
+    from ibo_b200 import _lib
+    rs = np.random.RandomState(N)
+    d = 3
+    X = rs.rand(N, d)
+    Y = rs.randn(N)
+    gp = orc.GPOracle(orc.KernelSpec(orc.K_MATERN5, [0.5, 1.0], d), X, Y, 0.05)
+    _lib.set_option("chol_pair", pair)
+    try:
+        m = _model(orc.K_MATERN5, [0.5, 1.0], X, Y, 0.05)
+        L = m.matrix(1)
+        W = m.matrix(2)
+        m.close()
+    finally:
+        _lib.set_option("chol_pair", -1)
+    assert np.max(np.abs(L - gp.L)) < 1e-12
+    assert np.max(np.abs(W.dot(gp.L) - np.eye(N))) < 1e-10
+    assert np.array_equal(np.triu(L, 1), np.zeros_like(L)) and np.array_equal(np.triu(W, 1), np.zeros_like(W))
+
+
 EDGE = [
     # (name, kind, hyper, N, d, M, noise, box)  -- shapes around the 128-row blocks, d = 1, d > 32 (direct-difference K1),
     # and badly scaled inputs that trip K1's cancellation guard (|x/theta|^2 >> 256 -> per-pair direct differences)

@@ -22,3 +22,8 @@ compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest tests/test
 echo "memcheck int8 rc=$?"
 compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest tests/test_gpu_laplace.py -x -q -m gpu -k "assembled" 2>&1 | tail -6
 echo "memcheck pref-C rc=$?"
+# model build rewritten in round 2 (tensor-core diagonal block kernel, half-height tiles, paired block columns, four streams)
+compute-sanitizer --tool racecheck --error-exitcode 3 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "factor_schedules and 640" 2>&1 | tail -6
+echo "racecheck model build rc=$?"
+compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "factor_schedules" 2>&1 | tail -6
+echo "memcheck model build rc=$?"
