@@ -744,10 +744,7 @@ int append_rows(ibo_model* m, const double* X, const double* Y, int k, int* info
 // dynamic shared-memory opt-ins of the factorisation kernels (per device: ensure_attrs)
 static cudaError_t set_model_attrs() {
     const int tile_smem = TILE_SMEM_DOUBLES * 8;
-    cudaError_t e = cudaFuncSetAttribute(block_step_kernel<MODE_CHOL_PANEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(block_step_kernel<MODE_CHOL_TRAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(block_step_kernel<MODE_TRTRI_SCALE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(block_step_kernel<MODE_TRTRI_UPDATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem);
+    cudaError_t e = cudaFuncSetAttribute(block_step_kernel<MODE_TRTRI_SCALE>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem);
     const int half_smem = TileCfg<64>::SMEM_DOUBLES * 8;
     if (e == cudaSuccess) e = cudaFuncSetAttribute(block_step_kernel<MODE_CHOL_PANEL, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, half_smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(block_step_kernel<MODE_CHOL_TRAIL, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, half_smem);
