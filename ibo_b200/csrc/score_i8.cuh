@@ -234,45 +234,51 @@ __global__ void __launch_bounds__(256, (DMAX <= 8 ? 4 : (DMAX <= 16 ? 3 : 2))) k
     uint8_t* dst0 = Ki8 + ((size_t)T * (nb * 4) + (size_t)i * 4 + kg) * I8_B_STAGE;
 #pragma unroll 1
     for (int c16 = 0; c16 < 2; c16++) {
-        long long q[16];
+        // Balanced base-256 digits of (v - 1/2) 2^55, four values at a time: adding 128 to each of the six low bytes (one 64-bit add,
+        // carries included) turns every byte into digit + 128, the xor takes the 128 off again in two's complement; byte 6 is then
+        // the signed top digit (|q| <= 2^54, so it fits).  Digit t is byte 7 - t.  A 4 x 4 byte transpose (8 PRMT per four values
+        // and word half) lines the bytes of one digit up: sixteen values give the 16-byte store of one core-matrix row per digit.
+        uint32_t wd[7][4];
 #pragma unroll
-        for (int kk = 0; kk < 16; kk++) {
-            const int k = kg * 32 + c16 * 16 + kk;
-            const double2* xr = reinterpret_cast<const double2*>(sX + k * DMAX);
-            double r2a = 0.0, r2b = 0.0;
+        for (int v = 0; v < 4; v++) {
+            uint32_t lo[4], hi[4];
 #pragma unroll
-            for (int j2 = 0; j2 < DMAX / 2; j2++) {
-                const double2 x2 = xr[j2];
-                const double da = x2.x - xc[2 * j2], db = x2.y - xc[2 * j2 + 1];
-                r2a = fma(da, da, r2a);
-                r2b = fma(db, db, r2b);
+            for (int b = 0; b < 4; b++) {
+                const int k = kg * 32 + c16 * 16 + v * 4 + b;
+                const double2* xr = reinterpret_cast<const double2*>(sX + k * DMAX);
+                double r2a = 0.0, r2b = 0.0;
+#pragma unroll
+                for (int j2 = 0; j2 < DMAX / 2; j2++) {
+                    const double2 x2 = xr[j2];
+                    const double da = x2.x - xc[2 * j2], db = x2.y - xc[2 * j2 + 1];
+                    r2a = fma(da, da, r2a);
+                    r2b = fma(db, db, r2b);
+                }
+                const bool live = (i * 128 + k) < N;
+                const double val = live ? cov_r2_t<KC>(1.0, r2a + r2b) : 0.0;   // in [0, 1]
+                sy = fma(val, sAy[k], sy);
+                s1 = fma(val, sA1[k], s1);
+                // (v - 1/2) / 2 in [-1/4, 1/4] at 56 fractional bits, signed; rows beyond N contribute nothing (W is zero there)
+                const long long q = live ? __double2ll_rn((val - 0.5) * 36028797018963968.0) : 0ll;     // 2^55
+                const unsigned long long u = ((unsigned long long)q + 0x0000808080808080ull) ^ 0x0000808080808080ull;
+                lo[b] = (uint32_t)u; hi[b] = (uint32_t)(u >> 32);
             }
-            const bool live = (i * 128 + k) < N;
-            const double v = live ? cov_r2_t<KC>(1.0, r2a + r2b) : 0.0;   // in [0, 1]
-            sy = fma(v, sAy[k], sy);
-            s1 = fma(v, sA1[k], s1);
-            // (v - 1/2) / 2 in [-1/4, 1/4] at 56 fractional bits, signed; rows beyond N contribute nothing (W is zero there)
-            q[kk] = live ? __double2ll_rn((v - 0.5) * 36028797018963968.0) : 0ll;     // 2^55
+            const uint32_t l01 = __byte_perm(lo[0], lo[1], 0x5140), l23 = __byte_perm(lo[2], lo[3], 0x5140);
+            const uint32_t m01 = __byte_perm(lo[0], lo[1], 0x7362), m23 = __byte_perm(lo[2], lo[3], 0x7362);
+            const uint32_t h01 = __byte_perm(hi[0], hi[1], 0x5140), h23 = __byte_perm(hi[2], hi[3], 0x5140);
+            const uint32_t g01 = __byte_perm(hi[0], hi[1], 0x7362), g23 = __byte_perm(hi[2], hi[3], 0x7362);
+            wd[6][v] = __byte_perm(l01, l23, 0x5410);      // byte 0: digit 7 (least significant)
+            wd[5][v] = __byte_perm(l01, l23, 0x7632);      // byte 1: digit 6
+            wd[4][v] = __byte_perm(m01, m23, 0x5410);      // byte 2: digit 5
+            wd[3][v] = __byte_perm(m01, m23, 0x7632);      // byte 3: digit 4
+            wd[2][v] = __byte_perm(h01, h23, 0x5410);      // byte 4: digit 3
+            wd[1][v] = __byte_perm(h01, h23, 0x7632);      // byte 5: digit 2
+            wd[0][v] = __byte_perm(g01, g23, 0x5410);      // byte 6: digit 1 (most significant, takes the rest)
         }
         uint8_t* dst = dst0 + i8_canon(c, c16 * 16);
-        // balanced base-256 digits, least significant first (as the W digits)
 #pragma unroll
-        for (int t = I8_S; t >= 1; t--) {
-            uint32_t w4[4];
-#pragma unroll
-            for (int v = 0; v < 4; v++) {
-                uint32_t word = 0;
-#pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    long long qs = q[v * 4 + b], dgt;
-                    if (t > 1) { dgt = ((qs + 128) & 255) - 128; q[v * 4 + b] = (qs - dgt) >> 8; }
-                    else dgt = qs;
-                    word |= ((uint32_t)(int)dgt & 0xffu) << (8 * b);
-                }
-                w4[v] = word;
-            }
-            *reinterpret_cast<uint4*>(dst + (size_t)(t - 1) * I8_B_SLICE) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-        }
+        for (int t = I8_S; t >= 1; t--)
+            *reinterpret_cast<uint4*>(dst + (size_t)(t - 1) * I8_B_SLICE) = make_uint4(wd[t - 1][0], wd[t - 1][1], wd[t - 1][2], wd[t - 1][3]);
     }
     red[kg * 64 + c] = sy;
     red[256 + kg * 64 + c] = s1;
