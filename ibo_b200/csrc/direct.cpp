@@ -630,8 +630,8 @@ extern "C" int ibo_acqmax(ibo_model* m, const double* lb, const double* ub, int 
     if (!m || acq < 0 || acq > 2) { set_error("bad argument"); return IBO_E_BADARG; }
     GpuObjective g{m, acq, ymax, parm, flags, IBO_OK, 0.0, 0, 0};
     if (flags & IBO_FLAG_SHARD) {
-        const char* e = getenv("IBO_SHARD_MIN");       // batches below this many points stay on every rank (latency)
-        g.shard_min = e ? atol(e) : 64L * ibo_comm_size();
+        const long sm = ibo::get_option(ibo::OPT_SHARD_MIN);       // batches below this many points stay on every rank (latency)
+        g.shard_min = sm > 0 ? sm : 64L * ibo_comm_size();
     }
     double fmin = 0;
     auto t0 = std::chrono::steady_clock::now();
