@@ -33,6 +33,9 @@ namespace ibo {
 void set_error(const std::string& s);
 int eval_neg_acq(ibo_model* m, const double* Xs, long n, int acq, double ymax, double parm, int flags, double* y);
 int batch_uses_i8(ibo_model* m, long n, int flags);
+bool tiny_server_fits(const ibo_model* m, long n);
+int tiny_server_eval(ibo_model* m, const double* X, long n, int acq, double ymax, double parm, int flags, double* y);
+void tiny_server_stop(ibo_model* m);
 
 namespace {
 
@@ -570,6 +573,7 @@ void scalar_batch(void* user, long n, int ndim, const double* X, double* y) {
 struct GpuObjective {
     ibo_model* m; int acq; double ymax, parm; int flags; int rc; double t_eval; long batches, points;
     long shard_min = 0; long sharded_batches = 0; std::vector<double> mine, all;
+    bool server = false;      // a model of one row-block: batches go to the resident kernel of tiny.cu
 };
 void gpu_batch(void* user, long n, int ndim, const double* X, double* y) {
     GpuObjective* g = static_cast<GpuObjective*>(user);
@@ -607,7 +611,10 @@ void gpu_batch(void* user, long n, int ndim, const double* X, double* y) {
                 if (b > a) std::memcpy(y + a, g->all.data() + (size_t)r * (per + 1), sizeof(double) * (size_t)(b - a));
             }
         g->sharded_batches++;
+    } else if (g->server && tiny_server_fits(g->m, n)) {
+        g->rc = tiny_server_eval(g->m, X, n, g->acq, g->ymax, g->parm, g->flags, y);
     } else {
+        if (g->server) tiny_server_stop(g->m);      // the resident kernel owns the model's stream: it leaves before anything else is launched
         g->rc = eval_neg_acq(g->m, X, n, g->acq, g->ymax, g->parm, g->flags, y);
     }
     g->t_eval += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -633,10 +640,12 @@ extern "C" int ibo_acqmax(ibo_model* m, const double* lb, const double* ub, int 
         const long sm = ibo::get_option(ibo::OPT_SHARD_MIN);       // batches below this many points stay on every rank (latency)
         g.shard_min = sm > 0 ? sm : 64L * ibo_comm_size();
     }
+    g.server = !(flags & IBO_FLAG_SHARD);
     double fmin = 0;
     auto t0 = std::chrono::steady_clock::now();
     // the GPU objective is a pure function of the point (DESIGN.md "Determinism"): the driver may speculate
     int rc = run_direct(gpu_batch, &g, ibo_model_dim(m), lb, ub, maxiter, maxtime, maxsample, flags | IBO_FLAG_DIRECT_SPECULATE, &fmin, optx, nsamples, iterations);
+    tiny_server_stop(m);
     if (ibo::get_option(ibo::OPT_DIRECT_TIMING)) {
         double tt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         fprintf(stderr, "[ibo_acqmax] total %.3f ms, GPU batches %.3f ms (%ld batches, %ld sharded, %ld points, %.1f us/batch), host driver %.3f ms\n",

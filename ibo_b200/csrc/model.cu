@@ -961,6 +961,9 @@ static void free_model(ibo_model* m) {
         for (ibo_model* o : g_live) if (o->var_model == m) o->var_model = nullptr;
     }
     cudaSetDevice(m->device);
+    tiny_server_stop(m);
+    if (m->hServer) pinned_put(m->hServer);
+    if (m->dSrvCount) cudaFree(m->dSrvCount);
     if (m->stream2) cudaStreamSynchronize(m->stream2);
     if (m->stream3) cudaStreamSynchronize(m->stream3);
     if (m->stream4) cudaStreamSynchronize(m->stream4);

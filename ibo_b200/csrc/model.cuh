@@ -63,6 +63,9 @@ struct ibo_model {
     double* dBlkBest = nullptr; long long* dBlkIdx = nullptr; size_t blkCap = 0;
     double* dBest = nullptr;  long long* dBestIdx = nullptr;      // final argmax
     double* hPinned = nullptr; size_t pinnedCap = 0;              // pinned staging for small batches
+    // batch server of the fused small-model kernel (tiny.cu): mailbox in mapped pinned memory, resident kernel on `stream`
+    double* hServer = nullptr; unsigned long long* dSrvCount = nullptr; bool srvRunning = false; long long srvSeq = 0;
+    int srvAcq = 0, srvFlags = 0, srvCtas = 0; double srvYmax = 0, srvParm = 0;
     std::map<long, std::pair<int*, int>> unitTables;              // K2 work tables (device), keyed by shape and group count
     std::map<long, std::pair<int, int>> planCache;                // K2 launch plan (MT, G) per number of 32-candidate CTA tiles
     // profile of the last call
@@ -81,6 +84,10 @@ struct ScoreReq;
 // fused single-launch path for models of one row-block (tiny.cu)
 bool tiny_eligible(const ibo_model* m, long M);
 int score_tiny(ibo_model* m, const double* cand, long M, const ScoreReq& rq, double* out, const double* host_cand);
+// batch server for one DIRECT query on such a model: y[i] = -acq(X[i]); the first call starts the resident kernel, stop ends it
+bool tiny_server_fits(const ibo_model* m, long n);
+int tiny_server_eval(ibo_model* m, const double* X, long n, int acq, double ymax, double parm, int flags, double* y);
+void tiny_server_stop(ibo_model* m);
 int grow(double** p, size_t* cap, size_t need);
 cudaError_t pool_malloc(void** p, size_t bytes);
 void pool_free(void* p);

@@ -13,6 +13,8 @@
 // A candidate's value is a function of (model, x) only (fixed summation orders), so DIRECT trajectories stay reproducible.
 #include "model.cuh"
 #include "scoremath.cuh"
+#include <atomic>
+#include <chrono>
 #include <cstring>
 #include <mutex>
 
@@ -38,14 +40,46 @@ struct TinyParams {
     double sf2, noise, ymax, parm, ptheta;
 };
 
+// Batch server (SERVER = true): for the length of one DIRECT query the kernel stays resident -- a handful of CTAs with the factors
+// staged in shared memory once -- and takes its batches from a mailbox in mapped pinned host memory: the host writes the candidates
+// and publishes (batch number, size) in one word, every CTA that owns a tile scores it, writes the values into the mailbox and
+// releases its own `done` word.  A batch then costs three dependent PCIe round trips (control word, candidates, values) instead of
+// a kernel launch, a re-staging of W and a stream synchronisation.  All mailbox traffic uses system-scope loads / stores (a resident kernel must not find
+// stale host data in L2); an idle server gives up after two seconds so that nothing spins on the GPU if the host goes away.
+struct TinyMailbox {
+    long long ctrl;      // host -> device: (batch number << 24) | candidates in the batch; -1 = quit.  One word, one PCIe read per poll.
+    long long pad[15];
+    long long done[16];  // device -> host: done[c] = number of the last batch CTA c finished (only CTAs that own a tile report)
+    double data[1];      // candidates [M][d], then the values [M]
+};
+constexpr size_t MAILBOX_DOUBLES = (1u << 17) - 32;     // one pinned staging buffer of the pool (1 MiB)
+constexpr int SERVER_CTAS = 16;
+
+__device__ __forceinline__ long long ld_relaxed_sys(const long long* p) {
+    long long v; asm volatile("ld.relaxed.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
+    double v; asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_sys(long long* p, long long v) {
+    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
+}
+
 __device__ __forceinline__ void cp_async8(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src));
 }
 
-template <int KC>
-__global__ void __launch_bounds__(128) tiny_fused_kernel(const __grid_constant__ TinyParams P, const __grid_constant__ CandInline I) {
+template <int KC, bool SERVER>
+__global__ void __launch_bounds__(128) tiny_fused_kernel(const __grid_constant__ TinyParams P, const __grid_constant__ CandInline I,
+                                                         TinyMailbox* mb, unsigned long long* srv) {
     extern __shared__ double sm[];
-    const double* __restrict__ cands = P.cand ? P.cand : I.x;
+    const double* cands = SERVER ? mb->data : (P.cand ? P.cand : I.x);
+    long Mcur = SERVER ? 0 : P.M;
+    double* scoreOut = P.score;
+    auto ld_cand = [&](size_t i) -> double { return SERVER ? ld_relaxed_sys(cands + i) : cands[i]; };
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = P.d, XS = d | 1;                   // odd row stride of the training inputs
     const int nside = P.side[1].N > 0 ? 2 : 1;
@@ -79,26 +113,56 @@ __global__ void __launch_bounds__(128) tiny_fused_kernel(const __grid_constant__
     asm volatile("cp.async.commit_group;");
     // The first tile's candidates are fetched while the copies above are in flight: for a DIRECT batch they come over PCIe
     // (mapped host memory), the longest latency in the kernel -- everything else hides behind it.
-    const long ntile = (P.M + TC - 1) / TC;
-    for (int idx = tid; idx < TC * d; idx += 128) {
-        const int j = idx / d, q = idx - j * d;
-        long m = (long)blockIdx.x * TC + j; if (m >= P.M) m = P.M - 1;
-        sC[idx] = cands[(size_t)m * d + q];
-    }
+    if (!SERVER)
+        for (int idx = tid; idx < TC * d; idx += 128) {
+            const int j = idx / d, q = idx - j * d;
+            long m = (long)blockIdx.x * TC + j; if (m >= Mcur) m = Mcur - 1;
+            sC[idx] = cands[(size_t)m * d + q];
+        }
     const int N0 = P.side[0].N;
     const double by = tid < N0 ? P.betaY[tid] : 0.0;
     const double b1 = (tid < N0 && P.npb > 0) ? P.beta1[tid] : 0.0;
     double best = -INFINITY;
     long long bestIdx = 0x7fffffffffffffffLL;
     asm volatile("cp.async.wait_group 0;");
-    for (long t = blockIdx.x; t < ntile; t += gridDim.x) {
+    __shared__ long long sh_seq, sh_M;
+    long long lastSeq = 0;
+    unsigned batchNo = 0;
+  next_batch:
+    if (SERVER) {
+        // CTA 0 watches the host's mailbox (one PCIe read per poll) and passes each new batch on through device memory, where
+        // the other CTAs wait: sixteen CTAs polling host memory at once made a batch cost 78 us instead of 24
+        if (tid == 0) {
+            long long w;
+            if (blockIdx.x == 0) {
+                const unsigned long long t0 = global_timer_ns();
+                while ((w = ld_relaxed_sys(&mb->ctrl)) >= 0 && (w >> 24) == lastSeq)
+                    if (global_timer_ns() - t0 > 2000000000ull) { w = -2; break; }      // idle for 2 s: everybody leaves (the host restarts the server)
+                asm volatile("fence.acq_rel.sys;" ::: "memory");                         // the candidates were written before the word
+                asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(srv + 1), "l"((unsigned long long)w) : "memory");
+            } else {
+                unsigned long long v;
+                do { asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(srv + 1) : "memory"); }
+                while ((long long)v >= 0 && ((long long)v >> 24) == lastSeq);
+                w = (long long)v;
+            }
+            sh_seq = w < 0 ? w : (w >> 24);
+            sh_M = w < 0 ? 0 : (w & 0xffffff);
+        }
+        __syncthreads();
+        if (sh_seq < 0) return;
+        lastSeq = sh_seq; batchNo++;
+        Mcur = (long)sh_M;
+        scoreOut = mb->data + (size_t)Mcur * d;
+    }
+    for (long t = blockIdx.x; t < (Mcur + TC - 1) / TC; t += gridDim.x) {
         const long m0 = t * TC;
-        if (t != blockIdx.x) {
+        if (SERVER || t != blockIdx.x) {
             __syncthreads();                 // previous tile's scratch is free
             for (int idx = tid; idx < TC * d; idx += 128) {
                 const int j = idx / d, q = idx - j * d;
-                long m = m0 + j; if (m >= P.M) m = P.M - 1;
-                sC[idx] = cands[(size_t)m * d + q];
+                long m = m0 + j; if (m >= Mcur) m = Mcur - 1;
+                sC[idx] = ld_cand((size_t)m * d + q);
             }
         }
         double q_sum = 0, p_sum = 0, p1_sum = 0;           // of candidate m0 + tid (threads 0..7)
@@ -155,7 +219,7 @@ __global__ void __launch_bounds__(128) tiny_fused_kernel(const __grid_constant__
                 if (s == 0) { p_sum = p; p1_sum = p1; }     // the mean always from the model itself (gaussianprocess/__init__.py:214-223)
             }
         }
-        if (tid < TC && m0 + tid < P.M) {
+        if (tid < TC && m0 + tid < Mcur) {
             const long m = m0 + tid;
             double mean0 = 0.0;
             if (P.npb > 0) mean0 = prior_mean(sC + tid * d, d, P.npb, P.pmeans, P.pbeta, P.ptheta, P.plb, P.pwidth);
@@ -167,11 +231,18 @@ __global__ void __launch_bounds__(128) tiny_fused_kernel(const __grid_constant__
             if (P.s2) P.s2[m] = s2;
             if (P.acq >= 0) {
                 const double val = acq_value(P.acq, P.mode_py, mu, s2, P.ymax, P.parm);
-                if (P.score) P.score[m] = val;
+                if (scoreOut) scoreOut[m] = val;
                 if (val == val) { if (val > best || (val == best && m < bestIdx)) { best = val; bestIdx = m; } }
                 else if (bestIdx == 0x7fffffffffffffffLL) bestIdx = m;      // NaN never wins, but an all-NaN set still names an index
             }
         }
+    }
+    if (SERVER) {
+        __syncthreads();
+        // a CTA that scored a tile releases its own done word (the release orders its value stores before it); the host waits for
+        // exactly the CTAs that own tiles of this batch
+        if (tid == 0 && (long)blockIdx.x < (Mcur + TC - 1) / TC) st_release_sys(&mb->done[blockIdx.x], lastSeq);
+        goto next_batch;
     }
     if (P.acq < 0 || !P.want_argmax) return;
     // the tile owners (threads 0..7, all in warp 0) combine: lowest index wins ties
@@ -210,9 +281,12 @@ __global__ void __launch_bounds__(256) tiny_argmax_kernel(const double* __restri
 
 cudaError_t set_tiny_attrs() {
     const int maxsm = 200 * 1024;
-    cudaError_t e = cudaFuncSetAttribute(tiny_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tiny_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tiny_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
+    cudaError_t e = cudaFuncSetAttribute(tiny_fused_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tiny_fused_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tiny_fused_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tiny_fused_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tiny_fused_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tiny_fused_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxsm);
     return e;
 }
 
@@ -283,9 +357,9 @@ int score_tiny(ibo_model* m, const double* cand, long M, const ScoreReq& rq, dou
         Ip = &Ilocal;
     }
     if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[0], st));
-    if (m->kind <= IBO_KERNEL_SE_ISO) tiny_fused_kernel<0><<<grid, 128, smem, st>>>(P, *Ip);
-    else if (m->kind == IBO_KERNEL_MATERN3) tiny_fused_kernel<1><<<grid, 128, smem, st>>>(P, *Ip);
-    else tiny_fused_kernel<2><<<grid, 128, smem, st>>>(P, *Ip);
+    if (m->kind <= IBO_KERNEL_SE_ISO) tiny_fused_kernel<0, false><<<grid, 128, smem, st>>>(P, *Ip, nullptr, nullptr);
+    else if (m->kind == IBO_KERNEL_MATERN3) tiny_fused_kernel<1, false><<<grid, 128, smem, st>>>(P, *Ip, nullptr, nullptr);
+    else tiny_fused_kernel<2, false><<<grid, 128, smem, st>>>(P, *Ip, nullptr, nullptr);
     long nlaunch = 1;
     if (P.want_argmax) {
         tiny_argmax_kernel<<<1, 256, 0, st>>>(m->dBlkBest, m->dBlkIdx, grid, out + 3 * M, reinterpret_cast<long long*>(out + 3 * M + 1));
@@ -300,6 +374,94 @@ int score_tiny(ibo_model* m, const double* cand, long M, const ScoreReq& rq, dou
     }
     IBO_CUDA_TRY(cudaGetLastError());
     return IBO_OK;
+}
+
+// ---- batch server (host side) ---------------------------------------------------------------------
+bool tiny_server_fits(const ibo_model* m, long n) {
+    return n >= 1 && get_option(OPT_TINY_SERVER) != 0 && tiny_eligible(m, n) && (size_t)n * (m->d + 1) <= MAILBOX_DOUBLES;
+}
+
+static int tiny_server_start(ibo_model* m, int acq, double ymax, double parm, int flags) {
+    const cudaError_t ae = ensure_attrs(m->device, ATTR_TINY, set_tiny_attrs);
+    if (ae != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ae)); return IBO_E_CUDA; }
+    cudaStream_t st = m->stream;
+    if (!m->hServer) IBO_CUDA_TRY(pinned_get(&m->hServer));
+    if (!m->dSrvCount) IBO_CUDA_TRY(cudaMalloc(&m->dSrvCount, 4 * sizeof(unsigned long long)));
+    TinyMailbox* mb = reinterpret_cast<TinyMailbox*>(m->hServer);
+    mb->ctrl = 0;
+    for (int c = 0; c < 16; c++) mb->done[c] = 0;
+    m->srvSeq = 0;
+    IBO_CUDA_TRY(cudaMemsetAsync(m->dSrvCount, 0, 4 * sizeof(unsigned long long), st));
+    const ibo_model* vm = m->var_model;
+    const size_t smem = tiny_smem(m->N, vm ? vm->N : 0, m->d);
+    TinyParams P;
+    P.side[0] = TinySide{m->dW, m->dXt, m->dCenter, m->N};
+    P.side[1] = vm ? TinySide{vm->dW, vm->dXt, vm->dCenter, vm->N} : TinySide{nullptr, nullptr, nullptr, 0};
+    P.betaY = m->dBetaY; P.beta1 = m->dBeta1; P.invTheta = m->dInvTheta; P.cand = nullptr;
+    P.pmeans = m->dPmeans; P.pbeta = m->dPbeta; P.plb = m->dPlb; P.pwidth = m->dPwidth;
+    P.score = nullptr; P.mu = nullptr; P.s2 = nullptr;
+    P.blkBest = nullptr; P.blkIdx = nullptr;
+    P.M = 0; P.d = m->d; P.acq = acq; P.mode_py = (flags & IBO_FLAG_MODE_PY) ? 1 : 0; P.npb = m->npb;
+    P.want_argmax = 0;
+    P.sf2 = m->sf2; P.noise = m->noise; P.ymax = ymax; P.parm = parm; P.ptheta = m->ptheta;
+    static CandInline none;
+    const int grid = std::min(SERVER_CTAS, dev_info(m->device).sms);
+    m->srvCtas = grid;
+    if (m->kind <= IBO_KERNEL_SE_ISO) tiny_fused_kernel<0, true><<<grid, 128, smem, st>>>(P, none, mb, m->dSrvCount);
+    else if (m->kind == IBO_KERNEL_MATERN3) tiny_fused_kernel<1, true><<<grid, 128, smem, st>>>(P, none, mb, m->dSrvCount);
+    else tiny_fused_kernel<2, true><<<grid, 128, smem, st>>>(P, none, mb, m->dSrvCount);
+    IBO_CUDA_TRY(cudaGetLastError());
+    g_launches++;
+    m->srvRunning = true;
+    m->srvAcq = acq; m->srvYmax = ymax; m->srvParm = parm; m->srvFlags = flags;
+    return IBO_OK;
+}
+
+void tiny_server_stop(ibo_model* m) {
+    if (!m || !m->srvRunning) return;
+    cudaSetDevice(m->device);
+    TinyMailbox* mb = reinterpret_cast<TinyMailbox*>(m->hServer);
+    std::atomic_thread_fence(std::memory_order_release);
+    *reinterpret_cast<volatile long long*>(&mb->ctrl) = -1;
+    cudaStreamSynchronize(m->stream);
+    m->srvRunning = false;
+}
+
+int tiny_server_eval(ibo_model* m, const double* X, long n, int acq, double ymax, double parm, int flags, double* y) {
+    IBO_CUDA_TRY(cudaSetDevice(m->device));
+    if (m->srvRunning && (acq != m->srvAcq || ymax != m->srvYmax || parm != m->srvParm || flags != m->srvFlags)) tiny_server_stop(m);
+    for (int attempt = 0; attempt < 3; attempt++) {
+        if (!m->srvRunning) { int rc = tiny_server_start(m, acq, ymax, parm, flags); if (rc) return rc; }
+        TinyMailbox* mb = reinterpret_cast<TinyMailbox*>(m->hServer);
+        const size_t nin = (size_t)n * m->d;
+        std::memcpy(mb->data, X, sizeof(double) * nin);
+        const long long seq = ++m->srvSeq;
+        std::atomic_thread_fence(std::memory_order_release);
+        *reinterpret_cast<volatile long long*>(&mb->ctrl) = (seq << 24) | (long long)n;
+        // wait for the values: plain reads of host memory; every 2^16 spins make sure the kernel is still there
+        const int nwait = (int)std::min<long>((n + TC - 1) / TC, m->srvCtas);
+        const auto t0 = std::chrono::steady_clock::now();
+        bool gone = false;
+        int c = 0;
+        for (unsigned long spins = 1; c < nwait; spins++) {
+            if (*reinterpret_cast<volatile long long*>(&mb->done[c]) == seq) { c++; continue; }
+            if ((spins & 0xffff) == 0) {
+                const cudaError_t q = cudaStreamQuery(m->stream);
+                if (q == cudaSuccess) { gone = true; break; }      // the kernel left (its idle timeout raced with this batch): once more
+                if (q != cudaErrorNotReady) { m->srvRunning = false; set_error(std::string("small-model batch server: ") + cudaGetErrorString(q)); cudaGetLastError(); return IBO_E_CUDA; }
+                if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 20.0) {
+                    set_error("small-model batch server: no answer for 20 s"); return IBO_E_CUDA;
+                }
+            }
+        }
+        if (gone) { m->srvRunning = false; continue; }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        const double* sc = mb->data + nin;
+        for (long i = 0; i < n; i++) y[i] = -sc[i];
+        return IBO_OK;
+    }
+    set_error("small-model batch server: the kernel keeps leaving");
+    return IBO_E_CUDA;
 }
 
 }  // namespace ibo

@@ -222,6 +222,8 @@ int ibo_debug_exp(int device, const double* x, long n, double* out_fast, double*
  *   narrow_mt (0), k2_deep (-1), pdl (1), kstar_direct (0), tiny (-1)   shape / launch switches of the small-batch path
  *   debug_plan (0), direct_timing (0)   diagnostics on stderr
  *   shard_min (0)     sharded DIRECT: batches below this many points are not sharded (0: 64 x ranks)
+ *   tiny_server (1)   DIRECT on a model of <= 128 observations: the fused kernel stays resident for the query and takes its batches
+ *                     from a mailbox in mapped host memory (0: one launch per batch)
  *   chol_pair (-1)    model build: block columns in pairs (256-deep trailing updates); -1: from 48 block columns on, 0 / 1 forced
  * Unknown names return IBO_E_BADARG. */
 int ibo_set_option(const char* name, long value);

@@ -105,3 +105,64 @@ def test_tiny_direct_matches_general_path_and_reference_goldens_still_hold():
     o2, x2 = _general(lambda: maximizeEI(gp, b, xi=0.01, maxiter=50, maxtime=10 ** 6, maxsample=10000))
     n2 = cdirectGP.last["nsamples"]
     assert n1 == n2 and np.allclose(x1, x2, rtol=0, atol=1e-12) and abs(o1 - o2) <= 1e-10 * abs(o1)
+
+
+def test_batch_server_gives_the_bits_of_the_per_batch_launches():
+    """DIRECT on a one-row-block model: the resident kernel fed through the mailbox (option tiny_server, default) and one launch
+    per batch are the same arithmetic in the same order -- same optimum bit for bit, same samples -- for every acquisition
+    function, with a prior mean, and when queries, score() calls and appends alternate on the same model."""
+    from ibo_b200 import _lib
+    rs = np.random.RandomState(11)
+    d, N = 3, 90
+    X = rs.rand(N, d); Y = np.sin(3 * X).sum(axis=1)
+    pr = orc.PriorSpec(rs.rand(3, d), 0.2 * rs.randn(3), 3.0, np.zeros(d), np.ones(d))
+    lb, ub = np.zeros(d), np.ones(d)
+    for prior in (None, pr):
+        m = _lib.Model(_lib.KERNEL_MATERN3, [0.6, 1.0], X, Y, 0.05, prior=prior)
+        try:
+            for acq, parm in ((_lib.ACQ_EI, 0.01), (_lib.ACQ_PI, 0.01), (_lib.ACQ_UCB, 1.3)):
+                for fl in (_lib.FLAG_MODE_CPP, _lib.FLAG_MODE_PY):
+                    a = m.acqmax(lb, ub, acq, float(Y.max()), parm, flags=fl, maxiter=40, maxsample=10 ** 6)
+                    _lib.set_option("tiny_server", 0)
+                    try:
+                        b = m.acqmax(lb, ub, acq, float(Y.max()), parm, flags=fl, maxiter=40, maxsample=10 ** 6)
+                    finally:
+                        _lib.set_option("tiny_server", 1)
+                    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and a[2] == b[2] and a[3] == b[3]
+            # queries back to back with other work on the same stream in between
+            Xs = rs.rand(37, d)
+            ref = m.score(Xs, _lib.ACQ_EI, float(Y.max()), 0.01)[0]
+            first = m.acqmax(lb, ub, _lib.ACQ_EI, float(Y.max()), 0.01, maxiter=25, maxsample=10 ** 6)
+            for _ in range(20):
+                again = m.acqmax(lb, ub, _lib.ACQ_EI, float(Y.max()), 0.01, maxiter=25, maxsample=10 ** 6)
+                assert again[0] == first[0] and np.array_equal(again[1], first[1]) and again[2] == first[2]
+                assert np.array_equal(m.score(Xs, _lib.ACQ_EI, float(Y.max()), 0.01)[0], ref)
+            m.append(rs.rand(2, d), rs.rand(2))
+            after = m.acqmax(lb, ub, _lib.ACQ_EI, float(Y.max()), 0.01, maxiter=25, maxsample=10 ** 6)
+            _lib.set_option("tiny_server", 0)
+            try:
+                after0 = m.acqmax(lb, ub, _lib.ACQ_EI, float(Y.max()), 0.01, maxiter=25, maxsample=10 ** 6)
+            finally:
+                _lib.set_option("tiny_server", 1)
+            assert after[0] == after0[0] and np.array_equal(after[1], after0[1]) and after[2] == after0[2]
+        finally:
+            m.close()
+
+
+def test_batch_server_side_by_side_queries():
+    """ibo_acqmax_many on small models: one resident kernel per model handle, all on one device"""
+    from ibo_b200 import _lib
+    rs = np.random.RandomState(12)
+    d = 2
+    models, want = [], []
+    lb, ub = np.zeros(d), np.ones(d)
+    try:
+        for q in range(4):
+            X = rs.rand(40 + 10 * q, d); Y = np.cos(4 * X).sum(axis=1)
+            models.append(_lib.Model(_lib.KERNEL_SE_ARD, [0.3, 0.4], X, Y, 0.1))
+            want.append(models[-1].acqmax(lb, ub, _lib.ACQ_EI, float(Y.max()), 0.01, maxiter=30, maxsample=10 ** 6) + (float(Y.max()),))
+        opt, optx, ns, it = _lib.acqmax_many(models, lb, ub, _lib.ACQ_EI, [w[4] for w in want], 0.01, maxiter=30, maxsample=10 ** 6)
+        for q in range(4):
+            assert opt[q] == want[q][0] and np.array_equal(optx[q], want[q][1]) and ns[q] == want[q][2]
+    finally:
+        for m in models: m.close()

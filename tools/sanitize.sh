@@ -27,3 +27,6 @@ compute-sanitizer --tool racecheck --error-exitcode 3 python -m pytest tests/tes
 echo "racecheck model build rc=$?"
 compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "factor_schedules" 2>&1 | tail -6
 echo "memcheck model build rc=$?"
+# resident batch server of the small-model kernel (mailbox in mapped host memory); under the sanitizer its idle timeout also fires
+compute-sanitizer --tool memcheck --error-exitcode 3 python -m pytest tests/test_gpu_tiny.py -x -q -m gpu -k "batch_server" 2>&1 | tail -6
+echo "memcheck batch server rc=$?"
