@@ -377,8 +377,24 @@ int score_tiny(ibo_model* m, const double* cand, long M, const ScoreReq& rq, dou
 }
 
 // ---- batch server (host side) ---------------------------------------------------------------------
+// Resident kernels must all fit on the device at once (a CTA that never becomes resident never answers): at most four servers
+// per device (64 CTAs of <= 200 KB shared memory on 148 SMs); further side-by-side queries (ibo_acqmax_many) launch per batch.
+static std::mutex g_srv_mu;
+static int g_srv_active[16] = {0};
+constexpr int SERVERS_PER_DEVICE = 4;
+
 bool tiny_server_fits(const ibo_model* m, long n) {
-    return n >= 1 && get_option(OPT_TINY_SERVER) != 0 && tiny_eligible(m, n) && (size_t)n * (m->d + 1) <= MAILBOX_DOUBLES;
+    if (!(n >= 1 && get_option(OPT_TINY_SERVER) != 0 && tiny_eligible(m, n) && (size_t)n * (m->d + 1) <= MAILBOX_DOUBLES)) return false;
+    if (m->srvRunning) return true;
+    std::lock_guard<std::mutex> lk(g_srv_mu);
+    return g_srv_active[m->device & 15] < SERVERS_PER_DEVICE;
+}
+
+static void server_gone(ibo_model* m) {      // the kernel is no longer there (idle timeout, error)
+    if (!m->srvRunning) return;
+    m->srvRunning = false;
+    std::lock_guard<std::mutex> lk(g_srv_mu);
+    g_srv_active[m->device & 15]--;
 }
 
 static int tiny_server_start(ibo_model* m, int acq, double ymax, double parm, int flags) {
@@ -412,6 +428,7 @@ static int tiny_server_start(ibo_model* m, int acq, double ymax, double parm, in
     else tiny_fused_kernel<2, true><<<grid, 128, smem, st>>>(P, none, mb, m->dSrvCount);
     IBO_CUDA_TRY(cudaGetLastError());
     g_launches++;
+    { std::lock_guard<std::mutex> lk(g_srv_mu); g_srv_active[m->device & 15]++; }
     m->srvRunning = true;
     m->srvAcq = acq; m->srvYmax = ymax; m->srvParm = parm; m->srvFlags = flags;
     return IBO_OK;
@@ -425,6 +442,8 @@ void tiny_server_stop(ibo_model* m) {
     *reinterpret_cast<volatile long long*>(&mb->ctrl) = -1;
     cudaStreamSynchronize(m->stream);
     m->srvRunning = false;
+    std::lock_guard<std::mutex> lk(g_srv_mu);
+    g_srv_active[m->device & 15]--;
 }
 
 int tiny_server_eval(ibo_model* m, const double* X, long n, int acq, double ymax, double parm, int flags, double* y) {
@@ -448,13 +467,13 @@ int tiny_server_eval(ibo_model* m, const double* X, long n, int acq, double ymax
             if ((spins & 0xffff) == 0) {
                 const cudaError_t q = cudaStreamQuery(m->stream);
                 if (q == cudaSuccess) { gone = true; break; }      // the kernel left (its idle timeout raced with this batch): once more
-                if (q != cudaErrorNotReady) { m->srvRunning = false; set_error(std::string("small-model batch server: ") + cudaGetErrorString(q)); cudaGetLastError(); return IBO_E_CUDA; }
+                if (q != cudaErrorNotReady) { server_gone(m); set_error(std::string("small-model batch server: ") + cudaGetErrorString(q)); cudaGetLastError(); return IBO_E_CUDA; }
                 if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 20.0) {
                     set_error("small-model batch server: no answer for 20 s"); return IBO_E_CUDA;
                 }
             }
         }
-        if (gone) { m->srvRunning = false; continue; }
+        if (gone) { server_gone(m); continue; }
         std::atomic_thread_fence(std::memory_order_acquire);
         const double* sc = mb->data + nin;
         for (long i = 0; i < n; i++) y[i] = -sc[i];

@@ -150,19 +150,20 @@ def test_batch_server_gives_the_bits_of_the_per_batch_launches():
 
 
 def test_batch_server_side_by_side_queries():
-    """ibo_acqmax_many on small models: one resident kernel per model handle, all on one device"""
+    """ibo_acqmax_many on small models: one resident kernel per model handle, all on one device (at most four at a time, the
+    other queries launch per batch)"""
     from ibo_b200 import _lib
     rs = np.random.RandomState(12)
     d = 2
     models, want = [], []
     lb, ub = np.zeros(d), np.ones(d)
     try:
-        for q in range(4):
+        for q in range(6):
             X = rs.rand(40 + 10 * q, d); Y = np.cos(4 * X).sum(axis=1)
             models.append(_lib.Model(_lib.KERNEL_SE_ARD, [0.3, 0.4], X, Y, 0.1))
             want.append(models[-1].acqmax(lb, ub, _lib.ACQ_EI, float(Y.max()), 0.01, maxiter=30, maxsample=10 ** 6) + (float(Y.max()),))
         opt, optx, ns, it = _lib.acqmax_many(models, lb, ub, _lib.ACQ_EI, [w[4] for w in want], 0.01, maxiter=30, maxsample=10 ** 6)
-        for q in range(4):
+        for q in range(6):
             assert opt[q] == want[q][0] and np.array_equal(optx[q], want[q][1]) and ns[q] == want[q][2]
     finally:
         for m in models: m.close()
