@@ -20,7 +20,7 @@ enum {
     OPT_SHARD_MIN,       // sharded DIRECT: batches below this many points stay on every rank (0: 64 x ranks)
     OPT_I8_GUARD,        // 1 (default): candidates with sigma^2 < 2^-10 on the INT8 path are re-scored by the DMMA kernels
     OPT_I8_MIN_BATCH,    // batches of at least this many candidates (and at most narrow_max) also take the INT8 path (-1: measured break-even rule, 0: only wide batches)
-    OPT_I8_RB_PER_CTA,   // row-blocks a CTA of the INT8 K2 sweeps (G = nb / this many CTAs share a candidate tile)
+    OPT_I8_RB_PER_CTA,   // row-blocks a CTA of the INT8 K2 sweeps (G = nb / this many CTAs share a candidate tile); 0: four groups whatever the size
     OPT_I8_NTM,          // 0 (default): every operand of the INT8 K2 in shared memory; 1: W digits 1..4 reach the tensor core through TMEM
                          // (measured 6-13 % slower under the power cap: profiles/r02_int8_k2.md)
     OPT_CHOL_PAIR,       // model build: block columns in pairs (256-deep trailing updates); -1 = from 48 block columns on, 0 / 1 forced

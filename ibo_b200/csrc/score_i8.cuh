@@ -590,10 +590,14 @@ static void launch_kstar_i8(ibo_model* m, const double* dCand, long tiles, long 
 // K2 of one chunk on the int8 path
 static void launch_trigemm_i8(ibo_model* m, long tiles, long Mpad, const uint8_t* Ki8, double* part, cudaStream_t st) {
     const int sms = dev_info(m->device).sms;
-    // row-blocks per CTA: nb / G.  More row-blocks per CTA = fewer CTA prologues (TMEM allocation, pipeline fill) per unit of
-    // work, fewer CTAs sharing a candidate tile's K* digits in L2 (option i8_rb_per_cta, default 4)
-    const int per = (int)std::max<long>(1, get_option(OPT_I8_RB_PER_CTA));
-    int G = std::max(1, m->nb / per);
+    // Row-block groups G (a CTA walks nb / G row-blocks of its candidate tile, dealt in snake order).  Fewer groups = fewer CTA
+    // prologues per unit of work and, above all, fewer passes over the tile's K* digits: the G CTAs of a tile share them through L2
+    // only while they walk in step, and at N = 8192 the digits of W (235 MB) push them out between passes.  Measured (one B200,
+    // tools/i8_bench.py): G = 4 is the best or within 1 % of it at every size -- N = 2048: 24.0 M evals/s (G = 2: 23.9, G = 1: 22.1),
+    // N = 4096: 5.96 M (G = 8: 5.92, G = 2: 5.79), N = 8192: 1.58 M (G = 16: 1.35, G = 8: 1.53, G = 2: 1.52).
+    // Option i8_rb_per_cta > 0 fixes the row-blocks per CTA instead (G = nb / value).
+    const long per = get_option(OPT_I8_RB_PER_CTA);
+    int G = per > 0 ? (int)std::max<long>(1, m->nb / per) : std::min(m->nb, 4);
     if (tiles * 2 * G < sms) G = (int)std::min<long>(m->nb, (sms + tiles * 2 - 1) / (tiles * 2));
     const dim3 grid(G, (unsigned)(tiles * 2));
     if (m->i8Ntm) trigemm_i8_kernel<4><<<grid, I8Cfg<4>::THREADS, I8Cfg<4>::SMEM, st>>>(reinterpret_cast<const uint8_t*>(m->dWi8s), reinterpret_cast<const uint8_t*>(m->dWi8t),

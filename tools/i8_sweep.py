@@ -23,7 +23,7 @@ for ct in (148, 296, 592, 1184):
     for per in (2, 4, 8):
         _lib.set_option("i8_rb_per_cta", per)
         print("chunk_tiles %4d  rb_per_cta %d: %.3f ms" % (ct, per, run()), flush=True)
-_lib.set_option("chunk_tiles", 0); _lib.set_option("i8_rb_per_cta", 4)
+_lib.set_option("chunk_tiles", 0); _lib.set_option("i8_rb_per_cta", 0)
 for pipe in (0, 1):
     _lib.set_option("i8_pipe", pipe)
     print("i8_pipe %d: %.3f ms" % (pipe, run()), flush=True)
