@@ -61,3 +61,37 @@ def test_no_cpu_fallback():
     res = L.acqmaxGP(2, _lib.dptr(lb), _lib.dptr(ub), _lib.dptr(invR), _lib.dptr(X), _lib.dptr(Y), 8, 0, 1, _lib.dptr(hy),
                      0, _lib.dptr(z), _lib.dptr(z), 0.0, _lib.dptr(z), _lib.dptr(z), 0.01, 0.1, 5, 30, 100)
     assert not res
+
+
+def documented_options():
+    """name -> default from the "options" section of the header ("name (default)" entries)"""
+    txt = open(os.path.join(ROOT, "include", "ibo_b200.h")).read()
+    sec = txt[txt.index("---- options"):txt.index("int ibo_set_option")]
+    return {n: int(v) for n, v in re.findall(r"\b([a-z][a-z0-9_]+) \((-?\d+)\)", sec)}
+
+
+def test_options_are_what_the_header_says():
+    """every option the header documents exists with the documented default (read in a fresh process: other tests change options),
+    unknown names are rejected, values round-trip, and IBO_<NAME> presets an option when the library is loaded"""
+    import subprocess
+    import sys
+    opts = documented_options()
+    assert len(opts) >= 18 and opts["int8"] == 1 and opts["i8_min_batch"] == -1 and opts["tiny_server"] == 1
+    code = ("import sys; sys.path.insert(0, %r)\nfrom ibo_b200 import _lib\n"
+            "print(' '.join('%%s=%%d' %% (n, _lib.get_option(n)) for n in %r))" % (ROOT, sorted(opts)))
+    env = {k: v for k, v in os.environ.items() if not k.startswith("IBO_")}
+    out = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, text=True, check=True).stdout.split()
+    assert dict((kv.split("=")[0], int(kv.split("=")[1])) for kv in out) == opts
+    env["IBO_INT8"] = "0"; env["IBO_CHOL_PAIR"] = "1"
+    out = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, text=True, check=True).stdout.split()
+    got = dict((kv.split("=")[0], int(kv.split("=")[1])) for kv in out)
+    assert got["int8"] == 0 and got["chol_pair"] == 1 and got["i8_guard"] == 1
+    L = _lib.lib()
+    v = ctypes.c_long(0)
+    assert L.ibo_set_option(b"no_such_option", 1) == _lib.E_BADARG and L.ibo_get_option(b"no_such_option", ctypes.byref(v)) == _lib.E_BADARG
+    old = _lib.get_option("narrow_mt")
+    try:
+        _lib.set_option("narrow_mt", 4)
+        assert _lib.get_option("narrow_mt") == 4
+    finally:
+        _lib.set_option("narrow_mt", old)
