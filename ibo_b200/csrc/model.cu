@@ -986,6 +986,7 @@ static void free_model(ibo_model* m) {
     if (m->evFar) cudaEventDestroy(m->evFar);
     if (m->stream4) cudaStreamDestroy(m->stream4);
     for (auto& e : m->evI8) if (e) cudaEventDestroy(e);
+    for (auto& e : m->evCopy) if (e) cudaEventDestroy(e);
     if (m->stream2) cudaStreamDestroy(m->stream2);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;

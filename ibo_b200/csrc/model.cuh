@@ -42,6 +42,7 @@ struct ibo_model {
     double* dWi8s = nullptr; double* dWi8t = nullptr; double* dRowScale = nullptr; double* dAlphaY = nullptr; double* dAlpha1 = nullptr;
     bool i8Valid = false; int i8Ntm = -1;
     cudaEvent_t evI8[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // K1 done [2], K2+K3 done [2], fork
+    cudaEvent_t evCopy[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}; // host candidates: chunk copy done [4], fork
     // guard pass of the INT8 path: per-candidate flags + block counts; index list, gathered candidates and their re-scored values
     double* dGuard = nullptr; size_t guardCap = 0;
     double* dGuardList = nullptr; size_t guardListCap = 0;

@@ -914,8 +914,10 @@ static bool i8_for_small_batch(const ibo_model* m, long M, int flags) {
 // Runs K1..K4 for M candidates resident at dCand; results land in m->dOut ([score|mu|s2][M]) and
 // the (best score, best index) pair at m->dOut[3M], [3M+1].  Everything is enqueued on m->stream; the only host
 // synchronisation is the 4-byte read of the guard count on the INT8 path of a small-noise model.
+// `hostWide`: the candidates are still in host memory (all M of them, destined for dCand): every chunk is copied on a separate
+// stream two chunks ahead of the kernels that read it, so that a call from host buffers pays for the first chunk's copy only.
 static int score_device(ibo_model* m, const double* dCand, long M, const ScoreReq& rq, double* outBase = nullptr,
-                        const double* hostCand = nullptr) {
+                        const double* hostCand = nullptr, const double* hostWide = nullptr) {
     cudaError_t ae = ensure_attrs(m->device, ATTR_SCORE, set_score_attrs);
     if (ae != cudaSuccess) { set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ae)); return IBO_E_CUDA; }
     if (m->d > 64) { set_error("d > 64 not supported"); return IBO_E_BADARG; }
@@ -923,6 +925,7 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
     if (!forceWide && tiny_eligible(m, M)) {       // N <= 128, small batch: one fused launch (tiny.cu)
         int rc0;
         if (!outBase && (rc0 = grow(&m->dOut, &m->outCap, (size_t)3 * M + 2))) return rc0;
+        if (hostWide) IBO_CUDA_TRY(cudaMemcpyAsync(const_cast<double*>(dCand), hostWide, sizeof(double) * (size_t)M * m->d, cudaMemcpyHostToDevice, m->stream));
         return score_tiny(m, dCand, M, rq, outBase ? outBase : m->dOut, hostCand);
     }
     cudaStream_t st = m->stream;
@@ -997,10 +1000,29 @@ static int score_device(ibo_model* m, const double* dCand, long M, const ScoreRe
     long nlaunch = 0, nK2 = 0;
     if (prof) IBO_CUDA_TRY(cudaEventRecord(m->ev[0], st));
     long blk0 = 0;
+    const long nchunks = (tilesTotal + chunkTiles - 1) / chunkTiles;
+    long copied = 0;                                    // chunks whose host -> device copy has been issued
+    cudaStream_t cs = m->stream3;                       // idle outside the model build; the copies run on the DMA engines
+    if (hostWide) {
+        for (auto& e : m->evCopy) if (!e) IBO_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        IBO_CUDA_TRY(cudaEventRecord(m->evCopy[4], st));                 // whatever still reads dCand from an earlier call
+        IBO_CUDA_TRY(cudaStreamWaitEvent(cs, m->evCopy[4], 0));
+    }
     for (long t0 = 0; t0 < tilesTotal; t0 += chunkTiles) {
         const long tiles = std::min(chunkTiles, tilesTotal - t0);
         const long m0 = t0 * TN;
         const long chunkM = std::min<long>(tiles * TN, M - m0);
+        if (hostWide) {
+            for (; copied < nchunks && copied <= ci + 2; copied++) {
+                const long c0 = copied * Mpad, cn = std::min<long>(Mpad, M - c0);
+                IBO_CUDA_TRY(cudaMemcpyAsync(const_cast<double*>(dCand) + (size_t)c0 * m->d, hostWide + (size_t)c0 * m->d,
+                                             sizeof(double) * (size_t)cn * m->d, cudaMemcpyHostToDevice, cs));
+                IBO_CUDA_TRY(cudaEventRecord(m->evCopy[copied & 3], cs));
+            }
+            // slot ci & 3 is re-recorded for chunk ci + 4 only two iterations from now, after these waits have been enqueued
+            IBO_CUDA_TRY(cudaStreamWaitEvent(st, m->evCopy[ci & 3], 0));
+            if (i8pipe) IBO_CUDA_TRY(cudaStreamWaitEvent(m->stream2, m->evCopy[ci & 3], 0));
+        }
         const long ctaTiles = narrow ? (chunkM + 31) / 32 : tiles;      // K2 CTAs along the candidate axis
         K2Plan pl = plan;
         if (!narrow && tiles != chunkTiles) pl.G = pick_groups_wide(nb, tiles, sms);      // last, shorter chunk
@@ -1147,8 +1169,7 @@ static int score_host(ibo_model* m, const double* Xs, long M, const ScoreReq& rq
         if (s2) std::memcpy(s2, ho + 2 * M, sizeof(double) * M);
         if (rq.acq >= 0 && rq.want_argmax) { hb = ho[3 * M]; std::memcpy(&hi, &ho[3 * M + 1], 8); }
     } else {
-        IBO_CUDA_TRY(cudaMemcpyAsync(m->dCand, Xs, sizeof(double) * nin, cudaMemcpyHostToDevice, st));
-        if ((rc = score_device(m, m->dCand, M, rq))) return rc;
+        if ((rc = score_device(m, m->dCand, M, rq, nullptr, nullptr, Xs))) return rc;
         if (scores) IBO_CUDA_TRY(cudaMemcpyAsync(scores, m->dOut, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
         if (mu) IBO_CUDA_TRY(cudaMemcpyAsync(mu, m->dOut + M, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
         if (s2) IBO_CUDA_TRY(cudaMemcpyAsync(s2, m->dOut + 2 * M, sizeof(double) * M, cudaMemcpyDeviceToHost, st));
