@@ -127,7 +127,6 @@ __global__ void __launch_bounds__(128) tiny_fused_kernel(const __grid_constant__
     asm volatile("cp.async.wait_group 0;");
     __shared__ long long sh_seq, sh_M;
     long long lastSeq = 0;
-    unsigned batchNo = 0;
   next_batch:
     if (SERVER) {
         // CTA 0 watches the host's mailbox (one PCIe read per poll) and passes each new batch on through device memory, where
@@ -151,7 +150,7 @@ __global__ void __launch_bounds__(128) tiny_fused_kernel(const __grid_constant__
         }
         __syncthreads();
         if (sh_seq < 0) return;
-        lastSeq = sh_seq; batchNo++;
+        lastSeq = sh_seq;
         Mcur = (long)sh_M;
         scoreOut = mb->data + (size_t)Mcur * d;
     }
